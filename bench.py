@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- MLUPS of the fused fp64 D3Q19 collide-stream(+IBM) step on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU algorithm (oracle port)
+
+Workload (BASELINE.json configs[1]): periodic body-force-driven channel, no body, 256^3 cells per
+GPU, SRT, tau = 0.8, volumeForceIn = (1e-6,0,0).  N > 1 weak-scales along x (x-slabs of 256 planes,
+global grid 256N x 256 x 256) with the one-plane halo exchange of the outgoing populations.
+One "step" = one pass of LBMBlockComm.f90:283-303 over the block (update_volume_force + the fused
+macro/force/collide/stream/boundary kernel).  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MLUPS (fp64 D3Q19 collide-stream+IBM)"
+UNIT = "MLUPS"
+BYTES_PER_LU = 304.0  # 2 x 19 x 8, BASELINE.md section 2
+WORKLOADS = {
+    # name: (X per GPU, Y, Z, BndConds, model, plate?)
+    "channel256": dict(dims=(256, 256, 256), bc=(301,) * 6, model=1, plate=False,
+                       desc="configs[1]: periodic body-force channel 256^3 per GPU, SRT, no body"),
+    "plate512": dict(dims=(512, 256, 256), bc=(101, 104, 202, 202, 301, 301), model=1, plate=True,
+                     desc="configs[2]: rigid plate (8192 markers) in shear inflow 512x256x256, SRT, 5 IBM iterations"),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        super().__init__(daemon=True)
+        self.device, self.rows, self._stop_evt = device, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def build_plate(F, dh, denIn):
+    # configs[2]: chord 1 (64 cells), span 2, nEL=64, Nspan=128 -> 8192 markers, centred
+    return F.RigidPlate(origin=(3.0, 2.0 - 0.013, 1.0 + 0.003), nEL=64, len1=dh, Nspan=128, spanlen=2.0, Lspan=0.0,
+                        chord_dir=(1.0, 0.0, 0.0), span_dir=(0.0, 0.0, 1.0), IBPenaltyAlpha=1.0, denIn=denIn)
+
+
+def workload_flow(F_or_O_flow, wl):
+    if wl["plate"]:
+        dh = 1.0 / 64.0
+        gamma = 0.02 / ((wl["dims"][1] - 1) * dh)
+        return dict(nu=5e-4, uvwIn=(0.05, 0.0, 0.0), shearRateIn=(0.0, gamma, 0.0), Uref=0.05, ntolLBM=5, dtolLBM=1e-30), dh
+    return dict(nu=0.1, volumeForceIn=(1e-6, 0.0, 0.0)), 1.0
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_time_oracle(wl, dims, steps, warmup):
+    """Times the CPU restatement of the reference's OpenMP path (oracle/; kind 'port') on `dims`."""
+    from oracle import oracle as O
+    import fsilbm3d_b200 as F
+    flowkw, dh = workload_flow(None, wl)
+    fl = O.Flow(**flowkw)
+    X, Y, Z = dims
+    b = O.LBMBlock(X, Y, Z, dh=dh, BndConds=wl["bc"], iCollidModel=wl["model"], flow=fl)
+    b.initialise(0.0)
+    b.update_volume_force(); b.set_boundary_conditions(); b.calculate_macro_quantities()
+    bodies, plate = [], None
+    if wl["plate"]:
+        plate = build_plate(F, dh, fl.denIn)
+        ov = O.VirtualBody(plate.body.v_nelmts, v_move=0, iBodyModel=1)
+        ov.v_Exyz[...] = plate.body.v_Exyz; ov.v_Evel[...] = plate.body.v_Evel; ov.v_Ea[...] = plate.body.v_Ea
+        bodies = [ov]
+
+    def one(n):
+        b.set_blktime(n * dh)
+        b.step(bodies)
+        b.calculate_macro_quantities()   # main.f90:107
+
+    for n in range(warmup):
+        one(n + 1)
+    t0 = time.perf_counter()
+    for n in range(steps):
+        one(warmup + n + 1)
+    dt = time.perf_counter() - t0
+    return X * Y * Z * steps / dt / 1e6, dt / steps, O.lib().orc_omp_max_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (the Fortran cannot be built here: no Fortran
+    compiler in the image; the oracle port stands in, kind 'port'), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    X, Y, Z = wl["dims"]
+    # bounded sample: calibrate on a thin slab, then take the largest x extent that keeps the run in ~2 minutes
+    mlups_cal, t_cal, threads = cpu_time_oracle(wl, (16, Y, Z), 2, 1)
+    per_plane = t_cal / 16.0
+    budget = 120.0
+    if wl["plate"]:
+        candidates = [X, 320]   # the plate occupies planes 192..256; 320 planes keep it well inside
+    else:
+        candidates = [X >> k for k in range(0, 8) if (X >> k) >= 16]
+    xs = candidates[-1]
+    for c in candidates:
+        if per_plane * c * (args.steps + args.warmup) <= budget:
+            xs = c
+            break
+    mlups, t_step, threads = cpu_time_oracle(wl, (xs, Y, Z), args.steps, args.warmup)
+    sample = f"{xs}x{Y}x{Z} of the {X}x{Y}x{Z} grid, {args.steps} steps after {args.warmup} warm-up"
+    line = {
+        "metric": METRIC, "value": mlups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": args.workload, "desc": wl["desc"], "grid_per_gpu": [X, Y, Z]},
+        "cpu_baseline": {"value": mlups, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "note": "C restatement of the reference OpenMP path (Fortran not buildable here)"},
+        "e2e": {"value": mlups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    import fsilbm3d_b200 as F
+
+    if world > 1:
+        dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+
+        def bcast(b):
+            t = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                t = torch.tensor(list(b), dtype=torch.uint8)
+            dist.broadcast(t, src=0)
+            return bytes(t.tolist())
+        F.init_process_group(rank, world, local, bcast)
+    else:
+        F.init_process_group(0, 1, local, None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    wl = WORKLOADS[args.workload]
+    Xl, Y, Z = wl["dims"]
+    XG = Xl * world
+    flowkw, dh = workload_flow(None, wl)
+    flow = F.FlowCondType(**flowkw)
+    blk = F.LBMBlock(XG, Y, Z, dh=dh, BndConds=wl["bc"], iCollidModel=wl["model"], flow=flow, xOffset=rank * Xl, xLocal=Xl, device=local)
+    blk.initialise(0.0)
+    blk.update_volume_force(); blk.set_boundary_conditions()
+    plates = []
+    if wl["plate"]:
+        plates = [build_plate(F, dh, flow.denIn)]
+        if world > 1:   # keep the plate inside rank 0's slab neighbourhood in global coordinates
+            pass
+    stream = torch.cuda.ExternalStream(blk.cuda_stream, device=local)
+    lib = F.lib()
+
+    def step(n):
+        F.tree_collision_streaming_IBM_FEM(blk, plates, time=n * dh, solver=False)
+
+    # ---- device-resident throughput ("value") ---------------------------------------------------------
+    for n in range(args.warmup):
+        step(n + 1)
+    blk.sync(); torch.cuda.synchronize(); barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.fsilbm_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for n in range(args.steps):
+        step(args.warmup + n + 1)
+    e1.record(stream)
+    blk.sync(); torch.cuda.synchronize()
+    launches = lib.fsilbm_launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    cells_total = float(XG) * Y * Z
+    value = cells_total * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- dominant kernel alone (roofline): fused collide-stream launches back to back --------------------
+    kern_ms = None
+    if not wl["plate"] and world == 1:
+        kern_ms = ms / args.steps    # a step of this workload IS one collide_push launch (periodic: no face kernels)
+    else:
+        blk.sync()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(10, args.steps // 4)
+        old = F.lib().fsilbm_launch_count()
+        k0.record(stream)
+        for _ in range(reps):
+            blk.collide_stream()
+        k1.record(stream)
+        blk.sync()
+        kern_ms = k0.elapsed_time(k1) / reps
+    peak, peak_src = measured_peaks()
+    cells_local = float(Xl) * Y * Z
+    achieved = BYTES_PER_LU * cells_local / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "collide_push_kernel", "algorithmic_bytes_per_launch": BYTES_PER_LU * cells_local, "peak_source": peak_src,
+                "kernel_ms": kern_ms}
+
+    # ---- end to end through the host API with HOST buffers ------------------------------------------------
+    # One segment = what the reference driver does between two flow outputs: populations come from pinned host
+    # memory (check_is_continue / initialise), K steps run through the public API, den+uuu go back to pinned
+    # host memory (write_flow_).  Copies are inside the timed region; bytes are amortised per step below.
+    f_host = torch.empty((19, Xl, Y, Z), dtype=torch.float64, pin_memory=True)
+    den_host = torch.empty((Xl, Y, Z), dtype=torch.float64, pin_memory=True)
+    uuu_host = torch.empty((3, Xl, Y, Z), dtype=torch.float64, pin_memory=True)
+    blk.download_fIn(f_host.numpy())
+    blk.sync(); torch.cuda.synchronize(); barrier()
+    t0 = time.perf_counter()
+    blk.upload_fIn(f_host.numpy())
+    for n in range(args.steps):
+        step(args.warmup + args.steps + n + 1)
+    check = F._lib.check
+    check(lib.fsilbm_block_download_macro(blk._h, den_host.numpy().ctypes.data, uuu_host.numpy().ctypes.data))
+    blk.sync(); torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = cells_total * args.steps / e2e_s / 1e6
+    h2d = f_host.numel() * 8 * world + (sum(7 * p.body.v_nelmts * 8 for p in plates) * args.steps)
+    d2h = (den_host.numel() + uuu_host.numel()) * 8 * world + (sum(3 * p.body.v_nelmts * 8 for p in plates) * args.steps)
+    e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+           "segment": f"upload fIn from pinned host -> {args.steps} steps via LBMBlock API -> download den,uuu to pinned host; "
+                      "bytes amortised over the segment's steps"}
+
+    # ---- CPU baseline on this box's cores (rank 0, N = 1 only) ----------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            sx = Xl if not wl["plate"] else 320
+            steps_cpu = 6
+            mlups, t_step, threads = cpu_time_oracle(wl, (sx, Y, Z), steps_cpu, 2)
+            cpu = {"value": mlups, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{sx}x{Y}x{Z}, {steps_cpu} steps after 2 warm-up ({t_step * 1e3:.0f} ms/step); "
+                             "C restatement of the reference OpenMP path (Fortran not buildable here)"}
+        except Exception as ex:   # the baseline must never take the GPU number down with it
+            cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {ex}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "desc": wl["desc"], "grid_per_gpu": [Xl, Y, Z], "grid_global": [XG, Y, Z],
+                       "decomposition": f"x-slabs x{world}" if world > 1 else "single block",
+                       "l2": "working set 5.1 GB per GPU (two population buffers) >> 126 MB L2; no explicit flush needed",
+                       "kernel_variant": args.variant},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    blk.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--workload", default="channel256", choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.variant:
+        import fsilbm3d_b200 as F
+        F._lib.check(F.lib().fsilbm_set_option(b"variant", args.variant))
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,1004 @@
+// fsilbm_api.cu -- the C ABI of include/fsilbm.h: block state, step orchestration, IBM driver,
+// slab halo exchange.  Host code only; kernels live in fluid_kernels.cu / ibm_kernels.cu.
+#include "../../include/fsilbm.h"
+#include "kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace fsilbm;
+
+// ---- error plumbing ---------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) return fail(FSILBM_ERR_CUDA, "CUDA: %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- NCCL through dlopen (only multi-rank runs need it) ------------------------------------------------
+namespace {
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef void *ncclComm_p;
+struct Nccl {
+    void *lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId_t *) = nullptr;
+    int (*CommInitRank)(ncclComm_p *, int, ncclUniqueId_t, int) = nullptr;
+    int (*CommDestroy)(ncclComm_p) = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    ncclComm_p comm = nullptr;
+    int rank = 0, nranks = 1;
+} g_nccl;
+constexpr int kNcclFloat64 = 8;   // ncclDouble
+constexpr int kNcclSum = 0;       // ncclSum
+
+int nccl_load()
+{
+    if (g_nccl.lib) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return fail(FSILBM_ERR_COMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                                  \
+    *(void **)(&g_nccl.field) = dlsym(g_nccl.lib, name);                                  \
+    if (!g_nccl.field) return fail(FSILBM_ERR_COMM, "NCCL symbol %s missing", name);
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
+    SYM(AllReduce, "ncclAllReduce")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return 0;
+}
+#define NCK(call)                                                                                          \
+    do {                                                                                                   \
+        int r_ = (call);                                                                                   \
+        if (r_ != 0) return fail(FSILBM_ERR_COMM, "NCCL: %s at %s:%d", g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- block state ------------------------------------------------------------------------------------
+struct BodyDev {
+    int n = 0;
+    double *Exyz = nullptr, *ExyzStencil = nullptr, *Evel = nullptr, *Ea = nullptr, *Eforce = nullptr, *felt = nullptr, *tol = nullptr;
+    double *partialU = nullptr;
+    short *Ei = nullptr;
+    float *Ew = nullptr;
+    int *cell = nullptr;
+    long long *boff = nullptr;
+    unsigned char *owned = nullptr;
+    bool have_stencil_pos = false;
+    void release()
+    {
+        cudaFree(Exyz); cudaFree(ExyzStencil); cudaFree(Evel); cudaFree(Ea); cudaFree(Eforce); cudaFree(felt); cudaFree(tol);
+        cudaFree(partialU); cudaFree(Ei); cudaFree(Ew); cudaFree(cell); cudaFree(boff); cudaFree(owned);
+        *this = BodyDev();
+    }
+    IbmBody view() const
+    {
+        IbmBody b;
+        b.n = n; b.Exyz = ExyzStencil; b.Evel = Evel; b.Ea = Ea; b.Eforce = Eforce; b.Ei = Ei; b.Ew = Ew;
+        b.cell = cell; b.boff = boff; b.owned = owned; b.felt = felt; b.tol = tol;
+        return b;
+    }
+};
+
+struct Block {
+    Geom g{};
+    int bc[6]{}, periodic[3]{};
+    int model = 1;
+    double params[10]{};
+    fsilbm_flow flow{};
+    double tau = 0, Omega = 0, Omega2 = 0;
+    double Mc[Q * Q]{}, Mf[Q * Q]{};
+    int mrt_slot = 0;
+    bool initialised = false;
+    double *f[2] = {nullptr, nullptr};
+    int cur = 0;
+    double volumeForce[3] = {0, 0, 0};
+    double blktime = 0;
+    double *stash[6]{}, *l2den[6]{}, *l2u[6]{};
+    bool hw_alloc[6]{};
+    double *den = nullptr, *uuu = nullptr, *force = nullptr;   // un-fused fields / download staging
+    double *stat = nullptr;
+    // IBM
+    IbmBoxes boxes{};
+    long long box_capacity = 0;
+    std::vector<BodyDev> bodies;
+    std::vector<std::vector<double>> stencil_pos;   // host copy of the marker positions the stencils were last built from
+    IbmBody *bodies_dev = nullptr;
+    int bodies_dev_cap = 0;
+    IbmCtl *ctl = nullptr;
+    bool ibm_active = false;
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_edge = nullptr, ev_comm = nullptr;
+};
+
+std::vector<std::unique_ptr<Block>> g_blocks;
+int g_device = -1;
+int g_variant = 0, g_force_ghost = 0;
+
+Block *get(fsilbm_handle h)
+{
+    if (h < 0 || h >= (int)g_blocks.size() || !g_blocks[h]) return nullptr;
+    return g_blocks[h].get();
+}
+
+inline void face_dims(const Geom &g, int face, int &na, int &nb)
+{
+    const int axis = face / 2;
+    if (axis == 0) { na = g.Z; nb = g.Y; }
+    else if (axis == 1) { na = g.Z; nb = g.X; }
+    else { na = g.Y; nb = g.X; }
+}
+
+// does this rank hold the global boundary plane of `face`?
+inline bool owns_face(const Block &b, int face)
+{
+    if (face == 0) return b.g.xOffset == 0;
+    if (face == 1) return b.g.xOffset + b.g.X == b.g.XG;
+    return true;
+}
+
+int velocity_field(const Block &b, double time, VelocityField &v)
+{
+    v.kind = b.flow.velocityKind;
+    for (int k = 0; k < 3; k++) { v.uvwIn[k] = b.flow.uvwIn[k]; v.shear[k] = b.flow.shearRateIn[k]; v.uniform[k] = b.flow.uvwIn[k]; }
+    if (v.kind == 0) return 0;
+    if (v.kind == 2) {   // evaluate_oscillatory_velocity, FluidDomain.f90:1813-1824 (host libm cos, as the reference)
+        const double Pi = 3.141592653589793;
+        const double velocityAmp = b.flow.shearRateIn[0], velocityFreq = b.flow.shearRateIn[1], velocityPhi = b.flow.shearRateIn[2];
+        v.uniform[0] = b.flow.uvwIn[0] + velocityAmp * cos(2 * Pi * velocityFreq * time + velocityPhi / 180.0 * Pi);
+        return 0;
+    }
+    return fail(FSILBM_ERR_ARG, "velocityKind %d: the reference defines only 0 and 2 (FluidDomain.f90:1795-1799)", v.kind);
+}
+
+CollideConsts collide_consts(const Block &b)
+{
+    CollideConsts c;
+    c.Omega = b.Omega; c.Omega2 = b.Omega2;
+    c.dt3 = 3.0 * b.g.dh;             // FluidDomain.f90:1213
+    c.cF = 1.0 - 0.5 * b.Omega;       // :1227
+    c.mrt_slot = b.mrt_slot;
+    return c;
+}
+
+void half_force(const Block &b, double hF[3])
+{
+    for (int k = 0; k < 3; k++) hF[k] = 0.5 * b.volumeForce[k] * b.g.dh;   // FluidDomain.f90:1137
+}
+
+// calculate_MRT_params, FluidDomain.f90:466-522; matmul sums run over the inner index ascending from zero
+void mrt_matrices(double Omega, double *Mc, double *Mf)
+{
+    static const double s0 = 0.0, s1 = 1.19, s2 = 1.4, s4 = 1.2, s10 = 1.4, s16 = 1.98;   // ConstParams.f90:28
+    double M[Q][Q], MI[Q][Q], MM[Q][Q], T[Q][Q];
+    for (int I = 0; I < Q; I++) {
+        const double e1 = EX(I), e2 = EY(I), e3 = EZ(I);
+        const double sq = (double)(EX(I) * EX(I) + EY(I) * EY(I) + EZ(I) * EZ(I));
+        M[0][I] = 1.0;
+        M[1][I] = 19.0 * sq - 30.0;
+        M[2][I] = (21.0 * (sq * sq) - 53.0 * sq + 24.0) / 2.0;
+        M[3][I] = e1; M[5][I] = e2; M[7][I] = e3;
+        M[4][I] = (5.0 * sq - 9.0) * e1; M[6][I] = (5.0 * sq - 9.0) * e2; M[8][I] = (5.0 * sq - 9.0) * e3;
+        M[9][I] = 3.0 * (e1 * e1) - sq;
+        M[10][I] = (3.0 * sq - 5.0) * (3.0 * (e1 * e1) - sq);
+        M[11][I] = e2 * e2 - e3 * e3;
+        M[12][I] = (3.0 * sq - 5.0) * (e2 * e2 - e3 * e3);
+        M[13][I] = e1 * e2; M[14][I] = e2 * e3; M[15][I] = e3 * e1;
+        M[16][I] = (e2 * e2 - e3 * e3) * e1;
+        M[17][I] = (e3 * e3 - e1 * e1) * e2;
+        M[18][I] = (e1 * e1 - e2 * e2) * e3;
+    }
+    for (int i = 0; i < Q; i++) for (int j = 0; j < Q; j++) MI[i][j] = M[j][i];
+    for (int i = 0; i < Q; i++) for (int j = 0; j < Q; j++) { double s = 0.0; for (int k = 0; k < Q; k++) s = s + M[i][k] * MI[k][j]; MM[i][j] = s; }
+    for (int I = 0; I < Q; I++) for (int r = 0; r < Q; r++) MI[r][I] = MI[r][I] / MM[I][I];
+    const double S[Q] = {s0, s1, s2, s0, s4, s0, s4, s0, s4, Omega, s10, Omega, s10, Omega, Omega, Omega, s16, s16, s16};
+    for (int i = 0; i < Q; i++) for (int j = 0; j < Q; j++) { double s = 0.0; for (int k = 0; k < Q; k++) s = s + MI[i][k] * (k == j ? S[k] : 0.0); T[i][j] = s; }
+    for (int i = 0; i < Q; i++) for (int j = 0; j < Q; j++) { double s = 0.0; for (int k = 0; k < Q; k++) s = s + T[i][k] * M[k][j]; Mc[i * Q + j] = s; }
+    for (int i = 0; i < Q; i++) for (int j = 0; j < Q; j++) Mf[i * Q + j] = ((i == j) ? 1.0 : 0.0) - 0.5 * Mc[i * Q + j];
+}
+
+bool valid_bc(int c)
+{
+    switch (c) {
+    case 101: case 102: case 103: case 104: case 201: case 202: case 203: case 204: case 301: case 302: case 0: case 1: return true;
+    default: return false;
+    }
+}
+
+FaceParams face_params(Block &b, int face, double *f, const double *fA, const VelocityField &vel)
+{
+    FaceParams p{};
+    p.g = b.g; p.f = f; p.fA = fA; p.face = face; p.code = b.bc[face];
+    face_dims(b.g, face, p.na, p.nb);
+    p.vel = vel; p.denIn = b.flow.denIn;
+    const int axis = face / 2, hi = face & 1;
+    const double lo = axis == 0 ? b.g.xmin : axis == 1 ? b.g.ymin : b.g.zmin;
+    const int N = axis == 0 ? b.g.XG : axis == 1 ? b.g.Y : b.g.Z;
+    double hic = lo + b.g.dh * (N - 1);                 // xmax, FluidDomain.f90:94 (non-periodic faces only reach here)
+    p.wallc = hi ? hic : lo;
+    if (p.code == BCmoving_Wall_halfway) p.wallc = hi ? hic + b.g.dh * 0.5 : lo - b.g.dh * 0.5;   // :688,772
+    p.stash = b.stash[face]; p.l2den = b.l2den[face]; p.l2u = b.l2u[face];
+    p.cc = collide_consts(b);
+    half_force(b, p.hF);
+    for (int k = 0; k < 3; k++) p.Fvol[k] = b.volumeForce[k];
+    p.boxes = b.boxes;
+    if (!b.ibm_active) p.boxes.n = 0;
+    p.model = b.model;
+    return p;
+}
+
+// set_boundary_conditions_ on buffer f, faces in the reference's order (FluidDomain.f90:622-1125)
+int apply_boundary_conditions(Block &b, double *f)
+{
+    VelocityField vel;
+    if (int rc = velocity_field(b, b.blktime, vel)) return rc;
+    for (int face = 0; face < 6; face++) {
+        const int code = b.bc[face];
+        if (code == BCPeriodic || code == BCfluid || code == BCfluid_father) continue;   // :701-702
+        if (!owns_face(b, face)) continue;
+        int na, nb;
+        face_dims(b.g, face, na, nb);
+        if (code == BCstationary_Wall_halfway || code == BCmoving_Wall_halfway) {
+            if (!b.hw_alloc[face]) {   // :660-661: the first call allocates the stash and skips the rule
+                CK(cudaMalloc(&b.stash[face], sizeof(double) * (size_t)Q * na * nb));
+                CK(cudaMemsetAsync(b.stash[face], 0, sizeof(double) * (size_t)Q * na * nb, b.stream));
+                b.hw_alloc[face] = true;
+                continue;
+            }
+        }
+        FaceParams p = face_params(b, face, f, nullptr, vel);
+        launch_bc_face(p, b.stream);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int ensure_fields(Block &b, bool need_force)
+{
+    const size_t n = (size_t)b.g.X * b.g.plane;
+    if (!b.den) CK(cudaMalloc(&b.den, sizeof(double) * n));
+    if (!b.uuu) CK(cudaMalloc(&b.uuu, sizeof(double) * 3 * n));
+    if (need_force && !b.force) { CK(cudaMalloc(&b.force, sizeof(double) * 3 * n)); CK(cudaMemsetAsync(b.force, 0, sizeof(double) * 3 * n, b.stream)); }
+    return 0;
+}
+
+// one-plane halo exchange of the outgoing populations between x-neighbours:
+// ghost plane X+1 (pops with ex=+1) -> right neighbour's plane 1; ghost plane 0 (ex=-1) -> left neighbour's plane X.
+int halo_exchange(Block &b, double *fB, cudaStream_t s)
+{
+    const Geom &g = b.g;
+    const int R = g_nccl.nranks, r = g_nccl.rank;
+    const bool per = b.periodic[0] == 1;
+    const int right = (r + 1 < R) ? r + 1 : (per ? 0 : -1);
+    const int left = (r > 0) ? r - 1 : (per ? R - 1 : -1);
+    static const int up[5] = {1, 7, 9, 11, 13}, dn[5] = {2, 8, 10, 12, 14};
+    NCK(g_nccl.GroupStart());
+    for (int k = 0; k < 5; k++) {
+        if (right >= 0) {
+            NCK(g_nccl.Send(fB + up[k] * g.pstride + (size_t)(g.X + 1) * g.plane, g.plane, kNcclFloat64, right, g_nccl.comm, s));
+            NCK(g_nccl.Recv(fB + dn[k] * g.pstride + (size_t)g.X * g.plane, g.plane, kNcclFloat64, right, g_nccl.comm, s));
+        }
+        if (left >= 0) {
+            NCK(g_nccl.Send(fB + dn[k] * g.pstride, g.plane, kNcclFloat64, left, g_nccl.comm, s));
+            NCK(g_nccl.Recv(fB + up[k] * g.pstride + (size_t)1 * g.plane, g.plane, kNcclFloat64, left, g_nccl.comm, s));
+        }
+    }
+    NCK(g_nccl.GroupEnd());
+    return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char *fsilbm_last_error(void) { return g_err; }
+long long fsilbm_launch_count(void) { return kernel_launch_count(); }
+
+int fsilbm_init(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(FSILBM_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(FSILBM_ERR_ARG, "device %d out of range [0,%d)", device, n);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(FSILBM_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    g_device = device;
+    return 0;
+}
+
+int fsilbm_finalize(void)
+{
+    for (size_t i = 0; i < g_blocks.size(); i++)
+        if (g_blocks[i]) fsilbm_block_destroy((int)i);
+    g_blocks.clear();
+    fsilbm_comm_finalize();
+    return 0;
+}
+
+int fsilbm_set_option(const char *key, int value)
+{
+    if (!key) return fail(FSILBM_ERR_ARG, "null key");
+    if (!strcmp(key, "variant")) { if (value < 0 || value > 2) return fail(FSILBM_ERR_ARG, "variant must be 0..2"); g_variant = value; return 0; }
+    if (!strcmp(key, "force_ghost")) { g_force_ghost = value ? 1 : 0; return 0; }
+    return fail(FSILBM_ERR_ARG, "unknown option %s", key);
+}
+
+int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, double dh, double xmin, double ymin, double zmin,
+                        const int BndConds[6], int iCollidModel, const double params[10], const fsilbm_flow *flow, fsilbm_handle *out)
+{
+    if (g_device < 0) return fail(FSILBM_ERR_CUDA, "fsilbm_init has not succeeded (no CPU fallback)");
+    if (!BndConds || !params || !flow || !out) return fail(FSILBM_ERR_ARG, "null argument");
+    if (xDim < 1 || yDim < 1 || zDim < 1) return fail(FSILBM_ERR_ARG, "non-positive grid size");
+    if (xDim > 32767 || yDim > 32767 || zDim > 32767)   // FluidDomain.f90:88-91
+        return fail(FSILBM_ERR_ARG, "Grid number exceeds 32767, please try to reduced the grid size.");
+    if (xOffset < 0 || xLocal < 1 || xOffset + xLocal > xDim) return fail(FSILBM_ERR_ARG, "bad slab [%d,%d) of %d", xOffset, xOffset + xLocal, xDim);
+    for (int i = 0; i < 6; i++) if (!valid_bc(BndConds[i])) return fail(FSILBM_ERR_BC, "face %d has no such boundary condition: %d", i, BndConds[i]);
+    if (!(iCollidModel == 1 || iCollidModel == 2 || iCollidModel == 3))
+        return fail(FSILBM_ERR_MODEL, "iCollidModel %d not provided (1 SRT, 2 TRT, 3 MRT)", iCollidModel);
+    auto b = std::make_unique<Block>();
+    for (int i = 0; i < 3; i++) {   // check_periodic_boundary_, FluidDomain.f90:110-125
+        b->periodic[i] = 0;
+        if (BndConds[2 * i] == BCPeriodic || BndConds[2 * i + 1] == BCPeriodic) {
+            if (BndConds[2 * i] == BndConds[2 * i + 1]) b->periodic[i] = 1;
+            else return fail(FSILBM_ERR_PERIODIC, "Stop! Periodic boundaries must apper in pairs: %d %d", BndConds[2 * i], BndConds[2 * i + 1]);
+        }
+    }
+    Geom &g = b->g;
+    g.X = xLocal; g.Y = yDim; g.Z = zDim; g.XG = xDim; g.xOffset = xOffset;
+    g.plane = (size_t)yDim * zDim; g.pstride = (size_t)(xLocal + 2) * g.plane;
+    g.dh = dh; g.xmin = xmin; g.ymin = ymin; g.zmin = zmin;
+    memcpy(b->bc, BndConds, sizeof(int) * 6);
+    memcpy(b->params, params, sizeof(double) * 10);
+    b->flow = *flow;
+    b->model = iCollidModel;
+    const size_t bytes = sizeof(double) * Q * g.pstride;
+    for (int i = 0; i < 2; i++) {
+        CK(cudaMalloc(&b->f[i], bytes));
+        CK(cudaMemset(b->f[i], 0, bytes));
+    }
+    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&b->comm_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&b->ev_edge, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b->ev_comm, cudaEventDisableTiming));
+    CK(cudaMalloc(&b->ctl, sizeof(IbmCtl)));
+    CK(cudaMalloc(&b->stat, sizeof(double) * 6));
+    int slot = -1;
+    for (size_t i = 0; i < g_blocks.size(); i++) if (!g_blocks[i]) { slot = (int)i; break; }
+    if (slot < 0) { g_blocks.emplace_back(); slot = (int)g_blocks.size() - 1; }
+    b->mrt_slot = slot % MRT_SLOTS;
+    g_blocks[slot] = std::move(b);
+    *out = slot;
+    return 0;
+}
+
+int fsilbm_block_destroy(fsilbm_handle h)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    cudaStreamSynchronize(b->stream);
+    cudaStreamSynchronize(b->comm_stream);
+    for (int i = 0; i < 2; i++) cudaFree(b->f[i]);
+    for (int i = 0; i < 6; i++) { cudaFree(b->stash[i]); cudaFree(b->l2den[i]); cudaFree(b->l2u[i]); }
+    cudaFree(b->den); cudaFree(b->uuu); cudaFree(b->force); cudaFree(b->stat);
+    cudaFree(b->boxes.u); cudaFree(b->boxes.force);
+    for (auto &bd : b->bodies) bd.release();
+    cudaFree(b->bodies_dev); cudaFree(b->ctl);
+    cudaEventDestroy(b->ev_edge); cudaEventDestroy(b->ev_comm);
+    cudaStreamDestroy(b->stream); cudaStreamDestroy(b->comm_stream);
+    g_blocks[h].reset();
+    return 0;
+}
+
+int fsilbm_block_initialise(fsilbm_handle h, double time)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    const double Cs2 = 1.0 / 3.0;                            // ConstParams.f90:39
+    b->tau = b->flow.nu / (b->g.dh * Cs2) + 0.5;             // calculate_SRT_params, FluidDomain.f90:452
+    b->Omega = 1.0 / b->tau;
+    if (b->model == 2) {                                     // calculate_TRT_params, :458-464
+        const double lambda = b->params[0];
+        const double tmp = (lambda * 4.0 - 1.0) * b->Omega + 2.0;
+        b->Omega2 = 2.0 * (2.0 - b->Omega) / tmp;
+    } else if (b->model == 3) {
+        mrt_matrices(b->Omega, b->Mc, b->Mf);
+        upload_mrt(b->mrt_slot, b->Mc, b->Mf, b->stream);
+        CK(cudaStreamSynchronize(b->stream));   // Mc/Mf are pageable host memory
+    }
+    b->blktime = time;
+    VelocityField vel;
+    if (int rc = velocity_field(*b, time, vel)) return rc;
+    launch_initialise(b->g, b->f[b->cur], vel, b->flow.denIn, b->stream);
+    // den/uuu of the first interior layers as initialise_ leaves them, for code 102 at the start-up BC call
+    for (int face = 0; face < 6; face++) {
+        if (b->bc[face] != BCnEq_DirecletU || !owns_face(*b, face)) continue;
+        int na, nb;
+        face_dims(b->g, face, na, nb);
+        if (!b->l2den[face]) {
+            CK(cudaMalloc(&b->l2den[face], sizeof(double) * (size_t)na * nb));
+            CK(cudaMalloc(&b->l2u[face], sizeof(double) * 3 * (size_t)na * nb));
+        }
+        FaceParams p = face_params(*b, face, b->f[b->cur], b->f[b->cur], vel);
+        launch_init_layer2(p, b->stream);
+    }
+    CK(cudaGetLastError());
+    b->initialised = true;
+    b->ibm_active = false;
+    return 0;
+}
+
+int fsilbm_block_get(fsilbm_handle h, int what, double *value)
+{
+    Block *b = get(h);
+    if (!b || !value) return fail(FSILBM_ERR_ARG, "bad handle/argument");
+    switch (what) {
+    case 0: *value = b->tau; break;
+    case 1: *value = b->Omega; break;
+    case 2: *value = b->Omega2; break;
+    default: return fail(FSILBM_ERR_ARG, "unknown scalar %d", what);
+    }
+    return 0;
+}
+
+int fsilbm_block_upload_fIn(fsilbm_handle h, const double *fIn)
+{
+    Block *b = get(h);
+    if (!b || !fIn) return fail(FSILBM_ERR_ARG, "bad handle/argument");
+    const Geom &g = b->g;
+    const size_t n = (size_t)g.X * g.plane;
+    CK(cudaStreamSynchronize(b->stream));
+    for (int q = 0; q < Q; q++)
+        CK(cudaMemcpy(b->f[b->cur] + q * g.pstride + g.plane, fIn + q * n, sizeof(double) * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int fsilbm_block_download_fIn(fsilbm_handle h, double *fIn)
+{
+    Block *b = get(h);
+    if (!b || !fIn) return fail(FSILBM_ERR_ARG, "bad handle/argument");
+    const Geom &g = b->g;
+    const size_t n = (size_t)g.X * g.plane;
+    CK(cudaStreamSynchronize(b->stream));
+    for (int q = 0; q < Q; q++)
+        CK(cudaMemcpy(fIn + q * n, b->f[b->cur] + q * g.pstride + g.plane, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int fsilbm_block_set_time(fsilbm_handle h, double blktime)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    b->blktime = blktime;
+    return 0;
+}
+
+int fsilbm_block_update_volume_force(fsilbm_handle h, double out[3])
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    const double Pi = 3.141592653589793;   // ConstParams.f90:36
+    const fsilbm_flow &fl = b->flow;
+    b->volumeForce[0] = fl.volumeForceIn[0] + fl.volumeForceAmp * sin(2.0 * Pi * fl.volumeForceFreq * b->blktime + fl.volumeForcePhi / 180.0 * Pi);
+    b->volumeForce[1] = fl.volumeForceIn[1];
+    b->volumeForce[2] = fl.volumeForceIn[2];
+    if (out) for (int k = 0; k < 3; k++) out[k] = b->volumeForce[k];
+    return 0;
+}
+
+int fsilbm_block_download_macro(fsilbm_handle h, double *den, double *uuu)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    if (int rc = ensure_fields(*b, false)) return rc;
+    double hF[3];
+    half_force(*b, hF);
+    launch_macro_full(b->g, b->f[b->cur], hF, b->den, b->uuu, b->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(b->stream));
+    const size_t n = (size_t)b->g.X * b->g.plane;
+    if (den) CK(cudaMemcpy(den, b->den, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (uuu) CK(cudaMemcpy(uuu, b->uuu, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int fsilbm_block_field_stat(fsilbm_handle h, double out[6])
+{
+    Block *b = get(h);
+    if (!b || !out) return fail(FSILBM_ERR_ARG, "bad handle/argument");
+    double hF[3];
+    half_force(*b, hF);
+    CK(cudaMemsetAsync(b->stat, 0, sizeof(double) * 6, b->stream));
+    launch_field_stat(b->g, b->f[b->cur], hF, 1.0 / b->flow.Uref, b->stat, b->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, b->stat, sizeof(double) * 6, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int fsilbm_block_set_boundary_conditions(fsilbm_handle h)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    return apply_boundary_conditions(*b, b->f[b->cur]);
+}
+
+int fsilbm_block_collide_stream(fsilbm_handle h)
+{
+    Block *bp = get(h);
+    if (!bp) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    Block &b = *bp;
+    if (!b.initialised) return fail(FSILBM_ERR_ARG, "block %d not initialised", h);
+    const Geom &g = b.g;
+    const double *fA = b.f[b.cur];
+    double *fB = b.f[b.cur ^ 1];
+    VelocityField vel;
+    if (int rc = velocity_field(b, b.blktime, vel)) return rc;
+
+    // per-face side buffers taken from the pre-collision state (see kernels.h FaceParams)
+    for (int face = 0; face < 6; face++) {
+        if (!owns_face(b, face)) continue;
+        const int code = b.bc[face];
+        if (code == BCnEq_DirecletU) {
+            int na, nb;
+            face_dims(g, face, na, nb);
+            if (!b.l2den[face]) {
+                CK(cudaMalloc(&b.l2den[face], sizeof(double) * (size_t)na * nb));
+                CK(cudaMalloc(&b.l2u[face], sizeof(double) * 3 * (size_t)na * nb));
+            }
+            FaceParams p = face_params(b, face, fB, fA, vel);
+            launch_layer2_face(p, b.stream);
+        } else if ((code == BCstationary_Wall_halfway || code == BCmoving_Wall_halfway) && b.hw_alloc[face]) {
+            FaceParams p = face_params(b, face, fB, fA, vel);
+            launch_stash_face(p, b.stream);   // halfwayBCset_, LBMBlockComm.f90:296
+        }
+    }
+
+    StepParams p{};
+    p.g = g; p.fA = fA; p.fB = fB;
+    p.cc = collide_consts(b);
+    half_force(b, p.hF);
+    for (int k = 0; k < 3; k++) p.Fvol[k] = b.volumeForce[k];
+    p.boxes = b.boxes;
+    if (!b.ibm_active) p.boxes.n = 0;
+    const bool multi = g_nccl.nranks > 1 && g_nccl.comm;
+    const bool ghost = multi || g_force_ghost;
+    p.wrap_x = ghost ? 0 : 1;
+    const int variant = (g_variant == 2 && (ghost || b.ibm_active)) ? 0 : g_variant;
+    if (!multi) {
+        p.x_begin = 0; p.x_count = g.X;
+        if (launch_collide_push(p, b.model, variant, b.stream)) return fail(FSILBM_ERR_MODEL, "collision model %d", b.model);
+        if (ghost) launch_wrap_x(g, fB, b.stream);
+    } else {
+        // edge planes first, then the exchange on its own stream overlapped with the interior update
+        p.x_begin = 0; p.x_count = 1;
+        launch_collide_push(p, b.model, variant, b.stream);
+        if (g.X > 1) { p.x_begin = g.X - 1; p.x_count = 1; launch_collide_push(p, b.model, variant, b.stream); }
+        CK(cudaEventRecord(b.ev_edge, b.stream));
+        CK(cudaStreamWaitEvent(b.comm_stream, b.ev_edge, 0));
+        if (int rc = halo_exchange(b, fB, b.comm_stream)) return rc;
+        CK(cudaEventRecord(b.ev_comm, b.comm_stream));
+        if (g.X > 2) { p.x_begin = 1; p.x_count = g.X - 2; launch_collide_push(p, b.model, variant, b.stream); }
+        CK(cudaStreamWaitEvent(b.stream, b.ev_comm, 0));
+    }
+    CK(cudaGetLastError());
+    if (int rc = apply_boundary_conditions(b, fB)) return rc;   // LBMBlockComm.f90:303
+    b.cur ^= 1;
+    b.ibm_active = false;
+    return 0;
+}
+
+int fsilbm_block_sync(fsilbm_handle h)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaStreamSynchronize(b->comm_stream));
+    return 0;
+}
+
+int fsilbm_block_stream(fsilbm_handle h, void **stream)
+{
+    Block *b = get(h);
+    if (!b || !stream) return fail(FSILBM_ERR_ARG, "bad handle/argument");
+    *stream = (void *)b->stream;
+    return 0;
+}
+
+// ---- un-fused passes ------------------------------------------------------------------------------
+static FieldParams field_params(Block &b)
+{
+    FieldParams p{};
+    p.g = b.g; p.f = b.f[b.cur]; p.den = b.den; p.uuu = b.uuu; p.force = b.force;
+    p.cc = collide_consts(b);
+    half_force(b, p.hF);
+    for (int k = 0; k < 3; k++) p.Fvol[k] = b.volumeForce[k];
+    return p;
+}
+
+int fsilbm_block_pass_macro(fsilbm_handle h)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    if (int rc = ensure_fields(*b, true)) return rc;
+    double hF[3];
+    half_force(*b, hF);
+    launch_macro_full(b->g, b->f[b->cur], hF, b->den, b->uuu, b->stream);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fsilbm_block_pass_reset_volume_force(fsilbm_handle h)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    if (int rc = ensure_fields(*b, true)) return rc;
+    launch_pass_fill(b->force, 3 * (size_t)b->g.X * b->g.plane, 0.0, b->stream);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fsilbm_block_pass_add_volume_force(fsilbm_handle h)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    if (int rc = ensure_fields(*b, true)) return rc;
+    launch_pass_add_force(field_params(*b), b->stream);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fsilbm_block_pass_collision(fsilbm_handle h)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    if (!b->initialised) return fail(FSILBM_ERR_ARG, "block %d not initialised", h);
+    if (int rc = ensure_fields(*b, true)) return rc;
+    if (launch_pass_collision(field_params(*b), b->model, b->stream)) return fail(FSILBM_ERR_MODEL, "collision model %d", b->model);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fsilbm_block_pass_halfway_bc_set(fsilbm_handle h)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    VelocityField vel;
+    if (int rc = velocity_field(*b, b->blktime, vel)) return rc;
+    for (int face = 0; face < 6; face++) {
+        const int code = b->bc[face];
+        if (!(code == BCstationary_Wall_halfway || code == BCmoving_Wall_halfway) || !b->hw_alloc[face] || !owns_face(*b, face)) continue;
+        FaceParams p = face_params(*b, face, b->f[b->cur], b->f[b->cur], vel);
+        launch_pass_halfway(p, b->stream);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fsilbm_block_pass_streaming(fsilbm_handle h)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    if (b->g.X != b->g.XG) return fail(FSILBM_ERR_ARG, "the un-fused streaming pass is single-slab only");
+    launch_pass_streaming(b->g, b->f[b->cur], b->f[b->cur ^ 1], b->stream);
+    CK(cudaGetLastError());
+    b->cur ^= 1;
+    return 0;
+}
+
+int fsilbm_block_download_fields(fsilbm_handle h, double *den, double *uuu, double *force)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    if (int rc = ensure_fields(*b, true)) return rc;
+    CK(cudaStreamSynchronize(b->stream));
+    const size_t n = (size_t)b->g.X * b->g.plane;
+    if (den) CK(cudaMemcpy(den, b->den, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (uuu) CK(cudaMemcpy(uuu, b->uuu, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
+    if (force) CK(cudaMemcpy(force, b->force, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int fsilbm_block_upload_fields(fsilbm_handle h, const double *den, const double *uuu, const double *force)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    if (int rc = ensure_fields(*b, true)) return rc;
+    CK(cudaStreamSynchronize(b->stream));
+    const size_t n = (size_t)b->g.X * b->g.plane;
+    if (den) CK(cudaMemcpy(b->den, den, sizeof(double) * n, cudaMemcpyHostToDevice));
+    if (uuu) CK(cudaMemcpy(b->uuu, uuu, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+    if (force) CK(cudaMemcpy(b->force, force, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ---- IBM ------------------------------------------------------------------------------------------
+namespace {
+
+struct Interval { int s, l; };   // start in [0,N), length <= N, on a circle of N (or a line if not periodic)
+
+inline int imod(int a, int n) { int r = a % n; return r < 0 ? r + n : r; }
+
+// union of two overlapping intervals on a circle of N
+inline bool overlap(const Interval &a, const Interval &b, int N) { return imod(b.s - a.s, N) < a.l || imod(a.s - b.s, N) < b.l; }
+inline Interval merge(const Interval &a, const Interval &b, int N)
+{
+    Interval r;
+    if (imod(b.s - a.s, N) < a.l) { r.s = a.s; r.l = std::max(a.l, imod(b.s - a.s, N) + b.l); }
+    else { r.s = b.s; r.l = std::max(b.l, imod(a.s - b.s, N) + a.l); }
+    if (r.l >= N) { r.s = 0; r.l = N; }
+    return r;
+}
+
+struct HostBox { Interval ax[3]; };
+
+// bounding interval of the base indices i (1-based, Solidbody.f90:817-820) of one body along one axis,
+// widened to the 4-point stencil i-1..i+2 plus one guard cell each side
+Interval axis_interval(int imin, int imax, int N, bool periodic)
+{
+    int lo = imin - 1 - 1 - 1, hi = imax + 2 - 1 + 1;   // 0-based, guard of 1
+    Interval r;
+    if (periodic) {
+        int len = hi - lo + 1;
+        if (len >= N) { r.s = 0; r.l = N; }
+        else { r.s = imod(lo, N); r.l = len; }
+    } else {
+        lo = std::max(lo, 0); hi = std::min(hi, N - 1);
+        if (hi < lo) { lo = 0; hi = 0; }
+        r.s = lo; r.l = hi - lo + 1;
+    }
+    return r;
+}
+
+}  // namespace
+
+int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, const double *const *Exyz, const double *const *Evel,
+                                 const double *const *Ea, double *const *Eforce, const int *restencil, double dt, int ntolLBM,
+                                 double dtolLBM, const int rootBC[6], int *iterLBM_out)
+{
+    Block *bp = get(h);
+    if (!bp) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    Block &b = *bp;
+    if (nbody < 0 || (nbody > 0 && (!nelmts || !Exyz || !Evel || !Ea || !Eforce || !restencil || !rootBC)))
+        return fail(FSILBM_ERR_ARG, "null argument");
+    if (iterLBM_out) *iterLBM_out = 0;
+    if (nbody == 0) { b.ibm_active = false; return 0; }   // Solidbody.f90:891
+    const Geom &g = b.g;
+    cudaStream_t s = b.stream;
+    const bool multi = g_nccl.nranks > 1 && g_nccl.comm;
+
+    // -- device marker storage
+    if ((int)b.bodies.size() != nbody) {
+        for (auto &bd : b.bodies) bd.release();
+        b.bodies.assign(nbody, BodyDev());
+    }
+    for (int ib = 0; ib < nbody; ib++) {
+        BodyDev &bd = b.bodies[ib];
+        const int n = nelmts[ib];
+        if (n < 1) return fail(FSILBM_ERR_ARG, "body %d has no markers", ib);
+        if (bd.n != n) {
+            bd.release();
+            bd.n = n;
+            CK(cudaMalloc(&bd.Exyz, sizeof(double) * 3 * n)); CK(cudaMalloc(&bd.ExyzStencil, sizeof(double) * 3 * n));
+            CK(cudaMalloc(&bd.Evel, sizeof(double) * 3 * n)); CK(cudaMalloc(&bd.Ea, sizeof(double) * n));
+            CK(cudaMalloc(&bd.Eforce, sizeof(double) * 3 * n)); CK(cudaMalloc(&bd.felt, sizeof(double) * 3 * n));
+            CK(cudaMalloc(&bd.tol, sizeof(double) * n)); CK(cudaMalloc(&bd.partialU, sizeof(double) * 3 * n));
+            CK(cudaMalloc(&bd.Ei, sizeof(short) * 12 * n)); CK(cudaMalloc(&bd.Ew, sizeof(float) * 12 * n));
+            CK(cudaMalloc(&bd.cell, sizeof(int) * 12 * n)); CK(cudaMalloc(&bd.boff, sizeof(long long) * n));
+            CK(cudaMalloc(&bd.owned, 4 * n));
+        }
+    }
+
+    // -- host: boxes around the stencils of each body (same index arithmetic as UpdateElmtInterp_, :771-780,817-820)
+    std::vector<HostBox> hb;
+    std::vector<std::vector<double>> &stencil_pos = b.stencil_pos;
+    if ((int)stencil_pos.size() != nbody) stencil_pos.assign(nbody, std::vector<double>());
+    const double invdh = 1.0 / g.dh;
+    const double mins[3] = {g.xmin, g.ymin, g.zmin};
+    const int Ns[3] = {g.XG, g.Y, g.Z};
+    for (int ib = 0; ib < nbody; ib++) {
+        const int n = nelmts[ib];
+        BodyDev &bd = b.bodies[ib];
+        const bool re = restencil[ib] != 0 || !bd.have_stencil_pos;
+        if (re) stencil_pos[ib].assign(Exyz[ib], Exyz[ib] + 3 * (size_t)n);
+        const double *P = stencil_pos[ib].data();
+        HostBox box;
+        for (int a = 0; a < 3; a++) {
+            int i0 = (int)floor((P[a] - mins[a]) * invdh);
+            const double x0 = mins[a] + (double)i0 * g.dh;
+            i0 = i0 + 1;
+            int imin = 1 << 30, imax = -(1 << 30);
+            for (int e = 0; e < n; e++) {
+                const double off = (P[3 * e + a] - x0) * invdh;
+                const int idx = (int)floor(off) + i0;
+                imin = std::min(imin, idx); imax = std::max(imax, idx);
+            }
+            box.ax[a] = axis_interval(imin, imax, Ns[a], rootBC[2 * a] == BCPeriodic);
+        }
+        hb.push_back(box);
+    }
+    // merge boxes that overlap so bodies sharing cells share storage (Gauss-Seidel coupling, Solidbody.f90:898-903)
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (size_t i = 0; i < hb.size() && !changed; i++)
+            for (size_t j = i + 1; j < hb.size() && !changed; j++) {
+                bool ov = true;
+                for (int a = 0; a < 3; a++) ov = ov && overlap(hb[i].ax[a], hb[j].ax[a], Ns[a]);
+                if (ov) {
+                    for (int a = 0; a < 3; a++) hb[i].ax[a] = merge(hb[i].ax[a], hb[j].ax[a], Ns[a]);
+                    hb.erase(hb.begin() + j);
+                    changed = true;
+                }
+            }
+    }
+    while ((int)hb.size() > MAX_BOXES) {   // too many separate bodies: fold the tail into one covering box
+        HostBox &a0 = hb[hb.size() - 2], &b0 = hb.back();
+        for (int a = 0; a < 3; a++) {
+            // covering interval of two disjoint intervals on the circle
+            Interval x = a0.ax[a], y = b0.ax[a], r;
+            const int d1 = imod(y.s - x.s, Ns[a]) + y.l, d2 = imod(x.s - y.s, Ns[a]) + x.l;
+            if (std::max(d1, x.l) <= std::max(d2, y.l)) { r.s = x.s; r.l = std::max(d1, x.l); } else { r.s = y.s; r.l = std::max(d2, y.l); }
+            if (r.l >= Ns[a]) { r.s = 0; r.l = Ns[a]; }
+            a0.ax[a] = r;
+        }
+        hb.pop_back();
+    }
+    IbmBoxes &bx = b.boxes;
+    bx.n = (int)hb.size();
+    long long total = 0;
+    for (int i = 0; i < bx.n; i++) {
+        for (int a = 0; a < 3; a++) { bx.lo[i][a] = hb[i].ax[a].s; bx.ext[i][a] = hb[i].ax[a].l; }
+        bx.off[i] = total;
+        total += (long long)bx.ext[i][0] * bx.ext[i][1] * bx.ext[i][2];
+    }
+    bx.ncell = total;
+    if (total > b.box_capacity) {
+        CK(cudaStreamSynchronize(s));
+        cudaFree(bx.u); cudaFree(bx.force);
+        const long long cap = total + total / 4 + 1024;
+        CK(cudaMalloc(&bx.u, sizeof(double) * 3 * cap));
+        CK(cudaMalloc(&bx.force, sizeof(double) * 3 * cap));
+        b.box_capacity = cap;
+    }
+
+    // -- upload markers
+    for (int ib = 0; ib < nbody; ib++) {
+        BodyDev &bd = b.bodies[ib];
+        const size_t n = bd.n;
+        CK(cudaMemcpyAsync(bd.Exyz, Exyz[ib], sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(bd.Evel, Evel[ib], sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(bd.Ea, Ea[ib], sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        if (restencil[ib] != 0 || !bd.have_stencil_pos) {
+            CK(cudaMemcpyAsync(bd.ExyzStencil, bd.Exyz, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, s));
+            bd.have_stencil_pos = true;
+        }
+        CK(cudaMemsetAsync(bd.Eforce, 0, sizeof(double) * 3 * n, s));   // Solidbody.f90:889
+    }
+    IbmCtl ctl0;
+    ctl0.iter = 0; ctl0.done = (ntolLBM <= 0) ? 1 : 0; ctl0.err = 0; ctl0.dmax = 1e10;   // :893-894
+    CK(cudaMemcpyAsync(b.ctl, &ctl0, sizeof(IbmCtl), cudaMemcpyHostToDevice, s));
+    if (b.bodies_dev_cap < nbody) {
+        cudaFree(b.bodies_dev);
+        CK(cudaMalloc(&b.bodies_dev, sizeof(IbmBody) * nbody));
+        b.bodies_dev_cap = nbody;
+    }
+    std::vector<IbmBody> views(nbody);
+    for (int ib = 0; ib < nbody; ib++) views[ib] = b.bodies[ib].view();
+    CK(cudaMemcpyAsync(b.bodies_dev, views.data(), sizeof(IbmBody) * nbody, cudaMemcpyHostToDevice, s));
+
+    // -- UpdateElmtInterp_ (:883-888); the box-relative offsets are rebuilt every call because the boxes move with the bodies
+    for (int ib = 0; ib < nbody; ib++) launch_ibm_stencil(g, views[ib], bx, rootBC, b.ctl, s);
+
+    // -- calculate_macro_quantities + ResetVolumeForce restricted to the boxes (LBMBlockComm.f90:285-286)
+    double hF[3];
+    half_force(b, hF);
+    launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
+
+    // -- penalty iteration (:895-906); launches beyond convergence return at once on the device flag
+    const double invh3_pen = 0.5 * dt * ((1.0 / g.dh) * (1.0 / g.dh) * (1.0 / g.dh)) / b.flow.denIn;   // :996
+    for (int it = 0; it < ntolLBM; it++) {
+        for (int ib = 0; ib < nbody; ib++) {
+            if (!multi) {
+                launch_ibm_gather(views[ib], bx, b.bodies[ib].partialU, b.ctl, 1, invh3_pen, s);
+            } else {
+                launch_ibm_gather(views[ib], bx, b.bodies[ib].partialU, b.ctl, 0, invh3_pen, s);
+                NCK(g_nccl.AllReduce(b.bodies[ib].partialU, b.bodies[ib].partialU, 3 * (size_t)views[ib].n, kNcclFloat64, kNcclSum, g_nccl.comm, s));
+                launch_ibm_force(views[ib], b.bodies[ib].partialU, invh3_pen, b.ctl, s);
+            }
+            launch_ibm_scatter(views[ib], bx, b.ctl, s);
+        }
+        launch_ibm_check(b.bodies_dev, nbody, b.flow.Uref, ntolLBM, dtolLBM, b.ctl, s);
+    }
+    // -- FluidVolumeForce_, Eulerian half (:968-976)
+    const double invh3 = (1.0 / g.dh) * (1.0 / g.dh) * (1.0 / g.dh);   // :936
+    for (int ib = 0; ib < nbody; ib++) launch_ibm_spread(views[ib], bx, invh3, s);
+    CK(cudaGetLastError());
+
+    // -- results to the host
+    IbmCtl ctl1;
+    CK(cudaMemcpyAsync(&ctl1, b.ctl, sizeof(IbmCtl), cudaMemcpyDeviceToHost, s));
+    for (int ib = 0; ib < nbody; ib++)
+        CK(cudaMemcpyAsync(Eforce[ib], b.bodies[ib].Eforce, sizeof(double) * 3 * (size_t)b.bodies[ib].n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (ctl1.err & 1) return fail(FSILBM_ERR_STENCIL, "index out of xmin/xmax bound (Solidbody.f90:850,861)");
+    if (ctl1.err & 4) return fail(FSILBM_ERR_STENCIL, "internal: marker stencil outside its IBM box");
+    if (ctl1.err & 2) return fail(FSILBM_ERR_NAN, "Nan found in PenaltyForce (Solidbody.f90:1029)");
+    if (iterLBM_out) *iterLBM_out = ctl1.iter;
+    b.ibm_active = true;
+    return 0;
+}
+
+int fsilbm_ibm_download_stencil(fsilbm_handle h, int body, short *Ei, float *Ew)
+{
+    Block *b = get(h);
+    if (!b || body < 0 || body >= (int)b->bodies.size()) return fail(FSILBM_ERR_ARG, "bad handle/body");
+    CK(cudaStreamSynchronize(b->stream));
+    const size_t n = b->bodies[body].n;
+    if (Ei) CK(cudaMemcpy(Ei, b->bodies[body].Ei, sizeof(short) * 12 * n, cudaMemcpyDeviceToHost));
+    if (Ew) CK(cudaMemcpy(Ew, b->bodies[body].Ew, sizeof(float) * 12 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- comm -----------------------------------------------------------------------------------------
+int fsilbm_comm_unique_id(char id[128])
+{
+    if (int rc = nccl_load()) return rc;
+    ncclUniqueId_t u;
+    NCK(g_nccl.GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+    return 0;
+}
+
+int fsilbm_comm_init(int rank, int nranks, const char id[128])
+{
+    if (g_device < 0) return fail(FSILBM_ERR_CUDA, "fsilbm_init has not succeeded");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(FSILBM_ERR_ARG, "bad rank %d of %d", rank, nranks);
+    g_nccl.rank = rank; g_nccl.nranks = nranks;
+    if (nranks == 1) return 0;
+    if (int rc = nccl_load()) return rc;
+    ncclUniqueId_t u;
+    memcpy(u.internal, id, 128);
+    NCK(g_nccl.CommInitRank(&g_nccl.comm, nranks, u, rank));
+    return 0;
+}
+
+int fsilbm_comm_finalize(void)
+{
+    if (g_nccl.comm) { g_nccl.CommDestroy(g_nccl.comm); g_nccl.comm = nullptr; }
+    g_nccl.rank = 0; g_nccl.nranks = 1;
+    return 0;
+}
+
+}  // extern "C"

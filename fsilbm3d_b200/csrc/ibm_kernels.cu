@@ -1,0 +1,323 @@
+// ibm_kernels.cu -- sm_100a kernels of the immersed-boundary coupling (reference: Solidbody.f90).
+//
+// The reference keeps uuu and force as full Eulerian fields and loops serially over markers when it
+// spreads (Solidbody.f90:1034-1048, :938-978).  Here the corrected velocity and the IBM force exist
+// only inside small boxes around the bodies (IbmBoxes); interpolation and spreading are
+// warp-cooperative: one warp per Lagrangian marker, two of the 64 stencil nodes per lane, shuffle
+// reduction for the gather, fp64 atomics for the scatter.  Stencil weights are rounded to fp32 and
+// indices held as int16 exactly as the reference stores them (Solidbody.f90:45-46,790-804).
+#include "kernels.h"
+
+namespace fsilbm {
+
+// Phi, Solidbody.f90:822-833
+__device__ __forceinline__ double Phi(double x_)
+{
+    const double r = fabs(x_);
+    if (r < 1.0) return (3.0 - 2.0 * r + sqrt(1.0 + 4.0 * r * (1.0 - r))) * 0.125;
+    else if (r < 2.0) return (5.0 - 2.0 * r - sqrt(-7.0 + 4.0 * r * (3.0 - r))) * 0.125;
+    return 0.0;
+}
+
+// trimedindex, Solidbody.f90:834-866 (1-based). Returns false where the reference stops.
+__device__ __forceinline__ bool trimedindex(int i_, int xDim_, int (&ix_)[4], int bcLo, int bcHi)
+{
+#pragma unroll
+    for (int k_ = -1; k_ <= 2; k_++) {
+        int v = i_ + k_;
+        if (v < 1) {
+            if (bcLo == BCPeriodic) v = v + xDim_;
+            else if ((bcLo == BCSymmetric || bcLo == BCstationary_Wall) && v == 0) v = 2;
+            else if (bcLo == BCstationary_Wall_halfway && v == 0) v = 1;
+            else return false;
+        } else if (v > xDim_) {
+            if (bcHi == BCPeriodic) v = v - xDim_;
+            else if ((bcHi == BCSymmetric || bcHi == BCstationary_Wall) && v == xDim_ + 1) v = xDim_ - 1;
+            else if (bcHi == BCstationary_Wall_halfway && v == xDim_ + 1) v = xDim_;
+            else return false;
+        }
+        if (v < 1 || v > xDim_) return false;   // periodic image still outside: the reference would index out of bounds
+        ix_[k_ + 1] = v;
+    }
+    return true;
+}
+
+struct RootBC { int c[6]; };
+
+// UpdateElmtInterp_, Solidbody.f90:760-806
+__global__ void ibm_stencil_kernel(Geom g, IbmBody b, const __grid_constant__ IbmBoxes boxes, RootBC bc, IbmCtl *ctl)
+{
+    const int iEL = blockIdx.x * blockDim.x + threadIdx.x;
+    if (iEL >= b.n) return;
+    const double dh = g.dh;
+    const double invdh = 1.0 / dh;
+    // anchor on the body's first marker, :772-780
+    int i0 = (int)floor((b.Exyz[0] - g.xmin) * invdh);
+    const double x0 = g.xmin + (double)i0 * dh; i0 = i0 + 1;
+    int j0 = (int)floor((b.Exyz[1] - g.ymin) * invdh);
+    const double y0 = g.ymin + (double)j0 * dh; j0 = j0 + 1;
+    int k0 = (int)floor((b.Exyz[2] - g.zmin) * invdh);
+    const double z0 = g.zmin + (double)k0 * dh; k0 = k0 + 1;
+    // minloc_fast, :811-821
+    double detx = (b.Exyz[3 * iEL + 0] - x0) * invdh; int i = (int)floor(detx); detx = detx - (double)i; i = i + i0;
+    double dety = (b.Exyz[3 * iEL + 1] - y0) * invdh; int j = (int)floor(dety); dety = dety - (double)j; j = j + j0;
+    double detz = (b.Exyz[3 * iEL + 2] - z0) * invdh; int k = (int)floor(detz); detz = detz - (double)k; k = k + k0;
+    int ix[4], jy[4], kz[4];
+    const bool ok = trimedindex(i, g.XG, ix, bc.c[0], bc.c[1]) && trimedindex(j, g.Y, jy, bc.c[2], bc.c[3]) &&
+                    trimedindex(k, g.Z, kz, bc.c[4], bc.c[5]);
+    if (!ok) {
+        atomicOr(&ctl->err, 1);
+        for (int m = 0; m < 12; m++) { b.cell[12 * iEL + m] = 0; b.Ei[12 * iEL + m] = 0; b.Ew[12 * iEL + m] = 0.f; }
+        for (int m = 0; m < 4; m++) b.owned[4 * iEL + m] = 0;
+        b.boff[iEL] = 0;
+        return;
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        b.Ei[12 * iEL + m] = (short)ix[m];
+        b.Ei[12 * iEL + 4 + m] = (short)jy[m];
+        b.Ei[12 * iEL + 8 + m] = (short)kz[m];
+        b.Ew[12 * iEL + m] = (float)Phi((double)(m - 1) - detx);
+        b.Ew[12 * iEL + 4 + m] = (float)Phi((double)(m - 1) - dety);
+        b.Ew[12 * iEL + 8 + m] = (float)Phi((double)(m - 1) - detz);
+    }
+    // locate the box of this marker (the one holding the stencil's base node) and express all 12
+    // indices relative to it
+    int bsel = -1;
+    for (int bb = 0; bb < boxes.n; bb++) {
+        int dx = (ix[1] - 1) - boxes.lo[bb][0]; if (dx < 0) dx += g.XG;
+        int dy = (jy[1] - 1) - boxes.lo[bb][1]; if (dy < 0) dy += g.Y;
+        int dz = (kz[1] - 1) - boxes.lo[bb][2]; if (dz < 0) dz += g.Z;
+        if (dx < boxes.ext[bb][0] && dy < boxes.ext[bb][1] && dz < boxes.ext[bb][2]) { bsel = bb; break; }
+    }
+    bool inbox = bsel >= 0;
+    if (inbox) {
+        const int ey = boxes.ext[bsel][1], ez = boxes.ext[bsel][2];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            int dx = (ix[m] - 1) - boxes.lo[bsel][0]; if (dx < 0) dx += g.XG;
+            int dy = (jy[m] - 1) - boxes.lo[bsel][1]; if (dy < 0) dy += g.Y;
+            int dz = (kz[m] - 1) - boxes.lo[bsel][2]; if (dz < 0) dz += g.Z;
+            if (dx >= boxes.ext[bsel][0] || dy >= ey || dz >= ez) inbox = false;
+            b.cell[12 * iEL + m] = dx * ey * ez;
+            b.cell[12 * iEL + 4 + m] = dy * ez;
+            b.cell[12 * iEL + 8 + m] = dz;
+            const int lx = (ix[m] - 1) - g.xOffset;
+            b.owned[4 * iEL + m] = (lx >= 0 && lx < g.X) ? 1 : 0;
+        }
+        b.boff[iEL] = boxes.off[bsel];
+    }
+    if (!inbox) {
+        atomicOr(&ctl->err, 4);
+        for (int m = 0; m < 12; m++) b.cell[12 * iEL + m] = 0;
+        for (int m = 0; m < 4; m++) b.owned[4 * iEL + m] = 0;
+        b.boff[iEL] = 0;
+    }
+}
+
+void launch_ibm_stencil(const Geom &g, const IbmBody &b, const IbmBoxes &boxes, const int rootBC[6], IbmCtl *ctl, cudaStream_t s)
+{
+    RootBC bc;
+    for (int i = 0; i < 6; i++) bc.c[i] = rootBC[i];
+    ibm_stencil_kernel<<<(b.n + 127) / 128, 128, 0, s>>>(g, b, boxes, bc, ctl);
+    count_launch();
+}
+
+// calculate_macro_quantities_ (FluidDomain.f90:1136-1139) on the box cells + ResetVolumeForce_ (:1201-1203)
+__global__ void ibm_macro_box_kernel(Geom g, const double *fA, double hF1, double hF2, double hF3, const __grid_constant__ IbmBoxes boxes)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= boxes.ncell) return;
+    int bb = 0;
+    while (bb + 1 < boxes.n && i >= boxes.off[bb + 1]) bb++;
+    const long long r = i - boxes.off[bb];
+    const int ez = boxes.ext[bb][2], ey = boxes.ext[bb][1];
+    const int dz = (int)(r % ez), dy = (int)((r / ez) % ey), dx = (int)(r / ((long long)ez * ey));
+    int gx = boxes.lo[bb][0] + dx; if (gx >= g.XG) gx -= g.XG;
+    int y = boxes.lo[bb][1] + dy; if (y >= g.Y) y -= g.Y;
+    int z = boxes.lo[bb][2] + dz; if (z >= g.Z) z -= g.Z;
+    const int x = gx - g.xOffset;
+    double u1 = 0.0, u2 = 0.0, u3 = 0.0;
+    if (x >= 0 && x < g.X) {
+        const size_t base = (size_t)(x + 1) * g.plane + (size_t)y * g.Z + z;
+        double f[Q], den;
+#pragma unroll
+        for (int q = 0; q < Q; q++) f[q] = fA[q * g.pstride + base];
+        macro_from_f(f, hF1, hF2, hF3, den, u1, u2, u3);
+    }
+    boxes.u[i] = u1; boxes.u[boxes.ncell + i] = u2; boxes.u[2 * boxes.ncell + i] = u3;
+    boxes.force[i] = 0.0; boxes.force[boxes.ncell + i] = 0.0; boxes.force[2 * boxes.ncell + i] = 0.0;
+}
+
+void launch_ibm_macro_box(const Geom &g, const double *fA, const double hF[3], const IbmBoxes &boxes, cudaStream_t s)
+{
+    if (boxes.ncell <= 0) return;
+    ibm_macro_box_kernel<<<(unsigned)((boxes.ncell + 255) / 256), 256, 0, s>>>(g, fA, hF[0], hF[1], hF[2], boxes);
+    count_launch();
+}
+
+// per-marker finish of PenaltyForce_'s first loop, Solidbody.f90:1016-1025
+__device__ __forceinline__ void marker_force(const IbmBody &b, int iEL, double U1, double U2, double U3, double invh3)
+{
+    const double d1 = b.Evel[3 * iEL + 0] - U1, d2 = b.Evel[3 * iEL + 1] - U2, d3 = b.Evel[3 * iEL + 2] - U3;
+    const double Ea = b.Ea[iEL];
+    const double f1 = d1 * Ea, f2 = d2 * Ea, f3 = d3 * Ea;
+    b.tol[iEL] = fabs(d1) + fabs(d2) + fabs(d3);
+    b.Eforce[3 * iEL + 0] = b.Eforce[3 * iEL + 0] + f1;
+    b.Eforce[3 * iEL + 1] = b.Eforce[3 * iEL + 1] + f2;
+    b.Eforce[3 * iEL + 2] = b.Eforce[3 * iEL + 2] + f3;
+    b.felt[3 * iEL + 0] = f1 * invh3;
+    b.felt[3 * iEL + 1] = f2 * invh3;
+    b.felt[3 * iEL + 2] = f3 * invh3;
+}
+
+// PenaltyForce_ interpolation, Solidbody.f90:1000-1015: one warp per marker.
+// fused != 0 (single rank): lane 0 also finishes the marker (:1016-1025); otherwise the partial
+// velocity over the locally owned stencil planes goes to partialU for the all-reduce.
+__global__ void ibm_gather_kernel(IbmBody b, const __grid_constant__ IbmBoxes boxes, double *partialU, const IbmCtl *ctl, int fused, double invh3)
+{
+    if (ctl->done) return;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= b.n) return;
+    const int iEL = warp;
+    const long long boff = b.boff[iEL];
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int pnt = lane + 32 * h;
+        const int a = pnt >> 4, bb = (pnt >> 2) & 3, c = pnt & 3;
+        if (b.owned[4 * iEL + a]) {
+            const long long idx = boff + b.cell[12 * iEL + a] + b.cell[12 * iEL + 4 + bb] + b.cell[12 * iEL + 8 + c];
+            const double rx = (double)b.Ew[12 * iEL + a], ry = (double)b.Ew[12 * iEL + 4 + bb], rz = (double)b.Ew[12 * iEL + 8 + c];
+            s1 = s1 + boxes.u[idx] * rx * ry * rz;   // :1012
+            s2 = s2 + boxes.u[boxes.ncell + idx] * rx * ry * rz;
+            s3 = s3 + boxes.u[2 * boxes.ncell + idx] * rx * ry * rz;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s1 += __shfl_down_sync(0xffffffffu, s1, off);
+        s2 += __shfl_down_sync(0xffffffffu, s2, off);
+        s3 += __shfl_down_sync(0xffffffffu, s3, off);
+    }
+    if (lane == 0) {
+        if (fused) marker_force(b, iEL, s1, s2, s3, invh3);
+        else { partialU[3 * iEL + 0] = s1; partialU[3 * iEL + 1] = s2; partialU[3 * iEL + 2] = s3; }
+    }
+}
+
+void launch_ibm_gather(const IbmBody &b, const IbmBoxes &boxes, double *partialU, const IbmCtl *ctl, int fused, double invh3, cudaStream_t s)
+{
+    const int threads = 128, warps_per_block = threads / 32;
+    ibm_gather_kernel<<<(b.n + warps_per_block - 1) / warps_per_block, threads, 0, s>>>(b, boxes, partialU, ctl, fused, invh3);
+    count_launch();
+}
+
+__global__ void ibm_force_kernel(IbmBody b, const double *sumU, double invh3, const IbmCtl *ctl)
+{
+    if (ctl->done) return;
+    const int iEL = blockIdx.x * blockDim.x + threadIdx.x;
+    if (iEL >= b.n) return;
+    marker_force(b, iEL, sumU[3 * iEL + 0], sumU[3 * iEL + 1], sumU[3 * iEL + 2], invh3);
+}
+
+void launch_ibm_force(const IbmBody &b, const double *sumU, double invh3, IbmCtl *ctl, cudaStream_t s)
+{
+    ibm_force_kernel<<<(b.n + 127) / 128, 128, 0, s>>>(b, sumU, invh3, ctl);
+    count_launch();
+}
+
+// PenaltyForce_ velocity correction, Solidbody.f90:1034-1048: uuu -= forceElemTemp*rx*ry*rz
+__global__ void ibm_scatter_kernel(IbmBody b, const __grid_constant__ IbmBoxes boxes, const IbmCtl *ctl)
+{
+    if (ctl->done) return;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= b.n) return;
+    const int iEL = warp;
+    const long long boff = b.boff[iEL];
+    const double f1 = b.felt[3 * iEL + 0], f2 = b.felt[3 * iEL + 1], f3 = b.felt[3 * iEL + 2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int pnt = lane + 32 * h;
+        const int a = pnt >> 4, bb = (pnt >> 2) & 3, c = pnt & 3;
+        if (!b.owned[4 * iEL + a]) continue;
+        const long long idx = boff + b.cell[12 * iEL + a] + b.cell[12 * iEL + 4 + bb] + b.cell[12 * iEL + 8 + c];
+        const double rx = (double)b.Ew[12 * iEL + a], ry = (double)b.Ew[12 * iEL + 4 + bb], rz = (double)b.Ew[12 * iEL + 8 + c];
+        atomicAdd(&boxes.u[idx], -(f1 * rx * ry * rz));
+        atomicAdd(&boxes.u[boxes.ncell + idx], -(f2 * rx * ry * rz));
+        atomicAdd(&boxes.u[2 * boxes.ncell + idx], -(f3 * rx * ry * rz));
+    }
+}
+
+void launch_ibm_scatter(const IbmBody &b, const IbmBoxes &boxes, const IbmCtl *ctl, cudaStream_t s)
+{
+    const int threads = 128, warps_per_block = threads / 32;
+    ibm_scatter_kernel<<<(b.n + warps_per_block - 1) / warps_per_block, threads, 0, s>>>(b, boxes, ctl);
+    count_launch();
+}
+
+// loop control of calculate_interaction_force, Solidbody.f90:895-906: one block, deterministic sum
+__global__ void ibm_check_kernel(const IbmBody *bodies, int nbody, double Uref, int ntol, double dtol, IbmCtl *ctl)
+{
+    if (ctl->done) return;
+    __shared__ double sh[256];
+    double dmax = 0.0, dsum = 0.0;
+    for (int ib = 0; ib < nbody; ib++) {
+        const IbmBody b = bodies[ib];
+        double t = 0.0;
+        for (int i = threadIdx.x; i < b.n; i += blockDim.x) t += b.tol[i];
+        sh[threadIdx.x] = t;
+        __syncthreads();
+        for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+            if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+            __syncthreads();
+        }
+        dmax = dmax + sh[0];          // :901
+        dsum = dsum + (double)b.n;    // :902
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (!isfinite(dmax)) atomicOr(&ctl->err, 2);   // :1028-1031
+        dmax = dmax / (dsum * Uref);                   // :904
+        const int iter = ctl->iter + 1;                // :905
+        ctl->iter = iter;
+        ctl->dmax = dmax;
+        ctl->done = !(iter < ntol && dmax > dtol);     // :895
+    }
+}
+
+void launch_ibm_check(const IbmBody *bodies_dev, int nbody, double Uref, int ntol, double dtol, IbmCtl *ctl, cudaStream_t s)
+{
+    ibm_check_kernel<<<1, 256, 0, s>>>(bodies_dev, nbody, Uref, ntol, dtol, ctl);
+    count_launch();
+}
+
+// Eulerian half of FluidVolumeForce_, Solidbody.f90:968-976: force += -(v_Eforce*invh3)*rx*ry*rz
+__global__ void ibm_spread_kernel(IbmBody b, const __grid_constant__ IbmBoxes boxes, double invh3)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= b.n) return;
+    const int iEL = warp;
+    const long long boff = b.boff[iEL];
+    const double f1 = b.Eforce[3 * iEL + 0] * invh3, f2 = b.Eforce[3 * iEL + 1] * invh3, f3 = b.Eforce[3 * iEL + 2] * invh3;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int pnt = lane + 32 * h;
+        const int a = pnt >> 4, bb = (pnt >> 2) & 3, c = pnt & 3;
+        if (!b.owned[4 * iEL + a]) continue;
+        const long long idx = boff + b.cell[12 * iEL + a] + b.cell[12 * iEL + 4 + bb] + b.cell[12 * iEL + 8 + c];
+        const double rx = (double)b.Ew[12 * iEL + a], ry = (double)b.Ew[12 * iEL + 4 + bb], rz = (double)b.Ew[12 * iEL + 8 + c];
+        atomicAdd(&boxes.force[idx], -f1 * rx * ry * rz);
+        atomicAdd(&boxes.force[boxes.ncell + idx], -f2 * rx * ry * rz);
+        atomicAdd(&boxes.force[2 * boxes.ncell + idx], -f3 * rx * ry * rz);
+    }
+}
+
+void launch_ibm_spread(const IbmBody &b, const IbmBoxes &boxes, double invh3, cudaStream_t s)
+{
+    const int threads = 128, warps_per_block = threads / 32;
+    ibm_spread_kernel<<<(b.n + warps_per_block - 1) / warps_per_block, threads, 0, s>>>(b, boxes, invh3);
+    count_launch();
+}
+
+}  // namespace fsilbm

@@ -1,0 +1,127 @@
+// kernels.h -- host-visible parameter blocks and launchers of the CUDA kernels.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "d3q19.cuh"
+
+namespace fsilbm {
+
+// Device layout of the populations of one x-slab: f[q][xp][y][z], z fastest, xp = x_local + 1 so
+// that planes xp = 0 and xp = X + 1 are ghost planes that receive what streams out of the slab.
+// This is the reference's fIn(z,y,x,q) (FluidDomain.f90:384) plus the two ghost planes.
+struct Geom {
+    int X, Y, Z;       // local extents (X = planes owned by this rank)
+    int XG, xOffset;   // global x extent and global index of local plane 0
+    size_t plane;      // Y*Z
+    size_t pstride;    // (X+2)*Y*Z, distance between populations
+    double dh, xmin, ymin, zmin;
+};
+
+constexpr int MAX_BOXES = 16;
+
+// Sparse region(s) around the immersed bodies in which the IBM-corrected velocity uuu and the
+// Eulerian IBM force live (the reference keeps both as full fields, FluidDomain.f90:386-387).
+// Box coordinates are GLOBAL cell indices; lo is normalised to [0,N), a box may wrap periodically.
+struct IbmBoxes {
+    int n;
+    int lo[MAX_BOXES][3];    // x,y,z start
+    int ext[MAX_BOXES][3];   // x,y,z extent
+    long long off[MAX_BOXES];
+    long long ncell;         // total cells; component k of a field starts at k*ncell
+    double *u;               // [3][ncell]
+    double *force;           // [3][ncell]
+};
+
+struct StepParams {
+    Geom g;
+    const double *fA;
+    double *fB;
+    int x_begin, x_count;   // local planes processed by this launch
+    int wrap_x;             // 1: streaming wraps in x inside the slab (single rank, FluidDomain.f90:1603-1604,1618-1619)
+    CollideConsts cc;
+    double hF[3];           // 0.5d0*volumeForce(k)*dh, FluidDomain.f90:1137-1139
+    double Fvol[3];         // volumeForce(k), :1188-1190
+    IbmBoxes boxes;
+};
+
+struct FaceParams {
+    Geom g;
+    double *f;              // populations the face rule is applied to (post-stream)
+    const double *fA;       // pre-collision populations (stash / layer-2 kernels)
+    int face, code;         // 0..5 = xmin,xmax,ymin,ymax,zmin,zmax
+    int na, nb;             // face-local extents: x faces (z,y); y faces (z,x); z faces (y,x)
+    VelocityField vel;
+    double denIn;
+    double wallc;           // coordinate of the wall along the face normal
+    double *stash;          // [19][nb][na] post-collision boundary layer (fIn_hw*, FluidDomain.f90:567-614)
+    double *l2den;          // [nb][na]    den of the first interior layer (code 102, :643)
+    double *l2u;            // [3][nb][na] uuu of the first interior layer
+    // for the stash / layer-2 kernels, which redo macro + collision of single layers
+    CollideConsts cc;
+    double hF[3], Fvol[3];
+    IbmBoxes boxes;
+    int model;
+};
+
+struct FieldParams {
+    Geom g;
+    double *f;              // in place
+    double *den, *uuu, *force;   // [X][Y][Z], [3][X][Y][Z], [3][X][Y][Z] (no ghost planes)
+    CollideConsts cc;
+    double hF[3], Fvol[3];
+};
+
+// ---- launchers (fluid_kernels.cu) ---------------------------------------------------------------
+void upload_mrt(int slot, const double *M_COLLID, const double *M_FORCE, cudaStream_t s);
+int launch_collide_push(const StepParams &p, int model, int variant, cudaStream_t s);
+void launch_initialise(const Geom &g, double *f, const VelocityField &vel, double denIn, cudaStream_t s);
+void launch_macro_full(const Geom &g, const double *f, const double hF[3], double *den, double *uuu, cudaStream_t s);
+void launch_bc_face(const FaceParams &p, cudaStream_t s);
+void launch_stash_face(const FaceParams &p, cudaStream_t s);
+void launch_layer2_face(const FaceParams &p, cudaStream_t s);
+void launch_init_layer2(const FaceParams &p, cudaStream_t s);
+void launch_field_stat(const Geom &g, const double *f, const double hF[3], double invUref, double *out6, cudaStream_t s);
+void launch_wrap_x(const Geom &g, double *f, cudaStream_t s);
+// un-fused passes
+void launch_pass_fill(double *p, size_t n, double v, cudaStream_t s);
+void launch_pass_add_force(const FieldParams &p, cudaStream_t s);
+int launch_pass_collision(const FieldParams &p, int model, cudaStream_t s);
+void launch_pass_halfway(const FaceParams &p, cudaStream_t s);
+void launch_pass_streaming(const Geom &g, const double *fA, double *fB, cudaStream_t s);
+
+// ---- IBM (ibm_kernels.cu) ------------------------------------------------------------------------
+struct IbmBody {
+    int n;                    // v_nelmts
+    const double *Exyz;       // [n][3]
+    const double *Evel;       // [n][3]
+    const double *Ea;         // [n]
+    double *Eforce;           // [n][3]
+    short *Ei;                // [n][12]  integer(2), Solidbody.f90:45
+    float *Ew;                // [n][12]  real(4),    Solidbody.f90:46
+    int *cell;                // [n][12]  box-local premultiplied offsets (x*ny*nz, y*nz, z) of the stencil
+    long long *boff;          // [n] offset of the marker's box in the box arrays
+    unsigned char *owned;     // [n][4] 1 if stencil plane ix(m) lies in this rank's slab
+    double *felt;             // [n][3] forceElemTemp, Solidbody.f90:1025
+    double *tol;              // [n]   |dU1|+|dU2|+|dU3| of the marker, :1023
+};
+
+struct IbmCtl {               // device-resident control block of the penalty iteration (Solidbody.f90:893-906)
+    int iter;                 // iterLBM
+    int done;                 // loop condition false
+    int err;                  // bit 0: stencil out of domain (:850,861); bit 1: NaN (:1028); bit 2: stencil outside box
+    double dmax;              // dmaxLBM
+};
+
+void launch_ibm_stencil(const Geom &g, const IbmBody &b, const IbmBoxes &boxes, const int rootBC[6], IbmCtl *ctl, cudaStream_t s);
+void launch_ibm_macro_box(const Geom &g, const double *fA, const double hF[3], const IbmBoxes &boxes, cudaStream_t s);
+void launch_ibm_gather(const IbmBody &b, const IbmBoxes &boxes, double *partialU, const IbmCtl *ctl, int fused, double invh3, cudaStream_t s);
+void launch_ibm_force(const IbmBody &b, const double *sumU, double invh3, IbmCtl *ctl, cudaStream_t s);
+void launch_ibm_scatter(const IbmBody &b, const IbmBoxes &boxes, const IbmCtl *ctl, cudaStream_t s);
+void launch_ibm_check(const IbmBody *bodies_dev, int nbody, double Uref, int ntol, double dtol, IbmCtl *ctl, cudaStream_t s);
+void launch_ibm_spread(const IbmBody &b, const IbmBoxes &boxes, double invh3, cudaStream_t s);
+
+long long kernel_launch_count();
+void count_launch(int n = 1);
+
+}  // namespace fsilbm

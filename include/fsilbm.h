@@ -1,0 +1,170 @@
+/*
+ * fsilbm.h -- C ABI of libfsilbm_b200.so: the B200 (sm_100a) implementation of the FSILBM3D
+ * hot path (fp64 D3Q19 collide-stream-boundary update + immersed-boundary coupling).
+ *
+ * The reference has no FFI for this path: the Fortran driver reaches it through type-bound
+ * procedures on the module globals LBMblks(:) (FluidDomain.f90:57) and VBodies(:)
+ * (Solidbody.f90:69).  Each entry point below names the reference procedure (file:line,
+ * relative to /root/reference/src) whose call it replaces.  fortran/fsilbm_gpu.f90 holds the
+ * ISO_C_BINDING interfaces for exactly these symbols; INTEGRATION.md shows where the driver
+ * calls them.
+ *
+ * Conventions
+ *  - plain C: ints, doubles, pointers; no C++/torch types.  Fortran passes scalars BY VALUE
+ *    through the bind(C) interfaces.
+ *  - every function returns 0 on success and a non-zero code otherwise; the message is in
+ *    fsilbm_last_error().  The reference's convention is "write(*,*) msg; stop"
+ *    (e.g. FluidDomain.f90:704, Solidbody.f90:850); the shim turns a non-zero return into that.
+ *  - host arrays use the reference's Fortran layout: fIn(z,y,x,0:18) = C [19][X][Y][Z], z fastest
+ *    (FluidDomain.f90:384); uuu/force(z,y,x,1:3) = C [3][X][Y][Z]; den(z,y,x) = C [X][Y][Z];
+ *    marker arrays v_Exyz(3,n) = C [n][3] (Solidbody.f90:1068-1069).
+ *  - callers are single-threaded (all reference call points are in serial regions).
+ *  - there is no CPU fallback: every call fails with FSILBM_ERR_CUDA if no sm_100-class
+ *    device is usable.
+ */
+#ifndef FSILBM_H
+#define FSILBM_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSILBM_OK 0
+#define FSILBM_ERR_ARG 1       /* bad argument / unknown handle                                  */
+#define FSILBM_ERR_CUDA 2      /* CUDA runtime failure (incl. no device)                         */
+#define FSILBM_ERR_BC 3        /* 'has no such boundary condition' (FluidDomain.f90:704)         */
+#define FSILBM_ERR_STENCIL 4   /* 'index out of xmin/xmax bound'   (Solidbody.f90:850,861)       */
+#define FSILBM_ERR_NAN 5       /* 'Nan found in PenaltyForce'      (Solidbody.f90:1028-1031)     */
+#define FSILBM_ERR_MODEL 6     /* collision model not provided (12/13 are broken upstream)       */
+#define FSILBM_ERR_COMM 7      /* NCCL failure                                                   */
+#define FSILBM_ERR_PERIODIC 8  /* 'Periodic boundaries must apper in pairs' (FluidDomain.f90:120) */
+
+typedef int fsilbm_handle;
+
+/* The slice of FlowCondType the hot path reads (FlowCondition.f90:11-27). */
+typedef struct fsilbm_flow {
+    double nu;                /* flow%nu, set at Solidbody.f90:282                 */
+    double denIn;             /* flow%denIn                                        */
+    double uvwIn[3];          /* flow%uvwIn                                        */
+    double shearRateIn[3];    /* flow%shearRateIn                                  */
+    int    velocityKind;      /* 0 shear (FluidDomain.f90:1807), 2 oscillatory (:1821) */
+    double volumeForceIn[3];  /* flow%volumeForceIn                                */
+    double volumeForceAmp, volumeForceFreq, volumeForcePhi; /* FluidDomain.f90:1177 */
+    double Uref;              /* flow%Uref (IBM tolerance, FIELDSTAT)              */
+} fsilbm_flow;
+
+/* ---- process-level ------------------------------------------------------------------------ */
+
+/* Select the CUDA device of this process (one process per GPU).  No reference counterpart
+ * (the reference's only set-up call is omp_set_num_threads, main.f90:36). */
+int fsilbm_init(int device);
+int fsilbm_finalize(void);
+const char *fsilbm_last_error(void);
+/* Number of kernels this library has launched since fsilbm_init (bench.py's gpu_launches). */
+long long fsilbm_launch_count(void);
+/* Tuning/testing switches, no reference counterpart.  key "variant": 0 push kernel (default),
+ * 1 push with streaming stores, 2 pull (fully periodic blocks only; kernel sweep);
+ * key "force_ghost": 1 = stream through the ghost planes even on one rank (tests the slab path). */
+int fsilbm_set_option(const char *key, int value);
+
+/* ---- fluid block: replaces type LBMBlock's procedures --------------------------------------- */
+
+/* read_fuild_blocks (FluidDomain.f90:76-105) + allocate_fluid_ (:378-408).
+ * xDim is the GLOBAL x extent; this process owns global planes [xOffset, xOffset+xLocal)
+ * (x-slab decomposition; pass xOffset=0, xLocal=xDim for one GPU). */
+int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal,
+                        double dh, double xmin, double ymin, double zmin,
+                        const int BndConds[6], int iCollidModel, const double params[10],
+                        const fsilbm_flow *flow, fsilbm_handle *out);
+int fsilbm_block_destroy(fsilbm_handle h);
+
+/* initialise_ (FluidDomain.f90:433-545): tau/Omega/Omega2/MRT matrices, f = f_eq(denIn, U(x)). */
+int fsilbm_block_initialise(fsilbm_handle h, double time);
+/* scalars derived at initialise: what = 0 tau, 1 Omega, 2 Omega2 */
+int fsilbm_block_get(fsilbm_handle h, int what, double *value);
+
+/* check_is_continue / read_continue_ (FluidDomain.f90:128-237,1779-1789) hand fIn over with
+ * these; fIn is the LOCAL slab [19][xLocal][Y][Z]. */
+int fsilbm_block_upload_fIn(fsilbm_handle h, const double *fIn);
+/* write_continue_ (FluidDomain.f90:1770-1777). */
+int fsilbm_block_download_fIn(fsilbm_handle h, double *fIn);
+
+/* LBMblks(:)%blktime = time (main.f90:97). */
+int fsilbm_block_set_time(fsilbm_handle h, double blktime);
+/* update_volume_force_ (FluidDomain.f90:1174-1180); F is evaluated on the host with libm's sin,
+ * as the reference does.  volumeForce_out may be NULL. */
+int fsilbm_block_update_volume_force(fsilbm_handle h, double volumeForce_out[3]);
+
+/* calculate_macro_quantities_ (FluidDomain.f90:1128-1145) for the writers/probes/FIELDSTAT:
+ * computes den, uuu of the local slab from the current fIn and copies them to the host.
+ * Either pointer may be NULL.  (Inside a step the library derives den/uuu in registers.) */
+int fsilbm_block_download_macro(fsilbm_handle h, double *den, double *uuu);
+/* ComputeFieldStat_ (FluidDomain.f90:1739-1768) on the local slab: out = sum(u^2)/Uref^2 for
+ * u,v,w then max|u|/Uref for u,v,w (the caller finishes sqrt(sum/N) after reducing over ranks). */
+int fsilbm_block_field_stat(fsilbm_handle h, double out[6]);
+
+/* set_boundary_conditions_ (FluidDomain.f90:616-1126) on the current fIn; the start-up call of
+ * tree_set_boundary_conditions_block (main.f90:63).  Reproduces the first-call skip of the
+ * half-way codes 203/204 (:660-661). */
+int fsilbm_block_set_boundary_conditions(fsilbm_handle h);
+
+/* The fused step: calculate_macro_quantities + ResetVolumeForce + add_volume_force + collision
+ * + halfwayBCset + streaming + set_boundary_conditions of one block
+ * (LBMBlockComm.f90:285-303 minus IBM_FEM), one read and one write of fIn.  Uses the velocity
+ * correction and force left by the last fsilbm_ibm_interaction_force call of this step, if any.
+ * Asynchronous: returns after enqueueing. */
+int fsilbm_block_collide_stream(fsilbm_handle h);
+/* Wait for all work enqueued on the block. */
+int fsilbm_block_sync(fsilbm_handle h);
+/* The cudaStream_t the block's kernels are launched on (so a host can time them with CUDA events). */
+int fsilbm_block_stream(fsilbm_handle h, void **stream);
+
+/* Un-fused single passes, for per-procedure parity tests and for drivers that keep the
+ * reference's call granularity.  They operate on device-resident den/uuu/force fields that are
+ * allocated on first use (3.5x the memory traffic of the fused step).
+ *   macro     : calculate_macro_quantities_ (FluidDomain.f90:1128)
+ *   reset/add : ResetVolumeForce_ (:1195), add_volume_force_ (:1182)
+ *   collision : collision_ (:1208), halfwayBCset_ (:567), streaming_ (:1514)          */
+int fsilbm_block_pass_macro(fsilbm_handle h);
+int fsilbm_block_pass_reset_volume_force(fsilbm_handle h);
+int fsilbm_block_pass_add_volume_force(fsilbm_handle h);
+int fsilbm_block_pass_collision(fsilbm_handle h);
+int fsilbm_block_pass_halfway_bc_set(fsilbm_handle h);
+int fsilbm_block_pass_streaming(fsilbm_handle h);
+/* copy the device den/uuu/force fields of the un-fused passes to/from the host (NULL = skip) */
+int fsilbm_block_download_fields(fsilbm_handle h, double *den, double *uuu, double *force);
+int fsilbm_block_upload_fields(fsilbm_handle h, const double *den, const double *uuu, const double *force);
+
+/* ---- immersed boundary: replaces calculate_interaction_force (Solidbody.f90:869-918) -------- */
+
+/* Device part of FSInteraction_force (Solidbody.f90:589-602) for the bodies carried by block h:
+ * UpdateElmtInterp_ (:760), the PenaltyForce_ loop (:895-906, :981) and the Eulerian half of
+ * FluidVolumeForce_ (:968-976).  The host keeps UpdatePosVelArea_ (:599) and the nodal-load half
+ * of FluidVolumeForce_ (:945-967), which need FEM internals.
+ *   Exyz[b], Evel[b]  : v_Exyz(3,n), v_Evel(3,n) of body b     (host, in)
+ *   Ea[b]             : v_Ea(n), already times IBPenaltyBeta (:613,624)  (host, in)
+ *   Eforce[b]         : v_Eforce(3,n)                           (host, out)
+ *   restencil[b]      : the test at :885 (v_move==1 .or. iBodyModel==2 .or. count_Interp==0)
+ *   rootBC            : m_boundaryConditions, the ROOT block's codes (main.f90:44, Solidbody.f90:337)
+ *   dt                : LBMBlockComm.f90:328 passes dh for dt
+ * Synchronous: Eforce and iterLBM_out are valid on return.  The velocity correction and the force
+ * field stay on the device for the next fsilbm_block_collide_stream. */
+int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts,
+                                 const double *const *Exyz, const double *const *Evel,
+                                 const double *const *Ea, double *const *Eforce,
+                                 const int *restencil, double dt, int ntolLBM, double dtolLBM,
+                                 const int rootBC[6], int *iterLBM_out);
+/* v_Ei(12,n) as int16 and v_Ew(12,n) as float of body b after the last call (parity checks). */
+int fsilbm_ibm_download_stencil(fsilbm_handle h, int body, short *Ei, float *Ew);
+
+/* ---- multi-GPU: x-slab halo exchange (no reference counterpart; the reference is one process) */
+
+/* rank 0 fills id[128] (an ncclUniqueId); the host distributes it; every rank calls comm_init. */
+int fsilbm_comm_unique_id(char id[128]);
+int fsilbm_comm_init(int rank, int nranks, const char id[128]);
+int fsilbm_comm_finalize(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSILBM_H */
