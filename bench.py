@@ -63,7 +63,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.1)
 
     def stop(self):
         self._stop_evt.set()
@@ -325,8 +325,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--workload", default="channel256", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", type=int, default=0)

@@ -269,7 +269,7 @@ def test_full_size_uniform_force_and_mass(F):
         gb.step()
     den, uuu = gb.download_macro()
     np.testing.assert_allclose(uuu[0], (n + 0.5) * Fx, rtol=1e-10)
-    assert np.max(np.abs(uuu[1:])) < 1e-18
+    assert np.max(np.abs(uuu[1:])) < 1e-15   # round-off only: no force, no gradient in y, z
     np.testing.assert_allclose(den, 1.0, rtol=1e-13)
     gb.close()
 
