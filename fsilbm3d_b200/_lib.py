@@ -64,6 +64,7 @@ def lib():
         "fsilbm_block_download_macro": [i, vp, vp], "fsilbm_block_field_stat": [i, pd],
         "fsilbm_block_set_boundary_conditions": [i], "fsilbm_block_collide_stream": [i], "fsilbm_block_sync": [i],
         "fsilbm_block_stream": [i, C.POINTER(C.c_void_p)],
+        "fsilbm_block_halo_transport": [i, pi],
         "fsilbm_block_pass_macro": [i], "fsilbm_block_pass_reset_volume_force": [i],
         "fsilbm_block_pass_add_volume_force": [i], "fsilbm_block_pass_collision": [i],
         "fsilbm_block_pass_halfway_bc_set": [i], "fsilbm_block_pass_streaming": [i],

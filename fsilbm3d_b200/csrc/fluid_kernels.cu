@@ -61,15 +61,26 @@ __device__ __forceinline__ void cell_state(const double (&f)[Q], const double (&
 
 // ---- the fused step -----------------------------------------------------------------------------
 // VARIANT 0: push (aligned loads, z-shifted stores).  VARIANT 1: same, streaming stores (st.global.cs).
-template <int MODEL, bool IBM, int VARIANT>
+// EDGE (multi-GPU edge planes): populations that leave the slab in x are stored straight into the neighbour
+// GPU's receive planes over NVLink (peer-mapped pointers p.halo_hi / p.halo_lo) instead of the local ghost
+// plane, and the last CTA of the launch publishes the step number to the neighbours' arrival flags, so the
+// transfer is part of the compute kernel and needs no copy engine, no NCCL kernel and no host involvement.
+__device__ __forceinline__ int halo_slot(int q)
+{   // position of q in [1,7,9,11,13] (ex=+1) or [2,8,10,12,14] (ex=-1)
+    return q <= 2 ? 0 : (q - 5) >> 1;
+}
+
+template <int MODEL, bool IBM, int VARIANT, bool EDGE>
 __global__ void __launch_bounds__(128, 4) collide_push_kernel(const __grid_constant__ StepParams p)
 {
     const int Z = p.g.Z, Y = p.g.Y, X = p.g.X;
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int x = p.x_begin + blockIdx.z;
-    if (z >= Z || y >= Y) return;
+    const bool active = (z < Z && y < Y);
+    if (!EDGE && !active) return;
     const size_t plane = p.g.plane, ps = p.g.pstride;
+    if (active) {
     const size_t base = (size_t)(x + 1) * plane + (size_t)y * Z + z;
 
     double f[Q];
@@ -95,8 +106,28 @@ __global__ void __launch_bounds__(128, 4) collide_push_kernel(const __grid_const
         const int iy = EY(q) == 0 ? 0 : (EY(q) > 0 ? 1 : 2);
         const int iz = EZ(q) == 0 ? 0 : (EZ(q) > 0 ? 1 : 2);
         double *dst = p.fB + q * ps + ox[ix] + oy[iy] + oz[iz];
+        if (EDGE) {
+            if (EX(q) > 0 && x == X - 1 && p.halo_hi) dst = p.halo_hi + (size_t)halo_slot(q) * plane + oy[iy] + oz[iz];
+            if (EX(q) < 0 && x == 0 && p.halo_lo) dst = p.halo_lo + (size_t)halo_slot(q) * plane + oy[iy] + oz[iz];
+        }
         if (VARIANT == 1) __stcs(dst, f[q]);
         else *dst = f[q];
+    }
+    }
+    if (EDGE) {
+        // publish: every thread's peer stores are fenced system-wide, the CTA counts in, the last CTA raises the flags
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+            const unsigned int done = atomicAdd(p.cta_counter, 1u);
+            if (done == total - 1) {
+                *p.cta_counter = 0;
+                __threadfence_system();
+                if (p.sig_hi && x == X - 1) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.sig_hi), "l"(p.step) : "memory"); }
+                if (p.sig_lo && x == 0) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.sig_lo), "l"(p.step) : "memory"); }
+            }
+        }
     }
 }
 
@@ -149,10 +180,17 @@ template <int VARIANT>
 static int launch_push_variant(const StepParams &p, int model, dim3 grid, dim3 block, cudaStream_t s)
 {
     const bool ibm = p.boxes.n > 0;
-    if (model == 1) { if (ibm) collide_push_kernel<1, true, VARIANT><<<grid, block, 0, s>>>(p); else collide_push_kernel<1, false, VARIANT><<<grid, block, 0, s>>>(p); }
-    else if (model == 2) { if (ibm) collide_push_kernel<2, true, VARIANT><<<grid, block, 0, s>>>(p); else collide_push_kernel<2, false, VARIANT><<<grid, block, 0, s>>>(p); }
-    else if (model == 3) { if (ibm) collide_push_kernel<3, true, VARIANT><<<grid, block, 0, s>>>(p); else collide_push_kernel<3, false, VARIANT><<<grid, block, 0, s>>>(p); }
+    const bool edge = p.cta_counter != nullptr;
+#define FSILBM_LAUNCH(M)                                                                                     \
+    do {                                                                                                     \
+        if (edge) { if (ibm) collide_push_kernel<M, true, VARIANT, true><<<grid, block, 0, s>>>(p); else collide_push_kernel<M, false, VARIANT, true><<<grid, block, 0, s>>>(p); } \
+        else { if (ibm) collide_push_kernel<M, true, VARIANT, false><<<grid, block, 0, s>>>(p); else collide_push_kernel<M, false, VARIANT, false><<<grid, block, 0, s>>>(p); } \
+    } while (0)
+    if (model == 1) FSILBM_LAUNCH(1);
+    else if (model == 2) FSILBM_LAUNCH(2);
+    else if (model == 3) FSILBM_LAUNCH(3);
     else return 1;
+#undef FSILBM_LAUNCH
     return 0;
 }
 
@@ -614,6 +652,48 @@ __global__ void wrap_x_kernel(Geom g, double *f)
 void launch_wrap_x(const Geom &g, double *f, cudaStream_t s)
 {
     wrap_x_kernel<<<(unsigned)((g.plane + 255) / 256), 256, 0, s>>>(g, f);
+    count_launch();
+}
+
+// Receiving side of the peer-memory halo.  Thread 0 of every CTA spins (acquire, system scope) until both
+// neighbours have published this step, then the CTA copies its share of the 10 received planes into the
+// streamed buffer: ex=+1 populations into local plane 0 (xp = 1), ex=-1 populations into plane X-1 (xp = X).
+__global__ void halo_unpack_kernel(const __grid_constant__ HaloUnpackParams p)
+{
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        int good = 1;
+        const unsigned long long *flags[2] = {p.flag_lo, p.flag_hi};
+        for (int sd = 0; sd < 2 && good; sd++) {
+            if (!flags[sd]) continue;
+            unsigned long long v;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags[sd]) : "memory");
+                if (v >= p.step) break;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > p.timeout_ns) { good = 0; atomicExch(p.err, 1); break; }
+                __nanosleep(200);
+            }
+        }
+        ok = good;
+    }
+    __syncthreads();
+    if (!ok) return;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.g.plane) return;
+    constexpr int up[5] = {1, 7, 9, 11, 13}, dn[5] = {2, 8, 10, 12, 14};
+    const Geom &g = p.g;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        if (p.recv_lo) p.fB[up[k] * g.pstride + (size_t)1 * g.plane + i] = __ldcg(p.recv_lo + (size_t)k * g.plane + i);
+        if (p.recv_hi) p.fB[dn[k] * g.pstride + (size_t)g.X * g.plane + i] = __ldcg(p.recv_hi + (size_t)k * g.plane + i);
+    }
+}
+void launch_halo_unpack(const HaloUnpackParams &p, cudaStream_t s)
+{
+    halo_unpack_kernel<<<(unsigned)((p.g.plane + 255) / 256), 256, 0, s>>>(p);
     count_launch();
 }
 

@@ -44,6 +44,7 @@ struct Nccl {
     int (*Send)(const void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_p, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -52,6 +53,7 @@ struct Nccl {
 } g_nccl;
 constexpr int kNcclFloat64 = 8;   // ncclDouble
 constexpr int kNcclSum = 0;       // ncclSum
+constexpr int kNcclChar = 0;      // ncclChar
 
 int nccl_load()
 {
@@ -71,6 +73,7 @@ int nccl_load()
     SYM(Send, "ncclSend")
     SYM(Recv, "ncclRecv")
     SYM(AllReduce, "ncclAllReduce")
+    SYM(AllGather, "ncclAllGather")
     SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd")
     SYM(GetErrorString, "ncclGetErrorString")
@@ -138,11 +141,24 @@ struct Block {
     bool ibm_active = false;
     cudaStream_t stream = nullptr, comm_stream = nullptr;
     cudaEvent_t ev_edge = nullptr, ev_comm = nullptr;
+    // peer-memory halo (multi-GPU): see halo_setup
+    struct Halo {
+        bool enabled = false;
+        int left = -1, right = -1;                 // neighbour ranks (-1: domain end)
+        unsigned char *region = nullptr;           // [4 x u64 flags | pad to 256 B][side 0/1][parity 0/1][5][Y][Z] doubles
+        unsigned char *peer_left = nullptr, *peer_right = nullptr;   // the neighbours' regions, peer-mapped through CUDA IPC
+        unsigned int *counters = nullptr;          // last-CTA counters of the two edge launches
+        int *err = nullptr;
+        unsigned long long step = 0;
+        size_t slot_bytes = 0;                     // 5 * Y * Z * 8
+    } halo;
 };
 
 std::vector<std::unique_ptr<Block>> g_blocks;
 int g_device = -1;
 int g_variant = 0, g_force_ghost = 0;
+int g_halo_timeout_s = 120;   // a neighbour this late is treated as lost (the wait kernel gives up, fsilbm_block_sync reports it)
+int g_halo_mode = 1;   // 1: edge kernels store into the neighbours' memory over NVLink (default); 0: ncclSend/ncclRecv
 
 Block *get(fsilbm_handle h)
 {
@@ -302,18 +318,111 @@ int halo_exchange(Block &b, double *fB, cudaStream_t s)
     const int left = (r > 0) ? r - 1 : (per ? R - 1 : -1);
     static const int up[5] = {1, 7, 9, 11, 13}, dn[5] = {2, 8, 10, 12, 14};
     NCK(g_nccl.GroupStart());
+    // NCCL pairs the sends and receives between two ranks in posting order.  With two ranks and a periodic x
+    // axis the left and the right neighbour are the same rank, so post sends as (up->right, dn->left) and
+    // receives as (up<-left, dn<-right): the peer's first send (its "up") then meets my first receive.
     for (int k = 0; k < 5; k++) {
-        if (right >= 0) {
-            NCK(g_nccl.Send(fB + up[k] * g.pstride + (size_t)(g.X + 1) * g.plane, g.plane, kNcclFloat64, right, g_nccl.comm, s));
-            NCK(g_nccl.Recv(fB + dn[k] * g.pstride + (size_t)g.X * g.plane, g.plane, kNcclFloat64, right, g_nccl.comm, s));
-        }
-        if (left >= 0) {
-            NCK(g_nccl.Send(fB + dn[k] * g.pstride, g.plane, kNcclFloat64, left, g_nccl.comm, s));
-            NCK(g_nccl.Recv(fB + up[k] * g.pstride + (size_t)1 * g.plane, g.plane, kNcclFloat64, left, g_nccl.comm, s));
-        }
+        if (right >= 0) NCK(g_nccl.Send(fB + up[k] * g.pstride + (size_t)(g.X + 1) * g.plane, g.plane, kNcclFloat64, right, g_nccl.comm, s));
+        if (left >= 0) NCK(g_nccl.Send(fB + dn[k] * g.pstride, g.plane, kNcclFloat64, left, g_nccl.comm, s));
+        if (left >= 0) NCK(g_nccl.Recv(fB + up[k] * g.pstride + (size_t)1 * g.plane, g.plane, kNcclFloat64, left, g_nccl.comm, s));
+        if (right >= 0) NCK(g_nccl.Recv(fB + dn[k] * g.pstride + (size_t)g.X * g.plane, g.plane, kNcclFloat64, right, g_nccl.comm, s));
     }
     NCK(g_nccl.GroupEnd());
     return 0;
+}
+
+
+constexpr size_t kHaloFlagBytes = 256;
+
+inline unsigned long long *halo_flag(unsigned char *region, int side, int parity) { return (unsigned long long *)region + (side * 2 + parity); }
+inline double *halo_slot_ptr(unsigned char *region, size_t slot_bytes, int side, int parity)
+{
+    return (double *)(region + kHaloFlagBytes + (size_t)(side * 2 + parity) * slot_bytes);
+}
+
+// Peer-memory halo set-up (collective over the communicator; every rank creates its blocks in the same order).
+// Each rank allocates a receive region, exports it with cudaIpcGetMemHandle, the 64-byte handles are all-gathered
+// with NCCL, and each rank maps its two neighbours' regions.  From then on the edge-plane launches of
+// collide_push_kernel store outgoing populations straight into the neighbour's region over NVLink and raise a
+// flag there; no NCCL call remains on the per-step path.  Returns 0 and leaves halo.enabled = false when IPC
+// is not available (the step then uses ncclSend/ncclRecv).
+int halo_setup(Block &b)
+{
+    Block::Halo &h = b.halo;
+    const int R = g_nccl.nranks, r = g_nccl.rank;
+    const bool per = b.periodic[0] == 1;
+    h.right = (r + 1 < R) ? r + 1 : (per ? 0 : -1);
+    h.left = (r > 0) ? r - 1 : (per ? R - 1 : -1);
+    h.slot_bytes = sizeof(double) * 5 * b.g.plane;
+    const size_t bytes = kHaloFlagBytes + 4 * h.slot_bytes;
+    CK(cudaMalloc(&h.region, bytes));
+    CK(cudaMemset(h.region, 0, bytes));
+    CK(cudaMalloc(&h.counters, 2 * sizeof(unsigned int)));
+    CK(cudaMemset(h.counters, 0, 2 * sizeof(unsigned int)));
+    CK(cudaMalloc(&h.err, sizeof(int)));
+    CK(cudaMemset(h.err, 0, sizeof(int)));
+    cudaIpcMemHandle_t mine;
+    int ok = cudaIpcGetMemHandle(&mine, h.region) == cudaSuccess ? 1 : 0;
+    if (!ok) cudaGetLastError();
+    // all-gather {ok flag, handle}
+    constexpr size_t rec = 128;
+    unsigned char hostrec[rec] = {0};
+    hostrec[0] = (unsigned char)ok;
+    memcpy(hostrec + 8, &mine, sizeof(mine));
+    unsigned char *dsend = nullptr, *drecv = nullptr;
+    CK(cudaMalloc(&dsend, rec));
+    CK(cudaMalloc(&drecv, rec * R));
+    CK(cudaMemcpy(dsend, hostrec, rec, cudaMemcpyHostToDevice));
+    NCK(g_nccl.AllGather(dsend, drecv, rec, kNcclChar, g_nccl.comm, b.stream));
+    CK(cudaStreamSynchronize(b.stream));
+    std::vector<unsigned char> all(rec * R);
+    CK(cudaMemcpy(all.data(), drecv, rec * R, cudaMemcpyDeviceToHost));
+    cudaFree(dsend); cudaFree(drecv);
+    int all_ok = 1;
+    for (int i = 0; i < R; i++) all_ok &= all[rec * i];
+    int opened = 1;
+    if (all_ok) {
+        auto open = [&](int peer, unsigned char **out) {
+            cudaIpcMemHandle_t hh;
+            memcpy(&hh, all.data() + rec * peer + 8, sizeof(hh));
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, hh, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = 0; return; }
+            *out = (unsigned char *)ptr;
+        };
+        if (h.left >= 0) open(h.left, &h.peer_left);
+        if (h.right >= 0 && opened) { if (h.right == h.left) h.peer_right = h.peer_left; else open(h.right, &h.peer_right); }
+    }
+    // agree on the outcome (a rank that could not map its neighbour forces everyone onto the NCCL path)
+    int *dflag = nullptr;
+    CK(cudaMalloc(&dflag, sizeof(int)));
+    int mineok = (all_ok && opened) ? 0 : 1;   // sum of failures
+    CK(cudaMemcpy(dflag, &mineok, sizeof(int), cudaMemcpyHostToDevice));
+    NCK(g_nccl.AllReduce(dflag, dflag, 1, 2 /* ncclInt32 */, kNcclSum, g_nccl.comm, b.stream));
+    CK(cudaStreamSynchronize(b.stream));
+    int failures = 0;
+    CK(cudaMemcpy(&failures, dflag, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(dflag);
+    h.enabled = failures == 0;
+    return 0;
+}
+
+void halo_teardown(Block &b)
+{
+    Block::Halo &h = b.halo;
+    if (!h.region) return;
+    if (h.peer_left) cudaIpcCloseMemHandle(h.peer_left);
+    if (h.peer_right && h.peer_right != h.peer_left) cudaIpcCloseMemHandle(h.peer_right);
+    if (g_nccl.comm) {   // nobody frees a region a neighbour may still be writing into
+        int *dflag = nullptr;
+        if (cudaMalloc(&dflag, sizeof(int)) == cudaSuccess) {
+            cudaMemset(dflag, 0, sizeof(int));
+            g_nccl.AllReduce(dflag, dflag, 1, 2, kNcclSum, g_nccl.comm, b.stream);
+            cudaStreamSynchronize(b.stream);
+            cudaFree(dflag);
+        }
+    }
+    cudaFree(h.region); cudaFree(h.counters); cudaFree(h.err);
+    h = Block::Halo();
 }
 
 }  // namespace
@@ -353,6 +462,8 @@ int fsilbm_set_option(const char *key, int value)
     if (!key) return fail(FSILBM_ERR_ARG, "null key");
     if (!strcmp(key, "variant")) { if (value < 0 || value > 2) return fail(FSILBM_ERR_ARG, "variant must be 0..2"); g_variant = value; return 0; }
     if (!strcmp(key, "force_ghost")) { g_force_ghost = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "halo_timeout_s")) { if (value < 1) return fail(FSILBM_ERR_ARG, "halo_timeout_s must be >= 1"); g_halo_timeout_s = value; return 0; }
+    if (!strcmp(key, "halo")) { if (value < 0 || value > 1) return fail(FSILBM_ERR_ARG, "halo must be 0 (NCCL) or 1 (peer stores)"); g_halo_mode = value; return 0; }
     return fail(FSILBM_ERR_ARG, "unknown option %s", key);
 }
 
@@ -390,11 +501,17 @@ int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, d
         CK(cudaMemset(b->f[i], 0, bytes));
     }
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&b->comm_stream, cudaStreamNonBlocking));
+    {   // the NCCL transport's stream outranks the compute stream so its CTAs are scheduled as soon as SM slots free up
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&b->comm_stream, cudaStreamNonBlocking, hi));
+    }
     CK(cudaEventCreateWithFlags(&b->ev_edge, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_comm, cudaEventDisableTiming));
     CK(cudaMalloc(&b->ctl, sizeof(IbmCtl)));
     CK(cudaMalloc(&b->stat, sizeof(double) * 6));
+    if (g_nccl.nranks > 1 && g_nccl.comm && g_halo_mode == 1)
+        if (int rc = halo_setup(*b)) return rc;
     int slot = -1;
     for (size_t i = 0; i < g_blocks.size(); i++) if (!g_blocks[i]) { slot = (int)i; break; }
     if (slot < 0) { g_blocks.emplace_back(); slot = (int)g_blocks.size() - 1; }
@@ -410,6 +527,7 @@ int fsilbm_block_destroy(fsilbm_handle h)
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
     cudaStreamSynchronize(b->stream);
     cudaStreamSynchronize(b->comm_stream);
+    halo_teardown(*b);
     for (int i = 0; i < 2; i++) cudaFree(b->f[i]);
     for (int i = 0; i < 6; i++) { cudaFree(b->stash[i]); cudaFree(b->l2den[i]); cudaFree(b->l2u[i]); }
     cudaFree(b->den); cudaFree(b->uuu); cudaFree(b->force); cudaFree(b->stat);
@@ -601,8 +719,27 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
         p.x_begin = 0; p.x_count = g.X;
         if (launch_collide_push(p, b.model, variant, b.stream)) return fail(FSILBM_ERR_MODEL, "collision model %d", b.model);
         if (ghost) launch_wrap_x(g, fB, b.stream);
+    } else if (b.halo.enabled) {
+        // Edge planes first: their kernel IS the transfer (peer stores over NVLink + arrival flag); then the
+        // interior on the same stream; then wait for the neighbours' flags and fold the received planes in.
+        Block::Halo &h = b.halo;
+        h.step++;
+        const int par = (int)(h.step & 1);
+        StepParams e = p;
+        e.step = h.step;
+        if (h.left >= 0) { e.halo_lo = halo_slot_ptr(h.peer_left, h.slot_bytes, 1, par); e.sig_lo = halo_flag(h.peer_left, 1, par); }
+        if (h.right >= 0) { e.halo_hi = halo_slot_ptr(h.peer_right, h.slot_bytes, 0, par); e.sig_hi = halo_flag(h.peer_right, 0, par); }
+        e.x_begin = 0; e.x_count = 1; e.cta_counter = h.counters;
+        launch_collide_push(e, b.model, variant, b.stream);
+        if (g.X > 1) { e.x_begin = g.X - 1; e.cta_counter = h.counters + 1; launch_collide_push(e, b.model, variant, b.stream); }
+        if (g.X > 2) { p.x_begin = 1; p.x_count = g.X - 2; launch_collide_push(p, b.model, variant, b.stream); }
+        HaloUnpackParams u{};
+        u.g = g; u.fB = fB; u.step = h.step; u.err = h.err; u.timeout_ns = (unsigned long long)g_halo_timeout_s * 1000000000ull;
+        if (h.left >= 0) { u.recv_lo = halo_slot_ptr(h.region, h.slot_bytes, 0, par); u.flag_lo = halo_flag(h.region, 0, par); }
+        if (h.right >= 0) { u.recv_hi = halo_slot_ptr(h.region, h.slot_bytes, 1, par); u.flag_hi = halo_flag(h.region, 1, par); }
+        launch_halo_unpack(u, b.stream);
     } else {
-        // edge planes first, then the exchange on its own stream overlapped with the interior update
+        // NCCL transport: edge planes first, then the exchange on its own stream overlapped with the interior update
         p.x_begin = 0; p.x_count = 1;
         launch_collide_push(p, b.model, variant, b.stream);
         if (g.X > 1) { p.x_begin = g.X - 1; p.x_count = 1; launch_collide_push(p, b.model, variant, b.stream); }
@@ -626,6 +763,19 @@ int fsilbm_block_sync(fsilbm_handle h)
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
     CK(cudaStreamSynchronize(b->stream));
     CK(cudaStreamSynchronize(b->comm_stream));
+    if (b->halo.enabled) {
+        int e = 0;
+        CK(cudaMemcpy(&e, b->halo.err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) return fail(FSILBM_ERR_COMM, "halo: a neighbour's arrival flag did not come within %d s (rank %d)", g_halo_timeout_s, g_nccl.rank);
+    }
+    return 0;
+}
+
+int fsilbm_block_halo_transport(fsilbm_handle h, int *mode)
+{
+    Block *b = get(h);
+    if (!b || !mode) return fail(FSILBM_ERR_ARG, "bad handle/argument");
+    *mode = (g_nccl.nranks > 1 && g_nccl.comm) ? (b->halo.enabled ? 2 : 1) : 0;
     return 0;
 }
 

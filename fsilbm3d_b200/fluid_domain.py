@@ -136,6 +136,12 @@ class LBMBlock:
         check(lib().fsilbm_block_sync(self._h))
 
     @property
+    def halo_transport(self) -> str:
+        m = C.c_int(0)
+        check(lib().fsilbm_block_halo_transport(self._h, C.byref(m)))
+        return {0: "none (single rank)", 1: "nccl send/recv", 2: "peer stores over NVLink (CUDA IPC) fused into the edge kernels"}[m.value]
+
+    @property
     def cuda_stream(self) -> int:
         """cudaStream_t (as an integer) the block's kernels run on, for CUDA-event timing."""
         p = C.c_void_p()

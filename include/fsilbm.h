@@ -64,7 +64,10 @@ const char *fsilbm_last_error(void);
 long long fsilbm_launch_count(void);
 /* Tuning/testing switches, no reference counterpart.  key "variant": 0 push kernel (default),
  * 1 push with streaming stores, 2 pull (fully periodic blocks only; kernel sweep);
- * key "force_ghost": 1 = stream through the ghost planes even on one rank (tests the slab path). */
+ * key "force_ghost": 1 = stream through the ghost planes even on one rank (tests the slab path);
+ * key "halo": 1 (default) peer-memory halo over NVLink, 0 ncclSend/ncclRecv (see fsilbm_block_halo_transport);
+ * key "halo_timeout_s": how long a rank waits for a neighbour's halo before fsilbm_block_sync reports
+ * FSILBM_ERR_COMM (default 120). */
 int fsilbm_set_option(const char *key, int value);
 
 /* ---- fluid block: replaces type LBMBlock's procedures --------------------------------------- */
@@ -163,6 +166,12 @@ int fsilbm_ibm_download_stencil(fsilbm_handle h, int body, short *Ei, float *Ew)
 int fsilbm_comm_unique_id(char id[128]);
 int fsilbm_comm_init(int rank, int nranks, const char id[128]);
 int fsilbm_comm_finalize(void);
+/* How block h exchanges its x-slab halo: 0 = single rank (x wraps inside the kernel), 1 = ncclSend/ncclRecv on a
+ * high-priority stream overlapped with the interior update, 2 = the edge-plane kernels store the outgoing
+ * populations straight into the neighbour GPUs' memory over NVLink (CUDA-IPC-mapped) and raise arrival flags there.
+ * Mode 2 is the default (fsilbm_set_option("halo", 1)); the library drops to mode 1 when IPC mapping is unavailable.
+ * Blocks of a multi-rank run must be created in the same order on every rank (creation is collective). */
+int fsilbm_block_halo_transport(fsilbm_handle h, int *mode);
 
 #ifdef __cplusplus
 }

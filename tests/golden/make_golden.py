@@ -1,0 +1,97 @@
+"""Generates tests/golden/*.npz from the independent numpy restatement (oracle/numpy_restatement.py).
+
+    python tests/golden/make_golden.py
+
+The reference itself cannot produce vectors here (Fortran, no compiler in the image: SURVEY F4), so the
+golden vectors come from the second restatement written separately from the C oracle.  The C oracle
+(tests/test_oracle_golden.py) and the CUDA path (tests/test_gpu_golden.py) are both held to them.
+Each file stores the case definition (so the tests rebuild the identical case), the seeded initial
+populations and the state after N steps.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import numpy_restatement as NR   # noqa: E402
+from tests.common import perturbed_state     # noqa: E402
+
+CASES = {
+    # name: dims, bc, model, params, dh, mins, flow, steps, plate
+    "srt_periodic_force": dict(dims=(8, 6, 10), bc=(301,) * 6, model=1, params=(0.0,) * 10, dh=1.0, mins=(0.0, 0.0, 0.0),
+                               flow=dict(nu=0.1, volumeForceIn=(1e-6, 2e-7, -3e-7)), steps=12),
+    "trt_halfway_channel": dict(dims=(6, 8, 10), bc=(301, 301, 203, 203, 301, 301), model=2, params=(3 / 16,) + (0.0,) * 9, dh=0.5,
+                                mins=(-1.0, 0.5, 2.0), flow=dict(nu=0.05, volumeForceIn=(1e-6, 0.0, 0.0)), steps=12),
+    "mrt_osc_force": dict(dims=(6, 6, 8), bc=(301,) * 6, model=3, params=(0.0,) * 10, dh=1.0, mins=(0.0, 0.0, 0.0),
+                          flow=dict(nu=0.08, volumeForceIn=(1e-6, 0.0, 0.0), volumeForceAmp=5e-7, volumeForceFreq=0.01, volumeForcePhi=30.0), steps=10),
+    "srt_all_faces_mixed": dict(dims=(7, 8, 9), bc=(102, 104, 202, 204, 203, 201), model=1, params=(0.0,) * 10, dh=0.5, mins=(-1.0, 0.5, 2.0),
+                                flow=dict(nu=0.05, uvwIn=(0.03, 0.0, 0.0), shearRateIn=(0.0, 5e-4, 2e-4)), steps=12),
+    "trt_inlet_outlet_symmetric": dict(dims=(8, 6, 7), bc=(101, 103, 302, 302, 301, 301), model=2, params=(0.25,) + (0.0,) * 9, dh=1.0,
+                                       mins=(0.0, 0.0, 0.0), flow=dict(nu=0.05, uvwIn=(0.04, 0.0, 0.0)), steps=12),
+    "srt_oscillatory_inflow": dict(dims=(8, 5, 6), bc=(101, 104, 301, 301, 301, 301), model=1, params=(0.0,) * 10, dh=1.0, mins=(0.0, 0.0, 0.0),
+                                   flow=dict(nu=0.05, uvwIn=(0.03, 0.0, 0.0), velocityKind=2, shearRateIn=(0.01, 0.02, 45.0)), steps=10),
+    "srt_plate_shear": dict(dims=(16, 14, 12), bc=(101, 104, 202, 202, 301, 301), model=1, params=(0.0,) * 10, dh=1.0, mins=(0.0, 0.0, 0.0),
+                            flow=dict(nu=0.05, uvwIn=(0.05, 0.0, 0.0), shearRateIn=(0.0, 2e-4, 0.0), Uref=0.05, ntolLBM=3, dtolLBM=1e-30), steps=8,
+                            plate=dict(origin=(5.3, 6.2, 3.4), nEL=4, len1=1.0, Nspan=5, spanlen=5.0, Lspan=0.0, chord_dir=(1.0, 0.3, 0.0))),
+    "srt_plate_periodic_wrap": dict(dims=(12, 10, 10), bc=(301,) * 6, model=1, params=(0.0,) * 10, dh=1.0, mins=(0.0, 0.0, 0.0),
+                                    flow=dict(nu=0.05, uvwIn=(0.03, 0.0, 0.0), Uref=0.03, ntolLBM=4, dtolLBM=1e-30), steps=8,
+                                    plate=dict(origin=(9.7, 4.2, 7.6), nEL=4, len1=1.0, Nspan=4, spanlen=4.0, Lspan=0.0, chord_dir=(1.0, 0.2, 0.0))),
+}
+
+
+def plate_markers(p, denIn, alpha=1.0):
+    """Markers of a rigid flat plate exactly as PlateUpdatePosVelArea_ lays them out (Solidbody.f90:604-646)."""
+    cd = np.asarray(p["chord_dir"], float); cd /= np.linalg.norm(cd)
+    sd = np.array([0.0, 0.0, 1.0])
+    nodes = np.asarray(p["origin"], float)[None, :] + np.arange(p["nEL"] + 1)[:, None] * p["len1"] * cd[None, :]
+    beta = -alpha * 2.0 * denIn
+    dl = p["spanlen"] / float(p["Nspan"])
+    xyz, ea = [], []
+    for i in range(p["nEL"]):
+        c = 0.5 * (nodes[i] + nodes[i + 1])
+        for s in range(1, p["Nspan"] + 1):
+            ls = dl * (0.5 + float(s - 1)) - p["Lspan"]
+            xyz.append(c + sd * ls)
+            ea.append(dl * p["len1"] * beta)
+    return np.array(xyz), np.zeros((len(xyz), 3)), np.array(ea)
+
+
+def run_case(name, c):
+    fl = NR.Flow(**c["flow"])
+    X, Y, Z = c["dims"]
+    b = NR.Block(X, Y, Z, dh=c["dh"], xmin=c["mins"][0], ymin=c["mins"][1], zmin=c["mins"][2], BndConds=c["bc"],
+                 iCollidModel=c["model"], params=c["params"], flow=fl)
+    b.initialise(0.0)
+    f0 = perturbed_state(c["dims"], fl)
+    b.f[...] = f0
+    b.update_volume_force(); b.set_boundary_conditions(); b.calculate_macro_quantities()   # main.f90:62-64
+    bodies = []
+    out = {}
+    if "plate" in c:
+        xyz, vel, ea = plate_markers(c["plate"], fl.denIn)
+        body = NR.Body(len(ea))
+        body.v_Exyz[...] = xyz; body.v_Evel[...] = vel; body.v_Ea[...] = ea
+        bodies = [body]
+        out.update(Exyz=xyz, Evel=vel, Ea=ea)
+    its = []
+    for n in range(1, c["steps"] + 1):
+        b.blktime = c["dh"] * n
+        its.append(b.step(bodies))
+    b.calculate_macro_quantities()   # main.f90:107
+    out.update(f0=f0, fIn=b.f, den=b.den, uuu=b.uuu, iters=np.array(its), case=json.dumps(c))
+    if bodies:
+        out.update(Eforce=bodies[0].v_Eforce, Ei=bodies[0].v_Ei, Ew=bodies[0].v_Ew)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: {X}x{Y}x{Z}, {c['steps']} steps, max|u| {np.abs(b.uuu).max():.3e}, mean rho {b.den.mean():.12f}")
+
+
+if __name__ == "__main__":
+    for name, c in CASES.items():
+        run_case(name, c)

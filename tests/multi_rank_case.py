@@ -35,8 +35,10 @@ def main():
         dict(name="periodic_plate_wrap", dims=(9 * world, 18, 20), bc=(301,) * 6, plate_origin="wrap",
              flow=dict(nu=0.05, uvwIn=(0.03, 0.0, 0.0), Uref=0.03, ntolLBM=4, dtolLBM=1e-30)),
     ]
+    F._lib.check(F.lib().fsilbm_set_option(b"halo_timeout_s", 30))
     ok = True
-    for case in cases:
+    for halo_mode, case in [(m, c) for m in (1, 0) for c in cases]:
+        F._lib.check(F.lib().fsilbm_set_option(b"halo", halo_mode))
         X, Y, Z = case["dims"]
         off, cnt = F.slab_range(X, rank, world)
         flow = F.FlowCondType(**case["flow"])
@@ -85,7 +87,7 @@ def main():
             exact = bool(np.array_equal(FF, ob.fIn))
             good = e_den <= 1e-12 and e_u <= 1e-12 and e_f <= 1e-12 and eF <= 1e-10
             ok &= good
-            print(f"[multi x{world}] {case['name']}: rel err den {e_den:.2e} u {e_u:.2e} f {e_f:.2e} force {eF:.2e} bit-exact {exact} -> {'OK' if good else 'FAIL'}", flush=True)
+            print(f"[multi x{world}] halo={gb.halo_transport!r} {case['name']}: rel err den {e_den:.2e} u {e_u:.2e} f {e_f:.2e} force {eF:.2e} bit-exact {exact} -> {'OK' if good else 'FAIL'}", flush=True)
         gb.close()
         dist.barrier()
     flag = torch.tensor([1 if ok else 0])
