@@ -16,6 +16,22 @@ def slab_range(xDim: int, rank: int, nranks: int) -> Tuple[int, int]:
     return sum(counts[:rank]), counts[rank]
 
 
+# populations that cross an x-face of a slab: eₓ=+1 go to the right neighbour, eₓ=-1 to the left (ConstParams.f90:13)
+UP_POPULATIONS = (1, 7, 9, 11, 13)
+DOWN_POPULATIONS = (2, 8, 10, 12, 14)
+
+
+def halo_plan(rank: int, nranks: int, periodic_x: bool):
+    """Neighbours of `rank` in the x-slab decomposition and what is exchanged with each per step.
+    Returns (left, right, UP_POPULATIONS, DOWN_POPULATIONS); a neighbour is -1 at a non-periodic domain end.
+    After the local push, ghost plane X+1 holds the UP populations for `right` (they become its plane 1) and ghost
+    plane 0 holds the DOWN populations for `left` (they become its plane X).  The same plan is hard-wired in
+    csrc/fsilbm_api.cu (halo_exchange / halo_setup); tests/test_multi_cpu.py replays it with gloo on CPU slabs."""
+    right = rank + 1 if rank + 1 < nranks else (0 if periodic_x else -1)
+    left = rank - 1 if rank > 0 else (nranks - 1 if periodic_x else -1)
+    return left, right, UP_POPULATIONS, DOWN_POPULATIONS
+
+
 def init_process_group(rank: int, nranks: int, device: int, broadcast_bytes) -> None:
     """Bind this process to `device` and join the library's NCCL communicator.
     broadcast_bytes(b: bytes|None) -> bytes must return rank 0's 128-byte id on every rank."""
