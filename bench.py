@@ -22,6 +22,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout must carry exactly one JSON line
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "MLUPS (fp64 D3Q19 collide-stream+IBM)"
 UNIT = "MLUPS"

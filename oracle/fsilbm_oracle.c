@@ -241,6 +241,7 @@ double *orc_block_fIn(orc_block *b) { return b->fIn; }
 double *orc_block_uuu(orc_block *b) { return b->uuu; }
 double *orc_block_force(orc_block *b) { return b->force; }
 double *orc_block_den(orc_block *b) { return b->den; }
+double *orc_block_tau_all(orc_block *b) { return b->tau_all; }
 double *orc_block_volumeForce(orc_block *b) { return b->volumeForce; }
 void orc_block_set_blktime(orc_block *b, double t) { b->blktime = t; }
 double orc_block_get(orc_block *b, int what)
@@ -993,6 +994,277 @@ int orc_step(orc_block *b, orc_body **bodies, int nbodies, const int rootBC[6], 
     orc_streaming(b);               /* :299 */
     if (orc_set_boundary_conditions(b)) return 4; /* :303 */
     return 0;
+}
+
+/* the two halves of orc_step, for the block-tree recursion (LBMBlockComm.f90:283-288 and :293-303) */
+int orc_step_pre(orc_block *b, orc_body **bodies, int nbodies, const int rootBC[6], int ntolLBM, double dtolLBM, int *iterLBM_out)
+{
+    orc_update_volume_force(b);
+    orc_calculate_macro_quantities(b);
+    orc_reset_volume_force(b);
+    int it = orc_calculate_interaction_force(bodies, nbodies, b->dh, b->dh, b->xmin, b->ymin, b->zmin, b->xDim, b->yDim,
+                                             b->zDim, b->uuu, b->force, rootBC, b->flow.denIn, b->flow.Uref, ntolLBM, dtolLBM);
+    if (it < 0) return 2;
+    if (iterLBM_out) *iterLBM_out = it;
+    orc_add_volume_force(b);
+    return 0;
+}
+int orc_step_post(orc_block *b)
+{
+    if (orc_collision(b)) return 3;
+    orc_halfway_bc_set(b);
+    orc_streaming(b);
+    if (orc_set_boundary_conditions(b)) return 4;
+    return 0;
+}
+
+/* ================================================================================== */
+/* Grid refinement: type CommPair and the father<->son transfers, LBMBlockComm.f90     */
+/* ================================================================================== */
+typedef struct {
+    orc_block *F, *S;
+    int sds[6], s[6], f[6], si[6], fi[6]; /* 1-based plane indices as in the reference (:14-15) */
+    int dimS[3], dimF[3];                 /* xDimS.. / xDimF.. (:16) */
+    int interpolateScheme;                /* flow%interpolateScheme (:825) */
+    double *fIn_F[6][2];                  /* fIn_F?t1 / t2: (0:18, b, a), q fastest (:220-260) */
+    double *tau_F[6][2];                  /* tau_F?t1 / t2: (b, a) */
+} orc_pair;
+
+/* in-plane axes of face j: b = the faster one, a = the slower one (x faces: z,y; y faces: z,x; z faces: y,x) */
+static void pair_axes(int j, int *axis, int *bAx, int *aAx)
+{
+    *axis = j / 2;
+    if (*axis == 0) { *bAx = 2; *aAx = 1; }
+    else if (*axis == 1) { *bAx = 2; *aAx = 0; }
+    else { *bAx = 1; *aAx = 0; }
+}
+/* linear index into a block's fIn from 1-based (x,y,z) given per axis */
+static size_t blk_idx(const orc_block *b, const int c[3], int q) { return F4(b, c[2] - 1, c[1] - 1, c[0] - 1, q); }
+static size_t blk_idx3(const orc_block *b, const int c[3]) { return F3(b, c[2] - 1, c[1] - 1, c[0] - 1); }
+
+/* build_blocks_comunication :32-96 + check_blocks_params :508-544 + allocate_fIn_tau :213-264 */
+orc_pair *orc_pair_create(orc_block *F, orc_block *S, int interpolateScheme)
+{
+    const int m_gridDelta = 2;
+    int r[3] = {1, 1, 1};
+    for (int k = 0; k < 3; k++) if (S->periodic_bc[k] == 1) r[k] = 0;
+    int flag = fabs(F->dh - S->dh * (double)m_gridDelta) > 1e-8 || (S->xDim % m_gridDelta) != r[0] ||
+               (S->yDim % m_gridDelta) != r[1] || (S->zDim % m_gridDelta) != r[2];
+    double res1 = (S->xmin - F->xmin) / F->dh + (S->ymin - F->ymin) / F->dh + (S->zmin - F->zmin) / F->dh;
+    double res2 = (S->xmax - F->xmin) / F->dh + (S->ymax - F->ymin) / F->dh + (S->zmax - F->zmin) / F->dh;
+    res1 = fabs(res1 - (double)lround(res1));
+    res2 = fabs(res2 - (double)lround(res2));
+    if (flag || res1 + res2 > 1e-8) return NULL; /* 'grid points do not match between fluid blocks' */
+    orc_pair *p = (orc_pair *)calloc(1, sizeof(orc_pair));
+    p->F = F; p->S = S; p->interpolateScheme = interpolateScheme;
+    for (int j = 0; j < 6; j++) {
+        if (S->BndConds[j] == BCfluid) p->sds[j] = (j % 2 == 0) ? 1 : -1;
+        else p->sds[j] = 0;
+    }
+    int sD[3] = {S->xDim, S->yDim, S->zDim};
+    for (int k = 0; k < 3; k++) if (S->periodic_bc[k] == 1) sD[k] = sD[k] - 1;
+    const double smin[3] = {S->xmin, S->ymin, S->zmin}, fmin[3] = {F->xmin, F->ymin, F->zmin};
+    int ratio = (int)floor(F->dh / S->dh + 0.5);
+    for (int k = 0; k < 3; k++) {
+        p->s[2 * k] = 1;
+        p->s[2 * k + 1] = sD[k];
+        p->f[2 * k] = (int)floor((smin[k] - fmin[k]) / F->dh + 1.5);
+        p->f[2 * k + 1] = p->f[2 * k] + (sD[k] - 1) / ratio;
+    }
+    for (int j = 0; j < 6; j++) {
+        p->si[j] = p->s[j] + p->sds[j] * ratio;
+        p->fi[j] = p->f[j] + p->sds[j];
+    }
+    p->dimS[0] = S->xDim; p->dimS[1] = S->yDim; p->dimS[2] = S->zDim;
+    for (int k = 0; k < 3; k++) p->dimF[k] = p->f[2 * k + 1] - p->f[2 * k] + 1;
+    for (int j = 0; j < 6; j++) {
+        if (S->BndConds[j] != BCfluid) continue;
+        int axis, bAx, aAx;
+        pair_axes(j, &axis, &bAx, &aAx);
+        size_t n = (size_t)p->dimF[bAx] * p->dimF[aAx];
+        for (int t = 0; t < 2; t++) {
+            p->fIn_F[j][t] = (double *)calloc(n * Q, sizeof(double));
+            p->tau_F[j][t] = (double *)calloc(n, sizeof(double));
+        }
+    }
+    return p;
+}
+void orc_pair_destroy(orc_pair *p)
+{
+    if (!p) return;
+    for (int j = 0; j < 6; j++) for (int t = 0; t < 2; t++) { free(p->fIn_F[j][t]); free(p->tau_F[j][t]); }
+    free(p);
+}
+/* out[0:6]=sds, [6:12]=s, [12:18]=f, [18:24]=si, [24:30]=fi, [30:33]=dimS, [33:36]=dimF */
+void orc_pair_get(const orc_pair *p, int out[36])
+{
+    for (int j = 0; j < 6; j++) { out[j] = p->sds[j]; out[6 + j] = p->s[j]; out[12 + j] = p->f[j]; out[18 + j] = p->si[j]; out[24 + j] = p->fi[j]; }
+    for (int k = 0; k < 3; k++) { out[30 + k] = p->dimS[k]; out[33 + k] = p->dimF[k]; }
+}
+
+/* extract_interpolate_layer :340-505 for one son; time = 1 or 2 */
+void orc_pair_extract_layer(orc_pair *p, int time)
+{
+    orc_block *F = p->F;
+    for (int j = 0; j < 6; j++) {
+        if (p->S->BndConds[j] != BCfluid) continue;
+        int axis, bAx, aAx;
+        pair_axes(j, &axis, &bAx, &aAx);
+        const int bF = p->dimF[bAx], aF = p->dimF[aAx];
+        double *ft = p->fIn_F[j][time - 1], *tt = p->tau_F[j][time - 1];
+        for (int a = 1; a <= aF; a++)
+            for (int b = 1; b <= bF; b++) {
+                int c[3];
+                c[axis] = p->f[j];
+                c[bAx] = b + p->f[2 * bAx] - 1;
+                c[aAx] = a + p->f[2 * aAx] - 1;
+                const size_t n = (size_t)(b - 1) + (size_t)bF * (a - 1);
+                for (int e = 0; e < Q; e++) ft[e + Q * n] = F->fIn[blk_idx(F, c, e)];
+                tt[n] = F->tau_all[blk_idx3(F, c)];
+            }
+        if (time == 2) { /* :370-377 */
+            const size_t n = (size_t)bF * aF;
+            double *f1 = p->fIn_F[j][0], *f2 = p->fIn_F[j][1], *t1 = p->tau_F[j][0], *t2 = p->tau_F[j][1];
+            for (size_t i = 0; i < n * Q; i++) f1[i] = 0.5 * (f1[i] + f2[i]);
+            for (size_t i = 0; i < n; i++) t1[i] = 0.5 * (t1[i] + t2[i]);
+        }
+    }
+}
+
+/* fIn_GridTransform :958-979 (Dupuis-Chopard rescale of the non-equilibrium part) */
+static void fIn_GridTransform(double fIn[Q], double coeff, const double volumeForce[3], double dh)
+{
+    double den = 0.0, m[3] = {0.0, 0.0, 0.0}, uuu[3];
+    for (int q = 0; q < Q; q++) den = den + fIn[q];
+    for (int k = 0; k < 3; k++) {
+        for (int q = 0; q < Q; q++) m[k] = m[k] + fIn[q] * ee[q][k];
+        uuu[k] = (m[k] + 0.5 * volumeForce[k] * dh) / den;
+    }
+    double uSqr = 0.0;
+    for (int k = 0; k < 3; k++) uSqr = uSqr + uuu[k] * uuu[k];
+    for (int q = 0; q < Q; q++) {
+        double uxyz = uuu[0] * ee[q][0] + uuu[1] * ee[q][1] + uuu[2] * ee[q][2];
+        double fEq = wt[q] * den * ((1.0 - 1.5 * uSqr) + uxyz * (3.0 + 4.5 * uxyz));
+        fIn[q] = fEq + coeff * (fIn[q] - fEq);
+    }
+}
+
+/* interpolate_fIn :808-905 (nq = 19) and interpolate_tau :907-956 (nq = 1, always linear).
+ * fF(0:nq-1, bF, aF) -> fS(0:nq-1, bS, aS), 1-based b,a as in the reference. */
+static void interpolate_plane(int nq, int scheme, int bF, int aF, const double *fF, int bS, int aS, double *fS)
+{
+#define FF(e, b, a) fF[(e) + (size_t)nq * ((size_t)((b) - 1) + (size_t)bF * ((a) - 1))]
+#define FS(e, b, a) fS[(e) + (size_t)nq * ((size_t)((b) - 1) + (size_t)bS * ((a) - 1))]
+    int r1 = 0, r2 = 0, bStmp = bS, aStmp = aS;
+    if (bS % 2 == 0) { bStmp = bS - 1; r2 = 1; }
+    if (aS % 2 == 0) { aStmp = aS - 1; r1 = 1; }
+    (void)aF;
+    for (int e = 0; e < nq; e++) {
+        if (scheme == 2) {
+            for (int b = 1; b <= bStmp; b += 2) {
+                int b1 = b / 2 + 1;
+                for (int a = 1; a <= aStmp; a += 2) {
+                    int a1 = a / 2 + 1;
+                    FS(e, b, a) = FF(e, b1, a1);
+                    if (1 == b) FS(e, b + 1, a) = 0.375 * FF(e, b1, a1) + 0.75 * FF(e, b1 + 1, a1) - 0.125 * FF(e, b1 + 2, a1);
+                    else if (b == bStmp - 2) FS(e, b + 1, a) = 0.375 * FF(e, b1 + 1, a1) + 0.75 * FF(e, b1, a1) - 0.125 * FF(e, b1 - 1, a1);
+                    else if (b != bStmp) FS(e, b + 1, a) = -0.0625 * FF(e, b1 - 1, a1) + 0.5625 * FF(e, b1, a1) + 0.5625 * FF(e, b1 + 1, a1) - 0.0625 * FF(e, b1 + 2, a1);
+                }
+            }
+            for (int b = 1; b <= bStmp; b++)
+                for (int a = 2; a <= aStmp; a += 2) {
+                    if (2 == a) FS(e, b, a) = 0.375 * FS(e, b, a - 1) + 0.75 * FS(e, b, a + 1) - 0.125 * FS(e, b, a + 3);
+                    else if (a == aStmp - 1) FS(e, b, a) = 0.375 * FS(e, b, a + 1) + 0.75 * FS(e, b, a - 1) - 0.125 * FS(e, b, a - 3);
+                    else FS(e, b, a) = -0.0625 * FS(e, b, a - 3) + 0.5625 * FS(e, b, a - 1) + 0.5625 * FS(e, b, a + 1) - 0.0625 * FS(e, b, a + 3);
+                }
+            if (r2 == 1)
+                for (int a = 1; a <= aStmp; a++)
+                    FS(e, bStmp + 1, a) = -0.0625 * FS(e, bStmp - 2, a) + 0.5625 * FS(e, bStmp, a) + 0.5625 * FS(e, 1, a) - 0.0625 * FS(e, 3, a);
+            if (r1 == 1) {
+                for (int b = 1; b <= bStmp; b++)
+                    FS(e, b, aStmp + 1) = -0.0625 * FS(e, b, aStmp - 2) + 0.5625 * FS(e, b, aStmp) + 0.5625 * FS(e, b, 1) - 0.0625 * FS(e, b, 3);
+                if (r2 == 1)
+                    FS(e, bStmp + 1, aStmp + 1) = -0.0625 * FS(e, bStmp + 1, aStmp - 2) + 0.5625 * FS(e, bStmp + 1, aStmp) + 0.5625 * FS(e, bStmp + 1, 1) - 0.0625 * FS(e, bStmp + 1, 3);
+            }
+        } else {
+            for (int b = 1; b <= bStmp; b += 2) {
+                int b1 = b / 2 + 1;
+                for (int a = 1; a <= aStmp; a += 2) {
+                    int a1 = a / 2 + 1;
+                    FS(e, b, a) = FF(e, b1, a1);
+                    if (b < bStmp) FS(e, b + 1, a) = (FF(e, b1, a1) + FF(e, b1 + 1, a1)) * 0.5;
+                }
+            }
+            for (int b = 1; b <= bStmp; b++)
+                for (int a = 2; a <= aStmp; a += 2) FS(e, b, a) = (FS(e, b, a - 1) + FS(e, b, a + 1)) * 0.5;
+            if (r2 == 1)
+                for (int a = 1; a <= aStmp; a++) FS(e, bStmp + 1, a) = (FS(e, bStmp, a) + FS(e, 1, a)) * 0.5;
+            if (r1 == 1) {
+                for (int b = 1; b <= bStmp; b++) FS(e, b, aStmp + 1) = (FS(e, b, aStmp) + FS(e, b, 1)) * 0.5;
+                if (r2 == 1) FS(e, bStmp + 1, aStmp + 1) = (FS(e, bStmp + 1, aStmp) + FS(e, bStmp + 1, 1)) * 0.5;
+            }
+        }
+    }
+#undef FF
+#undef FS
+}
+
+/* interpolation_father_to_son :655-806 */
+void orc_pair_father_to_son(orc_pair *p, int n_timeStep)
+{
+    const int m_gridDelta = 2;
+    orc_block *S = p->S, *F = p->F;
+    const double *VF = F->volumeForce;
+    const double dh = F->dh;
+    for (int j = 0; j < 6; j++) {
+        if (!((j % 2 == 0 && p->sds[j] == 1) || (j % 2 == 1 && p->sds[j] == -1))) continue;
+        int axis, bAx, aAx;
+        pair_axes(j, &axis, &bAx, &aAx);
+        const int bS = p->dimS[bAx], aS = p->dimS[aAx], bF = p->dimF[bAx], aF = p->dimF[aAx];
+        double *tmpf = (double *)calloc((size_t)Q * bS * aS, sizeof(double));
+        double *tmptau = (double *)calloc((size_t)bS * aS, sizeof(double));
+        const int t = n_timeStep == 0 ? 0 : 1;
+        interpolate_plane(Q, p->interpolateScheme, bF, aF, p->fIn_F[j][t], bS, aS, tmpf);
+        interpolate_plane(1, 1, bF, aF, p->tau_F[j][t], bS, aS, tmptau);
+        for (int a = 1; a <= aS; a++)
+            for (int b = 1; b <= bS; b++) {
+                int c[3];
+                c[axis] = p->s[j]; c[bAx] = b; c[aAx] = a;
+                const size_t n = (size_t)(b - 1) + (size_t)bS * (a - 1);
+                double coeff = (S->tau_all[blk_idx3(S, c)] / tmptau[n]) / (double)m_gridDelta;
+                fIn_GridTransform(tmpf + Q * n, coeff, VF, dh);
+                for (int e = 0; e < Q; e++) S->fIn[blk_idx(S, c, e)] = tmpf[e + Q * n];
+            }
+        free(tmpf); free(tmptau);
+    }
+}
+
+/* deliver_son_to_father :546-653 */
+void orc_pair_son_to_father(orc_pair *p)
+{
+    const int m_gridDelta = 2;
+    orc_block *S = p->S, *F = p->F;
+    const double *VF = S->volumeForce;
+    const double dh = S->dh;
+    for (int j = 0; j < 6; j++) {
+        if (!((j % 2 == 0 && p->sds[j] == 1) || (j % 2 == 1 && p->sds[j] == -1))) continue;
+        int axis, bAx, aAx;
+        pair_axes(j, &axis, &bAx, &aAx);
+        for (int aSn = p->si[2 * aAx]; aSn <= p->si[2 * aAx + 1]; aSn += m_gridDelta) {
+            int aFn = (aSn - p->si[2 * aAx]) / 2 + p->fi[2 * aAx];
+            for (int bSn = p->si[2 * bAx]; bSn <= p->si[2 * bAx + 1]; bSn += m_gridDelta) {
+                int bFn = (bSn - p->si[2 * bAx]) / 2 + p->fi[2 * bAx];
+                int cS[3], cF[3];
+                cS[axis] = p->si[j]; cS[bAx] = bSn; cS[aAx] = aSn;
+                cF[axis] = p->fi[j]; cF[bAx] = bFn; cF[aAx] = aFn;
+                double coeff = (F->tau_all[blk_idx3(F, cF)] / S->tau_all[blk_idx3(S, cS)]) * (double)m_gridDelta;
+                double tmpf[Q];
+                for (int e = 0; e < Q; e++) tmpf[e] = S->fIn[blk_idx(S, cS, e)];
+                fIn_GridTransform(tmpf, coeff, VF, dh);
+                for (int e = 0; e < Q; e++) F->fIn[blk_idx(F, cF, e)] = tmpf[e];
+            }
+        }
+    }
 }
 
 int orc_omp_max_threads(void)

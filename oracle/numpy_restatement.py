@@ -477,3 +477,207 @@ def calculate_interaction_force(blk, bodies, rootBC, dt=None):
     for b in bodies:
         FluidVolumeForce(b, blk)
     return it
+
+
+# ---- grid refinement: CommPair and father<->son transfers (LBMBlockComm.f90) ----------------------------------
+def grid_transform(f, coeff, volumeForce, dh):
+    """fIn_GridTransform, LBMBlockComm.f90:958-979, on arrays f[q, ...]."""
+    den = 0.0 + f[0]
+    for q in range(1, 19):
+        den = den + f[q]
+    u = []
+    for k in range(3):
+        m = 0.0 * f[0]
+        for q in range(19):
+            m = m + f[q] * float(EE[q, k])
+        u.append((m + 0.5 * volumeForce[k] * dh) / den)
+    uSqr = 0.0 + u[0] * u[0]
+    uSqr = uSqr + u[1] * u[1]
+    uSqr = uSqr + u[2] * u[2]
+    out = np.empty_like(f)
+    for q in range(19):
+        uxyz = u[0] * float(EE[q, 0]) + u[1] * float(EE[q, 1]) + u[2] * float(EE[q, 2])
+        fEq = WT[q] * den * ((1.0 - 1.5 * uSqr) + uxyz * (3.0 + 4.5 * uxyz))
+        out[q] = fEq + coeff * (f[q] - fEq)
+    return out
+
+
+def interpolate_plane(fF, aS, bS, scheme):
+    """interpolate_fIn (LBMBlockComm.f90:808-905) / interpolate_tau (:907-956) on arrays fF[..., aF, bF] -> [..., aS, bS]
+    (b is the reference's first, faster index)."""
+    lead = fF.shape[:-2]
+    fS = np.zeros(lead + (aS, bS))
+    bT = bS - 1 if bS % 2 == 0 else bS
+    aT = aS - 1 if aS % 2 == 0 else aS
+    nb, na = (bT + 1) // 2, (aT + 1) // 2
+    C = fF[..., :na, :nb]
+    fS[..., 0:aT:2, 0:bT:2] = C
+    if scheme == 2:
+        # even b (1-based) between coincident nodes, along b, rows with odd a only (:828-841)
+        for i in range(nb - 1):           # i = b1-1 for b = 2*i+1 ; target 0-based column 2*i+1
+            if i == 0:
+                v = 0.375 * C[..., :, 0] + 0.75 * C[..., :, 1] - 0.125 * C[..., :, 2]
+            elif 2 * i + 1 == bT - 2:
+                v = 0.375 * C[..., :, i + 1] + 0.75 * C[..., :, i] - 0.125 * C[..., :, i - 1]
+            else:
+                v = -0.0625 * C[..., :, i - 1] + 0.5625 * C[..., :, i] + 0.5625 * C[..., :, i + 1] - 0.0625 * fF[..., :na, i + 2]
+            fS[..., 0:aT:2, 2 * i + 1] = v
+        for a in range(1, aT, 2):         # 0-based odd rows = 1-based even a (:844-856)
+            a1 = a + 1                    # 1-based
+            if a1 == 2:
+                fS[..., a, :bT] = 0.375 * fS[..., a - 1, :bT] + 0.75 * fS[..., a + 1, :bT] - 0.125 * fS[..., a + 3, :bT]
+            elif a1 == aT - 1:
+                fS[..., a, :bT] = 0.375 * fS[..., a + 1, :bT] + 0.75 * fS[..., a - 1, :bT] - 0.125 * fS[..., a - 3, :bT]
+            else:
+                fS[..., a, :bT] = -0.0625 * fS[..., a - 3, :bT] + 0.5625 * fS[..., a - 1, :bT] + 0.5625 * fS[..., a + 1, :bT] - 0.0625 * fS[..., a + 3, :bT]
+        if bS % 2 == 0:
+            fS[..., :aT, bT] = -0.0625 * fS[..., :aT, bT - 3] + 0.5625 * fS[..., :aT, bT - 1] + 0.5625 * fS[..., :aT, 0] - 0.0625 * fS[..., :aT, 2]
+        if aS % 2 == 0:
+            fS[..., aT, :bT] = -0.0625 * fS[..., aT - 3, :bT] + 0.5625 * fS[..., aT - 1, :bT] + 0.5625 * fS[..., 0, :bT] - 0.0625 * fS[..., 2, :bT]
+            if bS % 2 == 0:
+                fS[..., aT, bT] = -0.0625 * fS[..., aT - 3, bT] + 0.5625 * fS[..., aT - 1, bT] + 0.5625 * fS[..., 0, bT] - 0.0625 * fS[..., 2, bT]
+    else:
+        fS[..., 0:aT:2, 1:bT:2] = (C[..., :, :-1] + C[..., :, 1:]) * 0.5
+        fS[..., 1:aT:2, :bT] = (fS[..., 0:aT - 1:2, :bT] + fS[..., 2:aT:2, :bT]) * 0.5
+        if bS % 2 == 0:
+            fS[..., :aT, bT] = (fS[..., :aT, bT - 1] + fS[..., :aT, 0]) * 0.5
+        if aS % 2 == 0:
+            fS[..., aT, :bT] = (fS[..., aT - 1, :bT] + fS[..., 0, :bT]) * 0.5
+            if bS % 2 == 0:
+                fS[..., aT, bT] = (fS[..., aT - 1, bT] + fS[..., 0, bT]) * 0.5
+    return fS
+
+
+class Pair:
+    """type CommPair (LBMBlockComm.f90:11-18), build_blocks_comunication (:32-96), and the transfers."""
+
+    def __init__(self, father: Block, son: Block, interpolateScheme=1):
+        self.F, self.S, self.scheme = father, son, interpolateScheme
+        F, S = father, son
+        sdims = [S.X, S.Y, S.Z]
+        r = [0 if S.periodic[k] else 1 for k in range(3)]
+        smax = [S.maxs[k] + (S.dh if S.periodic[k] else 0.0) for k in range(3)]
+        bad = abs(F.dh - S.dh * 2.0) > 1e-8 or any(sdims[k] % 2 != r[k] for k in range(3))
+        res1 = sum((S.mins[k] - F.mins[k]) / F.dh for k in range(3))
+        res2 = sum((smax[k] - F.mins[k]) / F.dh for k in range(3))
+        res = abs(res1 - round(res1)) + abs(res2 - round(res2))
+        if bad or res > 1e-8:
+            raise ValueError("grid points do not match between fluid blocks")
+        self.sds = [(1 if j % 2 == 0 else -1) if S.bc[j] == 0 else 0 for j in range(6)]
+        sD = [sdims[k] - (1 if S.periodic[k] else 0) for k in range(3)]
+        ratio = math.floor(F.dh / S.dh + 0.5)
+        self.s, self.f = [0] * 6, [0] * 6
+        for k in range(3):
+            self.s[2 * k], self.s[2 * k + 1] = 1, sD[k]
+            self.f[2 * k] = math.floor((S.mins[k] - F.mins[k]) / F.dh + 1.5)
+            self.f[2 * k + 1] = self.f[2 * k] + (sD[k] - 1) // ratio
+        self.si = [self.s[j] + self.sds[j] * ratio for j in range(6)]
+        self.fi = [self.f[j] + self.sds[j] for j in range(6)]
+        self.dimS = sdims
+        self.dimF = [self.f[2 * k + 1] - self.f[2 * k] + 1 for k in range(3)]
+        self.buf = {}      # (face, 't1'|'t2') -> (f[19,a,b], tau[a,b])
+
+    def _father_plane_index(self, j):
+        """index tuple (x,y,z slices, 0-based) of the father's plane f(j) over the son's footprint"""
+        axis = j // 2
+        idx = []
+        for k in range(3):
+            if k == axis:
+                idx.append(self.f[j] - 1)
+            else:
+                idx.append(slice(self.f[2 * k] - 1, self.f[2 * k] - 1 + self.dimF[k]))
+        return tuple(idx)
+
+    def extract_interpolate_layer(self, time):
+        """LBMBlockComm.f90:340-505."""
+        for j in range(6):
+            if self.S.bc[j] != 0:
+                continue
+            idx = self._father_plane_index(j)
+            f = self.F.f[(slice(None),) + idx].copy()
+            tau = self.F.tau_all[idx].copy()
+            self.buf[(j, time)] = (f, tau)
+            if time == 2:
+                f1, t1 = self.buf[(j, 1)]
+                self.buf[(j, 1)] = (0.5 * (f1 + f), 0.5 * (t1 + tau))
+
+    def interpolation_father_to_son(self, n_timeStep):
+        """LBMBlockComm.f90:655-806."""
+        S = self.S
+        for j in range(6):
+            if self.sds[j] == 0:
+                continue
+            axis = j // 2
+            inplane = [k for k in range(3) if k != axis]        # [a-axis, b-axis] in x<y<z order = (slower, faster)
+            aS, bS = self.dimS[inplane[0]], self.dimS[inplane[1]]
+            fF, tauF = self.buf[(j, 1 if n_timeStep == 0 else 2)]
+            tmpf = interpolate_plane(fF, aS, bS, self.scheme)
+            tmptau = interpolate_plane(tauF, aS, bS, 1)
+            idx = [slice(None)] * 3
+            idx[axis] = self.s[j] - 1
+            idx = tuple(idx)
+            coeff = (S.tau_all[idx] / tmptau) / 2.0
+            S.f[(slice(None),) + idx] = grid_transform(tmpf, coeff, self.F.volumeForce, self.F.dh)
+
+    def deliver_son_to_father(self):
+        """LBMBlockComm.f90:546-653."""
+        S, F = self.S, self.F
+        for j in range(6):
+            if self.sds[j] == 0:
+                continue
+            axis = j // 2
+            sidx, fidx = [None] * 3, [None] * 3
+            for k in range(3):
+                if k == axis:
+                    sidx[k], fidx[k] = self.si[j] - 1, self.fi[j] - 1
+                else:
+                    lo, hi = self.si[2 * k], self.si[2 * k + 1]
+                    n = (hi - lo) // 2 + 1
+                    sidx[k] = slice(lo - 1, hi, 2)
+                    fidx[k] = slice(self.fi[2 * k] - 1, self.fi[2 * k] - 1 + n)
+            sidx, fidx = tuple(sidx), tuple(fidx)
+            coeff = (F.tau_all[fidx] / S.tau_all[sidx]) * 2.0
+            F.f[(slice(None),) + fidx] = grid_transform(S.f[(slice(None),) + sidx].copy(), coeff, S.volumeForce, S.dh)
+
+
+class Node:
+    def __init__(self, block, bodies=()):
+        self.block, self.bodies, self.sons, self.comm = block, list(bodies), [], []
+
+    def add_son(self, node, interpolateScheme=1):
+        self.sons.append(node)
+        self.comm.append(Pair(self.block, node.block, interpolateScheme))
+        return node
+
+
+def tree_step(node, rootBC=None, iters=None):
+    """tree_collision_streaming_IBM_FEM, LBMBlockComm.f90:279-318 (FEM Solver excluded)."""
+    b = node.block
+    rootBC = b.bc if rootBC is None else rootBC
+    b.update_volume_force()
+    b.calculate_macro_quantities()
+    b.ResetVolumeForce()
+    it = calculate_interaction_force(b, node.bodies, rootBC) if node.bodies else 0
+    if iters is not None:
+        iters.append(it)
+    b.add_volume_force()
+    for p in node.comm:
+        p.extract_interpolate_layer(1)
+    b.collision()
+    b.halfwayBCset()
+    b.streaming()
+    b.set_boundary_conditions()
+    for p in node.comm:
+        p.extract_interpolate_layer(2)
+    for son, p in zip(node.sons, node.comm):
+        for n in range(2):
+            son.block.blktime = son.block.blktime + float(n) * son.block.dh
+            tree_step(son, rootBC, iters)
+            p.interpolation_father_to_son(n)
+        p.deliver_son_to_father()
+
+
+def set_blktime_all(node, time):
+    node.block.blktime = time
+    for s in node.sons:
+        set_blktime_all(s, time)

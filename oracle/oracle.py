@@ -95,6 +95,19 @@ def lib():
     L.orc_step.restype = i
     L.orc_step.argtypes = [vp, C.POINTER(vp), i, pi, i, d, pi]
     L.orc_omp_max_threads.restype = i
+    L.orc_step_pre.restype = i
+    L.orc_step_pre.argtypes = [vp, C.POINTER(vp), i, pi, i, d, pi]
+    L.orc_step_post.restype = i
+    L.orc_step_post.argtypes = [vp]
+    L.orc_pair_create.restype = vp
+    L.orc_pair_create.argtypes = [vp, vp, i]
+    L.orc_pair_destroy.argtypes = [vp]
+    L.orc_pair_get.argtypes = [vp, pi]
+    L.orc_pair_extract_layer.argtypes = [vp, i]
+    L.orc_pair_father_to_son.argtypes = [vp, i]
+    L.orc_pair_son_to_father.argtypes = [vp]
+    L.orc_block_tau_all.restype = pd
+    L.orc_block_tau_all.argtypes = [vp]
     _lib = L
     return L
 
@@ -181,6 +194,7 @@ class LBMBlock:
         self.force = _view(L.orc_block_force(self._h), (3, xDim, yDim, zDim))
         self.den = _view(L.orc_block_den(self._h), (xDim, yDim, zDim))
         self.volumeForce = _view(L.orc_block_volumeForce(self._h), (3,))
+        self.tau_all = _view(L.orc_block_tau_all(self._h), (xDim, yDim, zDim))
         self.blktime = 0.0
 
     def __del__(self):
@@ -261,3 +275,74 @@ class LBMBlock:
 
 def Phi(x: float) -> float:
     return lib().orc_Phi(x)
+
+
+class CommPair:
+    """type CommPair (LBMBlockComm.f90:11-18) with the father<->son transfers of :340-979."""
+
+    def __init__(self, father: LBMBlock, son: LBMBlock, interpolateScheme: int = 1):
+        self.father, self.son = father, son
+        self._h = lib().orc_pair_create(father._h, son._h, interpolateScheme)
+        if not self._h:
+            raise ValueError("grid points do not match between fluid blocks (LBMBlockComm.f90:537-540)")
+        out = (C.c_int * 36)()
+        lib().orc_pair_get(self._h, out)
+        v = list(out)
+        self.sds, self.s, self.f, self.si, self.fi = v[0:6], v[6:12], v[12:18], v[18:24], v[24:30]
+        self.dimS, self.dimF = v[30:33], v[33:36]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_pair_destroy(self._h)
+            self._h = None
+
+    def extract_interpolate_layer(self, time: int): lib().orc_pair_extract_layer(self._h, time)
+    def interpolation_father_to_son(self, n_timeStep: int): lib().orc_pair_father_to_son(self._h, n_timeStep)
+    def deliver_son_to_father(self): lib().orc_pair_son_to_father(self._h)
+
+
+class TreeNode:
+    """blockTreeNode (LBMBlockComm.f90:19-25): a block, the bodies it carries, its sons with their CommPairs."""
+
+    def __init__(self, block: LBMBlock, bodies: Sequence[VirtualBody] = (), rootBC=None):
+        self.block, self.bodies, self.sons, self.comm = block, list(bodies), [], []
+        self.rootBC = rootBC
+
+    def add_son(self, node: "TreeNode", interpolateScheme: int = 1):
+        self.sons.append(node)
+        self.comm.append(CommPair(self.block, node.block, interpolateScheme))
+        return node
+
+
+def tree_collision_streaming_IBM_FEM(node: TreeNode, rootBC=None, iters: Optional[list] = None):
+    """LBMBlockComm.f90:279-318 (FEM Solver excluded), recursion over the block tree."""
+    L = lib()
+    b = node.block
+    rootBC = b.BndConds if rootBC is None else rootBC
+    arr = (C.c_void_p * max(1, len(node.bodies)))(*[v._h for v in node.bodies])
+    it = C.c_int(0)
+    rc = L.orc_step_pre(b._h, arr, len(node.bodies), (C.c_int * 6)(*rootBC), b.flow.ntolLBM, b.flow.dtolLBM, C.byref(it))   # :283-288
+    if rc:
+        raise ValueError(f"oracle: step_pre failed rc={rc}")
+    if iters is not None:
+        iters.append(it.value)
+    for pair in node.comm:
+        pair.extract_interpolate_layer(1)                                 # :290
+    rc = L.orc_step_post(b._h)                                            # :293-303
+    if rc:
+        raise ValueError(f"oracle: step_post failed rc={rc}")
+    for pair in node.comm:
+        pair.extract_interpolate_layer(2)                                 # :305
+    for son, pair in zip(node.sons, node.comm):                           # :307-317
+        for n_timeStep in range(2):
+            son.block.set_blktime(son.block.blktime + float(n_timeStep) * son.block.dh)   # :311
+            tree_collision_streaming_IBM_FEM(son, rootBC, iters)
+            pair.interpolation_father_to_son(n_timeStep)
+        pair.deliver_son_to_father()
+
+
+def set_blktime_all(node: TreeNode, time: float):
+    """LBMblks(:)%blktime = time, main.f90:97."""
+    node.block.set_blktime(time)
+    for s in node.sons:
+        set_blktime_all(s, time)
