@@ -46,23 +46,204 @@ def init_process_group(rank: int, nranks: int, device: int, broadcast_bytes) -> 
     check(lib().fsilbm_comm_init(rank, nranks, raw))
 
 
-def tree_collision_streaming_IBM_FEM(block, plates: Sequence = (), time: Optional[float] = None,
-                                     rootBC=None, solver: bool = True) -> int:
-    """One pass of tree_collision_streaming_IBM_FEM (LBMBlockComm.f90:279-305) on a block without sons.
-    `plates` are RigidPlate-like objects (UpdatePosVelArea(), structure(), .body).  Returns iterLBM."""
+class CommPair:
+    """type CommPair (LBMBlockComm.f90:11-18) over the C ABI (fsilbm_pair_*)."""
+
+    def __init__(self, father, son, interpolateScheme: int = 1):
+        h = C.c_int(-1)
+        check(lib().fsilbm_pair_create(father._h, son._h, interpolateScheme, C.byref(h)))
+        self._h = h.value
+        self.father, self.son = father, son
+        out = (C.c_int * 36)()
+        check(lib().fsilbm_pair_info(self._h, out))
+        v = list(out)
+        self.sds, self.s, self.f, self.si, self.fi = v[0:6], v[6:12], v[12:18], v[18:24], v[24:30]
+        self.dimS, self.dimF = v[30:33], v[33:36]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            lib().fsilbm_pair_destroy(self._h)
+            self._h = None
+
+    def extract_interpolate_layer(self, time: int):
+        check(lib().fsilbm_pair_extract_layer(self._h, time))
+
+    def interpolation_father_to_son(self, n_timeStep: int):
+        check(lib().fsilbm_pair_father_to_son(self._h, n_timeStep))
+
+    def deliver_son_to_father(self):
+        check(lib().fsilbm_pair_son_to_father(self._h))
+
+
+class blockTreeNode:
+    """blockTreeNode (LBMBlockComm.f90:19-25): a block, the plates it carries (carriedBodies), its sons and CommPairs."""
+
+    def __init__(self, block, plates: Sequence = ()):
+        self.block, self.plates, self.sons, self.comm = block, list(plates), [], []
+
+    def add_son(self, node: "blockTreeNode", interpolateScheme: int = 1) -> "blockTreeNode":
+        self.sons.append(node)
+        self.comm.append(CommPair(self.block, node.block, interpolateScheme))
+        return node
+
+    def walk(self):
+        yield self
+        for s in self.sons:
+            yield from s.walk()
+
+
+MachineTolerace = 1.0e-12   # ConstParams.f90:36 (name as spelt there)
+
+
+def _extent(b):
+    """xmin..zmax of a block incl. the periodic extension of FluidDomain.f90:97-105."""
+    dims = (b.xDim, b.yDim, b.zDim)
+    mins = (b.xmin, b.ymin, b.zmin)
+    out = []
+    for k in range(3):
+        mx = mins[k] + b.dh * (dims[k] - 1)
+        if b.BndConds[2 * k] == 301 and b.BndConds[2 * k + 1] == 301:
+            mx = mx + b.dh
+        out += [mins[k], mx]
+    return out
+
+
+def CompareBlocks(bi, bj) -> int:
+    """FluidDomain.f90:1845-1972: 1 if block i contains j, -1 if i is inside j, 0 if separate or partially overlapping."""
+    vi, vj = _extent(bi), _extent(bj)
+    for (a, va, b, vb) in ((bi, vi, bj, vj), (bj, vj, bi, vi)):          # :1868-1902
+        pos = [c == 0 for c in a.BndConds]
+        if sum(pos) == 1:
+            for p in range(6):
+                if not pos[p]:
+                    continue
+                if p % 2 == 0:
+                    if b.BndConds[p + 1] == 1 and abs(vb[p + 1] - va[p] - b.dh) < MachineTolerace:
+                        va[p + 1] = va[p]
+                else:
+                    if b.BndConds[p - 1] == 1 and abs(va[p] - vb[p - 1] - b.dh) < MachineTolerace:
+                        va[p - 1] = va[p]
+    cnt = align = 0
+    for k in range(3):                                                  # :1903-1953
+        lo, hi = 2 * k, 2 * k + 1
+        d1 = vi[lo] < vj[lo] or abs(vi[lo] - vj[lo]) < MachineTolerace
+        d2 = vj[hi] < vi[hi] or abs(vj[hi] - vi[hi]) < MachineTolerace
+        d3 = vj[lo] < vi[lo] or abs(vj[lo] - vi[lo]) < MachineTolerace
+        d4 = vi[hi] < vj[hi] or abs(vi[hi] - vj[hi]) < MachineTolerace
+        d5, d6 = vi[hi] < vj[lo], vj[hi] < vi[lo]
+        if d1 and d2 and not (d3 and d4):
+            cnt += 1
+        elif d3 and d4 and not (d1 and d2):
+            cnt -= 1
+        elif d1 and d2 and d3 and d4:
+            align += 1
+        elif d5 or d6:
+            return 0
+    if align > 0:
+        if cnt < 0:
+            cnt -= align
+        if cnt > 0:
+            cnt += align
+    return 1 if cnt == 3 else (-1 if cnt == -3 else 0)
+
+
+def build_block_tree(blocks: Sequence, interpolateScheme: int = 1) -> blockTreeNode:
+    """build_block_tree (LBMBlockComm.f90:195-211): unique root by containment (findremove_blockTreeRoot :98-133),
+    the rest nested by array_to_tree (:135-193), one CommPair per father/son (build_blocks_comunication :32-96)."""
+    n = len(blocks)
+    nodes = [blockTreeNode(b) for b in blocks]
+
+    def nest(ids, root):
+        if not ids:
+            return
+        fa = {i: None for i in ids}
+        for a in range(len(ids) - 1):
+            for b in range(a + 1, len(ids)):
+                c = CompareBlocks(blocks[ids[a]], blocks[ids[b]])
+                if c == 1:
+                    fa[ids[b]] = ids[a]
+                elif c == -1:
+                    fa[ids[a]] = ids[b]
+        changed = True
+        while changed:                       # lift every block to its outermost container within this level (:154-165)
+            changed = False
+            for i in ids:
+                if fa[i] is not None and fa[fa[i]] is not None and fa[i] != fa[fa[i]]:
+                    fa[i] = fa[fa[i]]
+                    changed = True
+        roots = [i for i in ids if fa[i] is None]
+        for r in roots:
+            nodes[root].add_son(nodes[r], interpolateScheme)
+            nest([j for j in ids if fa[j] == r], r)
+
+    ids = list(range(n))
+    fa = {i: None for i in ids}
+    for a in range(n - 1):
+        for b in range(a + 1, n):
+            c = CompareBlocks(blocks[a], blocks[b])
+            if c == 1:
+                fa[b] = a
+            elif c == -1:
+                fa[a] = b
+    roots = [i for i in ids if fa[i] is None]
+    if len(roots) != 1:
+        raise ValueError("Error: there exist more than one block tree root")   # LBMBlockComm.f90:129-132
+    nest([i for i in ids if i != roots[0]], roots[0])
+    return nodes[roots[0]]
+
+
+def find_carrier_fluidblock(blocks: Sequence, x) -> int:
+    """FluidDomain.f90:1974-1996: index of the finest block containing point x."""
+    best, dh = -1, 1e10
+    for i, b in enumerate(blocks):
+        e = _extent(b)
+        if all(e[2 * k] <= x[k] <= e[2 * k + 1] for k in range(3)) and b.dh < dh:
+            best, dh = i, b.dh
+    if best < 0:
+        raise ValueError(f"Error: carrier fluid block not found {x}")
+    return best
+
+
+def set_blktime_all(node: blockTreeNode, time: float) -> None:
+    """LBMblks(:)%blktime = time, main.f90:97."""
+    for nd in node.walk():
+        nd.block.set_blktime(time)
+
+
+def tree_collision_streaming_IBM_FEM(node, plates: Sequence = (), time: Optional[float] = None,
+                                     rootBC=None, solver: bool = True, iters: Optional[list] = None) -> int:
+    """tree_collision_streaming_IBM_FEM (LBMBlockComm.f90:279-318).  `node` is a blockTreeNode, or a bare LBMBlock
+    (then `plates` are the bodies it carries and there are no sons).  `plates` are RigidPlate-like objects
+    (UpdatePosVelArea(), structure(), .body).  Returns iterLBM of this node's block."""
+    if not isinstance(node, blockTreeNode):
+        node = blockTreeNode(node, plates)
+    block, plates = node.block, node.plates
     if time is not None:
         block.set_blktime(time)
+    rootBC = block.BndConds if rootBC is None else rootBC
     block.update_volume_force()                                             # :283
     it = 0
-    if len(plates):
+    if len(plates):                                                         # IBM_FEM, :287 -> :320-338
         for p in plates:
             p.UpdatePosVelArea()                                            # Solidbody.f90:597-600
         it = block.calculate_interaction_force([p.body for p in plates], rootBC)   # :601
-        if solver:                                                          # IBM_FEM, LBMBlockComm.f90:333-335
+        if solver:
             nsub = block.flow.numsubstep
             dt_solid = block.dh / float(nsub)
             for isub in range(1, nsub + 1):
                 for p in plates:
                     p.structure(block.blktime, isub, block.dh, dt_solid)
+    if iters is not None:
+        iters.append(it)
+    for pair in node.comm:
+        pair.extract_interpolate_layer(1)                                   # :290
     block.collide_stream()                                                  # :285-303 fused
+    for pair in node.comm:
+        pair.extract_interpolate_layer(2)                                   # :305
+    for son, pair in zip(node.sons, node.comm):                             # :307-317
+        for n_timeStep in range(2):
+            son.block.set_blktime(son.block.blktime + float(n_timeStep) * son.block.dh)   # :311
+            tree_collision_streaming_IBM_FEM(son, rootBC=rootBC, solver=solver, iters=iters)
+            pair.interpolation_father_to_son(n_timeStep)
+        pair.deliver_son_to_father()
     return it

@@ -129,6 +129,7 @@ struct Block {
     double *stash[6]{}, *l2den[6]{}, *l2u[6]{};
     bool hw_alloc[6]{};
     double *den = nullptr, *uuu = nullptr, *force = nullptr;   // un-fused fields / download staging
+    double *tau_all = nullptr;                                 // [X][Y][Z], LES models only (FluidDomain.f90:1279,1422,1505)
     double *stat = nullptr;
     // IBM
     IbmBoxes boxes{};
@@ -156,6 +157,14 @@ struct Block {
 
 std::vector<std::unique_ptr<Block>> g_blocks;
 int g_device = -1;
+cudaStream_t g_stream = nullptr;   // every block of the process computes on this one stream: the reference walks its blocks sequentially too
+// type CommPair, LBMBlockComm.f90:11-18 (indices kept 1-based as in the reference)
+struct Pair {
+    int father = -1, son = -1, scheme = 1;
+    int sds[6]{}, s[6]{}, f[6]{}, si[6]{}, fi[6]{}, dimS[3]{}, dimF[3]{};
+    double *buf[6][2]{}, *tbuf[6][2]{};
+};
+std::vector<std::unique_ptr<Pair>> g_pairs;
 int g_variant = 0, g_force_ghost = 0;
 int g_halo_timeout_s = 120;   // a neighbour this late is treated as lost (the wait kernel gives up, fsilbm_block_sync reports it)
 int g_halo_mode = 1;   // 1: edge kernels store into the neighbours' memory over NVLink (default); 0: ncclSend/ncclRecv
@@ -445,15 +454,21 @@ int fsilbm_init(int device)
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(FSILBM_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
     g_device = device;
+    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     return 0;
 }
 
 int fsilbm_finalize(void)
 {
+    for (size_t i = 0; i < g_pairs.size(); i++)
+        if (g_pairs[i]) fsilbm_pair_destroy((int)i);
+    g_pairs.clear();
     for (size_t i = 0; i < g_blocks.size(); i++)
         if (g_blocks[i]) fsilbm_block_destroy((int)i);
     g_blocks.clear();
     fsilbm_comm_finalize();
+    if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+    g_device = -1;
     return 0;
 }
 
@@ -500,7 +515,7 @@ int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, d
         CK(cudaMalloc(&b->f[i], bytes));
         CK(cudaMemset(b->f[i], 0, bytes));
     }
-    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    b->stream = g_stream;
     {   // the NCCL transport's stream outranks the compute stream so its CTAs are scheduled as soon as SM slots free up
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -530,12 +545,12 @@ int fsilbm_block_destroy(fsilbm_handle h)
     halo_teardown(*b);
     for (int i = 0; i < 2; i++) cudaFree(b->f[i]);
     for (int i = 0; i < 6; i++) { cudaFree(b->stash[i]); cudaFree(b->l2den[i]); cudaFree(b->l2u[i]); }
-    cudaFree(b->den); cudaFree(b->uuu); cudaFree(b->force); cudaFree(b->stat);
+    cudaFree(b->den); cudaFree(b->uuu); cudaFree(b->force); cudaFree(b->stat); cudaFree(b->tau_all);
     cudaFree(b->boxes.u); cudaFree(b->boxes.force);
     for (auto &bd : b->bodies) bd.release();
     cudaFree(b->bodies_dev); cudaFree(b->ctl);
     cudaEventDestroy(b->ev_edge); cudaEventDestroy(b->ev_comm);
-    cudaStreamDestroy(b->stream); cudaStreamDestroy(b->comm_stream);
+    cudaStreamDestroy(b->comm_stream);
     g_blocks[h].reset();
     return 0;
 }
@@ -1118,6 +1133,167 @@ int fsilbm_ibm_download_stencil(fsilbm_handle h, int body, short *Ei, float *Ew)
     const size_t n = b->bodies[body].n;
     if (Ei) CK(cudaMemcpy(Ei, b->bodies[body].Ei, sizeof(short) * 12 * n, cudaMemcpyDeviceToHost));
     if (Ew) CK(cudaMemcpy(Ew, b->bodies[body].Ew, sizeof(float) * 12 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- grid refinement: CommPair and the father<->son transfers (LBMBlockComm.f90) -----------------------
+namespace {
+Pair *get_pair(int h)
+{
+    if (h < 0 || h >= (int)g_pairs.size() || !g_pairs[h]) return nullptr;
+    return g_pairs[h].get();
+}
+inline void pair_axes(int j, int &axis, int &bAx, int &aAx)
+{
+    axis = j / 2;
+    if (axis == 0) { bAx = 2; aAx = 1; } else if (axis == 1) { bAx = 2; aAx = 0; } else { bAx = 1; aAx = 0; }
+}
+// everything one son face needs; `force_of` selects whose volumeForce/dh enter fIn_GridTransform (0 father, 1 son)
+PairFaceParams pair_face(const Pair &p, Block &F, Block &S, int j, int force_of)
+{
+    PairFaceParams q{};
+    int axis, bAx, aAx;
+    pair_axes(j, axis, bAx, aAx);
+    q.gF = F.g; q.gS = S.g;
+    q.fF = F.f[F.cur]; q.fF_rw = F.f[F.cur]; q.fS = S.f[S.cur];
+    q.axis = axis; q.scheme = p.scheme;
+    q.bF = p.dimF[bAx]; q.aF = p.dimF[aAx]; q.bS = p.dimS[bAx]; q.aS = p.dimS[aAx];
+    q.fplane = p.f[j] - 1; q.fb0 = p.f[2 * bAx] - 1; q.fa0 = p.f[2 * aAx] - 1;
+    q.splane = p.s[j] - 1;
+    q.siplane = p.si[j] - 1; q.sib0 = p.si[2 * bAx] - 1; q.sia0 = p.si[2 * aAx] - 1;
+    q.fiplane = p.fi[j] - 1; q.fib0 = p.fi[2 * bAx] - 1; q.fia0 = p.fi[2 * aAx] - 1;
+    q.nb = (p.si[2 * bAx + 1] - p.si[2 * bAx]) / 2 + 1;
+    q.na = (p.si[2 * aAx + 1] - p.si[2 * aAx]) / 2 + 1;
+    for (int t = 0; t < 2; t++) { q.buf[t] = p.buf[j][t]; q.tbuf[t] = p.tbuf[j][t]; }
+    q.tauF = F.tau; q.tauS = S.tau; q.tauF_all = F.tau_all; q.tauS_all = S.tau_all;
+    half_force(force_of ? S : F, q.hF);
+    return q;
+}
+}  // namespace
+
+int fsilbm_pair_create(fsilbm_handle father, fsilbm_handle son, int interpolateScheme, int *pair)
+{
+    Block *F = get(father), *S = get(son);
+    if (!F || !S || !pair || father == son) return fail(FSILBM_ERR_ARG, "bad handle/argument");
+    if (g_nccl.nranks > 1 || F->g.X != F->g.XG || S->g.X != S->g.XG)
+        return fail(FSILBM_ERR_ARG, "refinement pairs need both blocks whole on one GPU (slab-split blocks with sons: not provided)");
+    const int m_gridDelta = 2;
+    const Geom &gf = F->g, &gs = S->g;
+    // check_blocks_params, LBMBlockComm.f90:508-544
+    int sdim[3] = {gs.X, gs.Y, gs.Z};
+    const double smin[3] = {gs.xmin, gs.ymin, gs.zmin}, fmin[3] = {gf.xmin, gf.ymin, gf.zmin};
+    double res1 = 0.0, res2 = 0.0;
+    bool flag = fabs(gf.dh - gs.dh * (double)m_gridDelta) > 1e-8;
+    for (int k = 0; k < 3; k++) {
+        const int r = S->periodic[k] == 1 ? 0 : 1;
+        flag = flag || (sdim[k] % m_gridDelta) != r;
+        double smax = smin[k] + gs.dh * (sdim[k] - 1);            // FluidDomain.f90:94-105
+        if (S->periodic[k] == 1) smax = smax + gs.dh;
+        res1 = res1 + (smin[k] - fmin[k]) / gf.dh;
+        res2 = res2 + (smax - fmin[k]) / gf.dh;
+    }
+    res1 = fabs(res1 - (double)lround(res1));
+    res2 = fabs(res2 - (double)lround(res2));
+    if (flag || res1 + res2 > 1e-8)
+        return fail(FSILBM_ERR_ARG, "grid points do not match between fluid blocks (LBMBlockComm.f90:537): if son block have periodic boundarys, "
+                                    "an even number of grid points is needed. Otherwise an odd number is needed.");
+    auto p = std::make_unique<Pair>();
+    p->father = father; p->son = son; p->scheme = interpolateScheme;
+    // build_blocks_comunication, :32-96
+    for (int j = 0; j < 6; j++) p->sds[j] = S->bc[j] == BCfluid ? ((j % 2 == 0) ? 1 : -1) : 0;
+    int sD[3];
+    for (int k = 0; k < 3; k++) sD[k] = sdim[k] - (S->periodic[k] == 1 ? 1 : 0);
+    const int ratio = (int)floor(gf.dh / gs.dh + 0.5);
+    for (int k = 0; k < 3; k++) {
+        p->s[2 * k] = 1; p->s[2 * k + 1] = sD[k];
+        p->f[2 * k] = (int)floor((smin[k] - fmin[k]) / gf.dh + 1.5);
+        p->f[2 * k + 1] = p->f[2 * k] + (sD[k] - 1) / ratio;
+        p->dimS[k] = sdim[k];
+        p->dimF[k] = p->f[2 * k + 1] - p->f[2 * k] + 1;
+    }
+    const int fdim[3] = {gf.X, gf.Y, gf.Z};
+    for (int k = 0; k < 3; k++)
+        if (p->f[2 * k] < 1 || p->f[2 * k + 1] > fdim[k]) return fail(FSILBM_ERR_ARG, "son block is not inside its father along axis %d", k);
+    for (int j = 0; j < 6; j++) { p->si[j] = p->s[j] + p->sds[j] * ratio; p->fi[j] = p->f[j] + p->sds[j]; }
+    // allocate_fIn_tau, :213-264
+    const bool need_tau = F->tau_all || S->tau_all;
+    for (int j = 0; j < 6; j++) {
+        if (S->bc[j] != BCfluid) continue;
+        int axis, bAx, aAx;
+        pair_axes(j, axis, bAx, aAx);
+        const size_t n = (size_t)p->dimF[bAx] * p->dimF[aAx];
+        for (int t = 0; t < 2; t++) {
+            CK(cudaMalloc(&p->buf[j][t], sizeof(double) * Q * n));
+            CK(cudaMemsetAsync(p->buf[j][t], 0, sizeof(double) * Q * n, g_stream));
+            if (need_tau) { CK(cudaMalloc(&p->tbuf[j][t], sizeof(double) * n)); CK(cudaMemsetAsync(p->tbuf[j][t], 0, sizeof(double) * n, g_stream)); }
+        }
+    }
+    int slot = -1;
+    for (size_t i = 0; i < g_pairs.size(); i++) if (!g_pairs[i]) { slot = (int)i; break; }
+    if (slot < 0) { g_pairs.emplace_back(); slot = (int)g_pairs.size() - 1; }
+    g_pairs[slot] = std::move(p);
+    *pair = slot;
+    return 0;
+}
+
+int fsilbm_pair_destroy(int pair)
+{
+    Pair *p = get_pair(pair);
+    if (!p) return fail(FSILBM_ERR_ARG, "bad pair %d", pair);
+    cudaStreamSynchronize(g_stream);
+    for (int j = 0; j < 6; j++) for (int t = 0; t < 2; t++) { cudaFree(p->buf[j][t]); cudaFree(p->tbuf[j][t]); }
+    g_pairs[pair].reset();
+    return 0;
+}
+
+int fsilbm_pair_info(int pair, int out[36])
+{
+    Pair *p = get_pair(pair);
+    if (!p || !out) return fail(FSILBM_ERR_ARG, "bad pair/argument");
+    for (int j = 0; j < 6; j++) { out[j] = p->sds[j]; out[6 + j] = p->s[j]; out[12 + j] = p->f[j]; out[18 + j] = p->si[j]; out[24 + j] = p->fi[j]; }
+    for (int k = 0; k < 3; k++) { out[30 + k] = p->dimS[k]; out[33 + k] = p->dimF[k]; }
+    return 0;
+}
+
+int fsilbm_pair_extract_layer(int pair, int time)
+{
+    Pair *p = get_pair(pair);
+    if (!p || (time != 1 && time != 2)) return fail(FSILBM_ERR_ARG, "bad pair/argument");
+    Block *F = get(p->father), *S = get(p->son);
+    if (!F || !S) return fail(FSILBM_ERR_ARG, "pair %d refers to a destroyed block", pair);
+    for (int j = 0; j < 6; j++) {
+        if (S->bc[j] != BCfluid) continue;   // :354
+        launch_pair_extract(pair_face(*p, *F, *S, j, 0), time, g_stream);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fsilbm_pair_father_to_son(int pair, int n_timeStep)
+{
+    Pair *p = get_pair(pair);
+    if (!p) return fail(FSILBM_ERR_ARG, "bad pair %d", pair);
+    Block *F = get(p->father), *S = get(p->son);
+    if (!F || !S) return fail(FSILBM_ERR_ARG, "pair %d refers to a destroyed block", pair);
+    for (int j = 0; j < 6; j++) {
+        if (p->sds[j] == 0) continue;
+        launch_pair_f2s(pair_face(*p, *F, *S, j, 0), n_timeStep == 0 ? 0 : 1, g_stream);   // father's volumeForce, dh: :663-664
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fsilbm_pair_son_to_father(int pair)
+{
+    Pair *p = get_pair(pair);
+    if (!p) return fail(FSILBM_ERR_ARG, "bad pair %d", pair);
+    Block *F = get(p->father), *S = get(p->son);
+    if (!F || !S) return fail(FSILBM_ERR_ARG, "pair %d refers to a destroyed block", pair);
+    for (int j = 0; j < 6; j++) {
+        if (p->sds[j] == 0) continue;
+        launch_pair_s2f(pair_face(*p, *F, *S, j, 1), g_stream);   // son's volumeForce, dh: :552-553
+    }
+    CK(cudaGetLastError());
     return 0;
 }
 

@@ -143,6 +143,30 @@ void launch_ibm_scatter(const IbmBody &b, const IbmBoxes &boxes, const IbmCtl *c
 void launch_ibm_check(const IbmBody *bodies_dev, int nbody, double Uref, int ntol, double dtol, IbmCtl *ctl, cudaStream_t s);
 void launch_ibm_spread(const IbmBody &b, const IbmBoxes &boxes, double invh3, cudaStream_t s);
 
+// ---- grid refinement (refine_kernels.cu): one son face coupled to its father, LBMBlockComm.f90:340-979 ----------
+struct PairFaceParams {
+    Geom gF, gS;
+    const double *fF;          // father populations (current buffer), read by extract
+    double *fF_rw;             // the same buffer, written by son->father
+    double *fS;                // son populations (current buffer)
+    int axis;                  // face normal: 0 x, 1 y, 2 z; in-plane axes b (faster) and a: x faces (z,y), y faces (z,x), z faces (y,x)
+    int scheme;                // flow%interpolateScheme: 2 = cubic, otherwise linear
+    int bF, aF, bS, aS;        // coarse footprint and son face extents
+    int fplane, fb0, fa0;      // father plane f(j) and footprint origin, 0-based
+    int splane;                // son boundary plane s(j), 0-based
+    int siplane, sib0, sia0;   // son inner plane si(j) and in-plane start, 0-based
+    int fiplane, fib0, fia0;   // father inner plane fi(j) and in-plane start, 0-based
+    int nb, na;                // father nodes overwritten by son->father
+    double *buf[2];            // fIn_F?t1 / t2, planar [q][aF][bF]
+    double *tbuf[2];           // tau_F?t1 / t2 [aF][bF]; null when neither block has a tau_all field
+    double tauF, tauS;         // block tau (constant-tau models)
+    const double *tauF_all, *tauS_all;   // tau_all fields [X][Y][Z] of LES blocks, else null
+    double hF[3];              // 0.5*volumeForce*dh of the block whose force enters fIn_GridTransform
+};
+void launch_pair_extract(const PairFaceParams &p, int time, cudaStream_t s);
+void launch_pair_f2s(const PairFaceParams &p, int t, cudaStream_t s);
+void launch_pair_s2f(const PairFaceParams &p, cudaStream_t s);
+
 long long kernel_launch_count();
 void count_launch(int n = 1);
 

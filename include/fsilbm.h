@@ -160,6 +160,25 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts,
 /* v_Ei(12,n) as int16 and v_Ew(12,n) as float of body b after the last call (parity checks). */
 int fsilbm_ibm_download_stencil(fsilbm_handle h, int body, short *Ei, float *Ew);
 
+/* ---- grid refinement: type CommPair and the father<->son transfers (LBMBlockComm.f90) ------------------- */
+
+/* build_blocks_comunication (LBMBlockComm.f90:32-96) + allocate_fIn_tau (:213-264) + check_blocks_params (:508-544)
+ * for one father/son pair: dh_father = 2*dh_son, son extents odd (even where the son is periodic), son corners on
+ * father nodes, else FSILBM_ERR_ARG with the reference's message.  Son faces with BndConds = 0 (BCfluid) are coupled.
+ * interpolateScheme is flow%interpolateScheme (2 = cubic, otherwise linear; FlowCondition.f90:71).
+ * The tree itself (build_block_tree :195, CompareBlocks) stays with the host. */
+int fsilbm_pair_create(fsilbm_handle father, fsilbm_handle son, int interpolateScheme, int *pair);
+int fsilbm_pair_destroy(int pair);
+/* out[0:6] sds, [6:12] s, [12:18] f, [18:24] si, [24:30] fi (1-based plane indices as in CommPair, :11-18),
+ * [30:33] xDimS,yDimS,zDimS, [33:36] xDimF,yDimF,zDimF */
+int fsilbm_pair_info(int pair, int out[36]);
+/* extract_interpolate_layer (:340-505) for this son: time 1 before the father's collision, 2 after its boundary step. */
+int fsilbm_pair_extract_layer(int pair, int time);
+/* interpolation_father_to_son (:655-806) with interpolate_fIn (:808), interpolate_tau (:907), fIn_GridTransform (:958). */
+int fsilbm_pair_father_to_son(int pair, int n_timeStep);
+/* deliver_son_to_father (:546-653). */
+int fsilbm_pair_son_to_father(int pair);
+
 /* ---- multi-GPU: x-slab halo exchange (no reference counterpart; the reference is one process) */
 
 /* rank 0 fills id[128] (an ncclUniqueId); the host distributes it; every rank calls comm_init. */

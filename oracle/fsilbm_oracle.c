@@ -54,6 +54,11 @@ enum {
 };
 static const double Pi = 3.141592653589793; /* ConstParams.f90:36 */
 static const double Cs2 = 1.0 / 3.0;        /* ConstParams.f90:39 */
+static const double Csmag = 0.17;           /* ConstParams.f90:40 */
+#define CsmagConst (2.0 * Csmag * Csmag * sqrt(2.0) * 9.0) /* :42 */
+static const double CWALE = 0.50;           /* :43 */
+#define CWALEConst (CWALE * CWALE)          /* :44 */
+#define CvremConst (2.5 * Csmag * Csmag)    /* :45 */
 
 /* incoming population sets per face, FluidDomain.f90:645,729,813,897,981,1065 */
 static const int face_in[6][5] = {{1, 7, 9, 11, 13}, {2, 8, 10, 12, 14}, {3, 7, 8, 15, 17},
@@ -417,11 +422,105 @@ void orc_reset_volume_force(orc_block *b)
 /* ================================================================================== */
 /* collision_, FluidDomain.f90:1208-1263 (SRT :1227, TRT :1230-1235, MRT :1238)        */
 /* ================================================================================== */
+/* ---- LES closures contained in collision_: smag :1265-1281, WALE :1311-1424, vrem :1435-1507 ------ */
+static void les_Q(const double fneq[Q], double *Q11, double *Q22, double *Q33, double *Q12, double *Q13, double *Q23)
+{
+    *Q11 = fneq[1] + fneq[2] + fneq[7] + fneq[8] + fneq[9] + fneq[10] + fneq[11] + fneq[12] + fneq[13] + fneq[14];
+    *Q22 = fneq[3] + fneq[4] + fneq[7] + fneq[8] + fneq[9] + fneq[10] + fneq[15] + fneq[16] + fneq[17] + fneq[18];
+    *Q33 = fneq[5] + fneq[6] + fneq[11] + fneq[12] + fneq[13] + fneq[14] + fneq[15] + fneq[16] + fneq[17] + fneq[18];
+    *Q12 = fneq[7] - fneq[8] - fneq[9] + fneq[10];
+    *Q13 = fneq[11] - fneq[12] - fneq[13] + fneq[14];
+    *Q23 = fneq[15] - fneq[16] - fneq[17] + fneq[18];
+}
+static double center_diff(double g1, double g2, double invdx) { return (g1 - g2) * invdx; }                  /* :1425-1429 */
+static double onesid_diff(double g1, double g2, double g3, double invdx) { return (-3.0 * g1 + 4.0 * g2 - g3) * invdx; } /* :1430-1434 */
+/* d(uuu(.,.,.,k))/d(axis) as the reference branches it: central inside, one-sided on the first/last plane.
+ * c = 0-based (x,y,z); the reference's "invdh" is dh (:1322,1444). */
+static double les_grad(const orc_block *b, int k, int axis, const int c[3], double invdh)
+{
+    const int dim[3] = {NX, NY, NZ};
+    int p[3] = {c[0], c[1], c[2]}, m[3] = {c[0], c[1], c[2]}, p2[3] = {c[0], c[1], c[2]};
+    if (c[axis] > 0 && c[axis] < dim[axis] - 1) {
+        p[axis] += 1; m[axis] -= 1;
+        return center_diff(b->uuu[F4(b, p[2], p[1], p[0], k)], b->uuu[F4(b, m[2], m[1], m[0], k)], invdh);
+    } else if (c[axis] == 0) {
+        p[axis] += 1; p2[axis] += 2;
+    } else {
+        p[axis] -= 1; p2[axis] -= 2;
+    }
+    return onesid_diff(b->uuu[F4(b, c[2], c[1], c[0], k)], b->uuu[F4(b, p[2], p[1], p[0], k)], b->uuu[F4(b, p2[2], p2[1], p2[0], k)], invdh);
+}
+static double les_smag(orc_block *b, const double fneq[Q], double rho, int x, int y, int z)
+{
+    double Q11, Q22, Q33, Q12, Q13, Q23;
+    les_Q(fneq, &Q11, &Q22, &Q33, &Q12, &Q13, &Q23);
+    double Qq = Q11 * Q11 + Q22 * Q22 + Q33 * Q33 + 2.0 * (Q12 * Q12 + Q13 * Q13 + Q23 * Q23);
+    double tau_t = sqrt(b->tau * b->tau + CsmagConst * sqrt(Qq) / rho);
+    b->tau_all[F3(b, z, y, x)] = 0.5 * (b->tau + tau_t);
+    return 2.0 / (b->tau + tau_t);
+}
+static double les_wale(orc_block *b, const double fneq[Q], double rho, int x, int y, int z)
+{
+    const double invdh = b->dh; /* sic, :1322 */
+    const int c[3] = {x, y, z};
+    double Q11, Q22, Q33, Q12, Q13, Q23;
+    les_Q(fneq, &Q11, &Q22, &Q33, &Q12, &Q13, &Q23);
+    double tau__ = b->tau_all[F3(b, z, y, x)];
+    double S11 = -1.5 * invdh * Q11 / (rho * tau__), S22 = -1.5 * invdh * Q22 / (rho * tau__), S33 = -1.5 * invdh * Q33 / (rho * tau__);
+    double S12 = -1.5 * invdh * Q12 / (rho * tau__), S13 = -1.5 * invdh * Q13 / (rho * tau__), S23 = -1.5 * invdh * Q23 / (rho * tau__);
+    double S = S11 * S11 + S22 * S22 + S33 * S33 + 2.0 * (S12 * S12 + S13 * S13 + S23 * S23);
+    double ox = les_grad(b, 2, 1, c, invdh);            /* dw/dy */
+    ox = 0.5 * (ox - les_grad(b, 1, 2, c, invdh));      /* - dv/dz */
+    double oy = les_grad(b, 0, 2, c, invdh);            /* du/dz */
+    oy = 0.5 * (oy - les_grad(b, 2, 0, c, invdh));      /* - dw/dx */
+    double oz = les_grad(b, 1, 0, c, invdh);            /* dv/dx */
+    oz = 0.5 * (oz - les_grad(b, 0, 1, c, invdh));      /* - du/dy */
+    double O12 = -0.5 * oz, O13 = 0.5 * oy, O23 = -0.5 * ox;
+    double O = 2.0 * (O12 * O12 + O23 * O23 + O13 * O13);
+    double SO11 = -(0.0 + S11 * S11 * O12 * O12 + S11 * S11 * O13 * O13 + 0.0 + S12 * S12 * O12 * O12 + S12 * S12 * O13 * O13 + 0.0 +
+                    S13 * S13 * O12 * O12 + S13 * S13 * O13 * O13);
+    double SO22 = -(S12 * S12 * O12 * O12 + 0.0 + S12 * S12 * O23 * O23 + S22 * S22 * O12 * O12 + 0.0 + S22 * S22 * O23 * O23 +
+                    S23 * S23 * O12 * O12 + 0.0 + S23 * S23 * O23 * O23);
+    double SO33 = -(S13 * S13 * O13 * O13 + S13 * S13 * O23 * O23 + 0.0 + S23 * S23 * O13 * O13 + S23 * S23 * O23 * O23 + 0.0 +
+                    S33 * S33 * O13 * O13 + S33 * S33 * O23 * O23 + 0.0);
+    double SO12 = -(0.0 + 0.0 + S11 * S12 * O13 * O23 + 0.0 + 0.0 + S12 * S22 * O13 * O23 + 0.0 + 0.0 + S13 * S23 * O13 * O23);
+    double SO13 = (0.0 + S11 * S13 * O12 * O23 + 0.0 + 0.0 + S12 * S23 * O12 * O23 + 0.0 + 0.0 + S13 * S33 * O12 * O23 + 0.0);
+    double SO23 = -(S12 * S13 * O12 * O13 + 0.0 + 0.0 + S22 * S23 * O12 * O13 + 0.0 + 0.0 + S23 * S33 * O12 * O13 + 0.0 + 0.0);
+    double SO = SO11 + SO22 + SO33 + 2.0 * (SO12 + SO13 + SO23);
+    double SdSd = (S * S + O * O) / 6.0 + 2.0 * S * O / 3.0 + 2.0 * SO;
+    double OP = pow(SdSd, 1.5) / (pow(S, 2.5) + pow(SdSd, 1.25));
+    if (!isfinite(OP) || OP < 0.0) OP = 0.0;
+    tau__ = (b->flow.nu + CWALEConst * OP * b->dh * b->dh) / (b->dh * Cs2) + 0.5;
+    b->tau_all[F3(b, z, y, x)] = tau__;
+    return 1.0 / tau__;
+}
+static double les_vrem(orc_block *b, int x, int y, int z)
+{
+    const double invdh = b->dh; /* sic, :1444 */
+    const int c[3] = {x, y, z};
+    double a[3][3], bb_[3][3]; /* a(i,j) = 0.5 * d u_i / d x_j */
+    for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++) a[i][j] = 0.5 * les_grad(b, i, j, c, invdh);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) bb_[i][j] = a[i][j] * a[i][j];
+    double b11 = bb_[0][0], b12 = bb_[0][1], b13 = bb_[0][2], b21 = bb_[1][0], b22 = bb_[1][1], b23 = bb_[1][2], b31 = bb_[2][0], b32 = bb_[2][1], b33 = bb_[2][2];
+    double a11 = a[0][0], a12 = a[0][1], a13 = a[0][2], a21 = a[1][0], a22 = a[1][1], a23 = a[1][2], a31 = a[2][0], a32 = a[2][1], a33 = a[2][2];
+    double aa = b11 + b12 + b13 + b21 + b22 + b23 + b31 + b32 + b33;
+    double bb = (b11 + b12 + b13) * (b21 + b22 + b23) - (a11 * a21 + a12 * a22 + a13 * a23) * (a11 * a21 + a12 * a22 + a13 * a23) +
+                (b11 + b12 + b13) * (b31 + b32 + b33) - (a11 * a31 + a12 * a32 + a13 * a33) * (a11 * a31 + a12 * a32 + a13 * a33) +
+                (b21 + b22 + b23) * (b31 + b32 + b33) - (a21 * a31 + a22 * a32 + a23 * a33) * (a21 * a31 + a22 * a32 + a23 * a33);
+    double OP = sqrt(bb / aa);
+    if (!isfinite(OP)) OP = 0.0;
+    double tau__ = (b->flow.nu + CvremConst * OP * b->dh * b->dh) / (b->dh * Cs2) + 0.5;
+    b->tau_all[F3(b, z, y, x)] = tau__;
+    return 1.0 / tau__;
+}
+
 int orc_collision(orc_block *b)
 {
     const double dt3 = 3.0 * b->dh; /* :1213 */
     const int model = b->iCollidModel;
-    if (model != 1 && model != 2 && model != 3) return 1;
+    if (model != 1 && model != 2 && model != 3 && model != 11 && model != 14 && model != 15) return 1; /* 12, 13 are broken upstream */
 #pragma omp parallel for schedule(static) num_threads(b->npsize)
     for (int x = 0; x < NX; x++)
         for (int y = 0; y < NY; y++)
@@ -465,6 +564,16 @@ int orc_collision(orc_block *b)
                     for (int q = 0; q < Q; q++) {
                         size_t i = F4(b, z, y, x, q);
                         b->fIn[i] = b->fIn[i] + fEq[q];
+                    }
+                } else if (model == 11 || model == 14 || model == 15) { /* :1239-1258 */
+                    double fneq[Q], omega;
+                    for (int q = 0; q < Q; q++) fneq[q] = -fEq[q];
+                    if (model == 11) omega = les_smag(b, fneq, den, x, y, z);
+                    else if (model == 14) omega = les_wale(b, fneq, den, x, y, z);
+                    else omega = les_vrem(b, x, y, z);
+                    for (int q = 0; q < Q; q++) {
+                        size_t i = F4(b, z, y, x, q);
+                        b->fIn[i] = b->fIn[i] + omega * fEq[q] + (1.0 - 0.5 * omega) * Flb[q];
                     }
                 } else { /* :1238 */
                     double mc[Q], mf[Q];

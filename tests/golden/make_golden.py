@@ -92,6 +92,38 @@ def run_case(name, c):
     print(f"{name}: {X}x{Y}x{Z}, {c['steps']} steps, max|u| {np.abs(b.uuu).max():.3e}, mean rho {b.den.mean():.12f}")
 
 
+REFINE_CASES = {
+    "refine_linear": dict(scheme=1, fbc=(102, 104, 301, 301, 203, 203), fdims=(14, 10, 10), sbc=(0,) * 6, sdims=(13, 9, 9), smins=(4.0, 3.0, 3.0),
+                          models=(1, 1), steps=6),
+    "refine_cubic_periodic_son": dict(scheme=2, fbc=(101, 104, 301, 301, 301, 301), fdims=(14, 10, 10), sbc=(0, 0, 301, 301, 0, 0), sdims=(13, 20, 11),
+                                      smins=(4.0, 0.0, 2.0), models=(2, 1), steps=6),
+}
+REFINE_FLOW = dict(nu=0.02, uvwIn=(0.03, 0.005, 0.0), Uref=0.03, volumeForceIn=(1e-6, 0.0, 0.0))
+REFINE_PARAMS = (0.25,) + (0.0,) * 9
+
+
+def run_refine_case(name, c):
+    fl = NR.Flow(**REFINE_FLOW)
+    Fb = NR.Block(*c["fdims"], dh=1.0, BndConds=c["fbc"], iCollidModel=c["models"][0], params=REFINE_PARAMS, flow=fl)
+    Sb = NR.Block(*c["sdims"], dh=0.5, xmin=c["smins"][0], ymin=c["smins"][1], zmin=c["smins"][2], BndConds=c["sbc"],
+                  iCollidModel=c["models"][1], params=REFINE_PARAMS, flow=fl)
+    Fb.initialise(0.0); Sb.initialise(0.0)
+    f0F, f0S = perturbed_state(c["fdims"], fl, seed=1), perturbed_state(c["sdims"], fl, seed=2)
+    Fb.f[...] = f0F; Sb.f[...] = f0S
+    root = NR.Node(Fb); root.add_son(NR.Node(Sb), c["scheme"])
+    for b in (Fb, Sb):
+        b.update_volume_force(); b.set_boundary_conditions(); b.calculate_macro_quantities()
+    for n in range(1, c["steps"] + 1):
+        NR.set_blktime_all(root, float(n))
+        NR.tree_step(root)
+    p = root.comm[0]
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), f0F=f0F, f0S=f0S, fF=Fb.f, fS=Sb.f,
+                        pair=np.array(p.sds + p.s + p.f + p.si + p.fi + p.dimS + p.dimF), case=json.dumps(c))
+    print(f"{name}: father {c['fdims']} son {c['sdims']} scheme {c['scheme']}, {c['steps']} father steps")
+
+
 if __name__ == "__main__":
     for name, c in CASES.items():
         run_case(name, c)
+    for name, c in REFINE_CASES.items():
+        run_refine_case(name, c)

@@ -44,3 +44,22 @@ def test_cuda_reproduces_golden(F, name):
         assert rel_err(bodies[0].v_Eforce, g["Eforce"]) <= TOL_FORCE
         assert rel_err(den, g["den"]) <= TOL_FLUID and rel_err(uuu, g["uuu"]) <= TOL_FLUID and rel_err(f, g["fIn"]) <= TOL_FLUID
     blk.close()
+
+
+@pytest.mark.parametrize("name", golden_names(refine=True))
+def test_cuda_reproduces_refinement_golden(F, name):
+    from tests.common import REFINE_FLOW, REFINE_PARAMS, run_golden_refine
+    case, g = load_golden(name)
+
+    def make_block(dims, dh, mins, bc, model):
+        b = F.LBMBlock(*dims, dh=dh, xmin=mins[0], ymin=mins[1], zmin=mins[2], BndConds=bc, iCollidModel=model, params=REFINE_PARAMS,
+                       flow=F.FlowCondType(**REFINE_FLOW))
+        b.initialise(0.0)
+        return b
+
+    def make_tree(Fb, Sb, scheme):
+        return F.build_block_tree([Fb, Sb], interpolateScheme=scheme)
+    Fb, Sb, p = run_golden_refine(case, g, make_block, make_tree, F.tree_collision_streaming_IBM_FEM, F.set_blktime_all)
+    assert list(g["pair"]) == p.sds + p.s + p.f + p.si + p.fi + p.dimS + p.dimF
+    assert np.array_equal(Fb.download_fIn(), g["fF"]) and np.array_equal(Sb.download_fIn(), g["fS"])
+    p.close(); Fb.close(); Sb.close()

@@ -72,3 +72,43 @@ def test_numpy_restatement_live_matches_c_oracle_unfused_passes(oracle):
             ob.set_boundary_conditions(); nb.set_boundary_conditions()
             assert np.array_equal(ob.fIn, nb.f), (model, n, "bc")
         assert abs(ob.tau - nb.tau) == 0 and abs(ob.Omega2 - nb.Omega2) == 0
+
+
+@pytest.mark.parametrize("name", golden_names(refine=True))
+def test_c_oracle_reproduces_refinement_golden(oracle, name):
+    from tests.common import REFINE_FLOW, REFINE_PARAMS, run_golden_refine
+    O = oracle
+    case, g = load_golden(name)
+
+    def make_block(dims, dh, mins, bc, model):
+        b = O.LBMBlock(*dims, dh=dh, xmin=mins[0], ymin=mins[1], zmin=mins[2], BndConds=bc, iCollidModel=model, params=REFINE_PARAMS, flow=O.Flow(**REFINE_FLOW))
+        b.initialise(0.0)
+        return b
+
+    def make_tree(Fb, Sb, scheme):
+        root = O.TreeNode(Fb); root.add_son(O.TreeNode(Sb), scheme)
+        return root
+    Fb, Sb, p = run_golden_refine(case, g, make_block, make_tree, O.tree_collision_streaming_IBM_FEM, O.set_blktime_all)
+    assert list(g["pair"]) == p.sds + p.s + p.f + p.si + p.fi + p.dimS + p.dimF
+    assert np.array_equal(Fb.fIn, g["fF"]) and np.array_equal(Sb.fIn, g["fS"])
+
+
+def test_refinement_keeps_uniform_flow_uniform(oracle):
+    """Known answer: a uniform equilibrium stays uniform through father->son interpolation, the non-equilibrium
+    rescale (zero non-equilibrium) and son->father restriction."""
+    O = oracle
+    fl = O.Flow(nu=0.02, uvwIn=(0.03, 0.01, -0.02), Uref=0.03)
+    Fb = O.LBMBlock(16, 12, 12, dh=1.0, BndConds=(301,) * 6, flow=fl)
+    Sb = O.LBMBlock(13, 9, 9, dh=0.5, xmin=5.0, ymin=4.0, zmin=4.0, BndConds=(0,) * 6, flow=fl)
+    Fb.initialise(0.0); Sb.initialise(0.0)
+    root = O.TreeNode(Fb); root.add_son(O.TreeNode(Sb), 2)
+    for b in (Fb, Sb):
+        b.update_volume_force(); b.set_boundary_conditions(); b.calculate_macro_quantities()
+    for n in range(1, 13):
+        O.set_blktime_all(root, float(n))
+        O.tree_collision_streaming_IBM_FEM(root)
+    for b in (Fb, Sb):
+        b.calculate_macro_quantities()
+        assert np.abs(b.den - 1.0).max() < 1e-14
+        for k, v in enumerate(fl.uvwIn):
+            assert np.abs(b.uuu[k] - v).max() < 1e-15
