@@ -61,7 +61,7 @@ def lib():
         "fsilbm_block_destroy": [i], "fsilbm_block_initialise": [i, d], "fsilbm_block_get": [i, i, pd],
         "fsilbm_block_upload_fIn": [i, vp], "fsilbm_block_download_fIn": [i, vp],
         "fsilbm_block_set_time": [i, d], "fsilbm_block_update_volume_force": [i, pd],
-        "fsilbm_block_download_macro": [i, vp, vp], "fsilbm_block_field_stat": [i, pd],
+        "fsilbm_block_download_macro": [i, vp, vp], "fsilbm_block_download_tau_all": [i, vp], "fsilbm_block_field_stat": [i, pd],
         "fsilbm_block_set_boundary_conditions": [i], "fsilbm_block_collide_stream": [i], "fsilbm_block_sync": [i],
         "fsilbm_block_stream": [i, C.POINTER(C.c_void_p)],
         "fsilbm_block_halo_transport": [i, pi],

@@ -109,7 +109,108 @@ struct CollideConsts {
     double dt3;               // 3.d0*dh, :1213
     double cF;                // 1.d0-0.5d0*Omega, :1227
     int mrt_slot;             // which c_MRT entry holds M_COLLID (:514) / M_FORCE (:521) of this block
+    double tau, nu, dh;       // LES closures (:1278, :1420, :1503)
 };
+
+// What the LES closures contained in collision_ need beyond the cell itself (models 11, 14, 15).
+struct LesCtx {
+    const double *uuu;        // [3][X][Y][Z] velocity field of this step (WALE, Vreman: neighbour differences); null for model 11
+    double *tau_all;          // [X][Y][Z] (FluidDomain.f90:1279,1422,1505)
+    int X, Y, Z;              // extents of the fields
+    int x, y, z;              // this cell
+    bool write_tau;           // false when a boundary layer is collided a second time for the half-way stash
+};
+
+// ConstParams.f90:40-45
+__device__ __forceinline__ double CsmagConst() { return 2.0 * 0.17 * 0.17 * sqrt(2.0) * 9.0; }
+__device__ __forceinline__ double CWALEConst() { return 0.50 * 0.50; }
+__device__ __forceinline__ double CvremConst() { return 2.5 * 0.17 * 0.17; }
+
+// center_diff / onesid_diff (FluidDomain.f90:1425-1434) of uuu(.,.,.,k) along `axis`, branching as the reference does
+__device__ __forceinline__ double les_grad(const LesCtx &c, int k, int axis, double invdh)
+{
+    const size_t n = (size_t)c.X * c.Y * c.Z;
+    const size_t stride = axis == 0 ? (size_t)c.Y * c.Z : (axis == 1 ? (size_t)c.Z : 1);
+    const int pos = axis == 0 ? c.x : (axis == 1 ? c.y : c.z), dim = axis == 0 ? c.X : (axis == 1 ? c.Y : c.Z);
+    const double *u = c.uuu + (size_t)k * n + ((size_t)c.x * c.Y + c.y) * c.Z + c.z;
+    if (pos > 0 && pos < dim - 1) return (u[stride] - *(u - stride)) * invdh;
+    if (pos == 0) return (-3.0 * u[0] + 4.0 * u[stride] - u[2 * stride]) * invdh;
+    return (-3.0 * u[0] + 4.0 * *(u - stride) - *(u - 2 * stride)) * invdh;
+}
+
+// smag (:1265-1281), WALE (:1311-1424), vrem (:1435-1507).  fneq = -(f_eq - f).  Returns omega0.
+template <int MODEL>
+__device__ __forceinline__ double les_omega(const double (&fEqmf)[Q], double rho, const CollideConsts &cc, const LesCtx &c)
+{
+    const size_t cell = ((size_t)c.x * c.Y + c.y) * c.Z + c.z;
+    if (MODEL == 15) {
+        const double invdh = cc.dh;   // sic, :1444
+        double a[3][3];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int i = 0; i < 3; i++) a[i][j] = 0.5 * les_grad(c, i, j, invdh);
+        const double b11 = a[0][0] * a[0][0], b12 = a[0][1] * a[0][1], b13 = a[0][2] * a[0][2];
+        const double b21 = a[1][0] * a[1][0], b22 = a[1][1] * a[1][1], b23 = a[1][2] * a[1][2];
+        const double b31 = a[2][0] * a[2][0], b32 = a[2][1] * a[2][1], b33 = a[2][2] * a[2][2];
+        const double aa = b11 + b12 + b13 + b21 + b22 + b23 + b31 + b32 + b33;
+        const double d12 = a[0][0] * a[1][0] + a[0][1] * a[1][1] + a[0][2] * a[1][2];
+        const double d13 = a[0][0] * a[2][0] + a[0][1] * a[2][1] + a[0][2] * a[2][2];
+        const double d23 = a[1][0] * a[2][0] + a[1][1] * a[2][1] + a[1][2] * a[2][2];
+        const double bb = (b11 + b12 + b13) * (b21 + b22 + b23) - d12 * d12 + (b11 + b12 + b13) * (b31 + b32 + b33) - d13 * d13 +
+                          (b21 + b22 + b23) * (b31 + b32 + b33) - d23 * d23;
+        double OP = sqrt(bb / aa);
+        if (!isfinite(OP)) OP = 0.0;
+        const double tau__ = (cc.nu + CvremConst() * OP * cc.dh * cc.dh) / (cc.dh * (1.0 / 3.0)) + 0.5;
+        if (c.write_tau) c.tau_all[cell] = tau__;
+        return 1.0 / tau__;
+    }
+    double fneq[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) fneq[q] = -fEqmf[q];
+    const double Q11 = fneq[1] + fneq[2] + fneq[7] + fneq[8] + fneq[9] + fneq[10] + fneq[11] + fneq[12] + fneq[13] + fneq[14];
+    const double Q22 = fneq[3] + fneq[4] + fneq[7] + fneq[8] + fneq[9] + fneq[10] + fneq[15] + fneq[16] + fneq[17] + fneq[18];
+    const double Q33 = fneq[5] + fneq[6] + fneq[11] + fneq[12] + fneq[13] + fneq[14] + fneq[15] + fneq[16] + fneq[17] + fneq[18];
+    const double Q12 = fneq[7] - fneq[8] - fneq[9] + fneq[10];
+    const double Q13 = fneq[11] - fneq[12] - fneq[13] + fneq[14];
+    const double Q23 = fneq[15] - fneq[16] - fneq[17] + fneq[18];
+    if (MODEL == 11) {
+        const double Qq = Q11 * Q11 + Q22 * Q22 + Q33 * Q33 + 2.0 * (Q12 * Q12 + Q13 * Q13 + Q23 * Q23);
+        const double tau_t = sqrt(cc.tau * cc.tau + CsmagConst() * sqrt(Qq) / rho);
+        if (c.write_tau) c.tau_all[cell] = 0.5 * (cc.tau + tau_t);
+        return 2.0 / (cc.tau + tau_t);
+    }
+    // MODEL == 14
+    const double invdh = cc.dh;   // sic, :1322
+    double tau__ = c.tau_all[cell];
+    const double S11 = -1.5 * invdh * Q11 / (rho * tau__), S22 = -1.5 * invdh * Q22 / (rho * tau__), S33 = -1.5 * invdh * Q33 / (rho * tau__);
+    const double S12 = -1.5 * invdh * Q12 / (rho * tau__), S13 = -1.5 * invdh * Q13 / (rho * tau__), S23 = -1.5 * invdh * Q23 / (rho * tau__);
+    const double S = S11 * S11 + S22 * S22 + S33 * S33 + 2.0 * (S12 * S12 + S13 * S13 + S23 * S23);
+    double ox = les_grad(c, 2, 1, invdh);
+    ox = 0.5 * (ox - les_grad(c, 1, 2, invdh));
+    double oy = les_grad(c, 0, 2, invdh);
+    oy = 0.5 * (oy - les_grad(c, 2, 0, invdh));
+    double oz = les_grad(c, 1, 0, invdh);
+    oz = 0.5 * (oz - les_grad(c, 0, 1, invdh));
+    const double O12 = -0.5 * oz, O13 = 0.5 * oy, O23 = -0.5 * ox;
+    const double O = 2.0 * (O12 * O12 + O23 * O23 + O13 * O13);
+    const double SO11 = -(0.0 + S11 * S11 * O12 * O12 + S11 * S11 * O13 * O13 + 0.0 + S12 * S12 * O12 * O12 + S12 * S12 * O13 * O13 + 0.0 +
+                          S13 * S13 * O12 * O12 + S13 * S13 * O13 * O13);
+    const double SO22 = -(S12 * S12 * O12 * O12 + 0.0 + S12 * S12 * O23 * O23 + S22 * S22 * O12 * O12 + 0.0 + S22 * S22 * O23 * O23 +
+                          S23 * S23 * O12 * O12 + 0.0 + S23 * S23 * O23 * O23);
+    const double SO33 = -(S13 * S13 * O13 * O13 + S13 * S13 * O23 * O23 + 0.0 + S23 * S23 * O13 * O13 + S23 * S23 * O23 * O23 + 0.0 +
+                          S33 * S33 * O13 * O13 + S33 * S33 * O23 * O23 + 0.0);
+    const double SO12 = -(0.0 + 0.0 + S11 * S12 * O13 * O23 + 0.0 + 0.0 + S12 * S22 * O13 * O23 + 0.0 + 0.0 + S13 * S23 * O13 * O23);
+    const double SO13 = (0.0 + S11 * S13 * O12 * O23 + 0.0 + 0.0 + S12 * S23 * O12 * O23 + 0.0 + 0.0 + S13 * S33 * O12 * O23 + 0.0);
+    const double SO23 = -(S12 * S13 * O12 * O13 + 0.0 + 0.0 + S22 * S23 * O12 * O13 + 0.0 + 0.0 + S23 * S33 * O12 * O13 + 0.0 + 0.0);
+    const double SO = SO11 + SO22 + SO33 + 2.0 * (SO12 + SO13 + SO23);
+    const double SdSd = (S * S + O * O) / 6.0 + 2.0 * S * O / 3.0 + 2.0 * SO;
+    double OP = pow(SdSd, 1.5) / (pow(S, 2.5) + pow(SdSd, 1.25));
+    if (!isfinite(OP) || OP < 0.0) OP = 0.0;
+    tau__ = (cc.nu + CWALEConst() * OP * cc.dh * cc.dh) / (cc.dh * (1.0 / 3.0)) + 0.5;
+    if (c.write_tau) c.tau_all[cell] = tau__;
+    return 1.0 / tau__;
+}
 
 // MRT matrices of up to MRT_SLOTS blocks, row-major [19][19]: [slot][0] = M_COLLID, [slot][1] = M_FORCE
 constexpr int MRT_SLOTS = 8;
@@ -146,10 +247,18 @@ __device__ __forceinline__ void collide_term(int q, const CellPre &c, double fq,
 #ifdef FSILBM_DEFINE_CONSTANTS
 template <int MODEL>
 __device__ __forceinline__ void collide(double (&f)[Q], double den, double u1, double u2, double u3, double F1, double F2,
-                                        double F3, const CollideConsts &c)
+                                        double F3, const CollideConsts &c, const LesCtx *les = nullptr)
 {
     const CellPre pre = cell_pre(den, u1, u2, u3, F1, F2, F3, c.dt3);
-    if (MODEL == 1) {   // :1227
+    if (MODEL == 11 || MODEL == 14 || MODEL == 15) {   // :1239-1258
+        double fEq[Q], Flb[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) collide_term(q, pre, f[q], fEq[q], Flb[q]);
+        const double omega = les_omega<MODEL>(fEq, den, c, *les);
+        const double cF = 1.0 - 0.5 * omega;
+#pragma unroll
+        for (int q = 0; q < Q; q++) f[q] = f[q] + omega * fEq[q] + cF * Flb[q];
+    } else if (MODEL == 1) {   // :1227
 #pragma unroll
         for (int q = 0; q < Q; q++) {
             double fEq, Flb;

@@ -89,7 +89,12 @@ __global__ void __launch_bounds__(128, 4) collide_push_kernel(const __grid_const
 
     double den, u1, u2, u3, F1, F2, F3;
     cell_state(f, p.hF, p.Fvol, p.boxes, IBM, p.g.xOffset + x, y, z, p.g.XG, Y, Z, den, u1, u2, u3, F1, F2, F3);
-    collide<MODEL>(f, den, u1, u2, u3, F1, F2, F3, p.cc);
+    if (MODEL >= 11) {
+        const LesCtx les{p.uuu, p.tau_all, X, Y, Z, x, y, z, true};
+        collide<MODEL>(f, den, u1, u2, u3, F1, F2, F3, p.cc, &les);
+    } else {
+        collide<MODEL>(f, den, u1, u2, u3, F1, F2, F3, p.cc);
+    }
 
     // streaming_: population q moves to (x+ex, y+ey, z+ez), periodic wrap on y and z always, on x
     // inside the slab only when this rank holds the whole x extent; otherwise into the ghost planes.
@@ -189,6 +194,9 @@ static int launch_push_variant(const StepParams &p, int model, dim3 grid, dim3 b
     if (model == 1) FSILBM_LAUNCH(1);
     else if (model == 2) FSILBM_LAUNCH(2);
     else if (model == 3) FSILBM_LAUNCH(3);
+    else if (VARIANT == 0 && model == 11) FSILBM_LAUNCH(11);
+    else if (VARIANT == 0 && model == 14) FSILBM_LAUNCH(14);
+    else if (VARIANT == 0 && model == 15) FSILBM_LAUNCH(15);
     else return 1;
 #undef FSILBM_LAUNCH
     return 0;
@@ -240,7 +248,8 @@ void launch_initialise(const Geom &g, double *f, const VelocityField &vel, doubl
 }
 
 // ---- calculate_macro_quantities_ over the slab (writers, probes, un-fused pass) --------------------
-__global__ void macro_full_kernel(Geom g, const double *f, double hF1, double hF2, double hF3, double *den, double *uuu)
+__global__ void macro_full_kernel(Geom g, const double *f, double hF1, double hF2, double hF3, double *den, double *uuu,
+                                  const __grid_constant__ IbmBoxes boxes)
 {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -252,18 +261,23 @@ __global__ void macro_full_kernel(Geom g, const double *f, double hF1, double hF
     for (int q = 0; q < Q; q++) fl[q] = f[q * g.pstride + base];
     double d, u1, u2, u3;
     macro_from_f(fl, hF1, hF2, hF3, d, u1, u2, u3);
+    if (boxes.n > 0) {   // the IBM-corrected velocity where a body is near (what collision_ and the LES differences see)
+        const long long bc = box_lookup(boxes, g.xOffset + x, y, z, g.XG, g.Y, g.Z);
+        if (bc >= 0) { u1 = boxes.u[bc]; u2 = boxes.u[boxes.ncell + bc]; u3 = boxes.u[2 * boxes.ncell + bc]; }
+    }
     const size_t n = (size_t)g.X * g.plane;
     const size_t c = (size_t)x * g.plane + (size_t)y * g.Z + z;
     if (den) den[c] = d;
     if (uuu) { uuu[c] = u1; uuu[n + c] = u2; uuu[2 * n + c] = u3; }
 }
 
-void launch_macro_full(const Geom &g, const double *f, const double hF[3], double *den, double *uuu, cudaStream_t s)
+void launch_macro_full(const Geom &g, const double *f, const double hF[3], double *den, double *uuu, cudaStream_t s, const IbmBoxes *boxes)
 {
     dim3 block; int bz, by;
     line_block(g.Z, block, bz, by);
     dim3 grid((g.Z + bz - 1) / bz, (g.Y + by - 1) / by, g.X);
-    macro_full_kernel<<<grid, block, 0, s>>>(g, f, hF[0], hF[1], hF[2], den, uuu);
+    IbmBoxes none{};
+    macro_full_kernel<<<grid, block, 0, s>>>(g, f, hF[0], hF[1], hF[2], den, uuu, boxes ? *boxes : none);
     count_launch();
 }
 
@@ -455,7 +469,12 @@ __global__ void stash_face_kernel(const __grid_constant__ FaceParams p)
     for (int q = 0; q < Q; q++) f[q] = p.fA[q * g.pstride + c1];
     double den, u1, u2, u3, F1, F2, F3;
     cell_state(f, p.hF, p.Fvol, p.boxes, p.boxes.n > 0, g.xOffset + x, y, z, g.XG, g.Y, g.Z, den, u1, u2, u3, F1, F2, F3);
-    collide<MODEL>(f, den, u1, u2, u3, F1, F2, F3, p.cc);
+    if (MODEL >= 11) {
+        const LesCtx les{p.uuu, p.tau_all, g.X, g.Y, g.Z, x, y, z, false};   // the main kernel writes tau_all, not this re-collision
+        collide<MODEL>(f, den, u1, u2, u3, F1, F2, F3, p.cc, &les);
+    } else {
+        collide<MODEL>(f, den, u1, u2, u3, F1, F2, F3, p.cc);
+    }
     const size_t sidx = (size_t)b * p.na + a, sstride = (size_t)p.na * p.nb;
 #pragma unroll
     for (int q = 0; q < Q; q++) p.stash[q * sstride + sidx] = f[q];
@@ -467,7 +486,10 @@ void launch_stash_face(const FaceParams &p, cudaStream_t s)
     face_grid(p, grid, block);
     if (p.model == 1) stash_face_kernel<1><<<grid, block, 0, s>>>(p);
     else if (p.model == 2) stash_face_kernel<2><<<grid, block, 0, s>>>(p);
-    else stash_face_kernel<3><<<grid, block, 0, s>>>(p);
+    else if (p.model == 3) stash_face_kernel<3><<<grid, block, 0, s>>>(p);
+    else if (p.model == 11) stash_face_kernel<11><<<grid, block, 0, s>>>(p);
+    else if (p.model == 14) stash_face_kernel<14><<<grid, block, 0, s>>>(p);
+    else stash_face_kernel<15><<<grid, block, 0, s>>>(p);
     count_launch();
 }
 
@@ -565,7 +587,12 @@ __global__ void collision_fields_kernel(const __grid_constant__ FieldParams p)
     double f[Q];
 #pragma unroll
     for (int q = 0; q < Q; q++) f[q] = p.f[q * g.pstride + base];
-    collide<MODEL>(f, p.den[c], p.uuu[c], p.uuu[n + c], p.uuu[2 * n + c], p.force[c], p.force[n + c], p.force[2 * n + c], p.cc);
+    if (MODEL >= 11) {
+        const LesCtx les{p.uuu, p.tau_all, g.X, g.Y, g.Z, x, y, z, true};
+        collide<MODEL>(f, p.den[c], p.uuu[c], p.uuu[n + c], p.uuu[2 * n + c], p.force[c], p.force[n + c], p.force[2 * n + c], p.cc, &les);
+    } else {
+        collide<MODEL>(f, p.den[c], p.uuu[c], p.uuu[n + c], p.uuu[2 * n + c], p.force[c], p.force[n + c], p.force[2 * n + c], p.cc);
+    }
 #pragma unroll
     for (int q = 0; q < Q; q++) p.f[q * g.pstride + base] = f[q];
 }
@@ -577,6 +604,9 @@ int launch_pass_collision(const FieldParams &p, int model, cudaStream_t s)
     if (model == 1) collision_fields_kernel<1><<<grid, block, 0, s>>>(p);
     else if (model == 2) collision_fields_kernel<2><<<grid, block, 0, s>>>(p);
     else if (model == 3) collision_fields_kernel<3><<<grid, block, 0, s>>>(p);
+    else if (model == 11) collision_fields_kernel<11><<<grid, block, 0, s>>>(p);
+    else if (model == 14) collision_fields_kernel<14><<<grid, block, 0, s>>>(p);
+    else if (model == 15) collision_fields_kernel<15><<<grid, block, 0, s>>>(p);
     else return 1;
     count_launch();
     return 0;

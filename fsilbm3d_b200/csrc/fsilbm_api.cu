@@ -212,6 +212,7 @@ CollideConsts collide_consts(const Block &b)
     c.dt3 = 3.0 * b.g.dh;             // FluidDomain.f90:1213
     c.cF = 1.0 - 0.5 * b.Omega;       // :1227
     c.mrt_slot = b.mrt_slot;
+    c.tau = b.tau; c.nu = b.flow.nu; c.dh = b.g.dh;
     return c;
 }
 
@@ -278,6 +279,7 @@ FaceParams face_params(Block &b, int face, double *f, const double *fA, const Ve
     p.boxes = b.boxes;
     if (!b.ibm_active) p.boxes.n = 0;
     p.model = b.model;
+    p.tau_all = b.tau_all; p.uuu = b.uuu;
     return p;
 }
 
@@ -492,8 +494,11 @@ int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, d
         return fail(FSILBM_ERR_ARG, "Grid number exceeds 32767, please try to reduced the grid size.");
     if (xOffset < 0 || xLocal < 1 || xOffset + xLocal > xDim) return fail(FSILBM_ERR_ARG, "bad slab [%d,%d) of %d", xOffset, xOffset + xLocal, xDim);
     for (int i = 0; i < 6; i++) if (!valid_bc(BndConds[i])) return fail(FSILBM_ERR_BC, "face %d has no such boundary condition: %d", i, BndConds[i]);
-    if (!(iCollidModel == 1 || iCollidModel == 2 || iCollidModel == 3))
-        return fail(FSILBM_ERR_MODEL, "iCollidModel %d not provided (1 SRT, 2 TRT, 3 MRT)", iCollidModel);
+    if (!(iCollidModel == 1 || iCollidModel == 2 || iCollidModel == 3 || iCollidModel == 11 || iCollidModel == 14 || iCollidModel == 15))
+        return fail(FSILBM_ERR_MODEL, "iCollidModel %d not provided (1 SRT, 2 TRT, 3 MRT, 11 Smagorinsky, 14 WALE, 15 Vreman; 12 and 13 read "
+                                      "uninitialised variables upstream, FluidDomain.f90:1245-1246,1292,1297-1304)", iCollidModel);
+    if ((iCollidModel == 14 || iCollidModel == 15) && xLocal != xDim)
+        return fail(FSILBM_ERR_MODEL, "iCollidModel %d differences velocity across x-planes; slab-split LES blocks are not provided", iCollidModel);
     auto b = std::make_unique<Block>();
     for (int i = 0; i < 3; i++) {   // check_periodic_boundary_, FluidDomain.f90:110-125
         b->periodic[i] = 0;
@@ -570,6 +575,12 @@ int fsilbm_block_initialise(fsilbm_handle h, double time)
         mrt_matrices(b->Omega, b->Mc, b->Mf);
         upload_mrt(b->mrt_slot, b->Mc, b->Mf, b->stream);
         CK(cudaStreamSynchronize(b->stream));   // Mc/Mf are pageable host memory
+    }
+    if (b->model >= 11) {                                    // tau_all = tau, FluidDomain.f90:454-455
+        const size_t n = (size_t)b->g.X * b->g.plane;
+        if (!b->tau_all) CK(cudaMalloc(&b->tau_all, sizeof(double) * n));
+        launch_pass_fill(b->tau_all, n, b->tau, b->stream);
+        if (b->model != 11) if (int rc = ensure_fields(*b, false)) return rc;
     }
     b->blktime = time;
     VelocityField vel;
@@ -667,6 +678,17 @@ int fsilbm_block_download_macro(fsilbm_handle h, double *den, double *uuu)
     return 0;
 }
 
+int fsilbm_block_download_tau_all(fsilbm_handle h, double *tau_all)
+{
+    Block *b = get(h);
+    if (!b || !tau_all) return fail(FSILBM_ERR_ARG, "bad handle/argument");
+    CK(cudaStreamSynchronize(b->stream));
+    const size_t n = (size_t)b->g.X * b->g.plane;
+    if (b->tau_all) { CK(cudaMemcpy(tau_all, b->tau_all, sizeof(double) * n, cudaMemcpyDeviceToHost)); }
+    else for (size_t i = 0; i < n; i++) tau_all[i] = b->tau;   // constant-tau models, FluidDomain.f90:454-455
+    return 0;
+}
+
 int fsilbm_block_field_stat(fsilbm_handle h, double out[6])
 {
     Block *b = get(h);
@@ -700,6 +722,13 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
     VelocityField vel;
     if (int rc = velocity_field(b, b.blktime, vel)) return rc;
 
+    if (b.model == 14 || b.model == 15) {
+        // WALE / Vreman difference the velocity of this step across neighbouring cells (FluidDomain.f90:1343-1385,
+        // 1445-1484): materialise uuu (with the IBM correction where a body is near) before the fused kernel.
+        double hF0[3];
+        half_force(b, hF0);
+        launch_macro_full(g, fA, hF0, nullptr, b.uuu, b.stream, b.ibm_active ? &b.boxes : nullptr);
+    }
     // per-face side buffers taken from the pre-collision state (see kernels.h FaceParams)
     for (int face = 0; face < 6; face++) {
         if (!owns_face(b, face)) continue;
@@ -726,10 +755,11 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
     for (int k = 0; k < 3; k++) p.Fvol[k] = b.volumeForce[k];
     p.boxes = b.boxes;
     if (!b.ibm_active) p.boxes.n = 0;
+    p.tau_all = b.tau_all; p.uuu = b.uuu;
     const bool multi = g_nccl.nranks > 1 && g_nccl.comm;
     const bool ghost = multi || g_force_ghost;
     p.wrap_x = ghost ? 0 : 1;
-    const int variant = (g_variant == 2 && (ghost || b.ibm_active)) ? 0 : g_variant;
+    const int variant = ((g_variant == 2 && (ghost || b.ibm_active)) || b.model >= 11) ? 0 : g_variant;
     if (!multi) {
         p.x_begin = 0; p.x_count = g.X;
         if (launch_collide_push(p, b.model, variant, b.stream)) return fail(FSILBM_ERR_MODEL, "collision model %d", b.model);
@@ -810,6 +840,7 @@ static FieldParams field_params(Block &b)
     p.cc = collide_consts(b);
     half_force(b, p.hF);
     for (int k = 0; k < 3; k++) p.Fvol[k] = b.volumeForce[k];
+    p.tau_all = b.tau_all;
     return p;
 }
 

@@ -51,6 +51,9 @@ struct StepParams {
     unsigned long long *sig_hi, *sig_lo;
     unsigned int *cta_counter;
     unsigned long long step;
+    // LES models (11 Smagorinsky, 14 WALE, 15 Vreman)
+    double *tau_all;          // [X][Y][Z]
+    const double *uuu;        // [3][X][Y][Z] velocity field of this step (models 14, 15), written by macro_full_kernel
 };
 
 // Receiving side of the peer-memory halo: wait for both neighbours' flags, then copy the received planes
@@ -83,6 +86,8 @@ struct FaceParams {
     double hF[3], Fvol[3];
     IbmBoxes boxes;
     int model;
+    double *tau_all;          // LES blocks
+    const double *uuu;
 };
 
 struct FieldParams {
@@ -91,13 +96,14 @@ struct FieldParams {
     double *den, *uuu, *force;   // [X][Y][Z], [3][X][Y][Z], [3][X][Y][Z] (no ghost planes)
     CollideConsts cc;
     double hF[3], Fvol[3];
+    double *tau_all;        // LES blocks
 };
 
 // ---- launchers (fluid_kernels.cu) ---------------------------------------------------------------
 void upload_mrt(int slot, const double *M_COLLID, const double *M_FORCE, cudaStream_t s);
 int launch_collide_push(const StepParams &p, int model, int variant, cudaStream_t s);
 void launch_initialise(const Geom &g, double *f, const VelocityField &vel, double denIn, cudaStream_t s);
-void launch_macro_full(const Geom &g, const double *f, const double hF[3], double *den, double *uuu, cudaStream_t s);
+void launch_macro_full(const Geom &g, const double *f, const double hF[3], double *den, double *uuu, cudaStream_t s, const IbmBoxes *boxes = nullptr);
 void launch_bc_face(const FaceParams &p, cudaStream_t s);
 void launch_stash_face(const FaceParams &p, cudaStream_t s);
 void launch_layer2_face(const FaceParams &p, cudaStream_t s);

@@ -112,6 +112,12 @@ class LBMBlock:
         check(lib().fsilbm_block_download_macro(self._h, den.ctypes.data, uuu.ctypes.data))
         return den, uuu
 
+    def download_tau_all(self) -> np.ndarray:
+        """tau_all (FluidDomain.f90:51), written by the LES collision models."""
+        t = np.empty(self.shape)
+        check(lib().fsilbm_block_download_tau_all(self._h, t.ctypes.data))
+        return t
+
     def ComputeFieldStat(self) -> np.ndarray:
         """ComputeFieldStat_, FluidDomain.f90:1739 (single slab): L2 u,v,w then Linfinity u,v,w."""
         out = (C.c_double * 6)()

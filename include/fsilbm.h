@@ -102,6 +102,9 @@ int fsilbm_block_update_volume_force(fsilbm_handle h, double volumeForce_out[3])
  * computes den, uuu of the local slab from the current fIn and copies them to the host.
  * Either pointer may be NULL.  (Inside a step the library derives den/uuu in registers.) */
 int fsilbm_block_download_macro(fsilbm_handle h, double *den, double *uuu);
+/* tau_all(z,y,x) (FluidDomain.f90:51): the local relaxation time the LES models 11/14/15 write during collision
+ * (:1279,1422,1505); the block's tau everywhere for the other models.  C [X][Y][Z] of the local slab. */
+int fsilbm_block_download_tau_all(fsilbm_handle h, double *tau_all);
 /* ComputeFieldStat_ (FluidDomain.f90:1739-1768) on the local slab: out = sum(u^2)/Uref^2 for
  * u,v,w then max|u|/Uref for u,v,w (the caller finishes sqrt(sum/N) after reducing over ranks). */
 int fsilbm_block_field_stat(fsilbm_handle h, double out[6]);

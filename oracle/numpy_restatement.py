@@ -228,8 +228,90 @@ class Block:
                 for k in range(19):
                     mf = mf + self.M_FORCE[i, k] * Flb[k]
                 f[i] = f[i] + mc + mf
+        elif self.model in (11, 14, 15):
+            fneq = [-e for e in fEq]
+            if self.model == 11:
+                omega = self._smag(fneq, den)
+            elif self.model == 14:
+                omega = self._wale(fneq, den)
+            else:
+                omega = self._vrem()
+            for q in range(19):
+                f[q] = f[q] + omega * fEq[q] + (1.0 - 0.5 * omega) * Flb[q]
         else:
             raise ValueError("model")
+
+    # ---- LES closures contained in collision_ (FluidDomain.f90:1265-1281, 1311-1424, 1435-1507) ------------
+    @staticmethod
+    def _Q(fn):
+        Q11 = fn[1] + fn[2] + fn[7] + fn[8] + fn[9] + fn[10] + fn[11] + fn[12] + fn[13] + fn[14]
+        Q22 = fn[3] + fn[4] + fn[7] + fn[8] + fn[9] + fn[10] + fn[15] + fn[16] + fn[17] + fn[18]
+        Q33 = fn[5] + fn[6] + fn[11] + fn[12] + fn[13] + fn[14] + fn[15] + fn[16] + fn[17] + fn[18]
+        Q12 = fn[7] - fn[8] - fn[9] + fn[10]
+        Q13 = fn[11] - fn[12] - fn[13] + fn[14]
+        Q23 = fn[15] - fn[16] - fn[17] + fn[18]
+        return Q11, Q22, Q33, Q12, Q13, Q23
+
+    def _grad(self, k, axis):
+        """d uuu(k) / d axis: center_diff inside, onesid_diff on the first/last plane; "invdh" is dh (sic, :1322,1444)."""
+        u = np.moveaxis(self.uuu[k], axis, 0)
+        g = np.empty_like(u)
+        invdh = self.dh
+        g[1:-1] = (u[2:] - u[:-2]) * invdh
+        g[0] = (-3.0 * u[0] + 4.0 * u[1] - u[2]) * invdh
+        g[-1] = (-3.0 * u[-1] + 4.0 * u[-2] - u[-3]) * invdh
+        return np.moveaxis(g, 0, axis)
+
+    def _smag(self, fneq, rho):
+        CsmagConst = 2.0 * 0.17 * 0.17 * math.sqrt(2.0) * 9.0
+        Q11, Q22, Q33, Q12, Q13, Q23 = self._Q(fneq)
+        Qq = Q11 * Q11 + Q22 * Q22 + Q33 * Q33 + 2.0 * (Q12 * Q12 + Q13 * Q13 + Q23 * Q23)
+        tau_t = np.sqrt(self.tau * self.tau + CsmagConst * np.sqrt(Qq) / rho)
+        self.tau_all = 0.5 * (self.tau + tau_t)
+        return 2.0 / (self.tau + tau_t)
+
+    def _wale(self, fneq, rho):
+        invdh = self.dh
+        Q11, Q22, Q33, Q12, Q13, Q23 = self._Q(fneq)
+        t = self.tau_all
+        S11, S22, S33 = -1.5 * invdh * Q11 / (rho * t), -1.5 * invdh * Q22 / (rho * t), -1.5 * invdh * Q33 / (rho * t)
+        S12, S13, S23 = -1.5 * invdh * Q12 / (rho * t), -1.5 * invdh * Q13 / (rho * t), -1.5 * invdh * Q23 / (rho * t)
+        S = S11 * S11 + S22 * S22 + S33 * S33 + 2.0 * (S12 * S12 + S13 * S13 + S23 * S23)
+        ox = 0.5 * (self._grad(2, 1) - self._grad(1, 2))
+        oy = 0.5 * (self._grad(0, 2) - self._grad(2, 0))
+        oz = 0.5 * (self._grad(1, 0) - self._grad(0, 1))
+        O12, O13, O23 = -0.5 * oz, 0.5 * oy, -0.5 * ox
+        O = 2.0 * (O12 * O12 + O23 * O23 + O13 * O13)
+        SO11 = -(0.0 + S11 * S11 * O12 * O12 + S11 * S11 * O13 * O13 + 0.0 + S12 * S12 * O12 * O12 + S12 * S12 * O13 * O13 + 0.0 + S13 * S13 * O12 * O12 + S13 * S13 * O13 * O13)
+        SO22 = -(S12 * S12 * O12 * O12 + 0.0 + S12 * S12 * O23 * O23 + S22 * S22 * O12 * O12 + 0.0 + S22 * S22 * O23 * O23 + S23 * S23 * O12 * O12 + 0.0 + S23 * S23 * O23 * O23)
+        SO33 = -(S13 * S13 * O13 * O13 + S13 * S13 * O23 * O23 + 0.0 + S23 * S23 * O13 * O13 + S23 * S23 * O23 * O23 + 0.0 + S33 * S33 * O13 * O13 + S33 * S33 * O23 * O23 + 0.0)
+        SO12 = -(0.0 + 0.0 + S11 * S12 * O13 * O23 + 0.0 + 0.0 + S12 * S22 * O13 * O23 + 0.0 + 0.0 + S13 * S23 * O13 * O23)
+        SO13 = (0.0 + S11 * S13 * O12 * O23 + 0.0 + 0.0 + S12 * S23 * O12 * O23 + 0.0 + 0.0 + S13 * S33 * O12 * O23 + 0.0)
+        SO23 = -(S12 * S13 * O12 * O13 + 0.0 + 0.0 + S22 * S23 * O12 * O13 + 0.0 + 0.0 + S23 * S33 * O12 * O13 + 0.0 + 0.0)
+        SO = SO11 + SO22 + SO33 + 2.0 * (SO12 + SO13 + SO23)
+        SdSd = (S * S + O * O) / 6.0 + 2.0 * S * O / 3.0 + 2.0 * SO
+        with np.errstate(all="ignore"):
+            OP = SdSd ** 1.5 / (S ** 2.5 + SdSd ** 1.25)
+        OP = np.where(np.isfinite(OP) & ~(OP < 0.0), OP, 0.0)
+        tau__ = (self.flow.nu + 0.5 * 0.5 * OP * self.dh * self.dh) / (self.dh * CS2) + 0.5
+        self.tau_all = tau__
+        return 1.0 / tau__
+
+    def _vrem(self):
+        a = [[0.5 * self._grad(i, j) for j in range(3)] for i in range(3)]
+        b = [[a[i][j] * a[i][j] for j in range(3)] for i in range(3)]
+        aa = b[0][0] + b[0][1] + b[0][2] + b[1][0] + b[1][1] + b[1][2] + b[2][0] + b[2][1] + b[2][2]
+        d12 = a[0][0] * a[1][0] + a[0][1] * a[1][1] + a[0][2] * a[1][2]
+        d13 = a[0][0] * a[2][0] + a[0][1] * a[2][1] + a[0][2] * a[2][2]
+        d23 = a[1][0] * a[2][0] + a[1][1] * a[2][1] + a[1][2] * a[2][2]
+        r1, r2, r3 = b[0][0] + b[0][1] + b[0][2], b[1][0] + b[1][1] + b[1][2], b[2][0] + b[2][1] + b[2][2]
+        bb = r1 * r2 - d12 * d12 + r1 * r3 - d13 * d13 + r2 * r3 - d23 * d23
+        with np.errstate(all="ignore"):
+            OP = np.sqrt(bb / aa)
+        OP = np.where(np.isfinite(OP), OP, 0.0)
+        tau__ = (self.flow.nu + 2.5 * 0.17 * 0.17 * OP * self.dh * self.dh) / (self.dh * CS2) + 0.5
+        self.tau_all = tau__
+        return 1.0 / tau__
 
     def halfwayBCset(self):
         """FluidDomain.f90:567-614 (copies only where the stash exists, which the reference guarantees by call order)."""

@@ -37,6 +37,12 @@ CASES = {
                                        mins=(0.0, 0.0, 0.0), flow=dict(nu=0.05, uvwIn=(0.04, 0.0, 0.0)), steps=12),
     "srt_oscillatory_inflow": dict(dims=(8, 5, 6), bc=(101, 104, 301, 301, 301, 301), model=1, params=(0.0,) * 10, dh=1.0, mins=(0.0, 0.0, 0.0),
                                    flow=dict(nu=0.05, uvwIn=(0.03, 0.0, 0.0), velocityKind=2, shearRateIn=(0.01, 0.02, 45.0)), steps=10),
+    "les_smag_halfway_channel": dict(dims=(8, 8, 10), bc=(301, 301, 203, 203, 301, 301), model=11, params=(0.0,) * 10, dh=1.0, mins=(0.0, 0.0, 0.0),
+                                     flow=dict(nu=0.002, uvwIn=(0.05, 0.0, 0.0), volumeForceIn=(1e-6, 0.0, 0.0)), steps=10, wave_amp=2e-2),
+    "les_wale_inflow": dict(dims=(9, 7, 8), bc=(101, 104, 201, 302, 301, 301), model=14, params=(0.0,) * 10, dh=0.5, mins=(0.0, 0.0, 0.0),
+                            flow=dict(nu=0.002, uvwIn=(0.05, 0.0, 0.0)), steps=10, wave_amp=2e-2),
+    "les_vrem_periodic": dict(dims=(7, 8, 9), bc=(301,) * 6, model=15, params=(0.0,) * 10, dh=1.0, mins=(0.0, 0.0, 0.0),
+                              flow=dict(nu=0.002, uvwIn=(0.05, 0.01, 0.0), volumeForceIn=(1e-6, 0.0, 0.0)), steps=10, wave_amp=2e-2),
     "srt_plate_shear": dict(dims=(16, 14, 12), bc=(101, 104, 202, 202, 301, 301), model=1, params=(0.0,) * 10, dh=1.0, mins=(0.0, 0.0, 0.0),
                             flow=dict(nu=0.05, uvwIn=(0.05, 0.0, 0.0), shearRateIn=(0.0, 2e-4, 0.0), Uref=0.05, ntolLBM=3, dtolLBM=1e-30), steps=8,
                             plate=dict(origin=(5.3, 6.2, 3.4), nEL=4, len1=1.0, Nspan=5, spanlen=5.0, Lspan=0.0, chord_dir=(1.0, 0.3, 0.0))),
@@ -69,7 +75,7 @@ def run_case(name, c):
     b = NR.Block(X, Y, Z, dh=c["dh"], xmin=c["mins"][0], ymin=c["mins"][1], zmin=c["mins"][2], BndConds=c["bc"],
                  iCollidModel=c["model"], params=c["params"], flow=fl)
     b.initialise(0.0)
-    f0 = perturbed_state(c["dims"], fl)
+    f0 = perturbed_state(c["dims"], fl, wave_amp=c.get("wave_amp", 1e-3))
     b.f[...] = f0
     b.update_volume_force(); b.set_boundary_conditions(); b.calculate_macro_quantities()   # main.f90:62-64
     bodies = []
@@ -86,6 +92,8 @@ def run_case(name, c):
         its.append(b.step(bodies))
     b.calculate_macro_quantities()   # main.f90:107
     out.update(f0=f0, fIn=b.f, den=b.den, uuu=b.uuu, iters=np.array(its), case=json.dumps(c))
+    if c["model"] >= 11:
+        out.update(tau_all=b.tau_all)
     if bodies:
         out.update(Eforce=bodies[0].v_Eforce, Ei=bodies[0].v_Ei, Ew=bodies[0].v_Ew)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)

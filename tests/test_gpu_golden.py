@@ -35,9 +35,15 @@ def test_cuda_reproduces_golden(F, name):
     den, uuu = blk.download_macro()
     f = blk.download_fIn()
     assert np.array_equal(its, g["iters"])
-    if not bodies:
+    if case["model"] == 14:
+        # WALE raises to the powers 1.5, 2.5, 1.25 (FluidDomain.f90:1415): CUDA's pow and libm's differ in the last bit
+        assert rel_err(den, g["den"]) <= TOL_FLUID and rel_err(uuu, g["uuu"]) <= TOL_FLUID and rel_err(f, g["fIn"]) <= TOL_FLUID
+        assert rel_err(blk.download_tau_all(), g["tau_all"]) <= TOL_FLUID
+    elif not bodies:
         assert np.array_equal(f, g["fIn"]), f"max |df| {np.abs(f - g['fIn']).max():.3e}"
         assert np.array_equal(den, g["den"]) and np.array_equal(uuu, g["uuu"])
+        if "tau_all" in g.files:
+            assert np.array_equal(blk.download_tau_all(), g["tau_all"])
     else:
         Ei, Ew = blk.download_stencil(0, bodies[0].v_nelmts)
         assert np.array_equal(Ei, g["Ei"]) and np.array_equal(Ew, g["Ew"])

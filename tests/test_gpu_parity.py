@@ -290,3 +290,50 @@ def test_full_size_streaming_period(F):
     for q, e in enumerate(ee):
         assert np.array_equal(f1[q], np.roll(f0[q], e, axis=(0, 1, 2))), q
     gb.close()
+
+
+# ---- LES collision models (FluidDomain.f90:1239-1258, closures :1265-1507) ------------------------------------
+@pytest.mark.parametrize("model", [11, 14, 15])
+@pytest.mark.parametrize("bc", [(301,) * 6, (101, 104, 203, 203, 201, 302)])
+def test_les_models(oracle, F, model, bc):
+    """Smagorinsky (local), WALE and Vreman (neighbour differences of this step's velocity, one-sided on the outer
+    planes; the reference's `invdh = dh` quirk kept), fused path and pass-by-pass path."""
+    from tests.common import make_pair, perturbed_state, rel_err
+    kw = dict(nu=0.002, uvwIn=(0.05, 0.0, 0.0), volumeForceIn=(1e-6, 0.0, 0.0))
+    dims = (12, 10, 36)
+    ob, gb = make_pair(oracle, F, dims, BndConds=bc, model=model, perturb=False, **kw)
+    f0 = perturbed_state(dims, ob.flow, wave_amp=2e-2)
+    ob.fIn[...] = f0; gb.upload_fIn(f0)
+    ob.set_boundary_conditions(); gb.set_boundary_conditions()
+    for n in range(1, 16):
+        ob.set_blktime(float(n)); gb.set_blktime(float(n))
+        ob.step(); gb.step()
+    exact = model != 14   # WALE uses pow(): last-bit differences between CUDA's and libm's pow
+    compare_fluid(ob, gb, exact=exact)
+    tg = gb.download_tau_all()
+    assert rel_err(tg, ob.tau_all) <= TOL_FLUID
+    assert ob.tau_all.max() > ob.tau * (1 + 1e-6)
+    # pass by pass on top of the same state
+    for n in range(3):
+        for b in (ob, gb):
+            b.update_volume_force(); b.calculate_macro_quantities(); b.ResetVolumeForce(); b.add_volume_force(); b.collision()
+            b.halfwayBCset(); b.streaming(); b.set_boundary_conditions()
+    compare_fluid(ob, gb, exact=exact)
+    gb.close()
+
+
+def test_les_with_plate(oracle, F):
+    """WALE with an immersed plate: the velocity differences must see the IBM-corrected velocity."""
+    from tests.common import make_pair, rel_err
+    flow = dict(nu=0.002, uvwIn=(0.05, 0.0, 0.0), Uref=0.05, ntolLBM=3, dtolLBM=1e-30)
+    ob, gb = make_pair(oracle, F, (28, 24, 20), BndConds=(101, 104, 301, 301, 301, 301), model=14, **flow)
+    pg, po, ovb = plates_pair(oracle, F, 1.0, origin=(9.3, 8.2, 5.4), nEL=6, Nspan=8)
+    for n in range(1, 13):
+        sync_oracle_body(ovb, po)
+        ob.set_blktime(float(n))
+        it_o = ob.step([ovb])
+        it_g = F.tree_collision_streaming_IBM_FEM(gb, [pg], time=float(n), solver=False)
+        assert it_o == it_g == 3
+        assert rel_err(pg.body.v_Eforce, ovb.v_Eforce) <= TOL_FORCE
+    compare_fluid(ob, gb, exact=False)
+    assert rel_err(gb.download_tau_all(), ob.tau_all) <= TOL_FLUID

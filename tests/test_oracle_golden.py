@@ -33,6 +33,9 @@ def test_c_oracle_reproduces_golden(oracle, name):
     assert np.array_equal(its, g["iters"])
     assert np.array_equal(blk.fIn, g["fIn"]), f"max |df| {np.abs(blk.fIn - g['fIn']).max():.3e}"
     assert np.array_equal(blk.den, g["den"]) and np.array_equal(blk.uuu, g["uuu"])
+    if "tau_all" in g.files:
+        assert np.array_equal(blk.tau_all, g["tau_all"])
+        assert g["tau_all"].max() > blk.tau * (1 + 1e-6)   # the closure really raised the relaxation time somewhere
     if bodies:
         assert np.array_equal(bodies[0].v_Ei, g["Ei"]) and np.array_equal(bodies[0].v_Ew, g["Ew"])
         assert np.array_equal(bodies[0].v_Eforce, g["Eforce"])
