@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfsilbm_b200.so")
-SOURCES = ["fluid_kernels.cu", "ibm_kernels.cu", "refine_kernels.cu", "fsilbm_api.cu"]
+SOURCES = ["fluid_kernels.cu", "ibm_kernels.cu", "refine_kernels.cu", "io_kernels.cu", "fsilbm_api.cu"]
 HEADERS = ["d3q19.cuh", "kernels.h", os.path.join("..", "..", "include", "fsilbm.h")]
 
 NVCC_FLAGS = [

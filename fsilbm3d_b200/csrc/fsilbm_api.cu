@@ -130,6 +130,9 @@ struct Block {
     bool hw_alloc[6]{};
     double *den = nullptr, *uuu = nullptr, *force = nullptr;   // un-fused fields / download staging
     double *tau_all = nullptr;                                 // [X][Y][Z], LES models only (FluidDomain.f90:1279,1422,1505)
+    double *uuu_ave = nullptr;                                 // [9][X][Y][Z], running means of calculate_turbulent_statistic_ (:1147)
+    float *outtmp = nullptr; size_t outtmp_cap = 0;            // OUTtmp staging of write_flow_ (:30,399-403)
+    double *scratch = nullptr; size_t scratch_cap = 0;         // probes / flux
     double *stat = nullptr;
     // IBM
     IbmBoxes boxes{};
@@ -551,6 +554,7 @@ int fsilbm_block_destroy(fsilbm_handle h)
     for (int i = 0; i < 2; i++) cudaFree(b->f[i]);
     for (int i = 0; i < 6; i++) { cudaFree(b->stash[i]); cudaFree(b->l2den[i]); cudaFree(b->l2u[i]); }
     cudaFree(b->den); cudaFree(b->uuu); cudaFree(b->force); cudaFree(b->stat); cudaFree(b->tau_all);
+    cudaFree(b->uuu_ave); cudaFree(b->outtmp); cudaFree(b->scratch);
     cudaFree(b->boxes.u); cudaFree(b->boxes.force);
     for (auto &bd : b->bodies) bd.release();
     cudaFree(b->bodies_dev); cudaFree(b->ctl);
@@ -829,6 +833,109 @@ int fsilbm_block_stream(fsilbm_handle h, void **stream)
     Block *b = get(h);
     if (!b || !stream) return fail(FSILBM_ERR_ARG, "bad handle/argument");
     *stream = (void *)b->stream;
+    return 0;
+}
+
+// ---- output / diagnostics computed on the device state ------------------------------------
+int fsilbm_block_write_flow_window(fsilbm_handle h, int offsetOutput, int outputtype, float *out)
+{
+    Block *b = get(h);
+    if (!b || !out) return fail(FSILBM_ERR_ARG, "bad handle/argument");
+    if (outputtype < 1) return 0;   // FluidDomain.f90:1639
+    const Geom &g = b->g;
+    // window in global x: [off, XG-off), intersected with the local slab
+    const int gx0 = std::max(offsetOutput, g.xOffset), gx1 = std::min(g.XG - offsetOutput, g.xOffset + g.X);
+    FlowWindowParams p{};
+    p.g = g; p.f = b->f[b->cur]; p.uuu_ave = b->uuu_ave;
+    p.x0 = gx0 - g.xOffset; p.off = offsetOutput;
+    p.nx = gx1 - gx0; p.ny = g.Y - 2 * offsetOutput; p.nz = g.Z - 2 * offsetOutput;
+    if (p.nx <= 0 || p.ny <= 0 || p.nz <= 0) return 0;
+    p.outputtype = outputtype;
+    if (outputtype >= 2 && !b->uuu_ave) return fail(FSILBM_ERR_ARG, "outputtype >= 2 needs fsilbm_block_turbulent_statistic to have run");
+    half_force(*b, p.hF);
+    p.denIn = b->flow.denIn; p.invUref = 1.0 / b->flow.Uref; p.invUrefs = 1.0 / b->flow.Uref / b->flow.Uref;   // :1650-1651
+    const int nfields = outputtype >= 2 ? 13 : 4;
+    const size_t n = (size_t)p.nx * p.ny * p.nz * nfields;
+    if (n > b->outtmp_cap) {
+        CK(cudaStreamSynchronize(b->stream));
+        cudaFree(b->outtmp);
+        CK(cudaMalloc(&b->outtmp, sizeof(float) * n));
+        b->outtmp_cap = n;
+    }
+    p.out = b->outtmp;
+    if (outputtype == 2) CK(cudaMemsetAsync(b->outtmp, 0, sizeof(float) * 4 * (n / nfields), b->stream));   // fields 0:3 are not refreshed (:1653)
+    launch_flow_window(p, b->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, b->outtmp, sizeof(float) * n, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int fsilbm_block_turbulent_statistic(fsilbm_handle h, int step, int step_s)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    if (step < step_s) return 0;   // :1152 (the outputtype >= 2 half of the test is the caller's)
+    const size_t n = (size_t)b->g.X * b->g.plane;
+    if (!b->uuu_ave) {
+        CK(cudaMalloc(&b->uuu_ave, sizeof(double) * 9 * n));
+        CK(cudaMemsetAsync(b->uuu_ave, 0, sizeof(double) * 9 * n, b->stream));
+    }
+    const float invStepF = 1 / (float)(step - step_s + 1);   // 'invStep = 1 / real(step - step_s + 1)': default real is real(4), :1153
+    double hF[3];
+    half_force(*b, hF);
+    launch_turbulent_statistic(b->g, b->f[b->cur], hF, b->uuu_ave, (double)invStepF, b->stream);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int ensure_scratch(Block &b, size_t n)
+{
+    if (n <= b.scratch_cap) return 0;
+    CK(cudaStreamSynchronize(b.stream));
+    cudaFree(b.scratch);
+    CK(cudaMalloc(&b.scratch, sizeof(double) * n));
+    b.scratch_cap = n;
+    return 0;
+}
+
+int fsilbm_block_fluid_flux(fsilbm_handle h, double out[3])
+{
+    Block *b = get(h);
+    if (!b || !out) return fail(FSILBM_ERR_ARG, "bad handle/argument");
+    const Geom &g = b->g;
+    const int gx[3] = {0, (g.XG + 1) / 2 - 1, g.XG - 1};   // x = 1, ixMid = (xDim+1)/2, xDim (1-based), :2032
+    int xl[3];
+    for (int k = 0; k < 3; k++) { xl[k] = gx[k] - g.xOffset; if (xl[k] < 0 || xl[k] >= g.X) xl[k] = -1; }
+    if (int rc = ensure_scratch(*b, 64)) return rc;
+    double hF[3];
+    half_force(*b, hF);
+    launch_fluid_flux(g, b->f[b->cur], hF, xl, b->scratch, b->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, b->scratch, sizeof(double) * 3, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int fsilbm_block_probe_velocity(fsilbm_handle h, int n, const double *coords, double *velocity)
+{
+    Block *b = get(h);
+    if (!b || n < 0 || (n > 0 && (!coords || !velocity))) return fail(FSILBM_ERR_ARG, "bad handle/argument");
+    if (n == 0) return 0;
+    const Geom &g = b->g;
+    const double mx[3] = {g.xmin + g.dh * (g.XG - 1), g.ymin + g.dh * (g.Y - 1), g.zmin + g.dh * (g.Z - 1)}, mn[3] = {g.xmin, g.ymin, g.zmin};
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++)
+            if (coords[3 * i + k] < mn[k] || coords[3 * i + k] > mx[k])
+                return fail(FSILBM_ERR_ARG, "fluid probe %d is not in selected block (FlowCondition.f90:212)", i + 1);
+    if (int rc = ensure_scratch(*b, (size_t)6 * n)) return rc;
+    CK(cudaMemcpyAsync(b->scratch, coords, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, b->stream));
+    double hF[3];
+    half_force(*b, hF);
+    launch_probe(g, b->f[b->cur], hF, n, b->scratch, b->scratch + 3 * n, b->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(velocity, b->scratch + 3 * n, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
     return 0;
 }
 

@@ -173,6 +173,22 @@ void launch_pair_extract(const PairFaceParams &p, int time, cudaStream_t s);
 void launch_pair_f2s(const PairFaceParams &p, int t, cudaStream_t s);
 void launch_pair_s2f(const PairFaceParams &p, cudaStream_t s);
 
+// ---- output / diagnostics on device state (io_kernels.cu) ---------------------------------------------------------
+struct FlowWindowParams {
+    Geom g;
+    const double *f;
+    const double *uuu_ave;    // [9][X][Y][Z], outputtype >= 2 only
+    float *out;               // [nfields][nx][ny][nz]
+    int x0, off;              // first local x plane of the window; offsetOutput (y and z windows start at `off`)
+    int nx, ny, nz;
+    int outputtype;
+    double hF[3], denIn, invUref, invUrefs;
+};
+void launch_flow_window(const FlowWindowParams &p, cudaStream_t s);
+void launch_turbulent_statistic(const Geom &g, const double *f, const double hF[3], double *ave, double invStep, cudaStream_t s);
+void launch_fluid_flux(const Geom &g, const double *f, const double hF[3], const int xl[3], double *out3, cudaStream_t s);
+void launch_probe(const Geom &g, const double *f, const double hF[3], int n, const double *coords, double *out, cudaStream_t s);
+
 long long kernel_launch_count();
 void count_launch(int n = 1);
 

@@ -118,6 +118,10 @@ class LBMBlock:
         check(lib().fsilbm_block_download_tau_all(self._h, t.ctypes.data))
         return t
 
+    def calculate_turbulent_statistic(self, step: int, step_s: int):
+        """calculate_turbulent_statistic_, FluidDomain.f90:1147-1172 (running means stay on the device)."""
+        check(lib().fsilbm_block_turbulent_statistic(self._h, step, step_s))
+
     def ComputeFieldStat(self) -> np.ndarray:
         """ComputeFieldStat_, FluidDomain.f90:1739 (single slab): L2 u,v,w then Linfinity u,v,w."""
         out = (C.c_double * 6)()

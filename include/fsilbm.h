@@ -109,6 +109,21 @@ int fsilbm_block_download_tau_all(fsilbm_handle h, double *tau_all);
  * u,v,w then max|u|/Uref for u,v,w (the caller finishes sqrt(sum/N) after reducing over ranks). */
 int fsilbm_block_field_stat(fsilbm_handle h, double out[6]);
 
+/* Output and diagnostics computed from the device state, so the host never needs full den/uuu arrays:
+ *  - write_flow_ staging (FluidDomain.f90:1640-1699): fills `out` = OUTtmp as real(4), C [nfields][nx][ny][nz] over the
+ *    window [offsetOutput, dim-offsetOutput) of the local slab; fields p,u,v,w (outputtype 1) or those + <u>,<v>,<w>,
+ *    <uu>,<vv>,<ww>,<uv>,<uw>,<vw> (13 fields, outputtype >= 2).  The caller writes the file header and these bytes
+ *    (and forks if it wants to: the buffer is plain host memory).
+ *  - calculate_turbulent_statistic_ (:1147-1172): running means kept on the device (real(4) 1/n quirk of :1153 kept).
+ *  - write_fluid_flux (:2019-2046): out = un-normalised fluxIn, fluxMid, fluxOut of the planes this rank owns
+ *    (sum over ranks, then divide by denIn*Uref*Zref*Yref as :2051-2054 does).
+ *  - write_fluid_information / grid_value_interpolation (FlowCondition.f90:195-222, Util.f90:123-157): trilinear
+ *    velocity at n probe points, C [n][3]; contributions of corners this rank owns (sum over ranks). */
+int fsilbm_block_write_flow_window(fsilbm_handle h, int offsetOutput, int outputtype, float *out);
+int fsilbm_block_turbulent_statistic(fsilbm_handle h, int step, int step_s);
+int fsilbm_block_fluid_flux(fsilbm_handle h, double out[3]);
+int fsilbm_block_probe_velocity(fsilbm_handle h, int n, const double *coords, double *velocity);
+
 /* set_boundary_conditions_ (FluidDomain.f90:616-1126) on the current fIn; the start-up call of
  * tree_set_boundary_conditions_block (main.f90:63).  Reproduces the first-call skip of the
  * half-way codes 203/204 (:660-661). */
