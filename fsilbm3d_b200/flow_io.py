@@ -102,7 +102,11 @@ def regrid_from_continue(block, saved) -> Optional[np.ndarray]:
     """The trilinear re-gridding of check_is_continue (FluidDomain.f90:166-224) for one current block: every node takes
     its populations from the finest saved block that contains it; nodes no saved block covers keep their value.
     Returns the new fIn (19,X,Y,Z) or None when nothing is covered."""
-    order = sorted(range(len(saved)), key=lambda i: saved[i]["dh"])           # sortdh, :153-165
+    order = list(range(len(saved)))                                            # sortdh, :153-165: as written there the swap
+    for i in range(len(saved) - 1):                                            # test compares the UNSORTED dh of slots i and j
+        for j in range(i + 1, len(saved)):
+            if saved[i]["dh"] > saved[j]["dh"]:
+                order[i], order[j] = order[j], order[i]
     f = np.array(block.download_fIn())
     X, Y, Z = block.xDim, block.yDim, block.zDim
     xC = block.xmin + np.arange(X) * block.dh
