@@ -142,6 +142,7 @@ struct Block {
     IbmBody *bodies_dev = nullptr;
     int bodies_dev_cap = 0;
     IbmCtl *ctl = nullptr;
+    unsigned int *ibm_barrier = nullptr;
     bool ibm_active = false;
     cudaStream_t stream = nullptr, comm_stream = nullptr;
     cudaEvent_t ev_edge = nullptr, ev_comm = nullptr;
@@ -170,6 +171,7 @@ struct Pair {
 std::vector<std::unique_ptr<Pair>> g_pairs;
 int g_variant = 0, g_force_ghost = 0;
 int g_halo_timeout_s = 120;   // a neighbour this late is treated as lost (the wait kernel gives up, fsilbm_block_sync reports it)
+int g_ibm_single_launch = 1;   // 1: calculate_interaction_force as one cooperative kernel on single-rank blocks; 0: one kernel per phase
 int g_halo_mode = 1;   // 1: edge kernels store into the neighbours' memory over NVLink (default); 0: ncclSend/ncclRecv
 
 Block *get(fsilbm_handle h)
@@ -482,6 +484,7 @@ int fsilbm_set_option(const char *key, int value)
     if (!key) return fail(FSILBM_ERR_ARG, "null key");
     if (!strcmp(key, "variant")) { if (value < 0 || value > 2) return fail(FSILBM_ERR_ARG, "variant must be 0..2"); g_variant = value; return 0; }
     if (!strcmp(key, "force_ghost")) { g_force_ghost = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "ibm_single_launch")) { g_ibm_single_launch = value ? 1 : 0; return 0; }
     if (!strcmp(key, "halo_timeout_s")) { if (value < 1) return fail(FSILBM_ERR_ARG, "halo_timeout_s must be >= 1"); g_halo_timeout_s = value; return 0; }
     if (!strcmp(key, "halo")) { if (value < 0 || value > 1) return fail(FSILBM_ERR_ARG, "halo must be 0 (NCCL) or 1 (peer stores)"); g_halo_mode = value; return 0; }
     return fail(FSILBM_ERR_ARG, "unknown option %s", key);
@@ -532,6 +535,8 @@ int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, d
     CK(cudaEventCreateWithFlags(&b->ev_edge, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_comm, cudaEventDisableTiming));
     CK(cudaMalloc(&b->ctl, sizeof(IbmCtl)));
+    CK(cudaMalloc(&b->ibm_barrier, sizeof(unsigned int)));
+    CK(cudaMemset(b->ibm_barrier, 0, sizeof(unsigned int)));
     CK(cudaMalloc(&b->stat, sizeof(double) * 6));
     if (g_nccl.nranks > 1 && g_nccl.comm && g_halo_mode == 1)
         if (int rc = halo_setup(*b)) return rc;
@@ -557,7 +562,7 @@ int fsilbm_block_destroy(fsilbm_handle h)
     cudaFree(b->uuu_ave); cudaFree(b->outtmp); cudaFree(b->scratch);
     cudaFree(b->boxes.u); cudaFree(b->boxes.force);
     for (auto &bd : b->bodies) bd.release();
-    cudaFree(b->bodies_dev); cudaFree(b->ctl);
+    cudaFree(b->bodies_dev); cudaFree(b->ctl); cudaFree(b->ibm_barrier);
     cudaEventDestroy(b->ev_edge); cudaEventDestroy(b->ev_comm);
     cudaStreamDestroy(b->comm_stream);
     g_blocks[h].reset();
@@ -1210,7 +1215,7 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         CK(cudaMemsetAsync(bd.Eforce, 0, sizeof(double) * 3 * n, s));   // Solidbody.f90:889
     }
     IbmCtl ctl0;
-    ctl0.iter = 0; ctl0.done = (ntolLBM <= 0) ? 1 : 0; ctl0.err = 0; ctl0.dmax = 1e10;   // :893-894
+    ctl0.iter = 0; ctl0.done = (ntolLBM <= 0) ? 1 : 0; ctl0.err = 0; ctl0.dmax = 1e10; ctl0.tol_acc = 0.0;   // :893-894
     CK(cudaMemcpyAsync(b.ctl, &ctl0, sizeof(IbmCtl), cudaMemcpyHostToDevice, s));
     if (b.bodies_dev_cap < nbody) {
         cudaFree(b.bodies_dev);
@@ -1221,32 +1226,70 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
     for (int ib = 0; ib < nbody; ib++) views[ib] = b.bodies[ib].view();
     CK(cudaMemcpyAsync(b.bodies_dev, views.data(), sizeof(IbmBody) * nbody, cudaMemcpyHostToDevice, s));
 
-    // -- UpdateElmtInterp_ (:883-888); the box-relative offsets are rebuilt every call because the boxes move with the bodies
-    for (int ib = 0; ib < nbody; ib++) launch_ibm_stencil(g, views[ib], bx, rootBC, b.ctl, s);
-
-    // -- calculate_macro_quantities + ResetVolumeForce restricted to the boxes (LBMBlockComm.f90:285-286)
     double hF[3];
     half_force(b, hF);
-    launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
-
-    // -- penalty iteration (:895-906); launches beyond convergence return at once on the device flag
     const double invh3_pen = 0.5 * dt * ((1.0 / g.dh) * (1.0 / g.dh) * (1.0 / g.dh)) / b.flow.denIn;   // :996
-    for (int it = 0; it < ntolLBM; it++) {
+    const double invh3 = (1.0 / g.dh) * (1.0 / g.dh) * (1.0 / g.dh);                                     // :936
+    bool single = !multi && g_ibm_single_launch && nbody <= MAX_IBM_PHASE_BODIES;
+    if (single) {
+        // one cooperative launch for UpdateElmtInterp_, the box macro, the whole penalty iteration and the force spreading
+        IbmLoopParams lp{};
+        lp.g = g; lp.bodies = b.bodies_dev; lp.nbody = nbody; lp.boxes = bx;
+        for (int k = 0; k < 6; k++) lp.rootBC[k] = rootBC[k];
+        lp.ctl = b.ctl; lp.fA = b.f[b.cur];
+        for (int k = 0; k < 3; k++) lp.hF[k] = hF[k];
+        lp.ntol = ntolLBM; lp.dtol = dtolLBM; lp.Uref = b.flow.Uref;
+        lp.dsum = 0.0;
+        for (int ib = 0; ib < nbody; ib++) lp.dsum = lp.dsum + (double)nelmts[ib];   // :902
+        lp.invh3_pen = invh3_pen; lp.invh3 = invh3; lp.barrier = b.ibm_barrier;
+        // phases: the k-th body (in body order) of every box group; a body's group is the merged box holding its first marker's cell
+        std::vector<int> group(nbody, 0);
         for (int ib = 0; ib < nbody; ib++) {
-            if (!multi) {
-                launch_ibm_gather(views[ib], bx, b.bodies[ib].partialU, b.ctl, 1, invh3_pen, s);
-            } else {
-                launch_ibm_gather(views[ib], bx, b.bodies[ib].partialU, b.ctl, 0, invh3_pen, s);
-                NCK(g_nccl.AllReduce(b.bodies[ib].partialU, b.bodies[ib].partialU, 3 * (size_t)views[ib].n, kNcclFloat64, kNcclSum, g_nccl.comm, s));
-                launch_ibm_force(views[ib], b.bodies[ib].partialU, invh3_pen, b.ctl, s);
+            const double *P = stencil_pos[ib].data();
+            int cidx[3];
+            for (int a = 0; a < 3; a++) cidx[a] = imod((int)floor((P[a] - mins[a]) * invdh), Ns[a]);
+            for (int k = 0; k < bx.n; k++) {
+                bool in = true;
+                for (int a = 0; a < 3; a++) in = in && imod(cidx[a] - bx.lo[k][a], Ns[a]) < bx.ext[k][a];
+                if (in) { group[ib] = k; break; }
             }
-            launch_ibm_scatter(views[ib], bx, b.ctl, s);
         }
-        launch_ibm_check(b.bodies_dev, nbody, b.flow.Uref, ntolLBM, dtolLBM, b.ctl, s);
+        std::vector<int> rank_in_group(nbody, 0), seen(bx.n > 0 ? bx.n : 1, 0);
+        int nphase = 0;
+        for (int ib = 0; ib < nbody; ib++) { rank_in_group[ib] = seen[group[ib]]++; nphase = std::max(nphase, rank_in_group[ib] + 1); }
+        lp.nphase = nphase;
+        int pos = 0, max_markers = 0;
+        for (int ph = 0; ph < nphase; ph++) {
+            lp.phase_start[ph] = pos;
+            int markers = 0;
+            for (int ib = 0; ib < nbody; ib++) if (rank_in_group[ib] == ph) { lp.phase_body[pos++] = ib; markers += nelmts[ib]; }
+            max_markers = std::max(max_markers, markers);
+        }
+        lp.phase_start[nphase] = pos;
+        if (launch_ibm_loop(lp, max_markers, s)) { cudaGetLastError(); single = false; }   // no cooperative launch: take the phase-by-phase path
     }
-    // -- FluidVolumeForce_, Eulerian half (:968-976)
-    const double invh3 = (1.0 / g.dh) * (1.0 / g.dh) * (1.0 / g.dh);   // :936
-    for (int ib = 0; ib < nbody; ib++) launch_ibm_spread(views[ib], bx, invh3, s);
+    if (!single) {
+        // -- UpdateElmtInterp_ (:883-888); the box-relative offsets are rebuilt every call because the boxes move with the bodies
+        for (int ib = 0; ib < nbody; ib++) launch_ibm_stencil(g, views[ib], bx, rootBC, b.ctl, s);
+        // -- calculate_macro_quantities + ResetVolumeForce restricted to the boxes (LBMBlockComm.f90:285-286)
+        launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
+        // -- penalty iteration (:895-906); launches beyond convergence return at once on the device flag
+        for (int it = 0; it < ntolLBM; it++) {
+            for (int ib = 0; ib < nbody; ib++) {
+                if (!multi) {
+                    launch_ibm_gather(views[ib], bx, b.bodies[ib].partialU, b.ctl, 1, invh3_pen, s);
+                } else {
+                    launch_ibm_gather(views[ib], bx, b.bodies[ib].partialU, b.ctl, 0, invh3_pen, s);
+                    NCK(g_nccl.AllReduce(b.bodies[ib].partialU, b.bodies[ib].partialU, 3 * (size_t)views[ib].n, kNcclFloat64, kNcclSum, g_nccl.comm, s));
+                    launch_ibm_force(views[ib], b.bodies[ib].partialU, invh3_pen, b.ctl, s);
+                }
+                launch_ibm_scatter(views[ib], bx, b.ctl, s);
+            }
+            launch_ibm_check(b.bodies_dev, nbody, b.flow.Uref, ntolLBM, dtolLBM, b.ctl, s);
+        }
+        // -- FluidVolumeForce_, Eulerian half (:968-976)
+        for (int ib = 0; ib < nbody; ib++) launch_ibm_spread(views[ib], bx, invh3, s);
+    }
     CK(cudaGetLastError());
 
     // -- results to the host

@@ -44,11 +44,9 @@ __device__ __forceinline__ bool trimedindex(int i_, int xDim_, int (&ix_)[4], in
 
 struct RootBC { int c[6]; };
 
-// UpdateElmtInterp_, Solidbody.f90:760-806
-__global__ void ibm_stencil_kernel(Geom g, IbmBody b, const __grid_constant__ IbmBoxes boxes, RootBC bc, IbmCtl *ctl)
+// UpdateElmtInterp_, Solidbody.f90:760-806, one marker
+__device__ __forceinline__ void stencil_marker(const Geom &g, const IbmBody &b, const IbmBoxes &boxes, const RootBC &bc, IbmCtl *ctl, int iEL)
 {
-    const int iEL = blockIdx.x * blockDim.x + threadIdx.x;
-    if (iEL >= b.n) return;
     const double dh = g.dh;
     const double invdh = 1.0 / dh;
     // anchor on the body's first marker, :772-780
@@ -115,6 +113,13 @@ __global__ void ibm_stencil_kernel(Geom g, IbmBody b, const __grid_constant__ Ib
     }
 }
 
+__global__ void ibm_stencil_kernel(Geom g, IbmBody b, const __grid_constant__ IbmBoxes boxes, RootBC bc, IbmCtl *ctl)
+{
+    const int iEL = blockIdx.x * blockDim.x + threadIdx.x;
+    if (iEL >= b.n) return;
+    stencil_marker(g, b, boxes, bc, ctl, iEL);
+}
+
 void launch_ibm_stencil(const Geom &g, const IbmBody &b, const IbmBoxes &boxes, const int rootBC[6], IbmCtl *ctl, cudaStream_t s)
 {
     RootBC bc;
@@ -124,10 +129,8 @@ void launch_ibm_stencil(const Geom &g, const IbmBody &b, const IbmBoxes &boxes, 
 }
 
 // calculate_macro_quantities_ (FluidDomain.f90:1136-1139) on the box cells + ResetVolumeForce_ (:1201-1203)
-__global__ void ibm_macro_box_kernel(Geom g, const double *fA, double hF1, double hF2, double hF3, const __grid_constant__ IbmBoxes boxes)
+__device__ __forceinline__ void macro_box_cell(const Geom &g, const double *fA, double hF1, double hF2, double hF3, const IbmBoxes &boxes, long long i)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= boxes.ncell) return;
     int bb = 0;
     while (bb + 1 < boxes.n && i >= boxes.off[bb + 1]) bb++;
     const long long r = i - boxes.off[bb];
@@ -147,6 +150,13 @@ __global__ void ibm_macro_box_kernel(Geom g, const double *fA, double hF1, doubl
     }
     boxes.u[i] = u1; boxes.u[boxes.ncell + i] = u2; boxes.u[2 * boxes.ncell + i] = u3;
     boxes.force[i] = 0.0; boxes.force[boxes.ncell + i] = 0.0; boxes.force[2 * boxes.ncell + i] = 0.0;
+}
+
+__global__ void ibm_macro_box_kernel(Geom g, const double *fA, double hF1, double hF2, double hF3, const __grid_constant__ IbmBoxes boxes)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= boxes.ncell) return;
+    macro_box_cell(g, fA, hF1, hF2, hF3, boxes, i);
 }
 
 void launch_ibm_macro_box(const Geom &g, const double *fA, const double hF[3], const IbmBoxes &boxes, cudaStream_t s)
@@ -174,14 +184,11 @@ __device__ __forceinline__ void marker_force(const IbmBody &b, int iEL, double U
 // PenaltyForce_ interpolation, Solidbody.f90:1000-1015: one warp per marker.
 // fused != 0 (single rank): lane 0 also finishes the marker (:1016-1025); otherwise the partial
 // velocity over the locally owned stencil planes goes to partialU for the all-reduce.
-__global__ void ibm_gather_kernel(IbmBody b, const __grid_constant__ IbmBoxes boxes, double *partialU, const IbmCtl *ctl, int fused, double invh3)
+// the 64-node gather of one marker by one warp; the sums are valid in lane 0
+__device__ __forceinline__ void gather_marker(const IbmBody &b, const IbmBoxes &boxes, int iEL, int lane, double &s1, double &s2, double &s3)
 {
-    if (ctl->done) return;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= b.n) return;
-    const int iEL = warp;
     const long long boff = b.boff[iEL];
-    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    s1 = 0.0; s2 = 0.0; s3 = 0.0;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int pnt = lane + 32 * h;
@@ -200,6 +207,16 @@ __global__ void ibm_gather_kernel(IbmBody b, const __grid_constant__ IbmBoxes bo
         s2 += __shfl_down_sync(0xffffffffu, s2, off);
         s3 += __shfl_down_sync(0xffffffffu, s3, off);
     }
+}
+
+__global__ void ibm_gather_kernel(IbmBody b, const __grid_constant__ IbmBoxes boxes, double *partialU, const IbmCtl *ctl, int fused, double invh3)
+{
+    if (ctl->done) return;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= b.n) return;
+    const int iEL = warp;
+    double s1, s2, s3;
+    gather_marker(b, boxes, iEL, lane, s1, s2, s3);
     if (lane == 0) {
         if (fused) marker_force(b, iEL, s1, s2, s3, invh3);
         else { partialU[3 * iEL + 0] = s1; partialU[3 * iEL + 1] = s2; partialU[3 * iEL + 2] = s3; }
@@ -228,12 +245,8 @@ void launch_ibm_force(const IbmBody &b, const double *sumU, double invh3, IbmCtl
 }
 
 // PenaltyForce_ velocity correction, Solidbody.f90:1034-1048: uuu -= forceElemTemp*rx*ry*rz
-__global__ void ibm_scatter_kernel(IbmBody b, const __grid_constant__ IbmBoxes boxes, const IbmCtl *ctl)
+__device__ __forceinline__ void scatter_marker(const IbmBody &b, const IbmBoxes &boxes, int iEL, int lane)
 {
-    if (ctl->done) return;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= b.n) return;
-    const int iEL = warp;
     const long long boff = b.boff[iEL];
     const double f1 = b.felt[3 * iEL + 0], f2 = b.felt[3 * iEL + 1], f3 = b.felt[3 * iEL + 2];
 #pragma unroll
@@ -247,6 +260,14 @@ __global__ void ibm_scatter_kernel(IbmBody b, const __grid_constant__ IbmBoxes b
         atomicAdd(&boxes.u[boxes.ncell + idx], -(f2 * rx * ry * rz));
         atomicAdd(&boxes.u[2 * boxes.ncell + idx], -(f3 * rx * ry * rz));
     }
+}
+
+__global__ void ibm_scatter_kernel(IbmBody b, const __grid_constant__ IbmBoxes boxes, const IbmCtl *ctl)
+{
+    if (ctl->done) return;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= b.n) return;
+    scatter_marker(b, boxes, warp, lane);
 }
 
 void launch_ibm_scatter(const IbmBody &b, const IbmBoxes &boxes, const IbmCtl *ctl, cudaStream_t s)
@@ -293,11 +314,8 @@ void launch_ibm_check(const IbmBody *bodies_dev, int nbody, double Uref, int nto
 }
 
 // Eulerian half of FluidVolumeForce_, Solidbody.f90:968-976: force += -(v_Eforce*invh3)*rx*ry*rz
-__global__ void ibm_spread_kernel(IbmBody b, const __grid_constant__ IbmBoxes boxes, double invh3)
+__device__ __forceinline__ void spread_marker(const IbmBody &b, const IbmBoxes &boxes, double invh3, int iEL, int lane)
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= b.n) return;
-    const int iEL = warp;
     const long long boff = b.boff[iEL];
     const double f1 = b.Eforce[3 * iEL + 0] * invh3, f2 = b.Eforce[3 * iEL + 1] * invh3, f3 = b.Eforce[3 * iEL + 2] * invh3;
 #pragma unroll
@@ -313,11 +331,123 @@ __global__ void ibm_spread_kernel(IbmBody b, const __grid_constant__ IbmBoxes bo
     }
 }
 
+__global__ void ibm_spread_kernel(IbmBody b, const __grid_constant__ IbmBoxes boxes, double invh3)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= b.n) return;
+    spread_marker(b, boxes, invh3, warp, lane);
+}
+
 void launch_ibm_spread(const IbmBody &b, const IbmBoxes &boxes, double invh3, cudaStream_t s)
 {
     const int threads = 128, warps_per_block = threads / 32;
     ibm_spread_kernel<<<(b.n + warps_per_block - 1) / warps_per_block, threads, 0, s>>>(b, boxes, invh3);
     count_launch();
+}
+
+
+// ---- the whole of calculate_interaction_force in ONE cooperative launch (single-rank blocks) -----------------------
+// Phases are separated by grid-wide barriers instead of kernel boundaries: stencils + box macro | per iteration and per
+// body group: gather+force | velocity correction | loop control | ... | force spreading.  Bodies whose stencil boxes
+// are disjoint cannot see each other's correction, so each phase processes one body of every box group at once; bodies
+// that share a box keep the reference's sequential (Gauss-Seidel) order, Solidbody.f90:898-903.
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &epoch)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (*((volatile unsigned int *)bar) < epoch) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) ibm_loop_kernel(const __grid_constant__ IbmLoopParams p)
+{
+    unsigned int epoch = 0;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthread = (long long)gridDim.x * blockDim.x;
+    RootBC bc;
+    for (int i = 0; i < 6; i++) bc.c[i] = p.rootBC[i];
+    // phase 0: UpdateElmtInterp_ for every marker, calculate_macro_quantities + ResetVolumeForce on the box cells
+    for (int ib = 0; ib < p.nbody; ib++) {
+        const IbmBody b = p.bodies[ib];
+        for (long long i = gthread; i < b.n; i += nthread) stencil_marker(p.g, b, p.boxes, bc, p.ctl, (int)i);
+    }
+    for (long long i = gthread; i < p.boxes.ncell; i += nthread) macro_box_cell(p.g, p.fA, p.hF[0], p.hF[1], p.hF[2], p.boxes, i);
+    grid_barrier(p.barrier, epoch);
+    __shared__ double sh_tol[8];
+    for (int it = 0; it < p.ntol; it++) {
+        if (((volatile IbmCtl *)p.ctl)->done) break;   // uniform: written before the last barrier
+        for (int ph = 0; ph < p.nphase; ph++) {
+            // PenaltyForce_ first loop (Solidbody.f90:1000-1027) for the ph-th body of every group
+            double tol = 0.0;
+            for (int k = p.phase_start[ph]; k < p.phase_start[ph + 1]; k++) {
+                const IbmBody b = p.bodies[p.phase_body[k]];
+                for (int m = gwarp; m < b.n; m += nwarp) {
+                    double s1, s2, s3;
+                    gather_marker(b, p.boxes, m, lane, s1, s2, s3);
+                    if (lane == 0) { marker_force(b, m, s1, s2, s3, p.invh3_pen); tol += b.tol[m]; }
+                }
+            }
+            if (lane == 0) sh_tol[threadIdx.x >> 5] = tol;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double t = 0.0;
+                for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh_tol[w];
+                if (t != 0.0 || !(t == t)) atomicAdd(&p.ctl->tol_acc, t);
+            }
+            grid_barrier(p.barrier, epoch);
+            // velocity correction (:1034-1048)
+            for (int k = p.phase_start[ph]; k < p.phase_start[ph + 1]; k++) {
+                const IbmBody b = p.bodies[p.phase_body[k]];
+                for (int m = gwarp; m < b.n; m += nwarp) scatter_marker(b, p.boxes, m, lane);
+            }
+            grid_barrier(p.barrier, epoch);
+        }
+        if (gthread == 0) {   // loop control, :895-906
+            IbmCtl *c = p.ctl;
+            double dmax = c->tol_acc;
+            if (!isfinite(dmax)) atomicOr(&c->err, 2);   // :1028-1031
+            dmax = dmax / (p.dsum * p.Uref);
+            c->iter = c->iter + 1;
+            c->dmax = dmax;
+            c->tol_acc = 0.0;
+            c->done = !(c->iter < p.ntol && dmax > p.dtol);
+            __threadfence();
+        }
+        grid_barrier(p.barrier, epoch);
+    }
+    // FluidVolumeForce_, Eulerian half (:968-976)
+    for (int ib = 0; ib < p.nbody; ib++) {
+        const IbmBody b = p.bodies[ib];
+        for (int m = gwarp; m < b.n; m += nwarp) spread_marker(b, p.boxes, p.invh3, m, lane);
+    }
+}
+
+int launch_ibm_loop(const IbmLoopParams &p, int max_markers, cudaStream_t s)
+{
+    static int max_blocks = 0;
+    if (!max_blocks) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ibm_loop_kernel, 256, 0);
+        max_blocks = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    int want = (max_markers + 7) / 8;           // one warp per marker of the largest phase
+    const long long cells = (p.boxes.ncell + 255) / 256;
+    if (cells > want) want = (int)(cells > max_blocks ? max_blocks : cells);
+    int blocks = want < 1 ? 1 : (want > max_blocks ? max_blocks : want);
+    if (cudaMemsetAsync(p.barrier, 0, sizeof(unsigned int), s) != cudaSuccess) return 1;   // the barrier counts up from zero in every launch
+    void *args[] = {(void *)&p};
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)ibm_loop_kernel, dim3(blocks), dim3(256), args, 0, s);
+    if (e != cudaSuccess) return 1;
+    count_launch();
+    return 0;
 }
 
 }  // namespace fsilbm

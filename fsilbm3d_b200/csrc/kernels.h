@@ -139,7 +139,28 @@ struct IbmCtl {               // device-resident control block of the penalty it
     int done;                 // loop condition false
     int err;                  // bit 0: stencil out of domain (:850,861); bit 1: NaN (:1028); bit 2: stencil outside box
     double dmax;              // dmaxLBM
+    double tol_acc;           // running sum of the markers' |dU| of the current iteration (single-launch path)
 };
+
+constexpr int MAX_IBM_PHASE_BODIES = 64;
+struct IbmLoopParams {        // the single-launch form of calculate_interaction_force (ibm_loop_kernel)
+    Geom g;
+    const IbmBody *bodies;    // device array [nbody]
+    int nbody;
+    IbmBoxes boxes;
+    int rootBC[6];
+    IbmCtl *ctl;
+    const double *fA;
+    double hF[3];
+    int ntol;
+    double dtol, Uref, dsum;  // dsum = total marker count (:902)
+    double invh3_pen, invh3;  // 0.5*dt/dh^3/denIn (:996) and 1/dh^3 (:936)
+    int nphase;               // bodies sharing a stencil box are taken one per phase, in body order
+    int phase_start[MAX_IBM_PHASE_BODIES + 1];
+    int phase_body[MAX_IBM_PHASE_BODIES];
+    unsigned int *barrier;    // grid barrier counter (zero between launches)
+};
+int launch_ibm_loop(const IbmLoopParams &p, int max_markers, cudaStream_t s);
 
 void launch_ibm_stencil(const Geom &g, const IbmBody &b, const IbmBoxes &boxes, const int rootBC[6], IbmCtl *ctl, cudaStream_t s);
 void launch_ibm_macro_box(const Geom &g, const double *fA, const double hF[3], const IbmBoxes &boxes, cudaStream_t s);

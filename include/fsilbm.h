@@ -65,6 +65,8 @@ long long fsilbm_launch_count(void);
 /* Tuning/testing switches, no reference counterpart.  key "variant": 0 push kernel (default),
  * 1 push with streaming stores, 2 pull (fully periodic blocks only; kernel sweep);
  * key "force_ghost": 1 = stream through the ghost planes even on one rank (tests the slab path);
+ * key "ibm_single_launch": 1 (default) the whole of calculate_interaction_force is one cooperative kernel on single-rank
+ * blocks, 0 one kernel per phase (the multi-rank path, which needs an all-reduce between gather and force);
  * key "halo": 1 (default) peer-memory halo over NVLink, 0 ncclSend/ncclRecv (see fsilbm_block_halo_transport);
  * key "halo_timeout_s": how long a rank waits for a neighbour's halo before fsilbm_block_sync reports
  * FSILBM_ERR_COMM (default 120). */
