@@ -323,7 +323,8 @@ def run_gpu(args):
             "config": {"workload": args.workload, "desc": wl["desc"], "grid_per_gpu": [Xl, Y, Z], "grid_global": [XG, Y, Z],
                        "decomposition": f"x-slabs x{world}" if world > 1 else "single block",
                        "l2": "working set 5.1 GB per GPU (two population buffers) >> 126 MB L2; no explicit flush needed",
-                       "kernel_variant": args.variant, "halo_transport": transport},
+                       "kernel_variant": args.variant, "halo_transport": transport,
+                       "ibm": ("ordered per-cell gather (bit-identical to the serial reference)" if args.ibm_ordered else "fp64 atomics") if wl["plate"] else None},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -343,6 +344,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flow-every", type=int, default=200, help="e2e leg: read den,uuu back to the host every this many steps")
     ap.add_argument("--halo", type=int, default=1, choices=[0, 1], help="multi-GPU halo transport: 1 peer stores over NVLink, 0 NCCL send/recv")
+    ap.add_argument("--ibm-ordered", type=int, default=1, choices=[0, 1],
+                    help="IBM spreading: 1 ordered per-cell gather (bit-identical to the serial reference), 0 fp64 atomics")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -353,6 +356,7 @@ def main():
     if args.variant:
         F._lib.check(F.lib().fsilbm_set_option(b"variant", args.variant))
     F._lib.check(F.lib().fsilbm_set_option(b"halo", args.halo))
+    F._lib.check(F.lib().fsilbm_set_option(b"ibm_ordered", args.ibm_ordered))
     run_gpu(args)
 
 

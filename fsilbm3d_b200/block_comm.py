@@ -227,6 +227,9 @@ def tree_collision_streaming_IBM_FEM(node, plates: Sequence = (), time: Optional
         for p in plates:
             p.UpdatePosVelArea()                                            # Solidbody.f90:597-600
         it = block.calculate_interaction_force([p.body for p in plates], rootBC)   # :601
+        for p in plates:                                                        # host half of FluidVolumeForce_ (Solidbody.f90:911,945-967)
+            if hasattr(p, "FluidVolumeForce"):
+                p.FluidVolumeForce()
         if solver:
             nsub = block.flow.numsubstep
             dt_solid = block.dh / float(nsub)

@@ -144,6 +144,11 @@ struct Block {
     IbmCtl *ctl = nullptr;
     unsigned int *ibm_barrier = nullptr;
     bool ibm_active = false;
+    IbmCsr csr{};                                              // cell-centric stencil lists of the ordered IBM mode
+    long long csr_cell_cap = 0, csr_entry_cap = 0;
+    void *csr_scan_tmp = nullptr; size_t csr_scan_bytes = 0;
+    bool csr_valid = false;
+    double *tol_partial = nullptr;
     cudaStream_t stream = nullptr, comm_stream = nullptr;
     cudaEvent_t ev_edge = nullptr, ev_comm = nullptr;
     // peer-memory halo (multi-GPU): see halo_setup
@@ -172,6 +177,7 @@ std::vector<std::unique_ptr<Pair>> g_pairs;
 int g_variant = 0, g_force_ghost = 0;
 int g_halo_timeout_s = 120;   // a neighbour this late is treated as lost (the wait kernel gives up, fsilbm_block_sync reports it)
 int g_ibm_single_launch = 1;   // 1: calculate_interaction_force as one cooperative kernel on single-rank blocks; 0: one kernel per phase
+int g_ibm_ordered = 1;         // 1: interpolation and spreading keep the reference's serial summation order (bit-reproducible); 0: shuffles + fp64 atomics
 int g_halo_mode = 1;   // 1: edge kernels store into the neighbours' memory over NVLink (default); 0: ncclSend/ncclRecv
 
 Block *get(fsilbm_handle h)
@@ -485,6 +491,7 @@ int fsilbm_set_option(const char *key, int value)
     if (!strcmp(key, "variant")) { if (value < 0 || value > 2) return fail(FSILBM_ERR_ARG, "variant must be 0..2"); g_variant = value; return 0; }
     if (!strcmp(key, "force_ghost")) { g_force_ghost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_single_launch")) { g_ibm_single_launch = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "ibm_ordered")) { g_ibm_ordered = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->csr_valid = false; return 0; }
     if (!strcmp(key, "halo_timeout_s")) { if (value < 1) return fail(FSILBM_ERR_ARG, "halo_timeout_s must be >= 1"); g_halo_timeout_s = value; return 0; }
     if (!strcmp(key, "halo")) { if (value < 0 || value > 1) return fail(FSILBM_ERR_ARG, "halo must be 0 (NCCL) or 1 (peer stores)"); g_halo_mode = value; return 0; }
     return fail(FSILBM_ERR_ARG, "unknown option %s", key);
@@ -563,6 +570,7 @@ int fsilbm_block_destroy(fsilbm_handle h)
     cudaFree(b->boxes.u); cudaFree(b->boxes.force);
     for (auto &bd : b->bodies) bd.release();
     cudaFree(b->bodies_dev); cudaFree(b->ctl); cudaFree(b->ibm_barrier);
+    cudaFree(b->csr.count); cudaFree(b->csr.off); cudaFree(b->csr.entry); cudaFree(b->csr_scan_tmp); cudaFree(b->tol_partial);
     cudaEventDestroy(b->ev_edge); cudaEventDestroy(b->ev_comm);
     cudaStreamDestroy(b->comm_stream);
     g_blocks[h].reset();
@@ -1111,6 +1119,7 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
     if ((int)b.bodies.size() != nbody) {
         for (auto &bd : b.bodies) bd.release();
         b.bodies.assign(nbody, BodyDev());
+        b.csr_valid = false;
     }
     for (int ib = 0; ib < nbody; ib++) {
         BodyDev &bd = b.bodies[ib];
@@ -1118,6 +1127,7 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         if (n < 1) return fail(FSILBM_ERR_ARG, "body %d has no markers", ib);
         if (bd.n != n) {
             bd.release();
+            b.csr_valid = false;
             bd.n = n;
             CK(cudaMalloc(&bd.Exyz, sizeof(double) * 3 * n)); CK(cudaMalloc(&bd.ExyzStencil, sizeof(double) * 3 * n));
             CK(cudaMalloc(&bd.Evel, sizeof(double) * 3 * n)); CK(cudaMalloc(&bd.Ea, sizeof(double) * n));
@@ -1140,7 +1150,7 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         const int n = nelmts[ib];
         BodyDev &bd = b.bodies[ib];
         const bool re = restencil[ib] != 0 || !bd.have_stencil_pos;
-        if (re) stencil_pos[ib].assign(Exyz[ib], Exyz[ib] + 3 * (size_t)n);
+        if (re) { stencil_pos[ib].assign(Exyz[ib], Exyz[ib] + 3 * (size_t)n); b.csr_valid = false; }
         const double *P = stencil_pos[ib].data();
         HostBox box;
         for (int a = 0; a < 3; a++) {
@@ -1231,6 +1241,36 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
     const double invh3_pen = 0.5 * dt * ((1.0 / g.dh) * (1.0 / g.dh) * (1.0 / g.dh)) / b.flow.denIn;   // :996
     const double invh3 = (1.0 / g.dh) * (1.0 / g.dh) * (1.0 / g.dh);                                     // :936
     bool single = !multi && g_ibm_single_launch && nbody <= MAX_IBM_PHASE_BODIES;
+    const bool ordered = g_ibm_ordered != 0;
+    if (ordered) {
+        // stencils first (the cell lists are built from them), then the lists; both survive while no body restencils
+        long long entries = 0;
+        for (int ib = 0; ib < nbody; ib++) entries += (long long)nelmts[ib] * 64;
+        if (bx.ncell + 1 > b.csr_cell_cap) {
+            CK(cudaStreamSynchronize(s));
+            cudaFree(b.csr.count); cudaFree(b.csr.off); cudaFree(b.csr_scan_tmp);
+            const long long cap = bx.ncell + bx.ncell / 4 + 1024;
+            CK(cudaMalloc(&b.csr.count, sizeof(int) * (size_t)cap));
+            CK(cudaMalloc(&b.csr.off, sizeof(int) * (size_t)cap));
+            b.csr_scan_bytes = ibm_csr_scan_bytes(cap);
+            CK(cudaMalloc(&b.csr_scan_tmp, b.csr_scan_bytes ? b.csr_scan_bytes : 1));
+            b.csr_cell_cap = cap;
+            b.csr_valid = false;
+        }
+        if (entries > b.csr_entry_cap) {
+            CK(cudaStreamSynchronize(s));
+            cudaFree(b.csr.entry);
+            CK(cudaMalloc(&b.csr.entry, sizeof(unsigned long long) * (size_t)entries));
+            b.csr_entry_cap = entries;
+            b.csr_valid = false;
+        }
+        if (!b.tol_partial) CK(cudaMalloc(&b.tol_partial, sizeof(double) * (size_t)ibm_loop_max_blocks()));
+        if (!b.csr_valid) {
+            for (int ib = 0; ib < nbody; ib++) launch_ibm_stencil(g, views[ib], bx, rootBC, b.ctl, s);
+            if (launch_ibm_csr_build(views.data(), nbody, bx, b.csr, b.csr_scan_tmp, b.csr_scan_bytes, s)) return fail(FSILBM_ERR_CUDA, "IBM cell-list build failed");
+            b.csr_valid = true;
+        }
+    }
     if (single) {
         // one cooperative launch for UpdateElmtInterp_, the box macro, the whole penalty iteration and the force spreading
         IbmLoopParams lp{};
@@ -1242,6 +1282,7 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         lp.dsum = 0.0;
         for (int ib = 0; ib < nbody; ib++) lp.dsum = lp.dsum + (double)nelmts[ib];   // :902
         lp.invh3_pen = invh3_pen; lp.invh3 = invh3; lp.barrier = b.ibm_barrier;
+        lp.ordered = ordered ? 1 : 0; lp.do_stencil = ordered ? 0 : 1; lp.csr = b.csr; lp.tol_partial = b.tol_partial;
         // phases: the k-th body (in body order) of every box group; a body's group is the merged box holding its first marker's cell
         std::vector<int> group(nbody, 0);
         for (int ib = 0; ib < nbody; ib++) {
@@ -1266,29 +1307,34 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
             max_markers = std::max(max_markers, markers);
         }
         lp.phase_start[nphase] = pos;
+        for (int ib = 0; ib < nbody; ib++) lp.phase_of_body[ib] = rank_in_group[ib];
         if (launch_ibm_loop(lp, max_markers, s)) { cudaGetLastError(); single = false; }   // no cooperative launch: take the phase-by-phase path
     }
     if (!single) {
-        // -- UpdateElmtInterp_ (:883-888); the box-relative offsets are rebuilt every call because the boxes move with the bodies
-        for (int ib = 0; ib < nbody; ib++) launch_ibm_stencil(g, views[ib], bx, rootBC, b.ctl, s);
+        // -- UpdateElmtInterp_ (:883-888); the box-relative offsets are rebuilt every call because the boxes move with the
+        //    bodies (the ordered mode did it above, together with its cell lists)
+        if (!ordered) for (int ib = 0; ib < nbody; ib++) launch_ibm_stencil(g, views[ib], bx, rootBC, b.ctl, s);
         // -- calculate_macro_quantities + ResetVolumeForce restricted to the boxes (LBMBlockComm.f90:285-286)
         launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
         // -- penalty iteration (:895-906); launches beyond convergence return at once on the device flag
         for (int it = 0; it < ntolLBM; it++) {
             for (int ib = 0; ib < nbody; ib++) {
+                auto gather = ordered ? launch_ibm_gather_ordered : launch_ibm_gather;
                 if (!multi) {
-                    launch_ibm_gather(views[ib], bx, b.bodies[ib].partialU, b.ctl, 1, invh3_pen, s);
+                    gather(views[ib], bx, b.bodies[ib].partialU, b.ctl, 1, invh3_pen, s);
                 } else {
-                    launch_ibm_gather(views[ib], bx, b.bodies[ib].partialU, b.ctl, 0, invh3_pen, s);
+                    gather(views[ib], bx, b.bodies[ib].partialU, b.ctl, 0, invh3_pen, s);
                     NCK(g_nccl.AllReduce(b.bodies[ib].partialU, b.bodies[ib].partialU, 3 * (size_t)views[ib].n, kNcclFloat64, kNcclSum, g_nccl.comm, s));
                     launch_ibm_force(views[ib], b.bodies[ib].partialU, invh3_pen, b.ctl, s);
                 }
-                launch_ibm_scatter(views[ib], bx, b.ctl, s);
+                if (ordered) launch_ibm_scatter_ordered(b.bodies_dev, ib, bx, b.csr, b.ctl, s);
+                else launch_ibm_scatter(views[ib], bx, b.ctl, s);
             }
             launch_ibm_check(b.bodies_dev, nbody, b.flow.Uref, ntolLBM, dtolLBM, b.ctl, s);
         }
         // -- FluidVolumeForce_, Eulerian half (:968-976)
-        for (int ib = 0; ib < nbody; ib++) launch_ibm_spread(views[ib], bx, invh3, s);
+        if (ordered) launch_ibm_spread_ordered(b.bodies_dev, bx, b.csr, invh3, s);
+        else for (int ib = 0; ib < nbody; ib++) launch_ibm_spread(views[ib], bx, invh3, s);
     }
     CK(cudaGetLastError());
 
@@ -1298,6 +1344,7 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
     for (int ib = 0; ib < nbody; ib++)
         CK(cudaMemcpyAsync(Eforce[ib], b.bodies[ib].Eforce, sizeof(double) * 3 * (size_t)b.bodies[ib].n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (ctl1.err) b.csr_valid = false;
     if (ctl1.err & 1) return fail(FSILBM_ERR_STENCIL, "index out of xmin/xmax bound (Solidbody.f90:850,861)");
     if (ctl1.err & 4) return fail(FSILBM_ERR_STENCIL, "internal: marker stencil outside its IBM box");
     if (ctl1.err & 2) return fail(FSILBM_ERR_NAN, "Nan found in PenaltyForce (Solidbody.f90:1029)");

@@ -8,6 +8,8 @@
 // indices held as int16 exactly as the reference stores them (Solidbody.f90:45-46,790-804).
 #include "kernels.h"
 
+#include <cub/device/device_scan.cuh>
+
 namespace fsilbm {
 
 // Phi, Solidbody.f90:822-833
@@ -346,6 +348,191 @@ void launch_ibm_spread(const IbmBody &b, const IbmBoxes &boxes, double invh3, cu
 }
 
 
+// ---- ordered (bit-reproducible) interpolation and spreading ---------------------------------------------------------
+// The reference interpolates with three nested serial loops (x outer, z inner; Solidbody.f90:1009-1015) and spreads
+// with a serial loop over the markers (:1034-1048, :938-978).  Floating-point addition does not associate, so a warp
+// shuffle tree or fp64 atomics give the same numbers only to round-off -- and inside a closed fluid-structure loop the
+// beam solver's ill-conditioned Newmark operator amplifies that round-off.  These variants keep the reference's
+// summation ORDER: one thread walks a marker's 64 nodes in loop order, and spreading is turned into a per-cell gather
+// over IbmCsr, whose entries are sorted in exactly the order the serial loops reach the cell.
+
+// PenaltyForce_ interpolation of one marker by one thread, nodes in the order of the loops at :1009-1015
+__device__ __forceinline__ void gather_marker_serial(const IbmBody &b, const IbmBoxes &boxes, int iEL, double &s1, double &s2, double &s3)
+{
+    const long long boff = b.boff[iEL];
+    int cx[4], cy[4], cz[4];
+    double rx[4], ry[4], rz[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        cx[m] = b.cell[12 * iEL + m]; cy[m] = b.cell[12 * iEL + 4 + m]; cz[m] = b.cell[12 * iEL + 8 + m];
+        rx[m] = (double)b.Ew[12 * iEL + m]; ry[m] = (double)b.Ew[12 * iEL + 4 + m]; rz[m] = (double)b.Ew[12 * iEL + 8 + m];
+    }
+    const double *u1 = boxes.u, *u2 = boxes.u + boxes.ncell, *u3 = boxes.u + 2 * boxes.ncell;
+    s1 = 0.0; s2 = 0.0; s3 = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        if (!b.owned[4 * iEL + a]) continue;
+#pragma unroll
+        for (int bb = 0; bb < 4; bb++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const long long idx = boff + cx[a] + cy[bb] + cz[c];
+                s1 = s1 + u1[idx] * rx[a] * ry[bb] * rz[c];   // :1012
+                s2 = s2 + u2[idx] * rx[a] * ry[bb] * rz[c];
+                s3 = s3 + u3[idx] * rx[a] * ry[bb] * rz[c];
+            }
+        }
+    }
+}
+
+__global__ void ibm_gather_ordered_kernel(IbmBody b, const __grid_constant__ IbmBoxes boxes, double *partialU, const IbmCtl *ctl, int fused, double invh3)
+{
+    if (ctl->done) return;
+    const int iEL = blockIdx.x * blockDim.x + threadIdx.x;
+    if (iEL >= b.n) return;
+    double s1, s2, s3;
+    gather_marker_serial(b, boxes, iEL, s1, s2, s3);
+    if (fused) marker_force(b, iEL, s1, s2, s3, invh3);
+    else { partialU[3 * iEL + 0] = s1; partialU[3 * iEL + 1] = s2; partialU[3 * iEL + 2] = s3; }
+}
+
+void launch_ibm_gather_ordered(const IbmBody &b, const IbmBoxes &boxes, double *partialU, const IbmCtl *ctl, int fused, double invh3, cudaStream_t s)
+{
+    ibm_gather_ordered_kernel<<<(b.n + 63) / 64, 64, 0, s>>>(b, boxes, partialU, ctl, fused, invh3);
+    count_launch();
+}
+
+__device__ __forceinline__ unsigned long long csr_key(int body, int marker, int node)
+{
+    return ((unsigned long long)body << 40) | ((unsigned long long)(unsigned int)marker << 8) | (unsigned long long)node;
+}
+
+// velocity correction of one box cell (:1034-1048): the entries of bodies whose phase is `ph` (or, with phase_of_body
+// null, of body `only_body`), in (body, marker, node) order
+__device__ __forceinline__ void scatter_cell(const IbmBody *bodies, const IbmBoxes &boxes, const IbmCsr &csr, long long c, const int *phase_of_body,
+                                             int ph, int only_body)
+{
+    const int beg = csr.off[c], end = csr.off[c + 1];
+    if (beg == end) return;
+    double u1 = boxes.u[c], u2 = boxes.u[boxes.ncell + c], u3 = boxes.u[2 * boxes.ncell + c];
+    bool any = false;
+    for (int e = beg; e < end; e++) {
+        const unsigned long long key = csr.entry[e];
+        const int body = (int)(key >> 40);
+        if (phase_of_body ? phase_of_body[body] != ph : body != only_body) continue;
+        const int m = (int)((key >> 8) & 0xffffffffull), node = (int)(key & 63ull);
+        const IbmBody &b = bodies[body];
+        const double rx = (double)b.Ew[12 * m + (node >> 4)], ry = (double)b.Ew[12 * m + 4 + ((node >> 2) & 3)], rz = (double)b.Ew[12 * m + 8 + (node & 3)];
+        u1 = u1 - b.felt[3 * m + 0] * rx * ry * rz;   // :1044
+        u2 = u2 - b.felt[3 * m + 1] * rx * ry * rz;
+        u3 = u3 - b.felt[3 * m + 2] * rx * ry * rz;
+        any = true;
+    }
+    if (any) { boxes.u[c] = u1; boxes.u[boxes.ncell + c] = u2; boxes.u[2 * boxes.ncell + c] = u3; }
+}
+
+// Eulerian half of FluidVolumeForce_ for one box cell (:968-976), all bodies in order
+__device__ __forceinline__ void spread_cell(const IbmBody *bodies, const IbmBoxes &boxes, const IbmCsr &csr, long long c, double invh3)
+{
+    const int beg = csr.off[c], end = csr.off[c + 1];
+    if (beg == end) return;
+    double f1 = boxes.force[c], f2 = boxes.force[boxes.ncell + c], f3 = boxes.force[2 * boxes.ncell + c];
+    for (int e = beg; e < end; e++) {
+        const unsigned long long key = csr.entry[e];
+        const int body = (int)(key >> 40), m = (int)((key >> 8) & 0xffffffffull), node = (int)(key & 63ull);
+        const IbmBody &b = bodies[body];
+        const double rx = (double)b.Ew[12 * m + (node >> 4)], ry = (double)b.Ew[12 * m + 4 + ((node >> 2) & 3)], rz = (double)b.Ew[12 * m + 8 + (node & 3)];
+        const double e1 = b.Eforce[3 * m + 0] * invh3, e2 = b.Eforce[3 * m + 1] * invh3, e3 = b.Eforce[3 * m + 2] * invh3;   // :968
+        f1 = f1 + (-e1 * rx * ry * rz);   // :972-974
+        f2 = f2 + (-e2 * rx * ry * rz);
+        f3 = f3 + (-e3 * rx * ry * rz);
+    }
+    boxes.force[c] = f1; boxes.force[boxes.ncell + c] = f2; boxes.force[2 * boxes.ncell + c] = f3;
+}
+
+__global__ void ibm_scatter_cells_kernel(const IbmBody *bodies, int body, const __grid_constant__ IbmBoxes boxes, IbmCsr csr, const IbmCtl *ctl)
+{
+    if (ctl->done) return;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < boxes.ncell) scatter_cell(bodies, boxes, csr, c, nullptr, 0, body);
+}
+
+void launch_ibm_scatter_ordered(const IbmBody *bodies_dev, int body, const IbmBoxes &boxes, const IbmCsr &csr, const IbmCtl *ctl, cudaStream_t s)
+{
+    ibm_scatter_cells_kernel<<<(unsigned)((boxes.ncell + 127) / 128), 128, 0, s>>>(bodies_dev, body, boxes, csr, ctl);
+    count_launch();
+}
+
+__global__ void ibm_spread_cells_kernel(const IbmBody *bodies, const __grid_constant__ IbmBoxes boxes, IbmCsr csr, double invh3)
+{
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < boxes.ncell) spread_cell(bodies, boxes, csr, c, invh3);
+}
+
+void launch_ibm_spread_ordered(const IbmBody *bodies_dev, const IbmBoxes &boxes, const IbmCsr &csr, double invh3, cudaStream_t s)
+{
+    ibm_spread_cells_kernel<<<(unsigned)((boxes.ncell + 127) / 128), 128, 0, s>>>(bodies_dev, boxes, csr, invh3);
+    count_launch();
+}
+
+// -- IbmCsr build: one thread per (marker, node)
+template <bool FILL>
+__global__ void ibm_csr_nodes_kernel(IbmBody b, int body, IbmCsr csr)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)b.n * 64) return;
+    const int iEL = (int)(t >> 6), node = (int)(t & 63);
+    const int a = node >> 4, bb = (node >> 2) & 3, c = node & 3;
+    if (!b.owned[4 * iEL + a]) return;
+    const long long idx = b.boff[iEL] + b.cell[12 * iEL + a] + b.cell[12 * iEL + 4 + bb] + b.cell[12 * iEL + 8 + c];
+    if (!FILL) atomicAdd(&csr.count[idx], 1);
+    else {
+        const int slot = atomicSub(&csr.count[idx], 1) - 1;   // counts run back down to zero
+        csr.entry[csr.off[idx] + slot] = csr_key(body, iEL, node);
+    }
+}
+
+__global__ void ibm_csr_sort_kernel(IbmCsr csr, long long ncell)
+{
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const int beg = csr.off[c], end = csr.off[c + 1];
+    for (int i = beg + 1; i < end; i++) {   // insertion sort: a cell sees a few dozen stencil nodes at most
+        const unsigned long long k = csr.entry[i];
+        int j = i - 1;
+        while (j >= beg && csr.entry[j] > k) { csr.entry[j + 1] = csr.entry[j]; j--; }
+        csr.entry[j + 1] = k;
+    }
+}
+
+size_t ibm_csr_scan_bytes(long long ncell)
+{
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int *)nullptr, (int *)nullptr, (int)(ncell + 1));
+    return bytes;
+}
+
+int launch_ibm_csr_build(const IbmBody *views, int nbody, const IbmBoxes &boxes, const IbmCsr &csr, void *scan_tmp, size_t scan_bytes, cudaStream_t s)
+{
+    if (cudaMemsetAsync(csr.count, 0, sizeof(int) * (size_t)(boxes.ncell + 1), s) != cudaSuccess) return 1;
+    for (int ib = 0; ib < nbody; ib++) {
+        const long long nt = (long long)views[ib].n * 64;
+        ibm_csr_nodes_kernel<false><<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(views[ib], ib, csr);
+        count_launch();
+    }
+    if (cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, csr.count, csr.off, (int)(boxes.ncell + 1), s) != cudaSuccess) return 1;
+    count_launch();
+    for (int ib = 0; ib < nbody; ib++) {
+        const long long nt = (long long)views[ib].n * 64;
+        ibm_csr_nodes_kernel<true><<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(views[ib], ib, csr);
+        count_launch();
+    }
+    ibm_csr_sort_kernel<<<(unsigned)((boxes.ncell + 127) / 128), 128, 0, s>>>(csr, boxes.ncell);
+    count_launch();
+    return 0;
+}
+
+
 // ---- the whole of calculate_interaction_force in ONE cooperative launch (single-rank blocks) -----------------------
 // Phases are separated by grid-wide barriers instead of kernel boundaries: stencils + box macro | per iteration and per
 // body group: gather+force | velocity correction | loop control | ... | force spreading.  Bodies whose stencil boxes
@@ -372,63 +559,110 @@ __global__ void __launch_bounds__(256) ibm_loop_kernel(const __grid_constant__ I
     const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthread = (long long)gridDim.x * blockDim.x;
     RootBC bc;
     for (int i = 0; i < 6; i++) bc.c[i] = p.rootBC[i];
-    // phase 0: UpdateElmtInterp_ for every marker, calculate_macro_quantities + ResetVolumeForce on the box cells
-    for (int ib = 0; ib < p.nbody; ib++) {
-        const IbmBody b = p.bodies[ib];
-        for (long long i = gthread; i < b.n; i += nthread) stencil_marker(p.g, b, p.boxes, bc, p.ctl, (int)i);
-    }
+    // phase 0: UpdateElmtInterp_ for every marker (unless done before the launch, which the ordered mode needs for its
+    // cell lists), calculate_macro_quantities + ResetVolumeForce on the box cells
+    if (p.do_stencil)
+        for (int ib = 0; ib < p.nbody; ib++) {
+            const IbmBody b = p.bodies[ib];
+            for (long long i = gthread; i < b.n; i += nthread) stencil_marker(p.g, b, p.boxes, bc, p.ctl, (int)i);
+        }
     for (long long i = gthread; i < p.boxes.ncell; i += nthread) macro_box_cell(p.g, p.fA, p.hF[0], p.hF[1], p.hF[2], p.boxes, i);
     grid_barrier(p.barrier, epoch);
-    __shared__ double sh_tol[8];
+    __shared__ double sh_tol[256];
     for (int it = 0; it < p.ntol; it++) {
         if (((volatile IbmCtl *)p.ctl)->done) break;   // uniform: written before the last barrier
+        double tol_block = 0.0;                        // ordered mode, thread 0: this block's share of the iteration's sum of |dU|
         for (int ph = 0; ph < p.nphase; ph++) {
             // PenaltyForce_ first loop (Solidbody.f90:1000-1027) for the ph-th body of every group
             double tol = 0.0;
-            for (int k = p.phase_start[ph]; k < p.phase_start[ph + 1]; k++) {
-                const IbmBody b = p.bodies[p.phase_body[k]];
-                for (int m = gwarp; m < b.n; m += nwarp) {
-                    double s1, s2, s3;
-                    gather_marker(b, p.boxes, m, lane, s1, s2, s3);
-                    if (lane == 0) { marker_force(b, m, s1, s2, s3, p.invh3_pen); tol += b.tol[m]; }
+            if (p.ordered) {
+                for (int k = p.phase_start[ph]; k < p.phase_start[ph + 1]; k++) {
+                    const IbmBody b = p.bodies[p.phase_body[k]];
+                    for (long long m = gthread; m < b.n; m += nthread) {
+                        double s1, s2, s3;
+                        gather_marker_serial(b, p.boxes, (int)m, s1, s2, s3);
+                        marker_force(b, (int)m, s1, s2, s3, p.invh3_pen);
+                        tol += b.tol[m];
+                    }
                 }
-            }
-            if (lane == 0) sh_tol[threadIdx.x >> 5] = tol;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double t = 0.0;
-                for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh_tol[w];
-                if (t != 0.0 || !(t == t)) atomicAdd(&p.ctl->tol_acc, t);
+                sh_tol[threadIdx.x] = tol;             // fixed-shape tree: the same sum on every run
+                __syncthreads();
+                for (int off = 128; off > 0; off >>= 1) {
+                    if ((int)threadIdx.x < off) sh_tol[threadIdx.x] += sh_tol[threadIdx.x + off];
+                    __syncthreads();
+                }
+                if (threadIdx.x == 0) {
+                    tol_block += sh_tol[0];
+                    if (ph == p.nphase - 1) p.tol_partial[blockIdx.x] = tol_block;
+                }
+            } else {
+                for (int k = p.phase_start[ph]; k < p.phase_start[ph + 1]; k++) {
+                    const IbmBody b = p.bodies[p.phase_body[k]];
+                    for (int m = gwarp; m < b.n; m += nwarp) {
+                        double s1, s2, s3;
+                        gather_marker(b, p.boxes, m, lane, s1, s2, s3);
+                        if (lane == 0) { marker_force(b, m, s1, s2, s3, p.invh3_pen); tol += b.tol[m]; }
+                    }
+                }
+                if (lane == 0) sh_tol[threadIdx.x >> 5] = tol;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double t = 0.0;
+                    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh_tol[w];
+                    if (t != 0.0 || !(t == t)) atomicAdd(&p.ctl->tol_acc, t);
+                }
             }
             grid_barrier(p.barrier, epoch);
             // velocity correction (:1034-1048)
-            for (int k = p.phase_start[ph]; k < p.phase_start[ph + 1]; k++) {
-                const IbmBody b = p.bodies[p.phase_body[k]];
-                for (int m = gwarp; m < b.n; m += nwarp) scatter_marker(b, p.boxes, m, lane);
+            if (p.ordered) {
+                for (long long c = gthread; c < p.boxes.ncell; c += nthread) scatter_cell(p.bodies, p.boxes, p.csr, c, p.phase_of_body, ph, 0);
+            } else {
+                for (int k = p.phase_start[ph]; k < p.phase_start[ph + 1]; k++) {
+                    const IbmBody b = p.bodies[p.phase_body[k]];
+                    for (int m = gwarp; m < b.n; m += nwarp) scatter_marker(b, p.boxes, m, lane);
+                }
             }
             grid_barrier(p.barrier, epoch);
         }
-        if (gthread == 0) {   // loop control, :895-906
-            IbmCtl *c = p.ctl;
-            double dmax = c->tol_acc;
-            if (!isfinite(dmax)) atomicOr(&c->err, 2);   // :1028-1031
-            dmax = dmax / (p.dsum * p.Uref);
-            c->iter = c->iter + 1;
-            c->dmax = dmax;
-            c->tol_acc = 0.0;
-            c->done = !(c->iter < p.ntol && dmax > p.dtol);
-            __threadfence();
+        if (blockIdx.x == 0) {   // loop control, :895-906
+            double dmax = 0.0;
+            if (p.ordered) {
+                double t = 0.0;
+                for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += ((volatile double *)p.tol_partial)[i];
+                sh_tol[threadIdx.x] = t;
+                __syncthreads();
+                for (int off = 128; off > 0; off >>= 1) {
+                    if ((int)threadIdx.x < off) sh_tol[threadIdx.x] += sh_tol[threadIdx.x + off];
+                    __syncthreads();
+                }
+                dmax = sh_tol[0];
+            }
+            if (threadIdx.x == 0) {
+                IbmCtl *c = p.ctl;
+                if (!p.ordered) dmax = c->tol_acc;
+                if (!isfinite(dmax)) atomicOr(&c->err, 2);   // :1028-1031
+                dmax = dmax / (p.dsum * p.Uref);
+                c->iter = c->iter + 1;
+                c->dmax = dmax;
+                c->tol_acc = 0.0;
+                c->done = !(c->iter < p.ntol && dmax > p.dtol);
+                __threadfence();
+            }
         }
         grid_barrier(p.barrier, epoch);
     }
     // FluidVolumeForce_, Eulerian half (:968-976)
-    for (int ib = 0; ib < p.nbody; ib++) {
-        const IbmBody b = p.bodies[ib];
-        for (int m = gwarp; m < b.n; m += nwarp) spread_marker(b, p.boxes, p.invh3, m, lane);
+    if (p.ordered) {
+        for (long long c = gthread; c < p.boxes.ncell; c += nthread) spread_cell(p.bodies, p.boxes, p.csr, c, p.invh3);
+    } else {
+        for (int ib = 0; ib < p.nbody; ib++) {
+            const IbmBody b = p.bodies[ib];
+            for (int m = gwarp; m < b.n; m += nwarp) spread_marker(b, p.boxes, p.invh3, m, lane);
+        }
     }
 }
 
-int launch_ibm_loop(const IbmLoopParams &p, int max_markers, cudaStream_t s)
+int ibm_loop_max_blocks()
 {
     static int max_blocks = 0;
     if (!max_blocks) {
@@ -438,6 +672,12 @@ int launch_ibm_loop(const IbmLoopParams &p, int max_markers, cudaStream_t s)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ibm_loop_kernel, 256, 0);
         max_blocks = sms * (per_sm > 0 ? per_sm : 1);
     }
+    return max_blocks;
+}
+
+int launch_ibm_loop(const IbmLoopParams &p, int max_markers, cudaStream_t s)
+{
+    const int max_blocks = ibm_loop_max_blocks();
     int want = (max_markers + 7) / 8;           // one warp per marker of the largest phase
     const long long cells = (p.boxes.ncell + 255) / 256;
     if (cells > want) want = (int)(cells > max_blocks ? max_blocks : cells);

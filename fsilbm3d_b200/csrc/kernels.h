@@ -142,6 +142,16 @@ struct IbmCtl {               // device-resident control block of the penalty it
     double tol_acc;           // running sum of the markers' |dU| of the current iteration (single-launch path)
 };
 
+// Cell-centric view of all stencils of a block: for every box cell the (body, marker, stencil node) triples that touch
+// it, sorted ascending -- i.e. in the order the reference's serial spreading loops visit the cell (bodies in order,
+// markers 1..n, x,y,z loops; Solidbody.f90:898-903,1034-1048,938-978).  Spreading as an ordered per-cell gather makes
+// the corrected velocity and the force field bit-identical to the serial reference and independent of scheduling.
+struct IbmCsr {
+    int *count;                   // [ncell+1] scratch of the build (zero outside it)
+    int *off;                     // [ncell+1] exclusive prefix of the per-cell entry counts
+    unsigned long long *entry;    // [off[ncell]]  body << 40 | marker << 8 | node (node = 16*a + 4*b + c)
+};
+
 constexpr int MAX_IBM_PHASE_BODIES = 64;
 struct IbmLoopParams {        // the single-launch form of calculate_interaction_force (ibm_loop_kernel)
     Geom g;
@@ -159,8 +169,21 @@ struct IbmLoopParams {        // the single-launch form of calculate_interaction
     int phase_start[MAX_IBM_PHASE_BODIES + 1];
     int phase_body[MAX_IBM_PHASE_BODIES];
     unsigned int *barrier;    // grid barrier counter (zero between launches)
+    int ordered;              // 1: ordered (bit-reproducible) gather / spreading through csr; 0: warp shuffles + fp64 atomics
+    int do_stencil;           // 1: phase 0 computes the stencils (atomic mode); 0: they were computed before the launch
+    IbmCsr csr;
+    int phase_of_body[MAX_IBM_PHASE_BODIES];
+    double *tol_partial;      // [gridDim.x] per-block sums of the markers' |dU| (ordered mode)
 };
 int launch_ibm_loop(const IbmLoopParams &p, int max_markers, cudaStream_t s);
+int ibm_loop_max_blocks();
+
+// build of IbmCsr after the stencils are known: count -> scan -> fill -> per-cell sort
+size_t ibm_csr_scan_bytes(long long ncell);
+int launch_ibm_csr_build(const IbmBody *views, int nbody, const IbmBoxes &boxes, const IbmCsr &csr, void *scan_tmp, size_t scan_bytes, cudaStream_t s);
+void launch_ibm_gather_ordered(const IbmBody &b, const IbmBoxes &boxes, double *partialU, const IbmCtl *ctl, int fused, double invh3, cudaStream_t s);
+void launch_ibm_scatter_ordered(const IbmBody *bodies_dev, int body, const IbmBoxes &boxes, const IbmCsr &csr, const IbmCtl *ctl, cudaStream_t s);
+void launch_ibm_spread_ordered(const IbmBody *bodies_dev, const IbmBoxes &boxes, const IbmCsr &csr, double invh3, cudaStream_t s);
 
 void launch_ibm_stencil(const Geom &g, const IbmBody &b, const IbmBoxes &boxes, const int rootBC[6], IbmCtl *ctl, cudaStream_t s);
 void launch_ibm_macro_box(const Geom &g, const double *fA, const double hF[3], const IbmBoxes &boxes, cudaStream_t s);

@@ -1,12 +1,13 @@
-// fsilbm_harness.cpp -- C++ stand-in for the reference's Fortran driver (PROGRAM main, main.f90:13-151) for runs
-// WITHOUT immersed bodies, linked against libfsilbm_b200.so through include/fsilbm.h only.
+// fsilbm_harness.cpp -- C++ stand-in for the reference's Fortran driver (PROGRAM main, main.f90:13-151), linked
+// against libfsilbm_b200.so through include/fsilbm.h only.
 //
 // Why it exists: the drop-in boundary is a C ABI meant for the Fortran driver, and no Fortran compiler exists in
 // the build image.  This program replays the driver's call sequence call for call -- same inFlow.dat,
 // same block tree (LBMBlockComm.f90:98-211), same output cadence (main.f90:115-141), same DatFlow / DatContinue /
 // DatInfo byte formats, same FIELDSTAT lines -- so the whole path from parameter file to result files can be
-// exercised.  Structural bodies (SolidBody section with nFish > 0) need the beam solver that stays in Fortran and
-// are refused here.  Citations: /root/reference/src.
+// exercised.  Structural bodies (SolidBody section with nFish > 0, plates given by a line mesh) run on the C++
+// restatement of the beam solver in beam_solver.cpp / solid_body.cpp, which stands where SolidSolver.f90 and the host
+// half of Solidbody.f90 stand in the real driver; only marker arrays cross the C ABI.  Citations: /root/reference/src.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -19,6 +20,7 @@
 
 #include "../include/fsilbm.h"
 #include "inflow.hpp"
+#include "solid_body.hpp"
 
 using harness::BlockSpec;
 using harness::FlowCond;
@@ -50,6 +52,10 @@ struct Node {   // blockTreeNode, LBMBlockComm.f90:19-25
 std::vector<Blk> g_blk;
 std::vector<Node> g_tree;
 int g_root = -1;
+harness::SolidBodies g_solid;                 // module SolidBody (VBodies and its m_* variables)
+std::vector<std::vector<int>> g_carried;      // LBMblks(:)%carriedBodies, 0-based body indices per block
+int g_numsubstep = 1;
+long long g_iterLBM_total = 0;
 const double MachineTolerace = 1.0e-12;   // ConstParams.f90:36
 
 // CompareBlocks, FluidDomain.f90:1845-1972
@@ -144,12 +150,66 @@ void tree_set_boundary_conditions_block(int node)   // LBMBlockComm.f90:266-277
     for (int s : g_tree[node].sons) tree_set_boundary_conditions_block(s);
 }
 
-// tree_collision_streaming_IBM_FEM, LBMBlockComm.f90:279-318 (no bodies: IBM_FEM has nothing to do)
+// find_carrier_fluidblock + FindCarrierFluidBlock, FluidDomain.f90:1974-2017
+void FindCarrierFluidBlock()
+{
+    g_carried.assign(g_blk.size(), std::vector<int>());
+    for (int iFish = 0; iFish < g_solid.m_nFish; iFish++) {
+        harness::VirtualBody &B = g_solid.VBodies[iFish];
+        const double *x = B.v_Exyz.data();   // first marker
+        double dh = 1e10;
+        int n = -1;
+        for (size_t i = 0; i < g_blk.size(); i++) {
+            const Blk &b = g_blk[i];
+            if (b.spec.xmin <= x[0] && x[0] <= b.xmax && b.spec.ymin <= x[1] && x[1] <= b.ymax && b.spec.zmin <= x[2] && x[2] <= b.zmax && b.spec.dh < dh) {
+                dh = b.spec.dh;
+                n = (int)i;
+            }
+        }
+        if (n == -1) throw std::runtime_error("Error: carrier fluid block not found");
+        B.v_carrierFluidId = n;
+        g_carried[n].push_back(iFish);
+    }
+}
+
+// IBM_FEM, LBMBlockComm.f90:320-338: FSInteraction_force (Solidbody.f90:589-602; the device half is one library call)
+// followed by numsubstep structural sub-steps
+void IBM_FEM(int node, double time)
+{
+    const std::vector<int> &bodies = g_carried[node];
+    if (bodies.empty()) return;
+    Blk &b = g_blk[node];
+    const double dh = b.spec.dh, dt_solid = dh / (double)g_numsubstep;
+    std::vector<int> nelmts, restencil;
+    std::vector<const double *> Exyz, Evel, Ea;
+    std::vector<double *> Eforce;
+    for (int iFish : bodies) {
+        harness::VirtualBody &B = g_solid.VBodies[iFish];
+        B.UpdatePosVelArea(g_solid.m_IBPenaltyAlpha, g_solid.m_denIn);                                  // Solidbody.f90:599
+        nelmts.push_back(B.v_nelmts);
+        restencil.push_back(B.v_move == 1 || B.rbm.iBodyModel == 2 || B.count_Interp == 0 ? 1 : 0);     // :885
+        Exyz.push_back(B.v_Exyz.data()); Evel.push_back(B.v_Evel.data()); Ea.push_back(B.v_Ea.data()); Eforce.push_back(B.v_Eforce.data());
+    }
+    int iterLBM = 0;
+    ck(fsilbm_ibm_interaction_force(b.h, (int)bodies.size(), nelmts.data(), Exyz.data(), Evel.data(), Ea.data(), Eforce.data(), restencil.data(),
+                                    dh, g_solid.m_ntolLBM, g_solid.m_dtolLBM, g_solid.m_boundaryConditions, &iterLBM));   // :869-918 on the device
+    g_iterLBM_total += iterLBM;
+    for (int iFish : bodies) {
+        harness::VirtualBody &B = g_solid.VBodies[iFish];
+        B.count_Interp = 1;
+        std::fill(B.rbm.lodFlow.begin(), B.rbm.lodFlow.end(), 0.0);                                     // :911
+    }
+    for (int iFish : bodies) g_solid.VBodies[iFish].NodalLoads();                                       // :945-967
+    for (int isubstep = 1; isubstep <= g_numsubstep; isubstep++) g_solid.Solver(bodies, time, isubstep, dh, dt_solid);   // LBMBlockComm.f90:333-335
+}
+
+// tree_collision_streaming_IBM_FEM, LBMBlockComm.f90:279-318
 void tree_collision_streaming_IBM_FEM(int node)
 {
     Blk &b = g_blk[node];
     ck(fsilbm_block_set_time(b.h, b.blktime));
     ck(fsilbm_block_update_volume_force(b.h, nullptr));                         // :283
+    IBM_FEM(node, b.blktime);                                                   // :287 (macro :285 and reset :286 happen on the device)
     for (int p : g_tree[node].comm) ck(fsilbm_pair_extract_layer(p, 1));        // :290
     ck(fsilbm_block_collide_stream(b.h));                                       // :285-303
     for (int p : g_tree[node].comm) ck(fsilbm_pair_extract_layer(p, 2));        // :305
@@ -377,7 +437,10 @@ int main(int argc, char **argv)
     try {
         harness::InFlow in = harness::read_inflow(parameterFile);
         FlowCond &flow = in.flow;
-        harness::calculate_reference_params(flow, in.solid.nFish);                 // main.f90:43
+        g_solid.read_solid_files(in, harness::Vec3{0.0, 0.0, 0.0});               // main.f90:30 (g = 0, :25)
+        g_solid.allocate_solid_memory(flow);                                       // main.f90:39 (reads the structural mesh files)
+        g_solid.calculate_reference_params(flow);                                  // main.f90:43
+        g_numsubstep = flow.numsubstep;
         if (parse_only) {
             std::printf("{\"npsize\": %d, \"isConCmpt\": %d, \"numsubstep\": %d, \"timeSimTotal\": %.17g, \"Re\": %.17g, \"denIn\": %.17g, "
                         "\"uvwIn\": [%.17g, %.17g, %.17g], \"velocityKind\": %d, \"Lref\": %.17g, \"Tref\": %.17g, \"Uref\": %.17g, \"nu\": %.17g, "
@@ -394,8 +457,8 @@ int main(int argc, char **argv)
             std::printf("]}\n");
             return 0;
         }
-        if (in.solid.nFish > 0) throw std::runtime_error("this harness runs fluid-only cases: the SolidBody section has nFish > 0 and the beam solver stays in the Fortran driver");
         mkdir("./DatFlow", 0755); mkdir("./DatContinue", 0755); mkdir("./DatInfo", 0755);
+        if (in.solid.nFish > 0) { mkdir("./DatBody", 0755); mkdir("./DatBodySpan", 0755); }
 
         ck(fsilbm_init(device));                                                   // main.f90:36 (omp_set_num_threads)
         fsilbm_flow cf{};
@@ -414,9 +477,24 @@ int main(int argc, char **argv)
         }
         double time = 0.0, start_time = 0.0;
         int step = 0;
-        for (Blk &b : g_blk) ck(fsilbm_block_initialise(b.h, time));               // main.f90:50
         build_block_tree(flow.interpolateScheme);                                  // main.f90:33 (after the blocks exist here)
+        g_solid.set_solidbody_parameters(flow, g_blk[g_root].spec.BndConds.data()); // main.f90:44-45
+        g_solid.Initialise_solid_bodies(0.0);                                      // main.f90:48
+        FindCarrierFluidBlock();                                                   // main.f90:49
+        for (Blk &b : g_blk) ck(fsilbm_block_initialise(b.h, time));               // main.f90:50
+        g_solid.Write_solid_Check("Check.dat");                                    // main.f90:55 (the fluid part of Check.dat is not reproduced)
         check_is_continue(step, start_time, flow.isConCmpt);                       // main.f90:58
+        harness::SolidBodies::write_information_titles(g_solid.m_nGroup, flow);    // main.f90:59
+        {
+            FILE *fh = std::fopen("./DatInfo/FluidFlux.dat", "w");
+            if (fh) { std::fprintf(fh, " VARIABLES = \"t\"  \"inlet\"  \"middle\"  \"outlet\"\n"); std::fclose(fh); }
+            for (int i = 1; i <= flow.fluidProbingNum; i++) {
+                char name[64];
+                std::snprintf(name, sizeof(name), "./DatInfo/FluidProbes_%04d.dat", i);
+                fh = std::fopen(name, "w");
+                if (fh) { std::fprintf(fh, " VARIABLES = \"t\"  \"u\"  \"v\"  \"w\" \n"); std::fclose(fh); }
+            }
+        }
         for (Blk &b : g_blk) ck(fsilbm_block_update_volume_force(b.h, nullptr));   // main.f90:62
         tree_set_boundary_conditions_block(g_root);                                // main.f90:63
         const double dt_fluid = g_blk[g_root].spec.dh;                             // main.f90:67
@@ -425,6 +503,11 @@ int main(int argc, char **argv)
         if (flow.timeWriteBegin >= start_time) start_ave = step + (int)nint((flow.timeWriteBegin - start_time) * flow.Tref / dt_fluid);
         std::printf(" the start step for fluid averaging(if used): %d\n", start_ave);
         write_flow_blocks(time, flow);                                             // main.f90:84
+        if (g_solid.m_nFish > 0) {                                                 // main.f90:85-87
+            g_solid.write_solid_field(time);
+            g_solid.Write_solid_v_bodies(time);
+            g_solid.Write_solid_v_forces(time);
+        }
         std::printf(" Time loop beginning\n");
         const double half = 0.5 * dt_fluid / flow.Tref;
         while (time / flow.Tref < flow.timeSimTotal) {                             // main.f90:93
@@ -436,17 +519,42 @@ int main(int argc, char **argv)
                 if (b.spec.outputtype >= 2) ck(fsilbm_block_turbulent_statistic(b.h, step, start_ave));
             const double tT = time / flow.Tref;
             if (on_cadence(tT, flow.timeContiDelta, half)) write_continue_blocks(step, tT);          // :117-119
-            if (tT - flow.timeWriteBegin >= -half && tT - flow.timeWriteEnd <= half)                 // :121
+            if (tT - flow.timeWriteBegin >= -half && tT - flow.timeWriteEnd <= half) {               // :121
+                if (g_solid.m_nFish > 0 && on_cadence(tT, flow.timeBodyDelta, half)) {               // :124-128
+                    g_solid.write_solid_field(time);
+                    g_solid.Write_solid_v_bodies(time);
+                    g_solid.Write_solid_v_forces(time);
+                }
                 if (on_cadence(tT, flow.timeFlowDelta, half)) write_flow_blocks(time, flow);         // :129-131
+            }
             if (on_cadence(tT, flow.timeInfoDelta, half)) {                                          // :134
                 write_fluid_flux(g_root, time, flow);
                 if (flow.inWhichBlock >= 1 && flow.inWhichBlock <= (int)g_blk.size()) write_fluid_information(time, flow);
                 else std::printf("Warning: invalid flow%%inWhichBlock = %d; it must be in [1, %zu].\n", flow.inWhichBlock, g_blk.size());
+                g_solid.write_solid_Information(time, flow.solidProbingNode);                        // :143
             }
         }
         std::printf(" Steps:%8d  Time/Tref:%14.8f\n", step, time / flow.Tref);
         std::printf("=========================================================\n");
         computeFieldStat_blocks();                                                 // main.f90:150
+        if (g_solid.m_nFish > 0) {   // not in the reference: a machine-readable end state of every body for the parity tests
+            FILE *fh = std::fopen("./DatInfo/BodiesFinal.txt", "w");
+            if (fh) {
+                for (int iFish = 0; iFish < g_solid.m_nFish; iFish++) {
+                    const harness::BeamSolver &r = g_solid.VBodies[iFish].rbm;
+                    std::fprintf(fh, "BODY %d nND %d iterFEM %.0f dnorm %.17g cg_iterations %lld\n", iFish + 1, r.nND, r.FishInfo[1], r.FishInfo[2], r.cg_iterations);
+                    for (int n = 0; n < r.nND; n++) {
+                        std::fprintf(fh, "NODE %d", n + 1);
+                        for (int k = 0; k < 6; k++) std::fprintf(fh, " %.17g", r.pos[6 * n + k]);
+                        for (int k = 0; k < 6; k++) std::fprintf(fh, " %.17g", r.vel[6 * n + k]);
+                        for (int k = 0; k < 6; k++) std::fprintf(fh, " %.17g", r.lodFlow[6 * n + k]);
+                        std::fprintf(fh, "\n");
+                    }
+                }
+                std::fclose(fh);
+            }
+            std::printf(" IBM iterations (total): %lld\n", g_iterLBM_total);
+        }
         std::printf(" kernel launches: %lld\n", fsilbm_launch_count());
         fsilbm_finalize();
     } catch (const std::exception &e) {

@@ -135,6 +135,28 @@ InFlow read_inflow(const std::string &filename)
     { auto v = items(r.next_data(), 2); s.dtolFEM = v[0]; s.ntolFEM = (int)v[1]; }
     { auto v = items(r.next_data(), 3); s.nFish = (int)v[0]; s.nGroup = (int)v[1]; s.isKB = (int)v[2]; }
     if (s.IBPenaltyAlpha <= 1e-6) throw std::runtime_error("ERROR: IBPenaltyalpha should be positive (default 1)");
+    for (int ig = 0; ig < s.nGroup; ig++) {   // Solidbody.f90:124-161
+        SolidGroup g;
+        { auto v = items(r.next_data(), 4); g.fishNum = (int)v[0]; g.numX = (int)v[1]; g.numY = (int)v[2]; g.numZ = (int)v[3]; }
+        {
+            std::string b = r.next_data();   // read(buffer,*) t_FEmeshName: first blank/comma-delimited item, quotes allowed
+            const size_t i0 = b.find_first_not_of(" \t");
+            if (i0 == std::string::npos) throw std::runtime_error("empty FE mesh name in the SolidBody section");
+            if (b[i0] == '\'' || b[i0] == '"') { const size_t j = b.find(b[i0], i0 + 1); g.FEmeshName = b.substr(i0 + 1, j == std::string::npos ? std::string::npos : j - i0 - 1); }
+            else { const size_t j = b.find_first_of(" \t,/", i0); g.FEmeshName = b.substr(i0, j == std::string::npos ? std::string::npos : j - i0); }
+        }
+        { auto v = items(r.next_data(), 2); g.iBodyModel = (int)v[0]; g.iBodyType = (int)v[1]; }
+        { auto v = items(r.next_data(), 3); for (int k = 0; k < 3; k++) g.isMotionGiven[k] = (int)v[k]; }
+        { auto v = items(r.next_data(), 3); for (int k = 0; k < 3; k++) g.isMotionGiven[3 + k] = (int)v[k]; }
+        { auto v = items(r.next_data(), 2); g.denR = v[0]; g.psR = v[1]; }
+        { auto v = items(r.next_data(), 2); if (s.isKB == 0) { g.EmR = v[0]; g.tcR = v[1]; } else { g.KB = v[0]; g.KS = v[1]; } }
+        { auto v = items(r.next_data(), 2); g.freq = v[0]; g.St = v[1]; }
+        auto vec3 = [&](std::array<double, 3> &a) { auto v = items(r.next_data(), 3); a = {v[0], v[1], v[2]}; };
+        vec3(g.firstXYZ); vec3(g.deltaXYZ); vec3(g.initXYZVel); vec3(g.XYZAmpl); vec3(g.XYZPhi); vec3(g.AoAo); vec3(g.AoAAmpl); vec3(g.AoAPhi);
+        if (ig < s.nGroup - 1) r.readequal();
+        if (s.isKB != 0 && s.isKB != 1) { g.EmR = 0.0; g.tcR = 0.0; g.KB = 0.0; g.KS = 0.0; }   // :178-183
+        in.groups.push_back(g);
+    }
 
     // read_fuild_blocks, FluidDomain.f90:61-108
     r.rewind();

@@ -2,7 +2,7 @@
 // harness (the real driver keeps its Fortran readers).  Citations: /root/reference/src.
 //   found_keyword  Util.f90:55-75    readNextData  Util.f90:89-104    readequal  Util.f90:106-121
 //   read_flow_conditions  FlowCondition.f90:31-77     read_probe_params  FlowCondition.f90:79-112
-//   read_fuild_blocks     FluidDomain.f90:61-108      read_solid_files   Solidbody.f90:73-203 (section header only)
+//   read_fuild_blocks     FluidDomain.f90:61-108      read_solid_files   Solidbody.f90:73-203 (the lines of the SolidBody section)
 #pragma once
 #include <array>
 #include <string>
@@ -24,8 +24,9 @@ struct FlowCond {                     // type FlowCondType, FlowCondition.f90:11
     int ntolLBM = 1;
     double dtolLBM = 1e-10;
     int interpolateScheme = 1;
-    // derived (calculate_reference_params, Solidbody.f90:219-284)
-    double nu = 0, Mu = 0, Aref = 0;
+    // derived (calculate_reference_params, Solidbody.f90:219-284; allocate_solid_memory, :286-326)
+    double nu = 0, Mu = 0, Aref = 0, Fref = 0, Eref = 0, Pref = 0;
+    double Asfac = 0, Lchod = 0, Lspan = 0, AR = 0;
     // probes
     int fluidProbingNum = 0, inWhichBlock = 0, solidProbingNum = 0;
     std::vector<std::array<double, 3>> fluidProbingCoords;
@@ -45,17 +46,28 @@ struct SolidHeader {                  // first five data lines of the SolidBody 
     int ntolFEM = 20, nFish = 0, nGroup = 0, isKB = 0;
 };
 
+struct SolidGroup {                   // the per-group lines of the SolidBody section, Solidbody.f90:124-161
+    int fishNum = 0, numX = 1, numY = 1, numZ = 1;
+    std::string FEmeshName;
+    int iBodyModel = 1, iBodyType = 1;
+    std::array<int, 6> isMotionGiven{};
+    double denR = 0, psR = 0, EmR = 0, tcR = 0, KB = 0, KS = 0, freq = 0, St = 0;
+    std::array<double, 3> firstXYZ{}, deltaXYZ{}, initXYZVel{}, XYZAmpl{}, XYZPhi{}, AoAo{}, AoAAmpl{}, AoAPhi{};
+};
+
 struct InFlow {
     FlowCond flow;
     std::vector<BlockSpec> blocks;
     SolidHeader solid;
+    std::vector<SolidGroup> groups;
 };
 
 // Throws std::runtime_error with the reference's message ("<keyword> is not found in inFlow.dat", "end of file
 // encounter in readNextData", ...) on malformed input.
 InFlow read_inflow(const std::string &filename);
 
-// calculate_reference_params (Solidbody.f90:219-284) for a run without bodies (m_nFish = 0).
+// calculate_reference_params (Solidbody.f90:219-284) for a run without bodies (m_nFish = 0); with bodies the
+// structural side supplies the kinematics (SolidBodies::calculate_reference_params in solid_body.hpp).
 void calculate_reference_params(FlowCond &flow, int nFish);
 
 }  // namespace harness

@@ -72,9 +72,10 @@ def test_two_block_run_files(oracle, harness, tmp_path):
     lines = [l for l in r.stdout.splitlines() if "FIELDSTAT" in l]
     assert len(lines) == 12
     assert lines[0] == f" FIELDSTAT L2 u {st[0][0]:18.12f}" and lines[9] == f" FIELDSTAT Linfinity u {st[1][3]:18.12f}"
-    # DatInfo: 4 cadence points (0.125, 0.25, 0.375, 0.5), flux + 2 probes
-    assert len(open(os.path.join(wd, "DatInfo", "FluidFlux.dat")).read().splitlines()) == 4
-    assert len(open(os.path.join(wd, "DatInfo", "FluidProbes_0002.dat")).read().splitlines()) == 4
+    # DatInfo: title line (write_information_titles, FlowCondition.f90:177-187) + 4 cadence points (0.125, 0.25, 0.375, 0.5)
+    flux = open(os.path.join(wd, "DatInfo", "FluidFlux.dat")).read().splitlines()
+    assert len(flux) == 5 and flux[0] == ' VARIABLES = "t"  "inlet"  "middle"  "outlet"'
+    assert len(open(os.path.join(wd, "DatInfo", "FluidProbes_0002.dat")).read().splitlines()) == 5
 
     # restart: continue file of t/Tref = 0.25 -> run on to 0.5.  check_is_continue (FluidDomain.f90:166-224) gives every
     # node the populations of the FINEST saved block containing it, so the father's nodes under the son take the son's

@@ -22,7 +22,7 @@ def harness():
 def test_parse_inflow(harness):
     r = subprocess.run([harness, "--parse-only", SAMPLE], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout
-    p = json.loads(r.stdout)
+    p = json.loads(r.stdout.strip().splitlines()[-1])   # the reference's start-up messages come first
     assert p["npsize"] == 2 and p["nblocks"] == 2 and p["nFish"] == 0 and p["fluidProbingNum"] == 2
     assert p["uvwIn"] == [0.04, 0.0, 0.0] and p["Re"] == 100.0            # '100.0d0' Fortran exponent
     # calculate_reference_params (Solidbody.f90:219-284): Uref = |uvwIn(1)|, Tref = Lref/Uref, nu = Uref*Lref/Re
