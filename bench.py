@@ -35,6 +35,15 @@ WORKLOADS = {
                        desc="configs[1]: periodic body-force channel 256^3 per GPU, SRT, no body"),
     "plate512": dict(dims=(512, 256, 256), bc=(101, 104, 202, 202, 301, 301), model=1, plate=True,
                      desc="configs[2]: rigid plate (8192 markers) in shear inflow 512x256x256, SRT, 5 IBM iterations"),
+    # configs[3]: 1024x512x512 at 8 GPUs = 128 x-planes per GPU.  One heaving FLEXIBLE plate (64 beam elements x 128 span markers),
+    # numsubstep = 4 structural sub-steps per fluid step on the host (C++ restatement of SolidSolver.f90), St = 0.3
+    "heave1024": dict(dims=(128, 512, 512), bc=(101, 104, 301, 301, 301, 301), model=1, plate="flex", layout="one_centre",
+                      group=dict(iBodyModel=2, denR=1.0, psR=0.3, KB=0.05, KS=800.0, freq=0.015, XYZAmpl=(0.0, 0.25, 0.0)), numsubstep=4,
+                      desc="configs[3]: heaving flexible plate (8192 markers, numsubstep 4, 5 IBM iterations) in uniform inflow, 128x512x512 per GPU"),
+    # configs[4]: 2048x512x512 at 8 GPUs = 256 x-planes per GPU, one passively flapping flexible plate per GPU slab, two staggered rows
+    "school2048": dict(dims=(256, 512, 512), bc=(101, 104, 301, 301, 301, 301), model=1, plate="flex", layout="one_per_slab",
+                       group=dict(iBodyModel=2, denR=1.0, psR=0.3, KB=0.05, KS=800.0, AoAo=(0.0, 0.0, 8.0)), numsubstep=2,
+                       desc="configs[4]: one flexible plate (8192 markers each) per GPU slab, two staggered rows, 256x512x512 per GPU, single root block"),
 }
 
 
@@ -85,7 +94,36 @@ def build_plate(F, dh, denIn):
                         chord_dir=(1.0, 0.0, 0.0), span_dir=(0.0, 0.0, 1.0), IBPenaltyAlpha=1.0, denIn=denIn)
 
 
+def build_flex(wl, world, rank=0):
+    """The flexible plates of configs[3]/[4] through the C++ structural side (harness/libfsilbm_solid.so): writes the
+    reference's two input files into a scratch directory and opens them.  Every rank holds every body (the beams are
+    advanced redundantly with the all-reduced forces)."""
+    import tempfile
+    import numpy as np
+    from fsilbm3d_b200 import solid_solver as S
+    dh = 1.0 / 64.0
+    Xl, Y, Z = wl["dims"]
+    wd = tempfile.mkdtemp(prefix=f"fsilbm_bench_r{rank}_")
+    xyz = np.zeros((65, 3)); xyz[:, 0] = np.linspace(0.0, 1.0, 65)   # chord 1 = 64 cells, 64 elements
+    S.write_plate_dat(os.path.join(wd, "plate.dat"), xyz, 1.0, 1.0, (0.0, 0.0, 1.0), Nspan=128)   # span 2 = 128 markers per element
+    groups = []
+    if wl["layout"] == "one_centre":
+        first = (0.5 * Xl * world * dh - 0.5 + 0.003, 0.5 * Y * dh - 0.013, 0.5 * Z * dh + 0.003)
+        groups.append(dict(wl["group"], fishNum=1, numXYZ=(1, 1, 1), mesh="plate.dat", firstXYZ=first))
+    else:
+        for r in range(world):   # one group per body so that the rows can be staggered
+            first = ((r + 0.5) * Xl * dh - 0.5 + 0.003, (0.375 if r % 2 == 0 else 0.625) * Y * dh - 0.013, 0.5 * Z * dh + 0.003)
+            groups.append(dict(wl["group"], fishNum=1, numXYZ=(1, 1, 1), mesh="plate.dat", firstXYZ=first))
+    txt = S.inflow_text(numsubstep=wl["numsubstep"], Re=100.0, uvwIn=(0.05, 0.0, 0.0), LrefType=0, UrefType=0, TrefType=0, ntolLBM=5, dtolLBM=1e-30,
+                        isKB=1, dtolFEM=1e-16, ntolFEM=20, blocks=[dict(dims=(Xl * world, Y, Z), dh=dh, BndConds=wl["bc"])], groups=groups)
+    with open(os.path.join(wd, "inFlow.dat"), "w") as f:
+        f.write(txt)
+    return S.SolidBodies("inFlow.dat", wl["bc"], cwd=wd)   # (its start-up messages go to stderr: see main())
+
+
 def workload_flow(F_or_O_flow, wl):
+    if wl["plate"] == "flex":
+        return dict(nu=5e-4, uvwIn=(0.05, 0.0, 0.0), Uref=0.05, ntolLBM=5, dtolLBM=1e-30, numsubstep=wl["numsubstep"]), 1.0 / 64.0
     if wl["plate"]:
         dh = 1.0 / 64.0
         gamma = 0.02 / ((wl["dims"][1] - 1) * dh)
@@ -99,13 +137,23 @@ def cpu_time_oracle(wl, dims, steps, warmup):
     from oracle import oracle as O
     import fsilbm3d_b200 as F
     flowkw, dh = workload_flow(None, wl)
+    flowkw.pop("numsubstep", None)
     fl = O.Flow(**flowkw)
     X, Y, Z = dims
     b = O.LBMBlock(X, Y, Z, dh=dh, BndConds=wl["bc"], iCollidModel=wl["model"], flow=fl)
     b.initialise(0.0)
     b.update_volume_force(); b.set_boundary_conditions(); b.calculate_macro_quantities()
     bodies, plate = [], None
-    if wl["plate"]:
+    if wl["plate"] == "flex":
+        # fluid + IBM on the initial markers of the first plate, re-stencilled every step as for a moving body; the
+        # structural solve is host code on both arms and is left out of the CPU sample
+        flowkw.pop("numsubstep", None)
+        sb = build_flex(dict(wl, dims=dims), 1)
+        for body in sb.VBodies[:1]:
+            ov = O.VirtualBody(body.v_nelmts, v_move=1, iBodyModel=2)
+            ov.v_Exyz[...] = body.v_Exyz; ov.v_Evel[...] = body.v_Evel; ov.v_Ea[...] = body.v_Ea
+            bodies.append(ov)
+    elif wl["plate"]:
         plate = build_plate(F, dh, fl.denIn)
         ov = O.VirtualBody(plate.body.v_nelmts, v_move=0, iBodyModel=1)
         ov.v_Exyz[...] = plate.body.v_Exyz; ov.v_Evel[...] = plate.body.v_Evel; ov.v_Ea[...] = plate.body.v_Ea
@@ -137,7 +185,9 @@ def run_reference(args):
     mlups_cal, t_cal, threads = cpu_time_oracle(wl, (16, Y, Z), 2, 1)
     per_plane = t_cal / 16.0
     budget = 120.0
-    if wl["plate"]:
+    if wl["plate"] == "flex":
+        candidates = [c for c in (X, X // 2) if c >= 128]   # the plate (64 cells of chord) sits at the slab centre
+    elif wl["plate"]:
         candidates = [X, 320]   # the plate occupies planes 192..256; 320 planes keep it well inside
     else:
         candidates = [X >> k for k in range(0, 8) if (X >> k) >= 16]
@@ -157,7 +207,20 @@ def run_reference(args):
                          "note": "C restatement of the reference OpenMP path (Fortran not buildable here)"},
         "e2e": {"value": mlups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's real stdout; everything else written to fd 1 by native libraries (NCCL's
+    version banner, the structural library's start-up messages) was diverted to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -201,17 +264,20 @@ def run_gpu(args):
     blk = F.LBMBlock(XG, Y, Z, dh=dh, BndConds=wl["bc"], iCollidModel=wl["model"], flow=flow, xOffset=rank * Xl, xLocal=Xl, device=local)
     blk.initialise(0.0)
     blk.update_volume_force(); blk.set_boundary_conditions()
-    plates = []
-    if wl["plate"]:
+    plates, sb = [], None
+    if wl["plate"] == "flex":
+        sb = build_flex(wl, world, rank)
+        plates = sb.plates
+    elif wl["plate"]:
         plates = [build_plate(F, dh, flow.denIn)]
-        if world > 1:   # keep the plate inside rank 0's slab neighbourhood in global coordinates
-            pass
     transport = blk.halo_transport
     stream = torch.cuda.ExternalStream(blk.cuda_stream, device=local)
     lib = F.lib()
 
+    flex = sb is not None
+
     def step(n):
-        F.tree_collision_streaming_IBM_FEM(blk, plates, time=n * dh, solver=False)
+        F.tree_collision_streaming_IBM_FEM(blk, plates, time=n * dh, solver=flex)
 
     # ---- device-resident throughput ("value") ---------------------------------------------------------
     for n in range(args.warmup):
@@ -306,7 +372,7 @@ def run_gpu(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            sx = Xl if not wl["plate"] else 320
+            sx = Xl if (not wl["plate"] or wl["plate"] == "flex") else 320
             steps_cpu = 6
             mlups, t_step, threads = cpu_time_oracle(wl, (sx, Y, Z), steps_cpu, 2)
             cpu = {"value": mlups, "unit": UNIT, "cores": threads, "kind": "port",
@@ -327,7 +393,7 @@ def run_gpu(args):
                        "ibm": ("ordered per-cell gather (bit-identical to the serial reference)" if args.ibm_ordered else "fp64 atomics") if wl["plate"] else None},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     blk.close()
     if world > 1:
         dist.destroy_process_group()
@@ -349,6 +415,10 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return

@@ -230,17 +230,20 @@ def tree_collision_streaming_IBM_FEM(node, plates: Sequence = (), time: Optional
         for p in plates:                                                        # host half of FluidVolumeForce_ (Solidbody.f90:911,945-967)
             if hasattr(p, "FluidVolumeForce"):
                 p.FluidVolumeForce()
-        if solver:
-            nsub = block.flow.numsubstep
-            dt_solid = block.dh / float(nsub)
-            for isub in range(1, nsub + 1):
-                for p in plates:
-                    p.structure(block.blktime, isub, block.dh, dt_solid)
     if iters is not None:
         iters.append(it)
     for pair in node.comm:
         pair.extract_interpolate_layer(1)                                   # :290
-    block.collide_stream()                                                  # :285-303 fused
+    block.collide_stream()                                                  # :285-303 fused; asynchronous launch
+    if len(plates) and solver:
+        # Solver (:333-335).  The reference runs it before the collision; it only advances the beams with the loads
+        # just computed and touches no fluid state, so it is issued here, after the launch, and the host structural
+        # solve overlaps the device's collide-stream of the same step.
+        nsub = block.flow.numsubstep
+        dt_solid = block.dh / float(nsub)
+        for isub in range(1, nsub + 1):
+            for p in plates:
+                p.structure(block.blktime, isub, block.dh, dt_solid)
     for pair in node.comm:
         pair.extract_interpolate_layer(2)                                   # :305
     for son, pair in zip(node.sons, node.comm):                             # :307-317

@@ -177,6 +177,8 @@ std::vector<std::unique_ptr<Pair>> g_pairs;
 int g_variant = 0, g_force_ghost = 0;
 int g_halo_timeout_s = 120;   // a neighbour this late is treated as lost (the wait kernel gives up, fsilbm_block_sync reports it)
 int g_ibm_single_launch = 1;   // 1: calculate_interaction_force as one cooperative kernel on single-rank blocks; 0: one kernel per phase
+int g_ibm_replicate = 1;       // multi-rank, ordered mode: 1 every rank runs the whole penalty iteration on all-reduced box velocities (one
+                               // collective per step, bit-identical to one GPU); 0 partial interpolation sums all-reduced per body and iteration
 int g_ibm_ordered = 1;         // 1: interpolation and spreading keep the reference's serial summation order (bit-reproducible); 0: shuffles + fp64 atomics
 int g_halo_mode = 1;   // 1: edge kernels store into the neighbours' memory over NVLink (default); 0: ncclSend/ncclRecv
 
@@ -491,6 +493,7 @@ int fsilbm_set_option(const char *key, int value)
     if (!strcmp(key, "variant")) { if (value < 0 || value > 2) return fail(FSILBM_ERR_ARG, "variant must be 0..2"); g_variant = value; return 0; }
     if (!strcmp(key, "force_ghost")) { g_force_ghost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_single_launch")) { g_ibm_single_launch = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "ibm_replicate")) { g_ibm_replicate = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->csr_valid = false; return 0; }
     if (!strcmp(key, "ibm_ordered")) { g_ibm_ordered = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->csr_valid = false; return 0; }
     if (!strcmp(key, "halo_timeout_s")) { if (value < 1) return fail(FSILBM_ERR_ARG, "halo_timeout_s must be >= 1"); g_halo_timeout_s = value; return 0; }
     if (!strcmp(key, "halo")) { if (value < 0 || value > 1) return fail(FSILBM_ERR_ARG, "halo must be 0 (NCCL) or 1 (peer stores)"); g_halo_mode = value; return 0; }
@@ -1240,8 +1243,14 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
     half_force(b, hF);
     const double invh3_pen = 0.5 * dt * ((1.0 / g.dh) * (1.0 / g.dh) * (1.0 / g.dh)) / b.flow.denIn;   // :996
     const double invh3 = (1.0 / g.dh) * (1.0 / g.dh) * (1.0 / g.dh);                                     // :936
-    bool single = !multi && g_ibm_single_launch && nbody <= MAX_IBM_PHASE_BODIES;
     const bool ordered = g_ibm_ordered != 0;
+    // Multi-rank, replicated form: the box velocities (owner's value, zero elsewhere: the sum is exact) are all-reduced
+    // once, then every rank runs the whole of calculate_interaction_force on the full boxes.  All ranks hold the same
+    // marker forces afterwards, bit-identical to the one-GPU result; the collide kernel of each rank reads its own planes.
+    const bool replicate = multi && ordered && g_ibm_replicate;
+    bool single = (!multi || replicate) && g_ibm_single_launch && nbody <= MAX_IBM_PHASE_BODIES;
+    Geom gsten = g;
+    if (replicate) { gsten.xOffset = 0; gsten.X = g.XG; }   // stencil_marker: every stencil plane counts as owned
     if (ordered) {
         // stencils first (the cell lists are built from them), then the lists; both survive while no body restencils
         long long entries = 0;
@@ -1266,10 +1275,14 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         }
         if (!b.tol_partial) CK(cudaMalloc(&b.tol_partial, sizeof(double) * (size_t)ibm_loop_max_blocks()));
         if (!b.csr_valid) {
-            for (int ib = 0; ib < nbody; ib++) launch_ibm_stencil(g, views[ib], bx, rootBC, b.ctl, s);
+            for (int ib = 0; ib < nbody; ib++) launch_ibm_stencil(gsten, views[ib], bx, rootBC, b.ctl, s);
             if (launch_ibm_csr_build(views.data(), nbody, bx, b.csr, b.csr_scan_tmp, b.csr_scan_bytes, s)) return fail(FSILBM_ERR_CUDA, "IBM cell-list build failed");
             b.csr_valid = true;
         }
+    }
+    if (replicate) {
+        launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
+        NCK(g_nccl.AllReduce(bx.u, bx.u, 3 * (size_t)bx.ncell, kNcclFloat64, kNcclSum, g_nccl.comm, s));
     }
     if (single) {
         // one cooperative launch for UpdateElmtInterp_, the box macro, the whole penalty iteration and the force spreading
@@ -1282,7 +1295,7 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         lp.dsum = 0.0;
         for (int ib = 0; ib < nbody; ib++) lp.dsum = lp.dsum + (double)nelmts[ib];   // :902
         lp.invh3_pen = invh3_pen; lp.invh3 = invh3; lp.barrier = b.ibm_barrier;
-        lp.ordered = ordered ? 1 : 0; lp.do_stencil = ordered ? 0 : 1; lp.csr = b.csr; lp.tol_partial = b.tol_partial;
+        lp.ordered = ordered ? 1 : 0; lp.do_stencil = ordered ? 0 : 1; lp.do_macro = replicate ? 0 : 1; lp.csr = b.csr; lp.tol_partial = b.tol_partial;
         // phases: the k-th body (in body order) of every box group; a body's group is the merged box holding its first marker's cell
         std::vector<int> group(nbody, 0);
         for (int ib = 0; ib < nbody; ib++) {
@@ -1315,12 +1328,12 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         //    bodies (the ordered mode did it above, together with its cell lists)
         if (!ordered) for (int ib = 0; ib < nbody; ib++) launch_ibm_stencil(g, views[ib], bx, rootBC, b.ctl, s);
         // -- calculate_macro_quantities + ResetVolumeForce restricted to the boxes (LBMBlockComm.f90:285-286)
-        launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
+        if (!replicate) launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
         // -- penalty iteration (:895-906); launches beyond convergence return at once on the device flag
         for (int it = 0; it < ntolLBM; it++) {
             for (int ib = 0; ib < nbody; ib++) {
                 auto gather = ordered ? launch_ibm_gather_ordered : launch_ibm_gather;
-                if (!multi) {
+                if (!multi || replicate) {
                     gather(views[ib], bx, b.bodies[ib].partialU, b.ctl, 1, invh3_pen, s);
                 } else {
                     gather(views[ib], bx, b.bodies[ib].partialU, b.ctl, 0, invh3_pen, s);

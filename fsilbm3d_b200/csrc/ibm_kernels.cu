@@ -566,7 +566,8 @@ __global__ void __launch_bounds__(256) ibm_loop_kernel(const __grid_constant__ I
             const IbmBody b = p.bodies[ib];
             for (long long i = gthread; i < b.n; i += nthread) stencil_marker(p.g, b, p.boxes, bc, p.ctl, (int)i);
         }
-    for (long long i = gthread; i < p.boxes.ncell; i += nthread) macro_box_cell(p.g, p.fA, p.hF[0], p.hF[1], p.hF[2], p.boxes, i);
+    if (p.do_macro)
+        for (long long i = gthread; i < p.boxes.ncell; i += nthread) macro_box_cell(p.g, p.fA, p.hF[0], p.hF[1], p.hF[2], p.boxes, i);
     grid_barrier(p.barrier, epoch);
     __shared__ double sh_tol[256];
     for (int it = 0; it < p.ntol; it++) {

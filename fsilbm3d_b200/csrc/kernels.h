@@ -171,6 +171,7 @@ struct IbmLoopParams {        // the single-launch form of calculate_interaction
     unsigned int *barrier;    // grid barrier counter (zero between launches)
     int ordered;              // 1: ordered (bit-reproducible) gather / spreading through csr; 0: warp shuffles + fp64 atomics
     int do_stencil;           // 1: phase 0 computes the stencils (atomic mode); 0: they were computed before the launch
+    int do_macro;             // 1: phase 0 fills the box cells from fA; 0: done before the launch (multi-rank: all-reduced box velocities)
     IbmCsr csr;
     int phase_of_body[MAX_IBM_PHASE_BODIES];
     double *tol_partial;      // [gridDim.x] per-block sums of the markers' |dU| (ordered mode)

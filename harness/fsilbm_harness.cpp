@@ -172,14 +172,24 @@ void FindCarrierFluidBlock()
     }
 }
 
-// IBM_FEM, LBMBlockComm.f90:320-338: FSInteraction_force (Solidbody.f90:589-602; the device half is one library call)
-// followed by numsubstep structural sub-steps
-void IBM_FEM(int node, double time)
+// IBM_FEM, LBMBlockComm.f90:320-338, in two halves: FSInteraction_force (Solidbody.f90:589-602; the device half is one
+// library call) and the numsubstep structural sub-steps.  The reference runs them back to back before the collision;
+// the sub-steps only advance the beams with the loads just computed and touch no fluid state, so the driver issues them
+// after the (asynchronous) collide-stream launch and the host structural solve overlaps the device work of the step.
+void IBM_FEM_solver(int node, double time)
+{
+    const std::vector<int> &bodies = g_carried[node];
+    if (bodies.empty()) return;
+    const double dh = g_blk[node].spec.dh, dt_solid = dh / (double)g_numsubstep;
+    for (int isubstep = 1; isubstep <= g_numsubstep; isubstep++) g_solid.Solver(bodies, time, isubstep, dh, dt_solid);   // LBMBlockComm.f90:333-335
+}
+
+void IBM_FEM_force(int node)
 {
     const std::vector<int> &bodies = g_carried[node];
     if (bodies.empty()) return;
     Blk &b = g_blk[node];
-    const double dh = b.spec.dh, dt_solid = dh / (double)g_numsubstep;
+    const double dh = b.spec.dh;
     std::vector<int> nelmts, restencil;
     std::vector<const double *> Exyz, Evel, Ea;
     std::vector<double *> Eforce;
@@ -200,7 +210,6 @@ void IBM_FEM(int node, double time)
         std::fill(B.rbm.lodFlow.begin(), B.rbm.lodFlow.end(), 0.0);                                     // :911
     }
     for (int iFish : bodies) g_solid.VBodies[iFish].NodalLoads();                                       // :945-967
-    for (int isubstep = 1; isubstep <= g_numsubstep; isubstep++) g_solid.Solver(bodies, time, isubstep, dh, dt_solid);   // LBMBlockComm.f90:333-335
 }
 
 // tree_collision_streaming_IBM_FEM, LBMBlockComm.f90:279-318
@@ -209,9 +218,10 @@ void tree_collision_streaming_IBM_FEM(int node)
     Blk &b = g_blk[node];
     ck(fsilbm_block_set_time(b.h, b.blktime));
     ck(fsilbm_block_update_volume_force(b.h, nullptr));                         // :283
-    IBM_FEM(node, b.blktime);                                                   // :287 (macro :285 and reset :286 happen on the device)
+    IBM_FEM_force(node);                                                        // :287 (macro :285 and reset :286 happen on the device)
     for (int p : g_tree[node].comm) ck(fsilbm_pair_extract_layer(p, 1));        // :290
     ck(fsilbm_block_collide_stream(b.h));                                       // :285-303
+    IBM_FEM_solver(node, b.blktime);                                            // :333-335, overlapping the launch above
     for (int p : g_tree[node].comm) ck(fsilbm_pair_extract_layer(p, 2));        // :305
     for (size_t i = 0; i < g_tree[node].sons.size(); i++) {                     // :307-317
         const int s = g_tree[node].sons[i];
