@@ -295,6 +295,13 @@ def run_gpu(args):
     blk.sync(); torch.cuda.synchronize()
     launches = lib.fsilbm_launch_count() - l0
     ms = e0.elapsed_time(e1)
+    structural = None
+    if flex:
+        b0 = sb.VBodies[0]
+        structural = {"host_ms_per_step_all_bodies": 1e3 * sum(p.host_seconds for p in plates) / (args.steps + args.warmup),
+                      "cg_iterations_per_step_body0": float(b0.FishInfo[3]) / (args.steps + args.warmup), "bodies": len(plates),
+                      "note": "C++ restatement of SolidSolver.f90 on one host core per rank, overlapped with the collide-stream launch; "
+                              "in the reference this is the Fortran driver's own work"}
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -390,6 +397,7 @@ def run_gpu(args):
                        "decomposition": f"x-slabs x{world}" if world > 1 else "single block",
                        "l2": "working set 5.1 GB per GPU (two population buffers) >> 126 MB L2; no explicit flush needed",
                        "kernel_variant": args.variant, "halo_transport": transport,
+                       "structural_solver": structural,
                        "ibm": ("ordered per-cell gather (bit-identical to the serial reference)" if args.ibm_ordered else "fp64 atomics") if wl["plate"] else None},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
@@ -410,6 +418,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flow-every", type=int, default=200, help="e2e leg: read den,uuu back to the host every this many steps")
     ap.add_argument("--halo", type=int, default=1, choices=[0, 1], help="multi-GPU halo transport: 1 peer stores over NVLink, 0 NCCL send/recv")
+    ap.add_argument("--ibm-single-launch", type=int, default=1, choices=[0, 1], help="IBM penalty iteration: 1 one cooperative kernel, 0 one kernel per phase")
     ap.add_argument("--ibm-ordered", type=int, default=1, choices=[0, 1],
                     help="IBM spreading: 1 ordered per-cell gather (bit-identical to the serial reference), 0 fp64 atomics")
     args = ap.parse_args()
@@ -427,6 +436,7 @@ def main():
         F._lib.check(F.lib().fsilbm_set_option(b"variant", args.variant))
     F._lib.check(F.lib().fsilbm_set_option(b"halo", args.halo))
     F._lib.check(F.lib().fsilbm_set_option(b"ibm_ordered", args.ibm_ordered))
+    F._lib.check(F.lib().fsilbm_set_option(b"ibm_single_launch", args.ibm_single_launch))
     run_gpu(args)
 
 

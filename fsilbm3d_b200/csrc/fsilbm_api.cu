@@ -149,6 +149,7 @@ struct Block {
     void *csr_scan_tmp = nullptr; size_t csr_scan_bytes = 0;
     bool csr_valid = false;
     double *tol_partial = nullptr;
+    unsigned long long *ibm_prof = nullptr; int ibm_prof_calls = 0;
     cudaStream_t stream = nullptr, comm_stream = nullptr;
     cudaEvent_t ev_edge = nullptr, ev_comm = nullptr;
     // peer-memory halo (multi-GPU): see halo_setup
@@ -1273,7 +1274,7 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
             b.csr_entry_cap = entries;
             b.csr_valid = false;
         }
-        if (!b.tol_partial) CK(cudaMalloc(&b.tol_partial, sizeof(double) * (size_t)ibm_loop_max_blocks()));
+        if (!b.tol_partial) CK(cudaMalloc(&b.tol_partial, sizeof(double) * 2 * (size_t)ibm_loop_max_blocks()));
         if (!b.csr_valid) {
             for (int ib = 0; ib < nbody; ib++) launch_ibm_stencil(gsten, views[ib], bx, rootBC, b.ctl, s);
             if (launch_ibm_csr_build(views.data(), nbody, bx, b.csr, b.csr_scan_tmp, b.csr_scan_bytes, s)) return fail(FSILBM_ERR_CUDA, "IBM cell-list build failed");
@@ -1295,6 +1296,9 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         lp.dsum = 0.0;
         for (int ib = 0; ib < nbody; ib++) lp.dsum = lp.dsum + (double)nelmts[ib];   // :902
         lp.invh3_pen = invh3_pen; lp.invh3 = invh3; lp.barrier = b.ibm_barrier;
+        static const bool want_prof = getenv("FSILBM_IBM_PROFILE") != nullptr;
+        if (want_prof && !b.ibm_prof) { CK(cudaMalloc(&b.ibm_prof, 64 * sizeof(unsigned long long))); CK(cudaMemset(b.ibm_prof, 0, 64 * sizeof(unsigned long long))); }
+        lp.prof = b.ibm_prof;
         lp.ordered = ordered ? 1 : 0; lp.do_stencil = ordered ? 0 : 1; lp.do_macro = replicate ? 0 : 1; lp.csr = b.csr; lp.tol_partial = b.tol_partial;
         // phases: the k-th body (in body order) of every box group; a body's group is the merged box holding its first marker's cell
         std::vector<int> group(nbody, 0);
@@ -1357,6 +1361,13 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
     for (int ib = 0; ib < nbody; ib++)
         CK(cudaMemcpyAsync(Eforce[ib], b.bodies[ib].Eforce, sizeof(double) * 3 * (size_t)b.bodies[ib].n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (b.ibm_prof && (b.ibm_prof_calls++ % 100) == 20) {
+        unsigned long long hp[64];
+        cudaMemcpy(hp, b.ibm_prof, sizeof(hp), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[ibm_loop phases, us]");
+        for (unsigned long long k = 1; k < hp[0] && k < 63; k++) fprintf(stderr, " %.1f", (double)(hp[1 + k] - hp[k]) * 1e-3);
+        fprintf(stderr, "  (ncell %lld)\n", (long long)bx.ncell);
+    }
     if (ctl1.err) b.csr_valid = false;
     if (ctl1.err & 1) return fail(FSILBM_ERR_STENCIL, "index out of xmin/xmax bound (Solidbody.f90:850,861)");
     if (ctl1.err & 4) return fail(FSILBM_ERR_STENCIL, "internal: marker stencil outside its IBM box");

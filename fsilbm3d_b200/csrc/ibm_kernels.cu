@@ -356,49 +356,71 @@ void launch_ibm_spread(const IbmBody &b, const IbmBoxes &boxes, double invh3, cu
 // summation ORDER: one thread walks a marker's 64 nodes in loop order, and spreading is turned into a per-cell gather
 // over IbmCsr, whose entries are sorted in exactly the order the serial loops reach the cell.
 
-// PenaltyForce_ interpolation of one marker by one thread, nodes in the order of the loops at :1009-1015
-__device__ __forceinline__ void gather_marker_serial(const IbmBody &b, const IbmBoxes &boxes, int iEL, double &s1, double &s2, double &s3)
+// PenaltyForce_ interpolation, ordered.  A block of 256 threads takes MARKERS_PER_BLOCK = 16 markers at a time: 16 lanes
+// per marker form the 64 products of its nodes in parallel -- lane l those of (a, b, c) = (h, l/4, l%4), h = 0..3, each as
+// the reference forms it, ((u*rx)*ry)*rz -- and park them in shared memory; then one thread per marker adds them in the
+// order of the loops at :1009-1015 (x outer, z inner) and finishes the marker (:1016-1025).  The 64-term chain of additions
+// is the only serial part and runs out of shared memory.
+constexpr int MARKER_LANES = 16;
+constexpr int MARKERS_PER_BLOCK = 16;   // 256 threads
+struct GatherSmem { double p[3][64][MARKERS_PER_BLOCK]; };   // [component][node][marker]: conflict-free both ways
+
+// m0: first marker of this block's batch.  Must be called by all 256 threads of the block.  Returns |dU| of the marker
+// finished by this thread (threads 0..15), else 0.
+__device__ __forceinline__ double gather_batch_ordered(const IbmBody &b, const IbmBoxes &boxes, int m0, GatherSmem &sm, double *partialU, int fused, double invh3)
 {
-    const long long boff = b.boff[iEL];
-    int cx[4], cy[4], cz[4];
-    double rx[4], ry[4], rz[4];
+    const int mi = threadIdx.x / MARKER_LANES, gl = threadIdx.x & (MARKER_LANES - 1);
+    const int iEL = m0 + mi;
+    if (iEL < b.n) {
+        const int bb = gl >> 2, c = gl & 3;
+        const long long base = b.boff[iEL] + b.cell[12 * iEL + 4 + bb] + b.cell[12 * iEL + 8 + c];
+        const double ry = (double)b.Ew[12 * iEL + 4 + bb], rz = (double)b.Ew[12 * iEL + 8 + c];
+        const double *u1 = boxes.u, *u2 = boxes.u + boxes.ncell, *u3 = boxes.u + 2 * boxes.ncell;
 #pragma unroll
-    for (int m = 0; m < 4; m++) {
-        cx[m] = b.cell[12 * iEL + m]; cy[m] = b.cell[12 * iEL + 4 + m]; cz[m] = b.cell[12 * iEL + 8 + m];
-        rx[m] = (double)b.Ew[12 * iEL + m]; ry[m] = (double)b.Ew[12 * iEL + 4 + m]; rz[m] = (double)b.Ew[12 * iEL + 8 + m];
-    }
-    const double *u1 = boxes.u, *u2 = boxes.u + boxes.ncell, *u3 = boxes.u + 2 * boxes.ncell;
-    s1 = 0.0; s2 = 0.0; s3 = 0.0;
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-        if (!b.owned[4 * iEL + a]) continue;
-#pragma unroll
-        for (int bb = 0; bb < 4; bb++) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const long long idx = boff + cx[a] + cy[bb] + cz[c];
-                s1 = s1 + u1[idx] * rx[a] * ry[bb] * rz[c];   // :1012
-                s2 = s2 + u2[idx] * rx[a] * ry[bb] * rz[c];
-                s3 = s3 + u3[idx] * rx[a] * ry[bb] * rz[c];
+        for (int a = 0; a < 4; a++) {
+            double p1 = 0.0, p2 = 0.0, p3 = 0.0;
+            if (b.owned[4 * iEL + a]) {
+                const long long idx = base + b.cell[12 * iEL + a];
+                const double rx = (double)b.Ew[12 * iEL + a];
+                p1 = u1[idx] * rx * ry * rz;   // :1012
+                p2 = u2[idx] * rx * ry * rz;
+                p3 = u3[idx] * rx * ry * rz;
             }
+            sm.p[0][16 * a + gl][mi] = p1; sm.p[1][16 * a + gl][mi] = p2; sm.p[2][16 * a + gl][mi] = p3;
         }
     }
+    __syncthreads();
+    double tol = 0.0;
+    if (threadIdx.x < MARKERS_PER_BLOCK && m0 + (int)threadIdx.x < b.n) {
+        const int m = m0 + threadIdx.x;
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            if (!b.owned[4 * m + a]) continue;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                s1 = s1 + sm.p[0][16 * a + k][threadIdx.x];
+                s2 = s2 + sm.p[1][16 * a + k][threadIdx.x];
+                s3 = s3 + sm.p[2][16 * a + k][threadIdx.x];
+            }
+        }
+        if (fused) { marker_force(b, m, s1, s2, s3, invh3); tol = b.tol[m]; }
+        else { partialU[3 * m + 0] = s1; partialU[3 * m + 1] = s2; partialU[3 * m + 2] = s3; }
+    }
+    __syncthreads();
+    return tol;
 }
 
-__global__ void ibm_gather_ordered_kernel(IbmBody b, const __grid_constant__ IbmBoxes boxes, double *partialU, const IbmCtl *ctl, int fused, double invh3)
+__global__ void __launch_bounds__(256) ibm_gather_ordered_kernel(IbmBody b, const __grid_constant__ IbmBoxes boxes, double *partialU, const IbmCtl *ctl, int fused, double invh3)
 {
     if (ctl->done) return;
-    const int iEL = blockIdx.x * blockDim.x + threadIdx.x;
-    if (iEL >= b.n) return;
-    double s1, s2, s3;
-    gather_marker_serial(b, boxes, iEL, s1, s2, s3);
-    if (fused) marker_force(b, iEL, s1, s2, s3, invh3);
-    else { partialU[3 * iEL + 0] = s1; partialU[3 * iEL + 1] = s2; partialU[3 * iEL + 2] = s3; }
+    __shared__ GatherSmem sm;
+    gather_batch_ordered(b, boxes, blockIdx.x * MARKERS_PER_BLOCK, sm, partialU, fused, invh3);
 }
 
 void launch_ibm_gather_ordered(const IbmBody &b, const IbmBoxes &boxes, double *partialU, const IbmCtl *ctl, int fused, double invh3, cudaStream_t s)
 {
-    ibm_gather_ordered_kernel<<<(b.n + 63) / 64, 64, 0, s>>>(b, boxes, partialU, ctl, fused, invh3);
+    ibm_gather_ordered_kernel<<<(b.n + MARKERS_PER_BLOCK - 1) / MARKERS_PER_BLOCK, 256, 0, s>>>(b, boxes, partialU, ctl, fused, invh3);
     count_launch();
 }
 
@@ -407,8 +429,10 @@ __device__ __forceinline__ unsigned long long csr_key(int body, int marker, int 
     return ((unsigned long long)body << 40) | ((unsigned long long)(unsigned int)marker << 8) | (unsigned long long)node;
 }
 
-// velocity correction of one box cell (:1034-1048): the entries of bodies whose phase is `ph` (or, with phase_of_body
-// null, of body `only_body`), in (body, marker, node) order
+// velocity correction of one box cell by one thread (:1034-1048): the entries of bodies whose phase is `ph` (or, with
+// phase_of_body null, of body `only_body`), in (body, marker, node) order.  One thread per cell keeps tens of thousands of
+// cells in flight, which hides the dependent loads of an entry (key -> marker -> weights, force) better than giving a
+// cell several lanes does: measured 5 us against 11 us per phase at 55k cells / 524k entries.
 __device__ __forceinline__ void scatter_cell(const IbmBody *bodies, const IbmBoxes &boxes, const IbmCsr &csr, long long c, const int *phase_of_body,
                                              int ph, int only_body)
 {
@@ -416,17 +440,31 @@ __device__ __forceinline__ void scatter_cell(const IbmBody *bodies, const IbmBox
     if (beg == end) return;
     double u1 = boxes.u[c], u2 = boxes.u[boxes.ncell + c], u3 = boxes.u[2 * boxes.ncell + c];
     bool any = false;
-    for (int e = beg; e < end; e++) {
-        const unsigned long long key = csr.entry[e];
-        const int body = (int)(key >> 40);
-        if (phase_of_body ? phase_of_body[body] != ph : body != only_body) continue;
-        const int m = (int)((key >> 8) & 0xffffffffull), node = (int)(key & 63ull);
-        const IbmBody &b = bodies[body];
-        const double rx = (double)b.Ew[12 * m + (node >> 4)], ry = (double)b.Ew[12 * m + 4 + ((node >> 2) & 3)], rz = (double)b.Ew[12 * m + 8 + (node & 3)];
-        u1 = u1 - b.felt[3 * m + 0] * rx * ry * rz;   // :1044
-        u2 = u2 - b.felt[3 * m + 1] * rx * ry * rz;
-        u3 = u3 - b.felt[3 * m + 2] * rx * ry * rz;
-        any = true;
+    for (int e0 = beg; e0 < end; e0 += 4) {
+        // four entries at a time: all keys, then all weights and forces, are fetched before the ordered subtraction, so the
+        // dependent loads of the entries overlap instead of queueing behind one another
+        unsigned long long key[4];
+        double q1[4], q2[4], q3[4];
+        bool act[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) key[j] = e0 + j < end ? csr.entry[e0 + j] : ~0ull;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int body = (int)(key[j] >> 40);
+            act[j] = e0 + j < end && (phase_of_body ? phase_of_body[body] == ph : body == only_body);
+            q1[j] = 0.0; q2[j] = 0.0; q3[j] = 0.0;
+            if (act[j]) {
+                const int m = (int)((key[j] >> 8) & 0xffffffffull), node = (int)(key[j] & 63ull);
+                const IbmBody &b = bodies[body];
+                const double rx = (double)b.Ew[12 * m + (node >> 4)], ry = (double)b.Ew[12 * m + 4 + ((node >> 2) & 3)], rz = (double)b.Ew[12 * m + 8 + (node & 3)];
+                q1[j] = b.felt[3 * m + 0] * rx * ry * rz;   // :1044
+                q2[j] = b.felt[3 * m + 1] * rx * ry * rz;
+                q3[j] = b.felt[3 * m + 2] * rx * ry * rz;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (act[j]) { u1 = u1 - q1[j]; u2 = u2 - q2[j]; u3 = u3 - q3[j]; any = true; }
     }
     if (any) { boxes.u[c] = u1; boxes.u[boxes.ncell + c] = u2; boxes.u[2 * boxes.ncell + c] = u3; }
 }
@@ -437,15 +475,27 @@ __device__ __forceinline__ void spread_cell(const IbmBody *bodies, const IbmBoxe
     const int beg = csr.off[c], end = csr.off[c + 1];
     if (beg == end) return;
     double f1 = boxes.force[c], f2 = boxes.force[boxes.ncell + c], f3 = boxes.force[2 * boxes.ncell + c];
-    for (int e = beg; e < end; e++) {
-        const unsigned long long key = csr.entry[e];
-        const int body = (int)(key >> 40), m = (int)((key >> 8) & 0xffffffffull), node = (int)(key & 63ull);
-        const IbmBody &b = bodies[body];
-        const double rx = (double)b.Ew[12 * m + (node >> 4)], ry = (double)b.Ew[12 * m + 4 + ((node >> 2) & 3)], rz = (double)b.Ew[12 * m + 8 + (node & 3)];
-        const double e1 = b.Eforce[3 * m + 0] * invh3, e2 = b.Eforce[3 * m + 1] * invh3, e3 = b.Eforce[3 * m + 2] * invh3;   // :968
-        f1 = f1 + (-e1 * rx * ry * rz);   // :972-974
-        f2 = f2 + (-e2 * rx * ry * rz);
-        f3 = f3 + (-e3 * rx * ry * rz);
+    for (int e0 = beg; e0 < end; e0 += 4) {
+        unsigned long long key[4];
+        double q1[4], q2[4], q3[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) key[j] = e0 + j < end ? csr.entry[e0 + j] : ~0ull;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            q1[j] = 0.0; q2[j] = 0.0; q3[j] = 0.0;
+            if (e0 + j < end) {
+                const int body = (int)(key[j] >> 40), m = (int)((key[j] >> 8) & 0xffffffffull), node = (int)(key[j] & 63ull);
+                const IbmBody &b = bodies[body];
+                const double rx = (double)b.Ew[12 * m + (node >> 4)], ry = (double)b.Ew[12 * m + 4 + ((node >> 2) & 3)], rz = (double)b.Ew[12 * m + 8 + (node & 3)];
+                const double e1 = b.Eforce[3 * m + 0] * invh3, e2 = b.Eforce[3 * m + 1] * invh3, e3 = b.Eforce[3 * m + 2] * invh3;   // :968
+                q1[j] = -e1 * rx * ry * rz;   // :972
+                q2[j] = -e2 * rx * ry * rz;
+                q3[j] = -e3 * rx * ry * rz;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (e0 + j < end) { f1 = f1 + q1[j]; f2 = f2 + q2[j]; f3 = f3 + q3[j]; }   // :974
     }
     boxes.force[c] = f1; boxes.force[boxes.ncell + c] = f2; boxes.force[2 * boxes.ncell + c] = f3;
 }
@@ -494,14 +544,25 @@ __global__ void ibm_csr_nodes_kernel(IbmBody b, int body, IbmCsr csr)
 
 __global__ void ibm_csr_sort_kernel(IbmCsr csr, long long ncell)
 {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per cell: rank sort of up to 32 keys (all distinct), longer lists by insertion
+    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= ncell) return;
-    const int beg = csr.off[c], end = csr.off[c + 1];
-    for (int i = beg + 1; i < end; i++) {   // insertion sort: a cell sees a few dozen stencil nodes at most
-        const unsigned long long k = csr.entry[i];
-        int j = i - 1;
-        while (j >= beg && csr.entry[j] > k) { csr.entry[j + 1] = csr.entry[j]; j--; }
-        csr.entry[j + 1] = k;
+    const int lane = threadIdx.x & 31;
+    const int beg = csr.off[c], end = csr.off[c + 1], cnt = end - beg;
+    if (cnt <= 1) return;
+    if (cnt <= 32) {
+        const unsigned long long k = lane < cnt ? csr.entry[beg + lane] : ~0ull;
+        int rank = 0;
+        for (int j = 0; j < cnt; j++) rank += __shfl_sync(0xffffffffu, k, j) < k ? 1 : 0;
+        __syncwarp();
+        if (lane < cnt) csr.entry[beg + rank] = k;
+    } else if (lane == 0) {
+        for (int i = beg + 1; i < end; i++) {
+            const unsigned long long k = csr.entry[i];
+            int j = i - 1;
+            while (j >= beg && csr.entry[j] > k) { csr.entry[j + 1] = csr.entry[j]; j--; }
+            csr.entry[j + 1] = k;
+        }
     }
 }
 
@@ -527,7 +588,7 @@ int launch_ibm_csr_build(const IbmBody *views, int nbody, const IbmBoxes &boxes,
         ibm_csr_nodes_kernel<true><<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(views[ib], ib, csr);
         count_launch();
     }
-    ibm_csr_sort_kernel<<<(unsigned)((boxes.ncell + 127) / 128), 128, 0, s>>>(csr, boxes.ncell);
+    ibm_csr_sort_kernel<<<(unsigned)((boxes.ncell * 32 + 127) / 128), 128, 0, s>>>(csr, boxes.ncell);
     count_launch();
     return 0;
 }
@@ -545,15 +606,32 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &ep
         epoch += gridDim.x;
         __threadfence();
         atomicAdd(bar, 1u);
-        while (*((volatile unsigned int *)bar) < epoch) { }
+        while (*((volatile unsigned int *)bar) < epoch) __nanosleep(40);   // back off: hundreds of pollers on one line delay the arrivals
         __threadfence();
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) ibm_loop_kernel(const __grid_constant__ IbmLoopParams p)
+__device__ __forceinline__ void prof_stamp(const IbmLoopParams &p, int &k)
+{
+    if (p.prof && blockIdx.x == 0 && threadIdx.x == 0 && k < 63) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.prof[1 + k] = t;
+        p.prof[0] = (unsigned long long)(k + 1);
+    }
+    k++;
+}
+
+__global__ void __launch_bounds__(256, 4) ibm_loop_kernel(const __grid_constant__ IbmLoopParams p)
 {
     unsigned int epoch = 0;
+    int pk = 0;
+    prof_stamp(p, pk);
+    if (p.prof) {   // profiling only: ten empty grid barriers, so that the first interval / 10 is the cost of one
+        for (int i = 0; i < 10; i++) grid_barrier(p.barrier, epoch);
+        prof_stamp(p, pk);
+    }
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
     const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthread = (long long)gridDim.x * blockDim.x;
@@ -569,22 +647,25 @@ __global__ void __launch_bounds__(256) ibm_loop_kernel(const __grid_constant__ I
     if (p.do_macro)
         for (long long i = gthread; i < p.boxes.ncell; i += nthread) macro_box_cell(p.g, p.fA, p.hF[0], p.hF[1], p.hF[2], p.boxes, i);
     grid_barrier(p.barrier, epoch);
+    prof_stamp(p, pk);
     __shared__ double sh_tol[256];
+    __shared__ GatherSmem sh_gather;
+    __shared__ IbmBody sh_bodies[MAX_IBM_PHASE_BODIES];   // the body table next to the SM: the cell loops dereference it per entry
+    for (int i = threadIdx.x; i < p.nbody; i += blockDim.x) sh_bodies[i] = p.bodies[i];
+    __syncthreads();
+    bool done = ((volatile IbmCtl *)p.ctl)->done != 0;   // ntolLBM <= 0; nothing writes it before the second barrier
     for (int it = 0; it < p.ntol; it++) {
-        if (((volatile IbmCtl *)p.ctl)->done) break;   // uniform: written before the last barrier
+        if (p.ordered ? done : (((volatile IbmCtl *)p.ctl)->done != 0)) break;   // uniform over the grid
         double tol_block = 0.0;                        // ordered mode, thread 0: this block's share of the iteration's sum of |dU|
+        double *tol_partial = p.tol_partial + (size_t)(it & 1) * gridDim.x;   // double-buffered: blocks may be one barrier apart
         for (int ph = 0; ph < p.nphase; ph++) {
             // PenaltyForce_ first loop (Solidbody.f90:1000-1027) for the ph-th body of every group
             double tol = 0.0;
             if (p.ordered) {
                 for (int k = p.phase_start[ph]; k < p.phase_start[ph + 1]; k++) {
-                    const IbmBody b = p.bodies[p.phase_body[k]];
-                    for (long long m = gthread; m < b.n; m += nthread) {
-                        double s1, s2, s3;
-                        gather_marker_serial(b, p.boxes, (int)m, s1, s2, s3);
-                        marker_force(b, (int)m, s1, s2, s3, p.invh3_pen);
-                        tol += b.tol[m];
-                    }
+                    const IbmBody &b = sh_bodies[p.phase_body[k]];
+                    for (int m0 = blockIdx.x * MARKERS_PER_BLOCK; m0 < b.n; m0 += gridDim.x * MARKERS_PER_BLOCK)   // uniform over the block
+                        tol += gather_batch_ordered(b, p.boxes, m0, sh_gather, nullptr, 1, p.invh3_pen);
                 }
                 sh_tol[threadIdx.x] = tol;             // fixed-shape tree: the same sum on every run
                 __syncthreads();
@@ -594,7 +675,7 @@ __global__ void __launch_bounds__(256) ibm_loop_kernel(const __grid_constant__ I
                 }
                 if (threadIdx.x == 0) {
                     tol_block += sh_tol[0];
-                    if (ph == p.nphase - 1) p.tol_partial[blockIdx.x] = tol_block;
+                    if (ph == p.nphase - 1) tol_partial[blockIdx.x] = tol_block;
                 }
             } else {
                 for (int k = p.phase_start[ph]; k < p.phase_start[ph + 1]; k++) {
@@ -614,9 +695,10 @@ __global__ void __launch_bounds__(256) ibm_loop_kernel(const __grid_constant__ I
                 }
             }
             grid_barrier(p.barrier, epoch);
+            prof_stamp(p, pk);
             // velocity correction (:1034-1048)
             if (p.ordered) {
-                for (long long c = gthread; c < p.boxes.ncell; c += nthread) scatter_cell(p.bodies, p.boxes, p.csr, c, p.phase_of_body, ph, 0);
+                for (long long c = gthread; c < p.boxes.ncell; c += nthread) scatter_cell(sh_bodies, p.boxes, p.csr, c, p.phase_of_body, ph, 0);
             } else {
                 for (int k = p.phase_start[ph]; k < p.phase_start[ph + 1]; k++) {
                     const IbmBody b = p.bodies[p.phase_body[k]];
@@ -624,23 +706,36 @@ __global__ void __launch_bounds__(256) ibm_loop_kernel(const __grid_constant__ I
                 }
             }
             grid_barrier(p.barrier, epoch);
+            prof_stamp(p, pk);
         }
-        if (blockIdx.x == 0) {   // loop control, :895-906
-            double dmax = 0.0;
-            if (p.ordered) {
-                double t = 0.0;
-                for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += ((volatile double *)p.tol_partial)[i];
-                sh_tol[threadIdx.x] = t;
+        // loop control, :895-906
+        if (p.ordered) {
+            // every block forms the same fixed-shape sum of the per-block partials (written before the barrier that ended the
+            // interpolation phase) and so reaches the same decision without a further barrier; block 0 records it for the host
+            double t = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += ((volatile double *)tol_partial)[i];
+            sh_tol[threadIdx.x] = t;
+            __syncthreads();
+            for (int off = 128; off > 0; off >>= 1) {
+                if ((int)threadIdx.x < off) sh_tol[threadIdx.x] += sh_tol[threadIdx.x + off];
                 __syncthreads();
-                for (int off = 128; off > 0; off >>= 1) {
-                    if ((int)threadIdx.x < off) sh_tol[threadIdx.x] += sh_tol[threadIdx.x + off];
-                    __syncthreads();
-                }
-                dmax = sh_tol[0];
             }
-            if (threadIdx.x == 0) {
+            double dmax = sh_tol[0];
+            __syncthreads();
+            const bool bad = !isfinite(dmax);               // :1028-1031
+            dmax = dmax / (p.dsum * p.Uref);
+            done = !(it + 1 < p.ntol && dmax > p.dtol);
+            if (gthread == 0) {
                 IbmCtl *c = p.ctl;
-                if (!p.ordered) dmax = c->tol_acc;
+                if (bad) atomicOr(&c->err, 2);
+                c->iter = it + 1;
+                c->dmax = dmax;
+                c->done = done ? 1 : 0;
+            }
+        } else {
+            if (gthread == 0) {
+                IbmCtl *c = p.ctl;
+                double dmax = c->tol_acc;
                 if (!isfinite(dmax)) atomicOr(&c->err, 2);   // :1028-1031
                 dmax = dmax / (p.dsum * p.Uref);
                 c->iter = c->iter + 1;
@@ -649,18 +744,19 @@ __global__ void __launch_bounds__(256) ibm_loop_kernel(const __grid_constant__ I
                 c->done = !(c->iter < p.ntol && dmax > p.dtol);
                 __threadfence();
             }
+            grid_barrier(p.barrier, epoch);
         }
-        grid_barrier(p.barrier, epoch);
     }
     // FluidVolumeForce_, Eulerian half (:968-976)
     if (p.ordered) {
-        for (long long c = gthread; c < p.boxes.ncell; c += nthread) spread_cell(p.bodies, p.boxes, p.csr, c, p.invh3);
+        for (long long c = gthread; c < p.boxes.ncell; c += nthread) spread_cell(sh_bodies, p.boxes, p.csr, c, p.invh3);
     } else {
         for (int ib = 0; ib < p.nbody; ib++) {
             const IbmBody b = p.bodies[ib];
             for (int m = gwarp; m < b.n; m += nwarp) spread_marker(b, p.boxes, p.invh3, m, lane);
         }
     }
+    prof_stamp(p, pk);
 }
 
 int ibm_loop_max_blocks()
@@ -680,7 +776,8 @@ int launch_ibm_loop(const IbmLoopParams &p, int max_markers, cudaStream_t s)
 {
     const int max_blocks = ibm_loop_max_blocks();
     int want = (max_markers + 7) / 8;           // one warp per marker of the largest phase
-    const long long cells = (p.boxes.ncell + 255) / 256;
+    long long cells = (p.boxes.ncell + 255) / 256;
+    if (p.ordered) want = (max_markers + MARKERS_PER_BLOCK - 1) / MARKERS_PER_BLOCK;   // 16 lanes per marker, one thread per box cell
     if (cells > want) want = (int)(cells > max_blocks ? max_blocks : cells);
     int blocks = want < 1 ? 1 : (want > max_blocks ? max_blocks : want);
     if (cudaMemsetAsync(p.barrier, 0, sizeof(unsigned int), s) != cudaSuccess) return 1;   // the barrier counts up from zero in every launch

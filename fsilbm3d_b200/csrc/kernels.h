@@ -174,7 +174,8 @@ struct IbmLoopParams {        // the single-launch form of calculate_interaction
     int do_macro;             // 1: phase 0 fills the box cells from fA; 0: done before the launch (multi-rank: all-reduced box velocities)
     IbmCsr csr;
     int phase_of_body[MAX_IBM_PHASE_BODIES];
-    double *tol_partial;      // [gridDim.x] per-block sums of the markers' |dU| (ordered mode)
+    double *tol_partial;      // [2][gridDim.x] per-block sums of the markers' |dU| (ordered mode), double-buffered over iterations
+    unsigned long long *prof; // optional [64] globaltimer stamps of block 0 at the phase boundaries (FSILBM_IBM_PROFILE=1)
 };
 int launch_ibm_loop(const IbmLoopParams &p, int max_markers, cudaStream_t s);
 int ibm_loop_max_blocks();

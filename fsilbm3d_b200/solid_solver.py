@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
+import time as _time
 from typing import Sequence
 
 import numpy as np
@@ -209,6 +210,7 @@ class Plate:
 
     def __init__(self, body: Body):
         self.body = body
+        self.host_seconds = 0.0   # wall time spent in the structural sub-steps (bench.py reports it)
 
     def UpdatePosVelArea(self):
         self.body.UpdatePosVelArea()
@@ -217,7 +219,9 @@ class Plate:
         self.body.FluidLoads()
 
     def structure(self, time: float, isubstep: int, deltat: float, subdeltat: float):
+        t0 = _time.perf_counter()
         self.body.structure(time, isubstep, deltat, subdeltat)
+        self.host_seconds += _time.perf_counter() - t0
 
 
 class SolidBodies:
