@@ -241,9 +241,13 @@ def tree_collision_streaming_IBM_FEM(node, plates: Sequence = (), time: Optional
         # solve overlaps the device's collide-stream of the same step.
         nsub = block.flow.numsubstep
         dt_solid = block.dh / float(nsub)
+        solver_all = getattr(plates[0], "solver_all", None)
         for isub in range(1, nsub + 1):
-            for p in plates:
-                p.structure(block.blktime, isub, block.dh, dt_solid)
+            if solver_all is not None:
+                solver_all(block.blktime, isub, block.dh, dt_solid)         # Solidbody.f90:386-398, threads over bodies
+            else:
+                for p in plates:
+                    p.structure(block.blktime, isub, block.dh, dt_solid)
     for pair in node.comm:
         pair.extract_interpolate_layer(2)                                   # :305
     for son, pair in zip(node.sons, node.comm):                             # :307-317

@@ -54,6 +54,7 @@ def lib():
         L.fsolid_fluid_loads.argtypes = [ctypes.c_int, ctypes.c_int]
         L.fsolid_set_lodflow.argtypes = [ctypes.c_int, ctypes.c_int, dp]
         L.fsolid_structure.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double]
+        L.fsolid_solver.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double]
         L.fsolid_get.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, dp]
         L.fsolid_write.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double]
         _lib = L
@@ -208,9 +209,11 @@ class Plate:
     """Adapter with the shape block_comm.tree_collision_streaming_IBM_FEM expects of a carried body (.body,
     UpdatePosVelArea(), FluidVolumeForce(), structure()): one VBodies(iFish) backed by the C++ beam solver."""
 
-    def __init__(self, body: Body):
+    def __init__(self, body: Body, owner: "SolidBodies" = None):
         self.body = body
         self.host_seconds = 0.0   # wall time spent in the structural sub-steps (bench.py reports it)
+        if owner is not None:
+            self.solver_all = owner.Solver   # block_comm: one call advances every body (threads over bodies, Solidbody.f90:392)
 
     def UpdatePosVelArea(self):
         self.body.UpdatePosVelArea()
@@ -246,16 +249,18 @@ class SolidBodies:
          self.denIn) = list(fl)[:13]
         self.ntolLBM, self.dtolLBM, self.numsubstep = int(fl[13]), fl[14], int(fl[15])
         self.VBodies = [Body(self, i) for i in range(lib().fsolid_nfish(self.h))]
-        self.plates = [Plate(b) for b in self.VBodies]
+        self.plates = [Plate(b, self) for b in self.VBodies]
+        self.host_seconds = 0.0
 
     def _ck(self, rc: int):
         if rc != 0:
             raise SolidError(lib().fsolid_last_error().decode())
 
     def Solver(self, time: float, isubstep: int, deltat: float, subdeltat: float):
-        """Solver, Solidbody.f90:386-398."""
-        for b in self.VBodies:
-            b.structure(time, isubstep, deltat, subdeltat)
+        """Solver, Solidbody.f90:386-398: every body, in parallel over the bodies as the reference's OpenMP loop."""
+        t0 = _time.perf_counter()
+        self._ck(lib().fsolid_solver(self.h, float(time), int(isubstep), float(deltat), float(subdeltat)))
+        self.host_seconds += _time.perf_counter() - t0
 
     def write(self, what: int, time: float, cwd: str):
         old = os.getcwd()

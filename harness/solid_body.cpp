@@ -2,8 +2,12 @@
 #include "solid_body.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
+#include <mutex>
 #include <stdexcept>
+#include <thread>
 
 #include "fortran_io.hpp"
 
@@ -299,7 +303,32 @@ void SolidBodies::Initialise_solid_bodies(double time)
 
 void SolidBodies::Solver(const std::vector<int> &bodies, double time, int isubstep, double deltat, double subdeltat)
 {
-    for (int iFish : bodies) VBodies[iFish].rbm.structure(iFish + 1, time, isubstep, deltat, subdeltat);
+    // !$OMP PARALLEL DO SCHEDULE(DYNAMIC) over the bodies (:392): the beams are independent of one another
+    size_t nt = std::thread::hardware_concurrency();
+    if (const char *e = std::getenv("FSILBM_SOLID_THREADS")) nt = (size_t)std::max(1, std::atoi(e));
+    nt = std::min(nt, bodies.size());
+    if (nt <= 1) {
+        for (int iFish : bodies) VBodies[iFish].rbm.structure(iFish + 1, time, isubstep, deltat, subdeltat);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::mutex err_mutex;
+    std::string err;
+    auto work = [&]() {
+        for (size_t i = next++; i < bodies.size(); i = next++) {
+            try {
+                VBodies[bodies[i]].rbm.structure(bodies[i] + 1, time, isubstep, deltat, subdeltat);
+            } catch (const std::exception &ex) {
+                std::lock_guard<std::mutex> lock(err_mutex);
+                if (err.empty()) err = ex.what();
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < nt; t++) pool.emplace_back(work);
+    work();
+    for (std::thread &t : pool) t.join();
+    if (!err.empty()) throw std::runtime_error(err);
 }
 
 void SolidBodies::write_solid_field(double time) const

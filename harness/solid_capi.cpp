@@ -128,6 +128,16 @@ int fsolid_structure(int handle, int b, double time, int isubstep, double deltat
     return guarded([&] { body(handle, b).rbm.structure(b + 1, time, isubstep, deltat, subdeltat); });
 }
 
+int fsolid_solver(int handle, double time, int isubstep, double deltat, double subdeltat)
+{
+    return guarded([&] {
+        Ctx &c = ctx(handle);
+        std::vector<int> all(c.solid.m_nFish);
+        for (int i = 0; i < c.solid.m_nFish; i++) all[i] = i;
+        c.solid.Solver(all, time, isubstep, deltat, subdeltat);
+    });
+}
+
 int fsolid_get(int handle, int b, int what, double *out)
 {
     return guarded([&] {

@@ -27,6 +27,7 @@ int fsolid_set_eforce(int handle, int body, const double *Eforce);              
 int fsolid_fluid_loads(int handle, int body);                                          /* lodFlow = 0 (:911) + nodal loads (:945-967) */
 int fsolid_set_lodflow(int handle, int body, const double *lodFlow);                   /* direct nodal loads (tests) */
 int fsolid_structure(int handle, int body, double time, int isubstep, double deltat, double subdeltat);   /* Beam_structure, SolidSolver.f90:1820 */
+int fsolid_solver(int handle, double time, int isubstep, double deltat, double subdeltat);                 /* Solver over all bodies, Solidbody.f90:386 (threads over bodies) */
 
 /* what: 0 pos(6,nND) 1 dsp 2 vel 3 acc 4 lodFlow(gEQ) 5 lodInte(gEQ) 6 {iFish, iterNR, dnorm, cg_iterations}
  *       7 triads per element {ee(3,3) n1(3,3) n2(3,3)} row-major [i][j] = triad(i+1,j+1)   8 mss(3,nND)
