@@ -44,6 +44,11 @@ WORKLOADS = {
     "school2048": dict(dims=(256, 512, 512), bc=(101, 104, 301, 301, 301, 301), model=1, plate="flex", layout="one_per_slab",
                        group=dict(iBodyModel=2, denR=1.0, psR=0.3, KB=0.05, KS=800.0, AoAo=(0.0, 0.0, 8.0)), numsubstep=2,
                        desc="configs[4]: one flexible plate (8192 markers each) per GPU slab, two staggered rows, 256x512x512 per GPU, single root block"),
+    # diagnostic: the eight plates of school2048 inside ONE 256x512x512 block (the IBM work every rank of the replicated
+    # form carries at 8 GPUs, without the collectives)
+    "school8x1": dict(dims=(256, 512, 512), bc=(101, 104, 301, 301, 301, 301), model=1, plate="flex", layout="lattice", lattice=(2, 4),
+                      group=dict(iBodyModel=2, denR=1.0, psR=0.3, KB=0.05, KS=800.0, AoAo=(0.0, 0.0, 8.0)), numsubstep=2,
+                      desc="diagnostic: eight flexible plates (8192 markers each) in one 256x512x512 block"),
 }
 
 
@@ -110,6 +115,12 @@ def build_flex(wl, world, rank=0):
     if wl["layout"] == "one_centre":
         first = (0.5 * Xl * world * dh - 0.5 + 0.003, 0.5 * Y * dh - 0.013, 0.5 * Z * dh + 0.003)
         groups.append(dict(wl["group"], fishNum=1, numXYZ=(1, 1, 1), mesh="plate.dat", firstXYZ=first))
+    elif wl["layout"] == "lattice":   # nx x ny plates inside ONE slab (diagnostic workload: every body on every GPU)
+        nx, ny = wl["lattice"]
+        for i in range(nx):
+            for j in range(ny):
+                first = ((i + 0.5) * Xl * world * dh / nx - 0.5 + 0.003, (j + 0.5) * Y * dh / ny - 0.013, 0.5 * Z * dh + 0.003)
+                groups.append(dict(wl["group"], fishNum=1, numXYZ=(1, 1, 1), mesh="plate.dat", firstXYZ=first))
     else:
         for r in range(world):   # one group per body so that the rows can be staggered
             first = ((r + 0.5) * Xl * dh - 0.5 + 0.003, (0.375 if r % 2 == 0 else 0.625) * Y * dh - 0.013, 0.5 * Z * dh + 0.003)
@@ -265,11 +276,22 @@ def run_gpu(args):
     blk.initialise(0.0)
     blk.update_volume_force(); blk.set_boundary_conditions()
     plates, sb = [], None
+    bodies_total = 0
     if wl["plate"] == "flex":
         sb = build_flex(wl, world, rank)
         plates = sb.plates
+        bodies_total = len(plates)
+        if world > 1:
+            # Per-rank body lists: a rank holds (feeds to the library and advances structurally) only the plates that can
+            # reach its slab -- chord box widened by 16 cells; the plates are anchored at their leading edge.  The IBM call is
+            # then collective (loop control all-reduced), a plate across a slab interface is held by both neighbours.
+            lo, hi = (rank * Xl - 16) * dh, ((rank + 1) * Xl + 16) * dh
+            plates = [p for p in plates if p.body.v_Exyz[:, 0].max() >= lo and p.body.v_Exyz[:, 0].min() <= hi]
+            F._lib.check(F.lib().fsilbm_set_option(b"ibm_force_exchange", 0))
+            blk.ibm_collective = True
     elif wl["plate"]:
         plates = [build_plate(F, dh, flow.denIn)]
+        bodies_total = 1
     transport = blk.halo_transport
     stream = torch.cuda.ExternalStream(blk.cuda_stream, device=local)
     lib = F.lib()
@@ -297,11 +319,12 @@ def run_gpu(args):
     ms = e0.elapsed_time(e1)
     structural = None
     if flex:
-        b0 = sb.VBodies[0]
+        b0 = plates[0].body if plates else sb.VBodies[0]
         structural = {"host_ms_per_step_all_bodies": 1e3 * (sb.host_seconds + sum(p.host_seconds for p in plates)) / (args.steps + args.warmup),
-                      "cg_iterations_per_step_body0": float(b0.FishInfo[3]) / (args.steps + args.warmup), "bodies": len(plates),
+                      "cg_iterations_per_step_body0": float(b0.FishInfo[3]) / (args.steps + args.warmup), "bodies": bodies_total,
+                      "bodies_held_by_rank0": len(plates),
                       "note": "C++ restatement of SolidSolver.f90 on the host (one thread per body, as the reference's OpenMP loop), overlapped with the collide-stream launch; "
-                              "in the reference this is the Fortran driver's own work"}
+                              "each rank advances the plates that reach its slab; in the reference this is the Fortran driver's own work"}
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -369,8 +392,13 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_val = cells_total * args.steps / e2e_s / 1e6
-    h2d = f_host.numel() * 8 * world + (sum(7 * p.body.v_nelmts * 8 for p in plates) * args.steps * world)
-    d2h = (den_host.numel() + uuu_host.numel()) * 8 * world * n_out + (sum(3 * p.body.v_nelmts * 8 for p in plates) * args.steps * world)
+    markers = float(sum(p.body.v_nelmts for p in plates))   # held by this rank
+    if world > 1:
+        t = torch.tensor([markers], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        markers = float(t.item())
+    h2d = f_host.numel() * 8 * world + 7 * 8 * markers * args.steps
+    d2h = (den_host.numel() + uuu_host.numel()) * 8 * world * n_out + 3 * 8 * markers * args.steps
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
            "segment": f"fIn uploaded from pinned host once, {args.steps} steps through the LBMBlock API with host arguments, den+uuu read back "
                       f"to pinned host every {flow_every} steps ({n_out} read-backs); wall clock, bytes averaged per step"}

@@ -73,6 +73,7 @@ def lib():
         "fsilbm_block_download_fields": [i, vp, vp, vp], "fsilbm_block_upload_fields": [i, vp, vp, vp],
         "fsilbm_ibm_interaction_force": [i, i, pi, ppd, ppd, ppd, ppd, pi, d, i, d, pi, pi],
         "fsilbm_ibm_download_stencil": [i, i, vp, vp],
+        "fsilbm_ibm_body_status": [i, i, vp],
         "fsilbm_pair_create": [i, i, i, pi], "fsilbm_pair_destroy": [i], "fsilbm_pair_info": [i, pi],
         "fsilbm_pair_extract_layer": [i, i], "fsilbm_pair_father_to_son": [i, i], "fsilbm_pair_son_to_father": [i],
         "fsilbm_comm_unique_id": [C.c_char_p], "fsilbm_comm_init": [i, i, C.c_char_p], "fsilbm_comm_finalize": [],

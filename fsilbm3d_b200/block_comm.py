@@ -223,29 +223,30 @@ def tree_collision_streaming_IBM_FEM(node, plates: Sequence = (), time: Optional
     rootBC = block.BndConds if rootBC is None else rootBC
     block.update_volume_force()                                             # :283
     it = 0
-    if len(plates):                                                         # IBM_FEM, :287 -> :320-338
+    collective = getattr(block, "ibm_collective", False)   # slab runs with per-rank body lists: every rank calls, even with no body
+    if len(plates) or collective:                                           # IBM_FEM, :287 -> :320-338
         for p in plates:
             p.UpdatePosVelArea()                                            # Solidbody.f90:597-600
-        it = block.calculate_interaction_force([p.body for p in plates], rootBC)   # :601
-        for p in plates:                                                        # host half of FluidVolumeForce_ (Solidbody.f90:911,945-967)
-            if hasattr(p, "FluidVolumeForce"):
-                p.FluidVolumeForce()
+        it = block.calculate_interaction_force([p.body for p in plates], rootBC, collective=collective)   # :601
     if iters is not None:
         iters.append(it)
     for pair in node.comm:
         pair.extract_interpolate_layer(1)                                   # :290
     block.collide_stream()                                                  # :285-303 fused; asynchronous launch
-    if len(plates) and solver:
-        # Solver (:333-335).  The reference runs it before the collision; it only advances the beams with the loads
-        # just computed and touches no fluid state, so it is issued here, after the launch, and the host structural
-        # solve overlaps the device's collide-stream of the same step.
-        nsub = block.flow.numsubstep
-        dt_solid = block.dh / float(nsub)
-        solver_all = getattr(plates[0], "solver_all", None)
-        for isub in range(1, nsub + 1):
-            if solver_all is not None:
-                solver_all(block.blktime, isub, block.dh, dt_solid)         # Solidbody.f90:386-398, threads over bodies
-            else:
+    # The host halves of FSInteraction_force -- nodal loads (Solidbody.f90:911,945-967) and Solver (:333-335) -- only read
+    # the marker forces just returned and touch no fluid state.  The reference runs them before the collision; here they
+    # are issued after the launch so that they overlap the device's collide-stream of the same step.
+    owner = getattr(plates[0], "owner", None) if len(plates) else None
+    if len(plates) and solver and owner is not None and all(getattr(p, "owner", None) is owner for p in plates):
+        owner.advance([p.body.index for p in plates], block.blktime, block.flow.numsubstep, block.dh)
+    elif len(plates):
+        for p in plates:
+            if hasattr(p, "FluidVolumeForce"):
+                p.FluidVolumeForce()
+        if solver:
+            nsub = block.flow.numsubstep
+            dt_solid = block.dh / float(nsub)
+            for isub in range(1, nsub + 1):
                 for p in plates:
                     p.structure(block.blktime, isub, block.dh, dt_solid)
     for pair in node.comm:

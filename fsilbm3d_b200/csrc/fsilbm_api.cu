@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <dlfcn.h>
 #include <memory>
 #include <string>
@@ -31,6 +32,11 @@ static int fail(int code, const char *fmt, ...)
         cudaError_t e_ = (call);                                                                              \
         if (e_ != cudaSuccess) return fail(FSILBM_ERR_CUDA, "CUDA: %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+static double wall_seconds()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 // ---- NCCL through dlopen (only multi-rank runs need it) ------------------------------------------------
 namespace {
@@ -87,6 +93,42 @@ int nccl_load()
     } while (0)
 
 // ---- block state ------------------------------------------------------------------------------------
+struct Interval { int s, l; };   // start in [0,N), length <= N, on a circle of N (or a line if not periodic)
+
+inline int imod(int a, int n) { int r = a % n; return r < 0 ? r + n : r; }
+
+// union of two overlapping intervals on a circle of N
+inline bool overlap(const Interval &a, const Interval &b, int N) { return imod(b.s - a.s, N) < a.l || imod(a.s - b.s, N) < b.l; }
+inline Interval merge(const Interval &a, const Interval &b, int N)
+{
+    Interval r;
+    if (imod(b.s - a.s, N) < a.l) { r.s = a.s; r.l = std::max(a.l, imod(b.s - a.s, N) + b.l); }
+    else { r.s = b.s; r.l = std::max(b.l, imod(a.s - b.s, N) + a.l); }
+    if (r.l >= N) { r.s = 0; r.l = N; }
+    return r;
+}
+
+struct HostBox { Interval ax[3]; };
+
+// bounding interval of the base indices i (1-based, Solidbody.f90:817-820) of one body along one axis,
+// widened to the 4-point stencil i-1..i+2 plus one guard cell each side
+Interval axis_interval(int imin, int imax, int N, bool periodic)
+{
+    int lo = imin - 1 - 1 - 1, hi = imax + 2 - 1 + 1;   // 0-based, guard of 1
+    Interval r;
+    if (periodic) {
+        int len = hi - lo + 1;
+        if (len >= N) { r.s = 0; r.l = N; }
+        else { r.s = imod(lo, N); r.l = len; }
+    } else {
+        lo = std::max(lo, 0); hi = std::min(hi, N - 1);
+        if (hi < lo) { lo = 0; hi = 0; }
+        r.s = lo; r.l = hi - lo + 1;
+    }
+    return r;
+}
+
+
 struct BodyDev {
     int n = 0;
     double *Exyz = nullptr, *ExyzStencil = nullptr, *Evel = nullptr, *Ea = nullptr, *Eforce = nullptr, *felt = nullptr, *tol = nullptr;
@@ -96,10 +138,14 @@ struct BodyDev {
     int *cell = nullptr;
     long long *boff = nullptr;
     unsigned char *owned = nullptr;
-    bool have_stencil_pos = false;
+    // Exyz, Evel, Ea and Eforce point into the block's packed marker / force buffers (Block::mk_dev, force_dev)
+    HostBox hbox{};             // box of the stencils last built (host index arithmetic of UpdateElmtInterp_)
+    int cidx[3] = {0, 0, 0};    // cell of the first marker at that time
+    bool have_box = false;
+    int status = 0;             // last call: 0 not iterated by this rank (no plane of its box here), 1 iterated, 2 iterated and led
     void release()
     {
-        cudaFree(Exyz); cudaFree(ExyzStencil); cudaFree(Evel); cudaFree(Ea); cudaFree(Eforce); cudaFree(felt); cudaFree(tol);
+        cudaFree(ExyzStencil); cudaFree(felt); cudaFree(tol);
         cudaFree(partialU); cudaFree(Ei); cudaFree(Ew); cudaFree(cell); cudaFree(boff); cudaFree(owned);
         *this = BodyDev();
     }
@@ -138,9 +184,18 @@ struct Block {
     IbmBoxes boxes{};
     long long box_capacity = 0;
     std::vector<BodyDev> bodies;
-    std::vector<std::vector<double>> stencil_pos;   // host copy of the marker positions the stencils were last built from
+    double *mk_dev = nullptr, *force_dev = nullptr;     // packed [per body: Exyz 3n | Evel 3n | Ea n] and [per body: Eforce 3n]
+    double *mk_pin = nullptr, *force_pin = nullptr;     // their pinned host mirrors
+    size_t marker_cap = 0, marker_total = 0;
+    std::vector<size_t> mk_off, f_off;
+    std::vector<int> active_prev;                       // bodies iterated by this rank at the last call
+    std::vector<int> plane_owner;                       // slab runs: rank owning each global x-plane
     IbmBody *bodies_dev = nullptr;
+    int *lead_dev = nullptr;
+    double *tol2 = nullptr;
     int bodies_dev_cap = 0;
+    cudaStream_t ibm_stream = nullptr;                  // marker upload, stencils and cell lists run beside the compute stream
+    cudaEvent_t ev_ibm = nullptr;
     IbmCtl *ctl = nullptr;
     unsigned int *ibm_barrier = nullptr;
     bool ibm_active = false;
@@ -150,6 +205,7 @@ struct Block {
     bool csr_valid = false;
     double *tol_partial = nullptr;
     unsigned long long *ibm_prof = nullptr; int ibm_prof_calls = 0;
+    double ibm_host_t[3] = {0.0, 0.0, 0.0};   // FSILBM_IBM_PROFILE: host seconds in box set-up / enqueue / wait, summed over 100 calls
     cudaStream_t stream = nullptr, comm_stream = nullptr;
     cudaEvent_t ev_edge = nullptr, ev_comm = nullptr;
     // peer-memory halo (multi-GPU): see halo_setup
@@ -180,6 +236,10 @@ int g_halo_timeout_s = 120;   // a neighbour this late is treated as lost (the w
 int g_ibm_single_launch = 1;   // 1: calculate_interaction_force as one cooperative kernel on single-rank blocks; 0: one kernel per phase
 int g_ibm_replicate = 1;       // multi-rank, ordered mode: 1 every rank runs the whole penalty iteration on all-reduced box velocities (one
                                // collective per step, bit-identical to one GPU); 0 partial interpolation sums all-reduced per body and iteration
+int g_ibm_local = 1;           // multi-rank, ordered mode: 1 a body is iterated only by the ranks whose planes its stencil box touches (default);
+                               // 0 the replicated / partial-sum forms below
+int g_ibm_force_exchange = 1;  // with ibm_local: 1 every rank passes the same bodies and gets every body's forces back (one all-reduce);
+                               // 0 every rank passes only the bodies near its slab (distributed lists; the call is then collective even with none)
 int g_ibm_ordered = 1;         // 1: interpolation and spreading keep the reference's serial summation order (bit-reproducible); 0: shuffles + fp64 atomics
 int g_halo_mode = 1;   // 1: edge kernels store into the neighbours' memory over NVLink (default); 0: ncclSend/ncclRecv
 
@@ -495,6 +555,8 @@ int fsilbm_set_option(const char *key, int value)
     if (!strcmp(key, "force_ghost")) { g_force_ghost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_single_launch")) { g_ibm_single_launch = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_replicate")) { g_ibm_replicate = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->csr_valid = false; return 0; }
+    if (!strcmp(key, "ibm_local")) { g_ibm_local = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->csr_valid = false; return 0; }
+    if (!strcmp(key, "ibm_force_exchange")) { g_ibm_force_exchange = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_ordered")) { g_ibm_ordered = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->csr_valid = false; return 0; }
     if (!strcmp(key, "halo_timeout_s")) { if (value < 1) return fail(FSILBM_ERR_ARG, "halo_timeout_s must be >= 1"); g_halo_timeout_s = value; return 0; }
     if (!strcmp(key, "halo")) { if (value < 0 || value > 1) return fail(FSILBM_ERR_ARG, "halo must be 0 (NCCL) or 1 (peer stores)"); g_halo_mode = value; return 0; }
@@ -545,6 +607,8 @@ int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, d
     }
     CK(cudaEventCreateWithFlags(&b->ev_edge, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_comm, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&b->ibm_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&b->ev_ibm, cudaEventDisableTiming));
     CK(cudaMalloc(&b->ctl, sizeof(IbmCtl)));
     CK(cudaMalloc(&b->ibm_barrier, sizeof(unsigned int)));
     CK(cudaMemset(b->ibm_barrier, 0, sizeof(unsigned int)));
@@ -573,7 +637,10 @@ int fsilbm_block_destroy(fsilbm_handle h)
     cudaFree(b->uuu_ave); cudaFree(b->outtmp); cudaFree(b->scratch);
     cudaFree(b->boxes.u); cudaFree(b->boxes.force);
     for (auto &bd : b->bodies) bd.release();
-    cudaFree(b->bodies_dev); cudaFree(b->ctl); cudaFree(b->ibm_barrier);
+    cudaStreamSynchronize(b->ibm_stream);
+    cudaFree(b->bodies_dev); cudaFree(b->lead_dev); cudaFree(b->tol2); cudaFree(b->ctl); cudaFree(b->ibm_barrier);
+    cudaFree(b->mk_dev); cudaFree(b->force_dev); cudaFreeHost(b->mk_pin); cudaFreeHost(b->force_pin);
+    cudaEventDestroy(b->ev_ibm); cudaStreamDestroy(b->ibm_stream);
     cudaFree(b->csr.count); cudaFree(b->csr.off); cudaFree(b->csr.entry); cudaFree(b->csr_scan_tmp); cudaFree(b->tol_partial);
     cudaEventDestroy(b->ev_edge); cudaEventDestroy(b->ev_comm);
     cudaStreamDestroy(b->comm_stream);
@@ -1065,45 +1132,6 @@ int fsilbm_block_upload_fields(fsilbm_handle h, const double *den, const double 
 }
 
 // ---- IBM ------------------------------------------------------------------------------------------
-namespace {
-
-struct Interval { int s, l; };   // start in [0,N), length <= N, on a circle of N (or a line if not periodic)
-
-inline int imod(int a, int n) { int r = a % n; return r < 0 ? r + n : r; }
-
-// union of two overlapping intervals on a circle of N
-inline bool overlap(const Interval &a, const Interval &b, int N) { return imod(b.s - a.s, N) < a.l || imod(a.s - b.s, N) < b.l; }
-inline Interval merge(const Interval &a, const Interval &b, int N)
-{
-    Interval r;
-    if (imod(b.s - a.s, N) < a.l) { r.s = a.s; r.l = std::max(a.l, imod(b.s - a.s, N) + b.l); }
-    else { r.s = b.s; r.l = std::max(b.l, imod(a.s - b.s, N) + a.l); }
-    if (r.l >= N) { r.s = 0; r.l = N; }
-    return r;
-}
-
-struct HostBox { Interval ax[3]; };
-
-// bounding interval of the base indices i (1-based, Solidbody.f90:817-820) of one body along one axis,
-// widened to the 4-point stencil i-1..i+2 plus one guard cell each side
-Interval axis_interval(int imin, int imax, int N, bool periodic)
-{
-    int lo = imin - 1 - 1 - 1, hi = imax + 2 - 1 + 1;   // 0-based, guard of 1
-    Interval r;
-    if (periodic) {
-        int len = hi - lo + 1;
-        if (len >= N) { r.s = 0; r.l = N; }
-        else { r.s = imod(lo, N); r.l = len; }
-    } else {
-        lo = std::max(lo, 0); hi = std::min(hi, N - 1);
-        if (hi < lo) { lo = 0; hi = 0; }
-        r.s = lo; r.l = hi - lo + 1;
-    }
-    return r;
-}
-
-}  // namespace
-
 int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, const double *const *Exyz, const double *const *Evel,
                                  const double *const *Ea, double *const *Eforce, const int *restencil, double dt, int ntolLBM,
                                  double dtolLBM, const int rootBC[6], int *iterLBM_out)
@@ -1114,13 +1142,24 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
     if (nbody < 0 || (nbody > 0 && (!nelmts || !Exyz || !Evel || !Ea || !Eforce || !restencil || !rootBC)))
         return fail(FSILBM_ERR_ARG, "null argument");
     if (iterLBM_out) *iterLBM_out = 0;
-    if (nbody == 0) { b.ibm_active = false; return 0; }   // Solidbody.f90:891
     const Geom &g = b.g;
-    cudaStream_t s = b.stream;
-    const bool multi = g_nccl.nranks > 1 && g_nccl.comm;
+    cudaStream_t s = b.stream, s2 = b.ibm_stream;
+    const bool multi = g_nccl.nranks > 1 && g_nccl.comm && g.X != g.XG;   // this block is split into x-slabs
+    const bool ordered = g_ibm_ordered != 0;
+    // Slab runs, default form ("local"): a body is iterated only by the ranks whose planes its stencil box touches.
+    // Shared boxes (a body across a slab interface) exchange their owned box planes pairwise and are then iterated
+    // redundantly -- bit-identically -- by their participants; the loop control is all-reduced (two numbers per iteration).
+    const bool local = multi && ordered && g_ibm_local;
+    const bool lists_replicated = g_ibm_force_exchange != 0;   // every rank passes the same bodies and wants every force back
+    if (nbody == 0 && !(local && !lists_replicated)) { b.ibm_active = false; return 0; }   // Solidbody.f90:891
+    static const bool want_prof = getenv("FSILBM_IBM_PROFILE") != nullptr;
+    const double tp0 = want_prof ? wall_seconds() : 0.0;
+    const int me = g_nccl.rank;
 
-    // -- device marker storage
-    if ((int)b.bodies.size() != nbody) {
+    // -- device marker storage: per-body scratch + one packed marker buffer and one packed force buffer (a single
+    //    H2D / D2H each, staged through pinned host memory so that the copies are truly asynchronous)
+    bool relayout = (int)b.bodies.size() != nbody;
+    if (relayout) {
         for (auto &bd : b.bodies) bd.release();
         b.bodies.assign(nbody, BodyDev());
         b.csr_valid = false;
@@ -1132,132 +1171,213 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         if (bd.n != n) {
             bd.release();
             b.csr_valid = false;
+            relayout = true;
             bd.n = n;
-            CK(cudaMalloc(&bd.Exyz, sizeof(double) * 3 * n)); CK(cudaMalloc(&bd.ExyzStencil, sizeof(double) * 3 * n));
-            CK(cudaMalloc(&bd.Evel, sizeof(double) * 3 * n)); CK(cudaMalloc(&bd.Ea, sizeof(double) * n));
-            CK(cudaMalloc(&bd.Eforce, sizeof(double) * 3 * n)); CK(cudaMalloc(&bd.felt, sizeof(double) * 3 * n));
+            CK(cudaMalloc(&bd.ExyzStencil, sizeof(double) * 3 * n));
+            CK(cudaMalloc(&bd.felt, sizeof(double) * 3 * n));
             CK(cudaMalloc(&bd.tol, sizeof(double) * n)); CK(cudaMalloc(&bd.partialU, sizeof(double) * 3 * n));
             CK(cudaMalloc(&bd.Ei, sizeof(short) * 12 * n)); CK(cudaMalloc(&bd.Ew, sizeof(float) * 12 * n));
             CK(cudaMalloc(&bd.cell, sizeof(int) * 12 * n)); CK(cudaMalloc(&bd.boff, sizeof(long long) * n));
             CK(cudaMalloc(&bd.owned, 4 * n));
         }
     }
+    if (relayout) {
+        size_t ntot = 0;
+        b.mk_off.assign(nbody, 0); b.f_off.assign(nbody, 0);
+        for (int ib = 0; ib < nbody; ib++) { b.mk_off[ib] = 7 * ntot; b.f_off[ib] = 3 * ntot; ntot += (size_t)nelmts[ib]; }
+        b.marker_total = ntot;
+        if (ntot > b.marker_cap) {
+            CK(cudaStreamSynchronize(s)); CK(cudaStreamSynchronize(s2));
+            cudaFree(b.mk_dev); cudaFree(b.force_dev); cudaFreeHost(b.mk_pin); cudaFreeHost(b.force_pin);
+            b.mk_dev = b.force_dev = b.mk_pin = b.force_pin = nullptr;
+            CK(cudaMalloc(&b.mk_dev, sizeof(double) * 7 * ntot)); CK(cudaMalloc(&b.force_dev, sizeof(double) * 3 * ntot));
+            CK(cudaMallocHost(&b.mk_pin, sizeof(double) * 7 * ntot)); CK(cudaMallocHost(&b.force_pin, sizeof(double) * 3 * ntot));
+            b.marker_cap = ntot;
+        }
+        for (int ib = 0; ib < nbody; ib++) {
+            BodyDev &bd = b.bodies[ib];
+            const size_t n = bd.n;
+            bd.Exyz = b.mk_dev + b.mk_off[ib]; bd.Evel = bd.Exyz + 3 * n; bd.Ea = bd.Evel + 3 * n;
+            bd.Eforce = b.force_dev + b.f_off[ib];
+        }
+    }
 
-    // -- host: boxes around the stencils of each body (same index arithmetic as UpdateElmtInterp_, :771-780,817-820)
-    std::vector<HostBox> hb;
-    std::vector<std::vector<double>> &stencil_pos = b.stencil_pos;
-    if ((int)stencil_pos.size() != nbody) stencil_pos.assign(nbody, std::vector<double>());
+    // -- host: box around the stencils of each body (same index arithmetic as UpdateElmtInterp_, :771-780,817-820).
+    //    floor((x - x0)*invdh) does not decrease with x, so the extreme indices are those of the extreme coordinates.
     const double invdh = 1.0 / g.dh;
     const double mins[3] = {g.xmin, g.ymin, g.zmin};
     const int Ns[3] = {g.XG, g.Y, g.Z};
+    std::vector<char> re(nbody, 0);
     for (int ib = 0; ib < nbody; ib++) {
-        const int n = nelmts[ib];
         BodyDev &bd = b.bodies[ib];
-        const bool re = restencil[ib] != 0 || !bd.have_stencil_pos;
-        if (re) { stencil_pos[ib].assign(Exyz[ib], Exyz[ib] + 3 * (size_t)n); b.csr_valid = false; }
-        const double *P = stencil_pos[ib].data();
-        HostBox box;
+        re[ib] = (restencil[ib] != 0 || !bd.have_box) ? 1 : 0;
+        if (!re[ib]) continue;
+        b.csr_valid = false;
+        const int n = bd.n;
+        const double *P = Exyz[ib];
+        double lo[3] = {P[0], P[1], P[2]}, hi[3] = {P[0], P[1], P[2]};
+        for (int e = 1; e < n; e++)
+            for (int a = 0; a < 3; a++) { const double v = P[3 * e + a]; lo[a] = v < lo[a] ? v : lo[a]; hi[a] = v > hi[a] ? v : hi[a]; }
         for (int a = 0; a < 3; a++) {
             int i0 = (int)floor((P[a] - mins[a]) * invdh);
             const double x0 = mins[a] + (double)i0 * g.dh;
+            bd.cidx[a] = imod(i0, Ns[a]);
             i0 = i0 + 1;
-            int imin = 1 << 30, imax = -(1 << 30);
-            for (int e = 0; e < n; e++) {
-                const double off = (P[3 * e + a] - x0) * invdh;
-                const int idx = (int)floor(off) + i0;
-                imin = std::min(imin, idx); imax = std::max(imax, idx);
-            }
-            box.ax[a] = axis_interval(imin, imax, Ns[a], rootBC[2 * a] == BCPeriodic);
+            const int imin = (int)floor((lo[a] - x0) * invdh) + i0, imax = (int)floor((hi[a] - x0) * invdh) + i0;
+            bd.hbox.ax[a] = axis_interval(imin, imax, Ns[a], rootBC[2 * a] == BCPeriodic);
         }
-        hb.push_back(box);
+        bd.have_box = true;
     }
     // merge boxes that overlap so bodies sharing cells share storage (Gauss-Seidel coupling, Solidbody.f90:898-903)
+    struct MBox { HostBox hb; std::vector<int> members; };
+    std::vector<MBox> mb(nbody);
+    for (int ib = 0; ib < nbody; ib++) { mb[ib].hb = b.bodies[ib].hbox; mb[ib].members.assign(1, ib); }
     for (bool changed = true; changed;) {
         changed = false;
-        for (size_t i = 0; i < hb.size() && !changed; i++)
-            for (size_t j = i + 1; j < hb.size() && !changed; j++) {
+        for (size_t i = 0; i < mb.size() && !changed; i++)
+            for (size_t j = i + 1; j < mb.size() && !changed; j++) {
                 bool ov = true;
-                for (int a = 0; a < 3; a++) ov = ov && overlap(hb[i].ax[a], hb[j].ax[a], Ns[a]);
+                for (int a = 0; a < 3; a++) ov = ov && overlap(mb[i].hb.ax[a], mb[j].hb.ax[a], Ns[a]);
                 if (ov) {
-                    for (int a = 0; a < 3; a++) hb[i].ax[a] = merge(hb[i].ax[a], hb[j].ax[a], Ns[a]);
-                    hb.erase(hb.begin() + j);
+                    for (int a = 0; a < 3; a++) mb[i].hb.ax[a] = merge(mb[i].hb.ax[a], mb[j].hb.ax[a], Ns[a]);
+                    mb[i].members.insert(mb[i].members.end(), mb[j].members.begin(), mb[j].members.end());
+                    mb.erase(mb.begin() + j);
                     changed = true;
                 }
             }
     }
-    while ((int)hb.size() > MAX_BOXES) {   // too many separate bodies: fold the tail into one covering box
-        HostBox &a0 = hb[hb.size() - 2], &b0 = hb.back();
+    // -- slab runs: which ranks own planes of each box
+    struct Run { int rank, dx0, dx1; };
+    std::vector<std::vector<Run>> runs(mb.size());
+    std::vector<char> keep(mb.size(), 1), shared(mb.size(), 0);
+    if (local) {
+        if (b.plane_owner.empty()) {   // collective, once: the x-slab of every rank
+            int mine[2] = {g.xOffset, g.X}, *dsend = nullptr, *drecv = nullptr;
+            CK(cudaMalloc(&dsend, sizeof(mine))); CK(cudaMalloc(&drecv, sizeof(mine) * g_nccl.nranks));
+            CK(cudaMemcpy(dsend, mine, sizeof(mine), cudaMemcpyHostToDevice));
+            NCK(g_nccl.AllGather(dsend, drecv, sizeof(mine), kNcclChar, g_nccl.comm, s));
+            CK(cudaStreamSynchronize(s));
+            std::vector<int> all(2 * g_nccl.nranks);
+            CK(cudaMemcpy(all.data(), drecv, sizeof(mine) * g_nccl.nranks, cudaMemcpyDeviceToHost));
+            cudaFree(dsend); cudaFree(drecv);
+            b.plane_owner.assign(g.XG, -1);
+            for (int r = 0; r < g_nccl.nranks; r++)
+                for (int x = all[2 * r]; x < all[2 * r] + all[2 * r + 1] && x < g.XG; x++) b.plane_owner[x] = r;
+            for (int x = 0; x < g.XG; x++) if (b.plane_owner[x] < 0) return fail(FSILBM_ERR_COMM, "x-plane %d belongs to no rank's slab", x);
+        }
+        for (size_t k = 0; k < mb.size(); k++) {
+            const Interval &ix = mb[k].hb.ax[0];
+            bool mine_in = false;
+            for (int dx = 0; dx < ix.l; dx++) {
+                const int r = b.plane_owner[(ix.s + dx) % g.XG];
+                if (runs[k].empty() || runs[k].back().rank != r) runs[k].push_back(Run{r, dx, dx + 1}); else runs[k].back().dx1 = dx + 1;
+                mine_in = mine_in || r == me;
+            }
+            keep[k] = mine_in ? 1 : 0;
+            for (const Run &r : runs[k]) if (r.rank != runs[k][0].rank) shared[k] = 1;
+        }
+    }
+    std::vector<int> kept;
+    for (size_t k = 0; k < mb.size(); k++) if (keep[k]) kept.push_back((int)k);
+    if (local && (int)kept.size() > MAX_BOXES) return fail(FSILBM_ERR_ARG, "more than %d separate stencil boxes touch this slab", MAX_BOXES);
+    while (!local && (int)kept.size() > MAX_BOXES) {   // too many separate bodies: fold the tail into one covering box
+        MBox &a0 = mb[kept[kept.size() - 2]], &b0 = mb[kept.back()];
         for (int a = 0; a < 3; a++) {
             // covering interval of two disjoint intervals on the circle
-            Interval x = a0.ax[a], y = b0.ax[a], r;
+            Interval x = a0.hb.ax[a], y = b0.hb.ax[a], r;
             const int d1 = imod(y.s - x.s, Ns[a]) + y.l, d2 = imod(x.s - y.s, Ns[a]) + x.l;
             if (std::max(d1, x.l) <= std::max(d2, y.l)) { r.s = x.s; r.l = std::max(d1, x.l); } else { r.s = y.s; r.l = std::max(d2, y.l); }
             if (r.l >= Ns[a]) { r.s = 0; r.l = Ns[a]; }
-            a0.ax[a] = r;
+            a0.hb.ax[a] = r;
         }
-        hb.pop_back();
+        a0.members.insert(a0.members.end(), b0.members.begin(), b0.members.end());
+        kept.pop_back();
+    }
+    // active bodies (caller order = device order, so the cell lists keep the reference's body order), their box group and
+    // whether this rank leads them (owns the first plane of their box: it reports their residual and their forces)
+    std::vector<int> group_of(nbody, -1), lead_of(nbody, 0);
+    for (size_t kk = 0; kk < kept.size(); kk++)
+        for (int ib : mb[kept[kk]].members) {
+            group_of[ib] = (int)kk;
+            lead_of[ib] = (!local || runs[kept[kk]][0].rank == me) ? 1 : 0;
+        }
+    std::vector<int> act;
+    for (int ib = 0; ib < nbody; ib++) {
+        if (group_of[ib] >= 0) act.push_back(ib);
+        b.bodies[ib].status = group_of[ib] < 0 ? 0 : (lead_of[ib] ? 2 : 1);
+    }
+    const int nact = (int)act.size();
+    {   // the set of active bodies decides the device body table and the cell lists
+        if (b.active_prev != act) { b.csr_valid = false; b.active_prev = act; }
     }
     IbmBoxes &bx = b.boxes;
-    bx.n = (int)hb.size();
+    bx.n = (int)kept.size();
     long long total = 0;
     for (int i = 0; i < bx.n; i++) {
-        for (int a = 0; a < 3; a++) { bx.lo[i][a] = hb[i].ax[a].s; bx.ext[i][a] = hb[i].ax[a].l; }
+        const HostBox &hb = mb[kept[i]].hb;
+        for (int a = 0; a < 3; a++) { bx.lo[i][a] = hb.ax[a].s; bx.ext[i][a] = hb.ax[a].l; }
         bx.off[i] = total;
         total += (long long)bx.ext[i][0] * bx.ext[i][1] * bx.ext[i][2];
     }
     bx.ncell = total;
     if (total > b.box_capacity) {
-        CK(cudaStreamSynchronize(s));
+        CK(cudaStreamSynchronize(s)); CK(cudaStreamSynchronize(s2));
         cudaFree(bx.u); cudaFree(bx.force);
         const long long cap = total + total / 4 + 1024;
         CK(cudaMalloc(&bx.u, sizeof(double) * 3 * cap));
         CK(cudaMalloc(&bx.force, sizeof(double) * 3 * cap));
         b.box_capacity = cap;
     }
+    const double tp1 = want_prof ? wall_seconds() : 0.0;
 
-    // -- upload markers
-    for (int ib = 0; ib < nbody; ib++) {
+    // -- side stream: marker upload, UpdateElmtInterp_ and the cell lists need nothing of the fluid state, so they run
+    //    beside whatever the compute stream is still doing (the collide-stream kernel of the previous step)
+    if (b.marker_total) CK(cudaMemsetAsync(b.force_dev, 0, sizeof(double) * 3 * b.marker_total, s2));   // Solidbody.f90:889
+    for (int k = 0; k < nact; k++) {
+        const int ib = act[k];
         BodyDev &bd = b.bodies[ib];
         const size_t n = bd.n;
-        CK(cudaMemcpyAsync(bd.Exyz, Exyz[ib], sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(bd.Evel, Evel[ib], sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(bd.Ea, Ea[ib], sizeof(double) * n, cudaMemcpyHostToDevice, s));
-        if (restencil[ib] != 0 || !bd.have_stencil_pos) {
-            CK(cudaMemcpyAsync(bd.ExyzStencil, bd.Exyz, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, s));
-            bd.have_stencil_pos = true;
-        }
-        CK(cudaMemsetAsync(bd.Eforce, 0, sizeof(double) * 3 * n, s));   // Solidbody.f90:889
+        double *pin = b.mk_pin + b.mk_off[ib];
+        memcpy(pin, Exyz[ib], sizeof(double) * 3 * n);
+        memcpy(pin + 3 * n, Evel[ib], sizeof(double) * 3 * n);
+        memcpy(pin + 6 * n, Ea[ib], sizeof(double) * n);
+        CK(cudaMemcpyAsync(bd.Exyz, pin, sizeof(double) * 7 * n, cudaMemcpyHostToDevice, s2));
+        if (re[ib]) CK(cudaMemcpyAsync(bd.ExyzStencil, bd.Exyz, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, s2));
     }
     IbmCtl ctl0;
     ctl0.iter = 0; ctl0.done = (ntolLBM <= 0) ? 1 : 0; ctl0.err = 0; ctl0.dmax = 1e10; ctl0.tol_acc = 0.0;   // :893-894
-    CK(cudaMemcpyAsync(b.ctl, &ctl0, sizeof(IbmCtl), cudaMemcpyHostToDevice, s));
-    if (b.bodies_dev_cap < nbody) {
-        cudaFree(b.bodies_dev);
-        CK(cudaMalloc(&b.bodies_dev, sizeof(IbmBody) * nbody));
-        b.bodies_dev_cap = nbody;
+    CK(cudaMemcpyAsync(b.ctl, &ctl0, sizeof(IbmCtl), cudaMemcpyHostToDevice, s2));
+    if (b.bodies_dev_cap < nact) {
+        CK(cudaStreamSynchronize(s)); CK(cudaStreamSynchronize(s2));
+        cudaFree(b.bodies_dev); cudaFree(b.lead_dev);
+        CK(cudaMalloc(&b.bodies_dev, sizeof(IbmBody) * nact));
+        CK(cudaMalloc(&b.lead_dev, sizeof(int) * nact));
+        b.bodies_dev_cap = nact;
     }
-    std::vector<IbmBody> views(nbody);
-    for (int ib = 0; ib < nbody; ib++) views[ib] = b.bodies[ib].view();
-    CK(cudaMemcpyAsync(b.bodies_dev, views.data(), sizeof(IbmBody) * nbody, cudaMemcpyHostToDevice, s));
+    std::vector<IbmBody> views(nact);
+    std::vector<int> lead(nact);
+    for (int k = 0; k < nact; k++) { views[k] = b.bodies[act[k]].view(); lead[k] = lead_of[act[k]]; }
+    if (nact) {
+        CK(cudaMemcpyAsync(b.bodies_dev, views.data(), sizeof(IbmBody) * nact, cudaMemcpyHostToDevice, s2));
+        CK(cudaMemcpyAsync(b.lead_dev, lead.data(), sizeof(int) * nact, cudaMemcpyHostToDevice, s2));
+    }
 
     double hF[3];
     half_force(b, hF);
     const double invh3_pen = 0.5 * dt * ((1.0 / g.dh) * (1.0 / g.dh) * (1.0 / g.dh)) / b.flow.denIn;   // :996
     const double invh3 = (1.0 / g.dh) * (1.0 / g.dh) * (1.0 / g.dh);                                     // :936
-    const bool ordered = g_ibm_ordered != 0;
-    // Multi-rank, replicated form: the box velocities (owner's value, zero elsewhere: the sum is exact) are all-reduced
-    // once, then every rank runs the whole of calculate_interaction_force on the full boxes.  All ranks hold the same
-    // marker forces afterwards, bit-identical to the one-GPU result; the collide kernel of each rank reads its own planes.
-    const bool replicate = multi && ordered && g_ibm_replicate;
-    bool single = (!multi || replicate) && g_ibm_single_launch && nbody <= MAX_IBM_PHASE_BODIES;
+    // Multi-rank, replicated form (ibm_local = 0): the box velocities (owner's value, zero elsewhere: the sum is exact) are
+    // all-reduced once, then every rank runs the whole of calculate_interaction_force on the full boxes of ALL bodies.
+    const bool replicate = multi && ordered && !local && g_ibm_replicate;
+    bool single = (!multi || replicate) && g_ibm_single_launch && nact <= MAX_IBM_PHASE_BODIES && nact > 0;
     Geom gsten = g;
-    if (replicate) { gsten.xOffset = 0; gsten.X = g.XG; }   // stencil_marker: every stencil plane counts as owned
-    if (ordered) {
+    if (replicate || local) { gsten.xOffset = 0; gsten.X = g.XG; }   // stencil_marker: every stencil plane counts as owned
+    if (ordered && nact) {
         // stencils first (the cell lists are built from them), then the lists; both survive while no body restencils
         long long entries = 0;
-        for (int ib = 0; ib < nbody; ib++) entries += (long long)nelmts[ib] * 64;
+        for (int k = 0; k < nact; k++) entries += (long long)views[k].n * 64;
         if (bx.ncell + 1 > b.csr_cell_cap) {
-            CK(cudaStreamSynchronize(s));
+            CK(cudaStreamSynchronize(s)); CK(cudaStreamSynchronize(s2));
             cudaFree(b.csr.count); cudaFree(b.csr.off); cudaFree(b.csr_scan_tmp);
             const long long cap = bx.ncell + bx.ncell / 4 + 1024;
             CK(cudaMalloc(&b.csr.count, sizeof(int) * (size_t)cap));
@@ -1268,7 +1388,7 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
             b.csr_valid = false;
         }
         if (entries > b.csr_entry_cap) {
-            CK(cudaStreamSynchronize(s));
+            CK(cudaStreamSynchronize(s)); CK(cudaStreamSynchronize(s2));
             cudaFree(b.csr.entry);
             CK(cudaMalloc(&b.csr.entry, sizeof(unsigned long long) * (size_t)entries));
             b.csr_entry_cap = entries;
@@ -1276,91 +1396,133 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         }
         if (!b.tol_partial) CK(cudaMalloc(&b.tol_partial, sizeof(double) * 2 * (size_t)ibm_loop_max_blocks()));
         if (!b.csr_valid) {
-            for (int ib = 0; ib < nbody; ib++) launch_ibm_stencil(gsten, views[ib], bx, rootBC, b.ctl, s);
-            if (launch_ibm_csr_build(views.data(), nbody, bx, b.csr, b.csr_scan_tmp, b.csr_scan_bytes, s)) return fail(FSILBM_ERR_CUDA, "IBM cell-list build failed");
+            for (int k = 0; k < nact; k++) launch_ibm_stencil(gsten, views[k], bx, rootBC, b.ctl, s2);
+            if (launch_ibm_csr_build(views.data(), nact, bx, b.csr, b.csr_scan_tmp, b.csr_scan_bytes, s2)) return fail(FSILBM_ERR_CUDA, "IBM cell-list build failed");
             b.csr_valid = true;
         }
     }
+    CK(cudaEventRecord(b.ev_ibm, s2));
+    CK(cudaStreamWaitEvent(s, b.ev_ibm, 0));
+
+    // -- compute stream: everything that reads the populations
     if (replicate) {
         launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
         NCK(g_nccl.AllReduce(bx.u, bx.u, 3 * (size_t)bx.ncell, kNcclFloat64, kNcclSum, g_nccl.comm, s));
     }
+    if (local) {
+        // every kept box: this rank's planes from its populations, zero elsewhere; then the participants of a shared box send
+        // one another the planes they own (ncclSend/ncclRecv between the two or three ranks concerned, no collective)
+        launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
+        bool any_shared = false;
+        for (int i = 0; i < bx.n; i++) any_shared = any_shared || shared[kept[i]];
+        if (any_shared) {
+            NCK(g_nccl.GroupStart());
+            for (int i = 0; i < bx.n; i++) {
+                const int k = kept[i];
+                if (!shared[k]) continue;
+                const size_t slab = (size_t)bx.ext[i][1] * bx.ext[i][2];
+                std::vector<int> parts;
+                for (const Run &r : runs[k]) if (std::find(parts.begin(), parts.end(), r.rank) == parts.end()) parts.push_back(r.rank);
+                for (int c = 0; c < 3; c++)
+                    for (const Run &r : runs[k]) {
+                        double *ptr = bx.u + (size_t)c * bx.ncell + bx.off[i] + (size_t)r.dx0 * slab;
+                        const size_t cnt = (size_t)(r.dx1 - r.dx0) * slab;
+                        if (r.rank == me) { for (int p : parts) if (p != me) NCK(g_nccl.Send(ptr, cnt, kNcclFloat64, p, g_nccl.comm, s)); }
+                        else NCK(g_nccl.Recv(ptr, cnt, kNcclFloat64, r.rank, g_nccl.comm, s));
+                    }
+            }
+            NCK(g_nccl.GroupEnd());
+        }
+    }
     if (single) {
         // one cooperative launch for UpdateElmtInterp_, the box macro, the whole penalty iteration and the force spreading
         IbmLoopParams lp{};
-        lp.g = g; lp.bodies = b.bodies_dev; lp.nbody = nbody; lp.boxes = bx;
+        lp.g = g; lp.bodies = b.bodies_dev; lp.nbody = nact; lp.boxes = bx;
         for (int k = 0; k < 6; k++) lp.rootBC[k] = rootBC[k];
         lp.ctl = b.ctl; lp.fA = b.f[b.cur];
         for (int k = 0; k < 3; k++) lp.hF[k] = hF[k];
         lp.ntol = ntolLBM; lp.dtol = dtolLBM; lp.Uref = b.flow.Uref;
         lp.dsum = 0.0;
-        for (int ib = 0; ib < nbody; ib++) lp.dsum = lp.dsum + (double)nelmts[ib];   // :902
+        for (int k = 0; k < nact; k++) lp.dsum = lp.dsum + (double)views[k].n;   // :902
         lp.invh3_pen = invh3_pen; lp.invh3 = invh3; lp.barrier = b.ibm_barrier;
-        static const bool want_prof = getenv("FSILBM_IBM_PROFILE") != nullptr;
         if (want_prof && !b.ibm_prof) { CK(cudaMalloc(&b.ibm_prof, 64 * sizeof(unsigned long long))); CK(cudaMemset(b.ibm_prof, 0, 64 * sizeof(unsigned long long))); }
         lp.prof = b.ibm_prof;
         lp.ordered = ordered ? 1 : 0; lp.do_stencil = ordered ? 0 : 1; lp.do_macro = replicate ? 0 : 1; lp.csr = b.csr; lp.tol_partial = b.tol_partial;
-        // phases: the k-th body (in body order) of every box group; a body's group is the merged box holding its first marker's cell
-        std::vector<int> group(nbody, 0);
-        for (int ib = 0; ib < nbody; ib++) {
-            const double *P = stencil_pos[ib].data();
-            int cidx[3];
-            for (int a = 0; a < 3; a++) cidx[a] = imod((int)floor((P[a] - mins[a]) * invdh), Ns[a]);
-            for (int k = 0; k < bx.n; k++) {
-                bool in = true;
-                for (int a = 0; a < 3; a++) in = in && imod(cidx[a] - bx.lo[k][a], Ns[a]) < bx.ext[k][a];
-                if (in) { group[ib] = k; break; }
-            }
-        }
-        std::vector<int> rank_in_group(nbody, 0), seen(bx.n > 0 ? bx.n : 1, 0);
+        // phases: the k-th body (in body order) of every box group
+        std::vector<int> rank_in_group(nact, 0), seen(bx.n > 0 ? bx.n : 1, 0);
         int nphase = 0;
-        for (int ib = 0; ib < nbody; ib++) { rank_in_group[ib] = seen[group[ib]]++; nphase = std::max(nphase, rank_in_group[ib] + 1); }
+        for (int k = 0; k < nact; k++) { rank_in_group[k] = seen[group_of[act[k]]]++; nphase = std::max(nphase, rank_in_group[k] + 1); }
         lp.nphase = nphase;
         int pos = 0, max_markers = 0;
         for (int ph = 0; ph < nphase; ph++) {
             lp.phase_start[ph] = pos;
             int markers = 0;
-            for (int ib = 0; ib < nbody; ib++) if (rank_in_group[ib] == ph) { lp.phase_body[pos++] = ib; markers += nelmts[ib]; }
+            for (int k = 0; k < nact; k++) if (rank_in_group[k] == ph) { lp.phase_body[pos++] = k; markers += views[k].n; }
             max_markers = std::max(max_markers, markers);
         }
         lp.phase_start[nphase] = pos;
-        for (int ib = 0; ib < nbody; ib++) lp.phase_of_body[ib] = rank_in_group[ib];
+        for (int k = 0; k < nact; k++) lp.phase_of_body[k] = rank_in_group[k];
         if (launch_ibm_loop(lp, max_markers, s)) { cudaGetLastError(); single = false; }   // no cooperative launch: take the phase-by-phase path
     }
     if (!single) {
         // -- UpdateElmtInterp_ (:883-888); the box-relative offsets are rebuilt every call because the boxes move with the
         //    bodies (the ordered mode did it above, together with its cell lists)
-        if (!ordered) for (int ib = 0; ib < nbody; ib++) launch_ibm_stencil(g, views[ib], bx, rootBC, b.ctl, s);
+        if (!ordered) for (int k = 0; k < nact; k++) launch_ibm_stencil(g, views[k], bx, rootBC, b.ctl, s);
         // -- calculate_macro_quantities + ResetVolumeForce restricted to the boxes (LBMBlockComm.f90:285-286)
-        if (!replicate) launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
+        if (!replicate && !local) launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
+        if (local && !b.tol2) CK(cudaMalloc(&b.tol2, 2 * sizeof(double)));
         // -- penalty iteration (:895-906); launches beyond convergence return at once on the device flag
         for (int it = 0; it < ntolLBM; it++) {
-            for (int ib = 0; ib < nbody; ib++) {
+            for (int k = 0; k < nact; k++) {
                 auto gather = ordered ? launch_ibm_gather_ordered : launch_ibm_gather;
-                if (!multi || replicate) {
-                    gather(views[ib], bx, b.bodies[ib].partialU, b.ctl, 1, invh3_pen, s);
+                BodyDev &bd = b.bodies[act[k]];
+                if (!multi || replicate || local) {
+                    gather(views[k], bx, bd.partialU, b.ctl, 1, invh3_pen, s);
                 } else {
-                    gather(views[ib], bx, b.bodies[ib].partialU, b.ctl, 0, invh3_pen, s);
-                    NCK(g_nccl.AllReduce(b.bodies[ib].partialU, b.bodies[ib].partialU, 3 * (size_t)views[ib].n, kNcclFloat64, kNcclSum, g_nccl.comm, s));
-                    launch_ibm_force(views[ib], b.bodies[ib].partialU, invh3_pen, b.ctl, s);
+                    gather(views[k], bx, bd.partialU, b.ctl, 0, invh3_pen, s);
+                    NCK(g_nccl.AllReduce(bd.partialU, bd.partialU, 3 * (size_t)views[k].n, kNcclFloat64, kNcclSum, g_nccl.comm, s));
+                    launch_ibm_force(views[k], bd.partialU, invh3_pen, b.ctl, s);
                 }
-                if (ordered) launch_ibm_scatter_ordered(b.bodies_dev, ib, bx, b.csr, b.ctl, s);
-                else launch_ibm_scatter(views[ib], bx, b.ctl, s);
+                if (ordered) launch_ibm_scatter_ordered(b.bodies_dev, k, bx, b.csr, b.ctl, s);
+                else launch_ibm_scatter(views[k], bx, b.ctl, s);
             }
-            launch_ibm_check(b.bodies_dev, nbody, b.flow.Uref, ntolLBM, dtolLBM, b.ctl, s);
+            if (local) {   // residual and marker count of the bodies this rank leads -> totals over all ranks -> the same decision everywhere
+                launch_ibm_tol_sum(b.bodies_dev, b.lead_dev, nact, b.ctl, b.tol2, s);
+                NCK(g_nccl.AllReduce(b.tol2, b.tol2, 2, kNcclFloat64, kNcclSum, g_nccl.comm, s));
+                launch_ibm_decide(b.tol2, b.flow.Uref, ntolLBM, dtolLBM, b.ctl, s);
+            } else {
+                launch_ibm_check(b.bodies_dev, nact, b.flow.Uref, ntolLBM, dtolLBM, b.ctl, s);
+            }
         }
         // -- FluidVolumeForce_, Eulerian half (:968-976)
-        if (ordered) launch_ibm_spread_ordered(b.bodies_dev, bx, b.csr, invh3, s);
-        else for (int ib = 0; ib < nbody; ib++) launch_ibm_spread(views[ib], bx, invh3, s);
+        if (ordered) { if (nact) launch_ibm_spread_ordered(b.bodies_dev, bx, b.csr, invh3, s); }
+        else for (int k = 0; k < nact; k++) launch_ibm_spread(views[k], bx, invh3, s);
     }
     CK(cudaGetLastError());
+    if (local && lists_replicated && b.marker_total) {
+        // every rank wants every body's forces: the leader's values plus zeros from everybody else (exact)
+        for (int k = 0; k < nact; k++)
+            if (!lead[k]) CK(cudaMemsetAsync(b.bodies[act[k]].Eforce, 0, sizeof(double) * 3 * (size_t)views[k].n, s));
+        NCK(g_nccl.AllReduce(b.force_dev, b.force_dev, 3 * b.marker_total, kNcclFloat64, kNcclSum, g_nccl.comm, s));
+    }
 
     // -- results to the host
     IbmCtl ctl1;
     CK(cudaMemcpyAsync(&ctl1, b.ctl, sizeof(IbmCtl), cudaMemcpyDeviceToHost, s));
-    for (int ib = 0; ib < nbody; ib++)
-        CK(cudaMemcpyAsync(Eforce[ib], b.bodies[ib].Eforce, sizeof(double) * 3 * (size_t)b.bodies[ib].n, cudaMemcpyDeviceToHost, s));
+    if (b.marker_total) CK(cudaMemcpyAsync(b.force_pin, b.force_dev, sizeof(double) * 3 * b.marker_total, cudaMemcpyDeviceToHost, s));
+    const double tp2 = want_prof ? wall_seconds() : 0.0;
     CK(cudaStreamSynchronize(s));
+    for (int ib = 0; ib < nbody; ib++) memcpy(Eforce[ib], b.force_pin + b.f_off[ib], sizeof(double) * 3 * (size_t)b.bodies[ib].n);
+    if (want_prof) {
+        const double tp3 = wall_seconds();
+        b.ibm_host_t[0] += tp1 - tp0; b.ibm_host_t[1] += tp2 - tp1; b.ibm_host_t[2] += tp3 - tp2;
+        if ((b.ibm_prof_calls % 100) == 20) {
+            fprintf(stderr, "[ibm host, us per call] boxes %.1f  enqueue %.1f  wait %.1f  (%d of %d bodies active)\n", b.ibm_host_t[0] * 1e4, b.ibm_host_t[1] * 1e4,
+                    b.ibm_host_t[2] * 1e4, nact, nbody);
+            b.ibm_host_t[0] = b.ibm_host_t[1] = b.ibm_host_t[2] = 0.0;
+        }
+        if (!b.ibm_prof) b.ibm_prof_calls++;
+    }
     if (b.ibm_prof && (b.ibm_prof_calls++ % 100) == 20) {
         unsigned long long hp[64];
         cudaMemcpy(hp, b.ibm_prof, sizeof(hp), cudaMemcpyDeviceToHost);
@@ -1373,7 +1535,15 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
     if (ctl1.err & 4) return fail(FSILBM_ERR_STENCIL, "internal: marker stencil outside its IBM box");
     if (ctl1.err & 2) return fail(FSILBM_ERR_NAN, "Nan found in PenaltyForce (Solidbody.f90:1029)");
     if (iterLBM_out) *iterLBM_out = ctl1.iter;
-    b.ibm_active = true;
+    b.ibm_active = bx.n > 0;
+    return 0;
+}
+
+int fsilbm_ibm_body_status(fsilbm_handle h, int nbody, int *status)
+{
+    Block *b = get(h);
+    if (!b || !status || nbody != (int)b->bodies.size()) return fail(FSILBM_ERR_ARG, "bad handle/argument");
+    for (int ib = 0; ib < nbody; ib++) status[ib] = b->bodies[ib].status;
     return 0;
 }
 

@@ -315,6 +315,53 @@ void launch_ibm_check(const IbmBody *bodies_dev, int nbody, double Uref, int nto
     count_launch();
 }
 
+// Loop control across ranks (slab runs in which every body is iterated only by the ranks whose planes its stencils touch):
+// each rank sums |dU| over the bodies it LEADS (fixed-shape tree) together with their marker count, the two numbers are
+// all-reduced, and every rank takes the same decision from the totals (Solidbody.f90:901-906).
+__global__ void __launch_bounds__(1024) ibm_tol_sum_kernel(const IbmBody *bodies, const int *lead, int nbody, const IbmCtl *ctl, double *out2)
+{
+    __shared__ double sh[1024];
+    double t = 0.0, cnt = 0.0;
+    if (!ctl->done)
+        for (int ib = 0; ib < nbody; ib++) {
+            if (!lead[ib]) continue;
+            const IbmBody b = bodies[ib];
+            for (int i = threadIdx.x; i < b.n; i += blockDim.x) t += b.tol[i];
+            cnt = cnt + (double)b.n;          // :902
+        }
+    sh[threadIdx.x] = t;
+    __syncthreads();
+    for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out2[0] = sh[0]; out2[1] = cnt; }
+}
+
+__global__ void ibm_decide_kernel(const double *in2, double Uref, int ntol, double dtol, IbmCtl *ctl)
+{
+    if (ctl->done) return;
+    double dmax = in2[0];
+    if (!isfinite(dmax)) atomicOr(&ctl->err, 2);   // :1028-1031
+    dmax = dmax / (in2[1] * Uref);                 // :904
+    const int iter = ctl->iter + 1;                // :905
+    ctl->iter = iter;
+    ctl->dmax = dmax;
+    ctl->done = !(iter < ntol && dmax > dtol);     // :895
+}
+
+void launch_ibm_tol_sum(const IbmBody *bodies_dev, const int *lead_dev, int nbody, const IbmCtl *ctl, double *out2, cudaStream_t s)
+{
+    ibm_tol_sum_kernel<<<1, 1024, 0, s>>>(bodies_dev, lead_dev, nbody, ctl, out2);
+    count_launch();
+}
+
+void launch_ibm_decide(const double *in2, double Uref, int ntol, double dtol, IbmCtl *ctl, cudaStream_t s)
+{
+    ibm_decide_kernel<<<1, 1, 0, s>>>(in2, Uref, ntol, dtol, ctl);
+    count_launch();
+}
+
 // Eulerian half of FluidVolumeForce_, Solidbody.f90:968-976: force += -(v_Eforce*invh3)*rx*ry*rz
 __device__ __forceinline__ void spread_marker(const IbmBody &b, const IbmBoxes &boxes, double invh3, int iEL, int lane)
 {

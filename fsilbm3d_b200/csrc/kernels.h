@@ -194,6 +194,9 @@ void launch_ibm_force(const IbmBody &b, const double *sumU, double invh3, IbmCtl
 void launch_ibm_scatter(const IbmBody &b, const IbmBoxes &boxes, const IbmCtl *ctl, cudaStream_t s);
 void launch_ibm_check(const IbmBody *bodies_dev, int nbody, double Uref, int ntol, double dtol, IbmCtl *ctl, cudaStream_t s);
 void launch_ibm_spread(const IbmBody &b, const IbmBoxes &boxes, double invh3, cudaStream_t s);
+// loop control of slab runs: local sum over the bodies this rank leads -> (all-reduce) -> decision, see ibm_kernels.cu
+void launch_ibm_tol_sum(const IbmBody *bodies_dev, const int *lead_dev, int nbody, const IbmCtl *ctl, double *out2, cudaStream_t s);
+void launch_ibm_decide(const double *in2, double Uref, int ntol, double dtol, IbmCtl *ctl, cudaStream_t s);
 
 // ---- grid refinement (refine_kernels.cu): one son face coupled to its father, LBMBlockComm.f90:340-979 ----------
 struct PairFaceParams {

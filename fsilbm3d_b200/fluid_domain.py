@@ -158,13 +158,16 @@ class LBMBlock:
         check(lib().fsilbm_block_stream(self._h, C.byref(p)))
         return p.value or 0
 
-    def calculate_interaction_force(self, bodies, rootBC=None, dt: Optional[float] = None) -> int:
-        """calculate_interaction_force, Solidbody.f90:869; returns iterLBM."""
+    def calculate_interaction_force(self, bodies, rootBC=None, dt: Optional[float] = None, collective: bool = False) -> int:
+        """calculate_interaction_force, Solidbody.f90:869; returns iterLBM.  `collective`: slab run in which every rank
+        passes only the bodies near its slab (option ibm_force_exchange = 0); the call is then made even with none."""
         n = len(bodies)
-        if n == 0:
-            check(lib().fsilbm_ibm_interaction_force(self._h, 0, None, None, None, None, None, None, self.dh, 0, 0.0, None, None))
-            return 0
         rootBC = self.BndConds if rootBC is None else rootBC
+        if n == 0:
+            it = C.c_int(0)
+            check(lib().fsilbm_ibm_interaction_force(self._h, 0, None, None, None, None, None, None, self.dh if dt is None else dt,
+                                                     self.flow.ntolLBM if collective else 0, self.flow.dtolLBM, (C.c_int * 6)(*rootBC), C.byref(it)))
+            return it.value
         nel = (C.c_int * n)(*[b.v_nelmts for b in bodies])
         vp = C.c_void_p
         for b in bodies:

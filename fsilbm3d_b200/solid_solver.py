@@ -55,6 +55,8 @@ def lib():
         L.fsolid_set_lodflow.argtypes = [ctypes.c_int, ctypes.c_int, dp]
         L.fsolid_structure.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double]
         L.fsolid_solver.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double]
+        L.fsolid_marker_ptrs.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.POINTER(dp)] * 4
+        L.fsolid_advance.argtypes = [ctypes.c_int, ctypes.c_int, ip, ctypes.c_double, ctypes.c_int, ctypes.c_double]
         L.fsolid_get.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, dp]
         L.fsolid_write.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double]
         _lib = L
@@ -158,20 +160,24 @@ class Body:
         self.nND, self.nEL, self.v_nelmts, self.v_move, self.iBodyModel, self.gEQ, _, self.v_type = list(info)
         self.count_Interp = 0
         n = self.v_nelmts
-        self.v_Exyz = np.zeros((n, 3)); self.v_Evel = np.zeros((n, 3)); self.v_Ea = np.zeros(n); self.v_Eforce = np.zeros((n, 3))
-        self.fetch_markers()
-
-    def fetch_markers(self):
-        self._o._ck(lib().fsolid_markers(self._o.h, self.index, _dp(self.v_Exyz), _dp(self.v_Evel), _dp(self.v_Ea)))
+        # the marker arrays ARE the structural library's own v_Exyz / v_Evel / v_Ea / v_Eforce (no copies either way)
+        dp = ctypes.POINTER(ctypes.c_double)
+        p = [dp(), dp(), dp(), dp()]
+        owner._ck(lib().fsolid_marker_ptrs(owner.h, index, *[ctypes.byref(q) for q in p]))
+        self.v_Exyz = np.ctypeslib.as_array(p[0], shape=(n, 3))
+        self.v_Evel = np.ctypeslib.as_array(p[1], shape=(n, 3))
+        self.v_Ea = np.ctypeslib.as_array(p[2], shape=(n,))
+        self.v_Eforce = np.ctypeslib.as_array(p[3], shape=(n, 3))
+        self.markers_fresh = False   # True after SolidBodies.advance(): UpdatePosVelArea_ of the coming step is done
 
     def UpdatePosVelArea(self):
+        if self.markers_fresh:
+            self.markers_fresh = False
+            return
         self._o._ck(lib().fsolid_update_pos_vel_area(self._o.h, self.index))
-        self.fetch_markers()
 
     def FluidLoads(self):
         """lodFlow = 0 (Solidbody.f90:911) then the nodal-load half of FluidVolumeForce_ (:945-967) from self.v_Eforce."""
-        f = np.ascontiguousarray(self.v_Eforce, float)
-        self._o._ck(lib().fsolid_set_eforce(self._o.h, self.index, _dp(f)))
         self._o._ck(lib().fsolid_fluid_loads(self._o.h, self.index))
         self.count_Interp = 1
 
@@ -212,8 +218,7 @@ class Plate:
     def __init__(self, body: Body, owner: "SolidBodies" = None):
         self.body = body
         self.host_seconds = 0.0   # wall time spent in the structural sub-steps (bench.py reports it)
-        if owner is not None:
-            self.solver_all = owner.Solver   # block_comm: one call advances every body (threads over bodies, Solidbody.f90:392)
+        self.owner = owner           # block_comm: one call per step does the host work of all carried bodies (threads over bodies)
 
     def UpdatePosVelArea(self):
         self.body.UpdatePosVelArea()
@@ -260,6 +265,17 @@ class SolidBodies:
         """Solver, Solidbody.f90:386-398: every body, in parallel over the bodies as the reference's OpenMP loop."""
         t0 = _time.perf_counter()
         self._ck(lib().fsolid_solver(self.h, float(time), int(isubstep), float(deltat), float(subdeltat)))
+        self.host_seconds += _time.perf_counter() - t0
+
+    def advance(self, bodies: Sequence[int], time: float, numsubstep: int, deltat: float):
+        """The host work of one step for `bodies` (indices), one thread per body: nodal loads from v_Eforce, the structural
+        sub-steps, UpdatePosVelArea_ for the next step (its call at the top of the next step then returns at once)."""
+        t0 = _time.perf_counter()
+        ids = (ctypes.c_int * len(bodies))(*bodies)
+        self._ck(lib().fsolid_advance(self.h, len(bodies), ids, float(time), int(numsubstep), float(deltat)))
+        for i in bodies:
+            self.VBodies[i].count_Interp = 1
+            self.VBodies[i].markers_fresh = True
         self.host_seconds += _time.perf_counter() - t0
 
     def write(self, what: int, time: float, cwd: str):

@@ -4,7 +4,9 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdlib>
+#include <functional>
 #include <mutex>
 #include <stdexcept>
 #include <thread>
@@ -301,34 +303,121 @@ void SolidBodies::Initialise_solid_bodies(double time)
     }
 }
 
-void SolidBodies::Solver(const std::vector<int> &bodies, double time, int isubstep, double deltat, double subdeltat)
+namespace {
+// Persistent workers for the loops over bodies (the reference's !$OMP PARALLEL DO SCHEDULE(DYNAMIC), Solidbody.f90:392):
+// the beams are independent of one another, and a step has several such loops, so the threads are kept between calls.
+class BodyPool {
+public:
+    ~BodyPool()
+    {
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (std::thread &t : workers_) t.join();
+    }
+    // fn(i) for i in [0, n), dynamically scheduled over at most `nthreads` threads (the caller is one of them)
+    void run(size_t n, size_t nthreads, const std::function<void(size_t)> &fn)
+    {
+        nthreads = std::min(nthreads, n);
+        if (nthreads <= 1) {
+            for (size_t i = 0; i < n; i++) fn(i);
+            return;
+        }
+        std::lock_guard<std::mutex> serial(run_mutex_);
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            while (workers_.size() + 1 < nthreads) workers_.emplace_back([this] { loop(); });
+            fn_ = &fn; n_ = n; next_.store(0);
+            wanted_ = nthreads - 1; busy_ = wanted_;
+            gen_++;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lock(m_);
+        done_.wait(lock, [this] { return busy_ == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    void work()
+    {
+        for (size_t i = next_++; i < n_; i = next_++) (*fn_)(i);
+    }
+    void loop()
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                cv_.wait(lock, [&] { return stop_ || (gen_ != seen && wanted_ > 0); });
+                if (stop_) return;
+                seen = gen_;
+                wanted_--;
+            }
+            work();
+            {
+                std::lock_guard<std::mutex> lock(m_);
+                busy_--;
+            }
+            done_.notify_all();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_, run_mutex_;
+    std::condition_variable cv_, done_;
+    const std::function<void(size_t)> *fn_ = nullptr;
+    size_t n_ = 0, wanted_ = 0, busy_ = 0;
+    std::atomic<size_t> next_{0};
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+};
+BodyPool g_pool;
+
+size_t body_threads()
 {
-    // !$OMP PARALLEL DO SCHEDULE(DYNAMIC) over the bodies (:392): the beams are independent of one another
     size_t nt = std::thread::hardware_concurrency();
     if (const char *e = std::getenv("FSILBM_SOLID_THREADS")) nt = (size_t)std::max(1, std::atoi(e));
-    nt = std::min(nt, bodies.size());
-    if (nt <= 1) {
-        for (int iFish : bodies) VBodies[iFish].rbm.structure(iFish + 1, time, isubstep, deltat, subdeltat);
-        return;
-    }
-    std::atomic<size_t> next{0};
+    return nt < 1 ? 1 : nt;
+}
+
+void over_bodies(const std::vector<int> &bodies, const std::function<void(int)> &per_body)
+{
     std::mutex err_mutex;
     std::string err;
-    auto work = [&]() {
-        for (size_t i = next++; i < bodies.size(); i = next++) {
-            try {
-                VBodies[bodies[i]].rbm.structure(bodies[i] + 1, time, isubstep, deltat, subdeltat);
-            } catch (const std::exception &ex) {
-                std::lock_guard<std::mutex> lock(err_mutex);
-                if (err.empty()) err = ex.what();
-            }
+    g_pool.run(bodies.size(), body_threads(), [&](size_t i) {
+        try {
+            per_body(bodies[i]);
+        } catch (const std::exception &ex) {
+            std::lock_guard<std::mutex> lock(err_mutex);
+            if (err.empty()) err = ex.what();
         }
-    };
-    std::vector<std::thread> pool;
-    for (size_t t = 1; t < nt; t++) pool.emplace_back(work);
-    work();
-    for (std::thread &t : pool) t.join();
+    });
     if (!err.empty()) throw std::runtime_error(err);
+}
+}  // namespace
+
+void SolidBodies::Solver(const std::vector<int> &bodies, double time, int isubstep, double deltat, double subdeltat)
+{
+    over_bodies(bodies, [&](int iFish) { VBodies[iFish].rbm.structure(iFish + 1, time, isubstep, deltat, subdeltat); });
+}
+
+// The host work of one step for the listed bodies, body by body in parallel: the nodal-load half of FluidVolumeForce_
+// (lodFlow = 0, Solidbody.f90:911; loads :945-967) from the v_Eforce just received, the numsubstep structural sub-steps of
+// FSInteraction_force's caller (LBMBlockComm.f90:333-335) and UpdatePosVelArea_ (:729) for the next step's markers.
+// Per body this is exactly the sequence the driver issues one call at a time.
+void SolidBodies::Advance(const std::vector<int> &bodies, double time, int numsubstep, double deltat)
+{
+    const double subdeltat = deltat / (double)numsubstep;
+    over_bodies(bodies, [&](int iFish) {
+        VirtualBody &B = VBodies[iFish];
+        B.count_Interp = 1;
+        std::fill(B.rbm.lodFlow.begin(), B.rbm.lodFlow.end(), 0.0);
+        B.NodalLoads();
+        for (int isub = 1; isub <= numsubstep; isub++) B.rbm.structure(iFish + 1, time, isub, deltat, subdeltat);
+        B.UpdatePosVelArea(m_IBPenaltyAlpha, m_denIn);
+    });
 }
 
 void SolidBodies::write_solid_field(double time) const

@@ -46,6 +46,7 @@ struct SolidBodies {   // the module variables and procedures of SolidBody
     void set_solidbody_parameters(const FlowCond &flow, const int BndConds[6]);                        // :328
     void Initialise_solid_bodies(double time);                                                         // :350
     void Solver(const std::vector<int> &bodies, double time, int isubstep, double deltat, double subdeltat);   // :386
+    void Advance(const std::vector<int> &bodies, double time, int numsubstep, double deltat);          // loads + sub-steps + markers, threads over bodies
     void write_solid_field(double time) const;                                                         // :477
     void Write_solid_v_bodies(double time) const;                                                      // :403
     void Write_solid_v_forces(double time) const;                                                      // :428

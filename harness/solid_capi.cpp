@@ -138,6 +138,28 @@ int fsolid_solver(int handle, double time, int isubstep, double deltat, double s
     });
 }
 
+int fsolid_marker_ptrs(int handle, int b, double **Exyz, double **Evel, double **Ea, double **Eforce)
+{
+    return guarded([&] {
+        harness::VirtualBody &B = body(handle, b);
+        if (Exyz) *Exyz = B.v_Exyz.data();
+        if (Evel) *Evel = B.v_Evel.data();
+        if (Ea) *Ea = B.v_Ea.data();
+        if (Eforce) *Eforce = B.v_Eforce.data();
+    });
+}
+
+int fsolid_advance(int handle, int nbodies, const int *bodies, double time, int numsubstep, double deltat)
+{
+    return guarded([&] {
+        Ctx &c = ctx(handle);
+        std::vector<int> list(bodies, bodies + nbodies);
+        for (int b : list) body(handle, b);
+        if (numsubstep < 1) throw std::runtime_error("fsolid_advance: numsubstep < 1");
+        c.solid.Advance(list, time, numsubstep, deltat);
+    });
+}
+
 int fsolid_get(int handle, int b, int what, double *out)
 {
     return guarded([&] {

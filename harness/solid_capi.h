@@ -29,6 +29,13 @@ int fsolid_set_lodflow(int handle, int body, const double *lodFlow);            
 int fsolid_structure(int handle, int body, double time, int isubstep, double deltat, double subdeltat);   /* Beam_structure, SolidSolver.f90:1820 */
 int fsolid_solver(int handle, double time, int isubstep, double deltat, double subdeltat);                 /* Solver over all bodies, Solidbody.f90:386 (threads over bodies) */
 
+/* The library's own marker arrays of a body (valid until fsolid_close; sizes 3n, 3n, n, 3n): lets a caller hand them to
+ * fsilbm_ibm_interaction_force without copies. */
+int fsolid_marker_ptrs(int handle, int body, double **Exyz, double **Evel, double **Ea, double **Eforce);
+/* One step of host work for the listed bodies, threads over bodies: nodal loads from v_Eforce (:911,945-967), `numsubstep`
+ * structural sub-steps (LBMBlockComm.f90:333-335), UpdatePosVelArea_ (:729) for the next step. */
+int fsolid_advance(int handle, int nbodies, const int *bodies, double time, int numsubstep, double deltat);
+
 /* what: 0 pos(6,nND) 1 dsp 2 vel 3 acc 4 lodFlow(gEQ) 5 lodInte(gEQ) 6 {iFish, iterNR, dnorm, cg_iterations}
  *       7 triads per element {ee(3,3) n1(3,3) n2(3,3)} row-major [i][j] = triad(i+1,j+1)   8 mss(3,nND)
  *       9 strainEnergy(2) per element after UpdateStrainEnergy   10 m_property(8) per element   11 x1(12) per element

@@ -177,6 +177,19 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts,
                                  const double *const *Ea, double *const *Eforce,
                                  const int *restencil, double dt, int ntolLBM, double dtolLBM,
                                  const int rootBC[6], int *iterLBM_out);
+/* Slab runs (x-slab decomposition over several GPUs).  By default a body is iterated only by the ranks whose planes its
+ * stencil box touches: a box inside one slab costs no communication at all, the two (rarely more) ranks sharing a box send
+ * one another the box planes they own and then iterate it redundantly, bit-identically; the loop control of :895-906 (sum of
+ * |dU| over ALL bodies) is all-reduced, two numbers per iteration, so the call is COLLECTIVE over the ranks of the block.
+ *   option "ibm_force_exchange" = 1 (default): every rank passes the SAME body list and gets every body's v_Eforce back
+ *     (one all-reduce of the leaders' values); nbody = 0 returns at once.
+ *   option "ibm_force_exchange" = 0: every rank passes only the bodies it holds -- at least every body whose stencil box
+ *     (and every body sharing cells with it) touches its slab, in the same relative order on every rank; bodies whose box
+ *     is elsewhere are ignored and get zero force.  Every rank calls every step, also with nbody = 0.
+ *   option "ibm_local" = 0 selects the earlier replicated form (box velocities all-reduced, every rank iterates all bodies).
+ * fsilbm_ibm_body_status: per body of the last call, 0 not iterated by this rank, 1 iterated, 2 iterated and led (this rank
+ * owns the first plane of its box and reported its residual and forces). */
+int fsilbm_ibm_body_status(fsilbm_handle h, int nbody, int *status);
 /* v_Ei(12,n) as int16 and v_Ew(12,n) as float of body b after the last call (parity checks). */
 int fsilbm_ibm_download_stencil(fsilbm_handle h, int body, short *Ei, float *Ew);
 

@@ -35,10 +35,22 @@ def main():
         dict(name="periodic_plate_wrap", dims=(9 * world, 18, 20), bc=(301,) * 6, plate_origin="wrap",
              flow=dict(nu=0.05, uvwIn=(0.03, 0.0, 0.0), Uref=0.03, ntolLBM=4, dtolLBM=1e-30)),
     ]
+    # IBM forms of a slab run (include/fsilbm.h "Slab runs"): local + same list on every rank (default), local + per-rank
+    # lists, the earlier replicated form; two plates (one inside the first slab, one across an interface) with a tolerance
+    # that ends the penalty iteration early on some steps, so the all-reduced loop control is what decides
+    two = dict(name="two_plates_dtol", dims=(12 * world + 2, 20, 24), bc=(102, 104, 202, 202, 301, 301), plate_origin="two",
+               flow=dict(nu=0.05, uvwIn=(0.04, 0.0, 0.0), shearRateIn=(0.0, 3e-4, 0.0), Uref=0.04, ntolLBM=6, dtolLBM=5e-2))
+    variants = [(1, c, dict(ibm_local=1, ibm_force_exchange=1)) for c in cases + [two]]
+    variants += [(0, c, dict(ibm_local=1, ibm_force_exchange=1)) for c in cases]
+    variants += [(1, c, dict(ibm_local=1, ibm_force_exchange=0)) for c in cases[1:] + [two]]
+    variants += [(1, cases[1], dict(ibm_local=0, ibm_force_exchange=1))]
     F._lib.check(F.lib().fsilbm_set_option(b"halo_timeout_s", 30))
     ok = True
-    for halo_mode, case in [(m, c) for m in (1, 0) for c in cases]:
+    iters_seen = set()
+    for halo_mode, case, opts in variants:
         F._lib.check(F.lib().fsilbm_set_option(b"halo", halo_mode))
+        for k, v in opts.items():
+            F._lib.check(F.lib().fsilbm_set_option(k.encode(), v))
         X, Y, Z = case["dims"]
         off, cnt = F.slab_range(X, rank, world)
         flow = F.FlowCondType(**case["flow"])
@@ -48,9 +60,25 @@ def main():
         gb.upload_fIn(np.ascontiguousarray(f0[:, off:off + cnt]))
         gb.update_volume_force(); gb.set_boundary_conditions()
         plates = []
-        if case["plate_origin"]:
+        if case["plate_origin"] == "two":
+            plates = [F.RigidPlate(origin=(3.4, 7.7, 6.1), nEL=5, len1=1.0, Nspan=8, spanlen=8.0, Lspan=0.0, chord_dir=(1.0, -0.1, 0.0), denIn=1.0),
+                      F.RigidPlate(origin=(X / 2.0 - 3.2, 9.3, 5.2), nEL=8, len1=1.0, Nspan=8, spanlen=8.0, Lspan=0.0, chord_dir=(1.0, 0.2, 0.0), denIn=1.0)]
+        elif case["plate_origin"]:
             ox = X / 2.0 - 4.2 if case["plate_origin"] == "mid" else X - 3.3
             plates = [F.RigidPlate(origin=(ox, 8.3, 5.2), nEL=8, len1=1.0, Nspan=8, spanlen=8.0, Lspan=0.0, chord_dir=(1.0, 0.2, 0.0), denIn=1.0)]
+        all_plates = plates
+        held = list(range(len(plates)))
+        if not opts["ibm_force_exchange"]:
+            # per-rank lists: a rank holds the plates whose markers come within 6 cells of its planes
+            def near(p):
+                xs = np.floor(p.body.v_Exyz[:, 0]).astype(int)
+                cells = set()
+                for d in range(-6, 7):
+                    cells.update(((xs + d) % X).tolist() if case["bc"][0] == 301 else (xs + d).tolist())
+                return any(off <= c < off + cnt for c in cells)
+            held = [i for i, p in enumerate(all_plates) if near(p)]
+            plates = [all_plates[i] for i in held]
+            gb.ibm_collective = True
         if rank == 0:
             from oracle import oracle as O
             of = O.Flow(**case["flow"])
@@ -59,7 +87,7 @@ def main():
             ob.fIn[...] = f0
             ob.update_volume_force(); ob.set_boundary_conditions(); ob.calculate_macro_quantities()
             ovs = []
-            for p in plates:
+            for p in all_plates:
                 ov = O.VirtualBody(p.body.v_nelmts, v_move=0, iBodyModel=1)
                 ov.v_Exyz[...] = p.body.v_Exyz; ov.v_Evel[...] = p.body.v_Evel; ov.v_Ea[...] = p.body.v_Ea
                 ovs.append(ov)
@@ -70,9 +98,11 @@ def main():
             if rank == 0:
                 ob.set_blktime(float(n))
                 it_o = ob.step(ovs)
-                if plates:
+                if all_plates:
                     ok &= (it_o == it_g)
-                    eF = max(eF, rel_err(plates[0].body.v_Eforce, ovs[0].v_Eforce))
+                    iters_seen.add((case["name"], it_o))
+                    for i, p in zip(held, plates):
+                        eF = max(eF, rel_err(p.body.v_Eforce, ovs[i].v_Eforce))
         den, uuu = gb.download_macro()
         floc = gb.download_fIn()
         # gather slabs on rank 0
@@ -88,9 +118,14 @@ def main():
             # north_star's tolerances; with the ordered, replicated IBM mode (default) the slabs are in fact bit-identical
             good = e_den <= 1e-12 and e_u <= 1e-12 and e_f <= 1e-12 and eF <= 1e-10 and exact
             ok &= good
-            print(f"[multi x{world}] halo={gb.halo_transport!r} {case['name']}: rel err den {e_den:.2e} u {e_u:.2e} f {e_f:.2e} force {eF:.2e} bit-exact {exact} -> {'OK' if good else 'FAIL'}", flush=True)
+            print(f"[multi x{world}] halo={gb.halo_transport!r} ibm={opts} {case['name']}: rel err den {e_den:.2e} u {e_u:.2e} f {e_f:.2e} force {eF:.2e} bit-exact {exact} -> {'OK' if good else 'FAIL'}", flush=True)
         gb.close()
         dist.barrier()
+    for k, v in dict(ibm_local=1, ibm_force_exchange=1).items():
+        F._lib.check(F.lib().fsilbm_set_option(k.encode(), v))
+    if rank == 0:
+        n_two = sorted(i for (nm, i) in iters_seen if nm == "two_plates_dtol")
+        print(f"[multi x{world}] iteration counts seen in two_plates_dtol: {n_two}", flush=True)
     ok &= flexible_plate_case(F, dist, rank, world, local)
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, src=0)
