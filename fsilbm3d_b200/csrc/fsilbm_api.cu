@@ -607,7 +607,11 @@ int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, d
     }
     CK(cudaEventCreateWithFlags(&b->ev_edge, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_comm, cudaEventDisableTiming));
-    CK(cudaStreamCreateWithFlags(&b->ibm_stream, cudaStreamNonBlocking));
+    {   // marker upload, stencils and cell lists slip in beside the running collide-stream kernel: their CTAs go first when SM slots free up
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&b->ibm_stream, cudaStreamNonBlocking, hi));
+    }
     CK(cudaEventCreateWithFlags(&b->ev_ibm, cudaEventDisableTiming));
     CK(cudaMalloc(&b->ctl, sizeof(IbmCtl)));
     CK(cudaMalloc(&b->ibm_barrier, sizeof(unsigned int)));
@@ -1216,8 +1220,12 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         const int n = bd.n;
         const double *P = Exyz[ib];
         double lo[3] = {P[0], P[1], P[2]}, hi[3] = {P[0], P[1], P[2]};
-        for (int e = 1; e < n; e++)
-            for (int a = 0; a < 3; a++) { const double v = P[3 * e + a]; lo[a] = v < lo[a] ? v : lo[a]; hi[a] = v > hi[a] ? v : hi[a]; }
+        for (int e = 1; e < n; e++) {
+            const double v0 = P[3 * e], v1 = P[3 * e + 1], v2 = P[3 * e + 2];
+            lo[0] = std::min(lo[0], v0); hi[0] = std::max(hi[0], v0);
+            lo[1] = std::min(lo[1], v1); hi[1] = std::max(hi[1], v1);
+            lo[2] = std::min(lo[2], v2); hi[2] = std::max(hi[2], v2);
+        }
         for (int a = 0; a < 3; a++) {
             int i0 = (int)floor((P[a] - mins[a]) * invdh);
             const double x0 = mins[a] + (double)i0 * g.dh;
@@ -1396,8 +1404,10 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         }
         if (!b.tol_partial) CK(cudaMalloc(&b.tol_partial, sizeof(double) * 2 * (size_t)ibm_loop_max_blocks()));
         if (!b.csr_valid) {
-            for (int k = 0; k < nact; k++) launch_ibm_stencil(gsten, views[k], bx, rootBC, b.ctl, s2);
-            if (launch_ibm_csr_build(views.data(), nact, bx, b.csr, b.csr_scan_tmp, b.csr_scan_bytes, s2)) return fail(FSILBM_ERR_CUDA, "IBM cell-list build failed");
+            int max_n = 0;
+            for (int k = 0; k < nact; k++) max_n = std::max(max_n, views[k].n);
+            launch_ibm_stencil_all(gsten, b.bodies_dev, nact, max_n, bx, rootBC, b.ctl, s2);
+            if (launch_ibm_csr_build(b.bodies_dev, nact, max_n, bx, b.csr, b.csr_scan_tmp, b.csr_scan_bytes, s2)) return fail(FSILBM_ERR_CUDA, "IBM cell-list build failed");
             b.csr_valid = true;
         }
     }

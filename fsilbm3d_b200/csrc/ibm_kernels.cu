@@ -122,6 +122,24 @@ __global__ void ibm_stencil_kernel(Geom g, IbmBody b, const __grid_constant__ Ib
     stencil_marker(g, b, boxes, bc, ctl, iEL);
 }
 
+// all bodies of a block in one launch: blockIdx.y = body
+__global__ void ibm_stencil_all_kernel(Geom g, const IbmBody *bodies, const __grid_constant__ IbmBoxes boxes, RootBC bc, IbmCtl *ctl)
+{
+    const IbmBody b = bodies[blockIdx.y];
+    const int iEL = blockIdx.x * blockDim.x + threadIdx.x;
+    if (iEL >= b.n) return;
+    stencil_marker(g, b, boxes, bc, ctl, iEL);
+}
+
+void launch_ibm_stencil_all(const Geom &g, const IbmBody *bodies_dev, int nbody, int max_n, const IbmBoxes &boxes, const int rootBC[6], IbmCtl *ctl, cudaStream_t s)
+{
+    if (nbody < 1) return;
+    RootBC bc;
+    for (int i = 0; i < 6; i++) bc.c[i] = rootBC[i];
+    ibm_stencil_all_kernel<<<dim3((max_n + 127) / 128, nbody), 128, 0, s>>>(g, bodies_dev, boxes, bc, ctl);
+    count_launch();
+}
+
 void launch_ibm_stencil(const Geom &g, const IbmBody &b, const IbmBoxes &boxes, const int rootBC[6], IbmCtl *ctl, cudaStream_t s)
 {
     RootBC bc;
@@ -574,8 +592,10 @@ void launch_ibm_spread_ordered(const IbmBody *bodies_dev, const IbmBoxes &boxes,
 
 // -- IbmCsr build: one thread per (marker, node)
 template <bool FILL>
-__global__ void ibm_csr_nodes_kernel(IbmBody b, int body, IbmCsr csr)
+__global__ void ibm_csr_nodes_kernel(const IbmBody *bodies, IbmCsr csr)
 {
+    const int body = blockIdx.y;
+    const IbmBody b = bodies[body];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)b.n * 64) return;
     const int iEL = (int)(t >> 6), node = (int)(t & 63);
@@ -620,21 +640,16 @@ size_t ibm_csr_scan_bytes(long long ncell)
     return bytes;
 }
 
-int launch_ibm_csr_build(const IbmBody *views, int nbody, const IbmBoxes &boxes, const IbmCsr &csr, void *scan_tmp, size_t scan_bytes, cudaStream_t s)
+int launch_ibm_csr_build(const IbmBody *bodies_dev, int nbody, int max_n, const IbmBoxes &boxes, const IbmCsr &csr, void *scan_tmp, size_t scan_bytes, cudaStream_t s)
 {
     if (cudaMemsetAsync(csr.count, 0, sizeof(int) * (size_t)(boxes.ncell + 1), s) != cudaSuccess) return 1;
-    for (int ib = 0; ib < nbody; ib++) {
-        const long long nt = (long long)views[ib].n * 64;
-        ibm_csr_nodes_kernel<false><<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(views[ib], ib, csr);
-        count_launch();
-    }
+    const dim3 grid((unsigned)(((long long)max_n * 64 + 255) / 256), nbody);   // blockIdx.y = body
+    ibm_csr_nodes_kernel<false><<<grid, 256, 0, s>>>(bodies_dev, csr);
+    count_launch();
     if (cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, csr.count, csr.off, (int)(boxes.ncell + 1), s) != cudaSuccess) return 1;
     count_launch();
-    for (int ib = 0; ib < nbody; ib++) {
-        const long long nt = (long long)views[ib].n * 64;
-        ibm_csr_nodes_kernel<true><<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(views[ib], ib, csr);
-        count_launch();
-    }
+    ibm_csr_nodes_kernel<true><<<grid, 256, 0, s>>>(bodies_dev, csr);
+    count_launch();
     ibm_csr_sort_kernel<<<(unsigned)((boxes.ncell * 32 + 127) / 128), 128, 0, s>>>(csr, boxes.ncell);
     count_launch();
     return 0;

@@ -182,7 +182,8 @@ int ibm_loop_max_blocks();
 
 // build of IbmCsr after the stencils are known: count -> scan -> fill -> per-cell sort
 size_t ibm_csr_scan_bytes(long long ncell);
-int launch_ibm_csr_build(const IbmBody *views, int nbody, const IbmBoxes &boxes, const IbmCsr &csr, void *scan_tmp, size_t scan_bytes, cudaStream_t s);
+int launch_ibm_csr_build(const IbmBody *bodies_dev, int nbody, int max_n, const IbmBoxes &boxes, const IbmCsr &csr, void *scan_tmp, size_t scan_bytes, cudaStream_t s);
+void launch_ibm_stencil_all(const Geom &g, const IbmBody *bodies_dev, int nbody, int max_n, const IbmBoxes &boxes, const int rootBC[6], IbmCtl *ctl, cudaStream_t s);
 void launch_ibm_gather_ordered(const IbmBody &b, const IbmBoxes &boxes, double *partialU, const IbmCtl *ctl, int fused, double invh3, cudaStream_t s);
 void launch_ibm_scatter_ordered(const IbmBody *bodies_dev, int body, const IbmBoxes &boxes, const IbmCsr &csr, const IbmCtl *ctl, cudaStream_t s);
 void launch_ibm_spread_ordered(const IbmBody *bodies_dev, const IbmBoxes &boxes, const IbmCsr &csr, double invh3, cudaStream_t s);
