@@ -214,6 +214,9 @@ struct Block {
         int left = -1, right = -1;                 // neighbour ranks (-1: domain end)
         unsigned char *region = nullptr;           // [4 x u64 flags | pad to 256 B][side 0/1][parity 0/1][5][Y][Z] doubles
         unsigned char *peer_left = nullptr, *peer_right = nullptr;   // the neighbours' regions, peer-mapped through CUDA IPC
+        std::vector<unsigned char *> peer;         // every rank's region (own pointer at the own rank): the IBM loop-control mailbox sits in its header
+        bool mailbox = false;                      // all ranks mapped and nranks <= MAX_PEERS
+        unsigned long long ctl_seq = 0;            // loop-control exchanges completed so far (identical on every rank)
         unsigned int *counters = nullptr;          // last-CTA counters of the two edge launches
         int *err = nullptr;
         unsigned long long step = 0;
@@ -417,12 +420,14 @@ int halo_exchange(Block &b, double *fB, cudaStream_t s)
 }
 
 
-constexpr size_t kHaloFlagBytes = 256;
+constexpr size_t kHaloFlagBytes = 256;                                                   // 4 x u64 arrival flags
+constexpr size_t kHaloMailboxBytes = sizeof(CtlSlot) * IBM_CTL_SLOTS * MAX_PEERS;        // loop-control mailbox [slot][rank]
+constexpr size_t kHaloHeaderBytes = ((kHaloFlagBytes + kHaloMailboxBytes + 4095) / 4096) * 4096;
 
 inline unsigned long long *halo_flag(unsigned char *region, int side, int parity) { return (unsigned long long *)region + (side * 2 + parity); }
 inline double *halo_slot_ptr(unsigned char *region, size_t slot_bytes, int side, int parity)
 {
-    return (double *)(region + kHaloFlagBytes + (size_t)(side * 2 + parity) * slot_bytes);
+    return (double *)(region + kHaloHeaderBytes + (size_t)(side * 2 + parity) * slot_bytes);
 }
 
 // Peer-memory halo set-up (collective over the communicator; every rank creates its blocks in the same order).
@@ -439,7 +444,7 @@ int halo_setup(Block &b)
     h.right = (r + 1 < R) ? r + 1 : (per ? 0 : -1);
     h.left = (r > 0) ? r - 1 : (per ? R - 1 : -1);
     h.slot_bytes = sizeof(double) * 5 * b.g.plane;
-    const size_t bytes = kHaloFlagBytes + 4 * h.slot_bytes;
+    const size_t bytes = kHaloHeaderBytes + 4 * h.slot_bytes;
     CK(cudaMalloc(&h.region, bytes));
     CK(cudaMemset(h.region, 0, bytes));
     CK(cudaMalloc(&h.counters, 2 * sizeof(unsigned int)));
@@ -474,8 +479,15 @@ int halo_setup(Block &b)
             if (cudaIpcOpenMemHandle(&ptr, hh, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = 0; return; }
             *out = (unsigned char *)ptr;
         };
-        if (h.left >= 0) open(h.left, &h.peer_left);
-        if (h.right >= 0 && opened) { if (h.right == h.left) h.peer_right = h.peer_left; else open(h.right, &h.peer_right); }
+        // every rank's region is mapped (not only the two neighbours'): the header also carries the mailbox through which the
+        // IBM penalty iteration exchanges its loop control (ibm_loop_kernel)
+        h.peer.assign(R, nullptr);
+        h.peer[r] = h.region;
+        for (int p = 0; p < R && opened; p++) if (p != r) open(p, &h.peer[p]);
+        if (opened) {
+            if (h.left >= 0) h.peer_left = h.peer[h.left];
+            if (h.right >= 0) h.peer_right = h.peer[h.right];
+        }
     }
     // agree on the outcome (a rank that could not map its neighbour forces everyone onto the NCCL path)
     int *dflag = nullptr;
@@ -488,6 +500,7 @@ int halo_setup(Block &b)
     CK(cudaMemcpy(&failures, dflag, sizeof(int), cudaMemcpyDeviceToHost));
     cudaFree(dflag);
     h.enabled = failures == 0;
+    h.mailbox = h.enabled && R <= MAX_PEERS;
     return 0;
 }
 
@@ -495,8 +508,8 @@ void halo_teardown(Block &b)
 {
     Block::Halo &h = b.halo;
     if (!h.region) return;
-    if (h.peer_left) cudaIpcCloseMemHandle(h.peer_left);
-    if (h.peer_right && h.peer_right != h.peer_left) cudaIpcCloseMemHandle(h.peer_right);
+    for (size_t p = 0; p < h.peer.size(); p++)
+        if (h.peer[p] && h.peer[p] != h.region) cudaIpcCloseMemHandle(h.peer[p]);
     if (g_nccl.comm) {   // nobody frees a region a neighbour may still be writing into
         int *dflag = nullptr;
         if (cudaMalloc(&dflag, sizeof(int)) == cudaSuccess) {
@@ -1377,7 +1390,19 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
     // Multi-rank, replicated form (ibm_local = 0): the box velocities (owner's value, zero elsewhere: the sum is exact) are
     // all-reduced once, then every rank runs the whole of calculate_interaction_force on the full boxes of ALL bodies.
     const bool replicate = multi && ordered && !local && g_ibm_replicate;
-    bool single = (!multi || replicate) && g_ibm_single_launch && nact <= MAX_IBM_PHASE_BODIES && nact > 0;
+    // slab runs: with every rank's mailbox mapped (peer memory) the loop control is exchanged from inside the single cooperative
+    // kernel; otherwise one kernel per phase with an ncclAllReduce of the two numbers per iteration
+    const bool mailbox = local && b.halo.mailbox && g_ibm_single_launch;
+    IbmCtlExchange xc{};
+    if (mailbox) {
+        xc.nranks = g_nccl.nranks; xc.rank = me;
+        for (int r = 0; r < g_nccl.nranks; r++) xc.mailbox[r] = b.halo.peer[r] + kHaloFlagBytes;
+        xc.seq_base = b.halo.ctl_seq + 1;
+        xc.timeout_ns = (unsigned long long)g_halo_timeout_s * 1000000000ull;
+        xc.cnt_local = 0.0;
+        for (int ib : act) if (lead_of[ib]) xc.cnt_local = xc.cnt_local + (double)nelmts[ib];
+    }
+    bool single = (!multi || replicate || mailbox) && g_ibm_single_launch && nact <= MAX_IBM_PHASE_BODIES && nact > 0;
     Geom gsten = g;
     if (replicate || local) { gsten.xOffset = 0; gsten.X = g.XG; }   // stencil_marker: every stencil plane counts as owned
     if (ordered && nact) {
@@ -1419,12 +1444,13 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
         NCK(g_nccl.AllReduce(bx.u, bx.u, 3 * (size_t)bx.ncell, kNcclFloat64, kNcclSum, g_nccl.comm, s));
     }
+    bool macro_done = replicate;
     if (local) {
         // every kept box: this rank's planes from its populations, zero elsewhere; then the participants of a shared box send
         // one another the planes they own (ncclSend/ncclRecv between the two or three ranks concerned, no collective)
-        launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
         bool any_shared = false;
         for (int i = 0; i < bx.n; i++) any_shared = any_shared || shared[kept[i]];
+        if (any_shared || !single) { launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s); macro_done = true; }
         if (any_shared) {
             NCK(g_nccl.GroupStart());
             for (int i = 0; i < bx.n; i++) {
@@ -1457,7 +1483,9 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         lp.invh3_pen = invh3_pen; lp.invh3 = invh3; lp.barrier = b.ibm_barrier;
         if (want_prof && !b.ibm_prof) { CK(cudaMalloc(&b.ibm_prof, 64 * sizeof(unsigned long long))); CK(cudaMemset(b.ibm_prof, 0, 64 * sizeof(unsigned long long))); }
         lp.prof = b.ibm_prof;
-        lp.ordered = ordered ? 1 : 0; lp.do_stencil = ordered ? 0 : 1; lp.do_macro = replicate ? 0 : 1; lp.csr = b.csr; lp.tol_partial = b.tol_partial;
+        lp.ordered = ordered ? 1 : 0; lp.do_stencil = ordered ? 0 : 1; lp.do_macro = macro_done ? 0 : 1; lp.csr = b.csr; lp.tol_partial = b.tol_partial;
+        for (int k = 0; k < nact; k++) lp.lead[k] = (unsigned char)lead[k];
+        lp.xc = xc;
         // phases: the k-th body (in body order) of every box group
         std::vector<int> rank_in_group(nact, 0), seen(bx.n > 0 ? bx.n : 1, 0);
         int nphase = 0;
@@ -1472,14 +1500,22 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         }
         lp.phase_start[nphase] = pos;
         for (int k = 0; k < nact; k++) lp.phase_of_body[k] = rank_in_group[k];
-        if (launch_ibm_loop(lp, max_markers, s)) { cudaGetLastError(); single = false; }   // no cooperative launch: take the phase-by-phase path
+        if (launch_ibm_loop(lp, max_markers, s)) {
+            cudaGetLastError();
+            if (mailbox) return fail(FSILBM_ERR_CUDA, "cooperative launch of the IBM iteration failed");   // the other ranks are in the mailbox protocol
+            single = false;   // no cooperative launch: take the phase-by-phase path
+        }
+    }
+    if (mailbox && nact == 0) {
+        launch_ibm_ctl_only(xc, ntolLBM, dtolLBM, b.flow.Uref, b.ctl, s);   // no body here: report zeros, follow the others' decision
+        single = true;
     }
     if (!single) {
         // -- UpdateElmtInterp_ (:883-888); the box-relative offsets are rebuilt every call because the boxes move with the
         //    bodies (the ordered mode did it above, together with its cell lists)
         if (!ordered) for (int k = 0; k < nact; k++) launch_ibm_stencil(g, views[k], bx, rootBC, b.ctl, s);
         // -- calculate_macro_quantities + ResetVolumeForce restricted to the boxes (LBMBlockComm.f90:285-286)
-        if (!replicate && !local) launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
+        if (!macro_done) launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
         if (local && !b.tol2) CK(cudaMalloc(&b.tol2, 2 * sizeof(double)));
         // -- penalty iteration (:895-906); launches beyond convergence return at once on the device flag
         for (int it = 0; it < ntolLBM; it++) {
@@ -1540,7 +1576,9 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         for (unsigned long long k = 1; k < hp[0] && k < 63; k++) fprintf(stderr, " %.1f", (double)(hp[1 + k] - hp[k]) * 1e-3);
         fprintf(stderr, "  (ncell %lld)\n", (long long)bx.ncell);
     }
+    if (mailbox) b.halo.ctl_seq += (unsigned long long)ctl1.iter;   // the same count on every rank
     if (ctl1.err) b.csr_valid = false;
+    if (ctl1.err & 8) return fail(FSILBM_ERR_COMM, "IBM loop control: a rank did not report within %d s (rank %d)", g_halo_timeout_s, me);
     if (ctl1.err & 1) return fail(FSILBM_ERR_STENCIL, "index out of xmin/xmax bound (Solidbody.f90:850,861)");
     if (ctl1.err & 4) return fail(FSILBM_ERR_STENCIL, "internal: marker stencil outside its IBM box");
     if (ctl1.err & 2) return fail(FSILBM_ERR_NAN, "Nan found in PenaltyForce (Solidbody.f90:1029)");

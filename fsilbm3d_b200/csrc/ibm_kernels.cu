@@ -674,6 +674,74 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &ep
     __syncthreads();
 }
 
+// Loop-control exchange of one iteration (see IbmCtlExchange in kernels.h).  Called by every thread of the block; `publish` is
+// true in exactly one block per rank.  Thread r < nranks stores this rank's numbers into rank r's mailbox, then waits for rank
+// r's entry in the own mailbox.  The totals are formed in rank order, so every block of every rank gets the same two numbers.
+// Returns false if a rank did not report within the time limit.
+struct CtlShared { double tol[MAX_PEERS], cnt[MAX_PEERS]; int bad; };
+__device__ __forceinline__ bool ctl_exchange(const IbmCtlExchange &xc, int it, double local_tol, bool publish, CtlShared &sh, double &tol_sum, double &cnt_sum)
+{
+    const unsigned long long seq = xc.seq_base + (unsigned long long)it;
+    const int slot = (int)(seq % IBM_CTL_SLOTS);
+    if (threadIdx.x == 0) sh.bad = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < xc.nranks) {
+        const int r = threadIdx.x;
+        if (publish) {
+            CtlSlot *dst = (CtlSlot *)xc.mailbox[r] + slot * xc.nranks + xc.rank;
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(&dst->tol), "d"(local_tol) : "memory");
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(&dst->cnt), "d"(xc.cnt_local) : "memory");
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&dst->seq), "l"(seq) : "memory");
+        }
+        const CtlSlot *src = (const CtlSlot *)xc.mailbox[xc.rank] + slot * xc.nranks + r;
+        unsigned long long t0, t1, v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(&src->seq) : "memory");
+            if (v == seq) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > xc.timeout_ns) { sh.bad = 1; __trap(); }   // a rank is lost: abort the launch (the blocks of a cooperative grid must not part ways)
+            __nanosleep(100);
+        }
+        double a, c;
+        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(a) : "l"(&src->tol) : "memory");
+        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(c) : "l"(&src->cnt) : "memory");
+        sh.tol[r] = a; sh.cnt[r] = c;
+    }
+    __syncthreads();
+    double t = 0.0, n = 0.0;
+    for (int r = 0; r < xc.nranks; r++) { t = t + sh.tol[r]; n = n + sh.cnt[r]; }
+    tol_sum = t; cnt_sum = n;
+    const bool ok = sh.bad == 0;
+    __syncthreads();
+    return ok;
+}
+
+// a rank whose slab no body touches: it reports zeros and follows the others' decision
+__global__ void ibm_ctl_only_kernel(const __grid_constant__ IbmCtlExchange xc, int ntol, double dtol, double Uref, IbmCtl *ctl)
+{
+    __shared__ CtlShared sh;
+    bool done = ctl->done != 0;
+    for (int it = 0; it < ntol && !done; it++) {
+        double dmax, cnt;
+        const bool ok = ctl_exchange(xc, it, 0.0, true, sh, dmax, cnt);
+        const bool bad = !isfinite(dmax);
+        dmax = dmax / (cnt * Uref);
+        done = !ok || !(it + 1 < ntol && dmax > dtol);
+        if (threadIdx.x == 0) {
+            if (bad) atomicOr(&ctl->err, 2);
+            if (!ok) atomicOr(&ctl->err, 8);
+            ctl->iter = it + 1; ctl->dmax = dmax; ctl->done = done ? 1 : 0;
+        }
+    }
+}
+
+void launch_ibm_ctl_only(const IbmCtlExchange &xc, int ntol, double dtol, double Uref, IbmCtl *ctl, cudaStream_t s)
+{
+    ibm_ctl_only_kernel<<<1, 32, 0, s>>>(xc, ntol, dtol, Uref, ctl);
+    count_launch();
+}
+
 __device__ __forceinline__ void prof_stamp(const IbmLoopParams &p, int &k)
 {
     if (p.prof && blockIdx.x == 0 && threadIdx.x == 0 && k < 63) {
@@ -711,6 +779,7 @@ __global__ void __launch_bounds__(256, 4) ibm_loop_kernel(const __grid_constant_
     grid_barrier(p.barrier, epoch);
     prof_stamp(p, pk);
     __shared__ double sh_tol[256];
+    __shared__ CtlShared sh_ctl;
     __shared__ GatherSmem sh_gather;
     __shared__ IbmBody sh_bodies[MAX_IBM_PHASE_BODIES];   // the body table next to the SM: the cell loops dereference it per entry
     for (int i = threadIdx.x; i < p.nbody; i += blockDim.x) sh_bodies[i] = p.bodies[i];
@@ -726,8 +795,11 @@ __global__ void __launch_bounds__(256, 4) ibm_loop_kernel(const __grid_constant_
             if (p.ordered) {
                 for (int k = p.phase_start[ph]; k < p.phase_start[ph + 1]; k++) {
                     const IbmBody &b = sh_bodies[p.phase_body[k]];
-                    for (int m0 = blockIdx.x * MARKERS_PER_BLOCK; m0 < b.n; m0 += gridDim.x * MARKERS_PER_BLOCK)   // uniform over the block
-                        tol += gather_batch_ordered(b, p.boxes, m0, sh_gather, nullptr, 1, p.invh3_pen);
+                    const bool lead = p.lead[p.phase_body[k]] != 0;   // a body across a slab interface is reported by one rank only
+                    for (int m0 = blockIdx.x * MARKERS_PER_BLOCK; m0 < b.n; m0 += gridDim.x * MARKERS_PER_BLOCK) {   // uniform over the block
+                        const double t = gather_batch_ordered(b, p.boxes, m0, sh_gather, nullptr, 1, p.invh3_pen);
+                        if (lead) tol += t;
+                    }
                 }
                 sh_tol[threadIdx.x] = tol;             // fixed-shape tree: the same sum on every run
                 __syncthreads();
@@ -782,13 +854,16 @@ __global__ void __launch_bounds__(256, 4) ibm_loop_kernel(const __grid_constant_
                 if ((int)threadIdx.x < off) sh_tol[threadIdx.x] += sh_tol[threadIdx.x + off];
                 __syncthreads();
             }
-            double dmax = sh_tol[0];
+            double dmax = sh_tol[0], dsum = p.dsum;
             __syncthreads();
+            bool heard = true;
+            if (p.xc.nranks > 1) heard = ctl_exchange(p.xc, it, dmax, blockIdx.x == 0, sh_ctl, dmax, dsum);   // totals over the ranks of the slab run
             const bool bad = !isfinite(dmax);               // :1028-1031
-            dmax = dmax / (p.dsum * p.Uref);
-            done = !(it + 1 < p.ntol && dmax > p.dtol);
+            dmax = dmax / (dsum * p.Uref);
+            done = !heard || !(it + 1 < p.ntol && dmax > p.dtol);
             if (gthread == 0) {
                 IbmCtl *c = p.ctl;
+                if (!heard) atomicOr(&c->err, 8);
                 if (bad) atomicOr(&c->err, 2);
                 c->iter = it + 1;
                 c->dmax = dmax;

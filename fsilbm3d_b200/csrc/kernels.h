@@ -153,6 +153,21 @@ struct IbmCsr {
 };
 
 constexpr int MAX_IBM_PHASE_BODIES = 64;
+
+// Loop control of the penalty iteration across the ranks of a slab run, exchanged through peer memory (NVLink) from inside
+// ibm_loop_kernel: every rank stores {sum of |dU| of the bodies it leads, their marker count, sequence number} into slot
+// [seq % IBM_CTL_SLOTS][own rank] of EVERY rank's mailbox and then reads the R entries of its own mailbox; all ranks add
+// them in rank order and so take the same decision (Solidbody.f90:895-906) without a collective call.
+constexpr int MAX_PEERS = 16;
+constexpr int IBM_CTL_SLOTS = 4;
+struct CtlSlot { double tol, cnt; unsigned long long seq, pad; };
+struct IbmCtlExchange {
+    int nranks, rank;                 // nranks <= 1: no exchange
+    unsigned char *mailbox[MAX_PEERS];  // every rank's mailbox (own included)
+    unsigned long long seq_base;      // sequence number of iteration 0 of this call
+    unsigned long long timeout_ns;
+    double cnt_local;                 // markers of the bodies this rank leads
+};
 struct IbmLoopParams {        // the single-launch form of calculate_interaction_force (ibm_loop_kernel)
     Geom g;
     const IbmBody *bodies;    // device array [nbody]
@@ -176,7 +191,11 @@ struct IbmLoopParams {        // the single-launch form of calculate_interaction
     int phase_of_body[MAX_IBM_PHASE_BODIES];
     double *tol_partial;      // [2][gridDim.x] per-block sums of the markers' |dU| (ordered mode), double-buffered over iterations
     unsigned long long *prof; // optional [64] globaltimer stamps of block 0 at the phase boundaries (FSILBM_IBM_PROFILE=1)
+    unsigned char lead[MAX_IBM_PHASE_BODIES];   // slab runs: 1 = this rank reports the body's residual (it owns the first plane of its box)
+    IbmCtlExchange xc;
 };
+// a rank that iterates no body still takes part in the loop-control exchange (one small block)
+void launch_ibm_ctl_only(const IbmCtlExchange &xc, int ntol, double dtol, double Uref, IbmCtl *ctl, cudaStream_t s);
 int launch_ibm_loop(const IbmLoopParams &p, int max_markers, cudaStream_t s);
 int ibm_loop_max_blocks();
 

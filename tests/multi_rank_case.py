@@ -44,6 +44,9 @@ def main():
     variants += [(0, c, dict(ibm_local=1, ibm_force_exchange=1)) for c in cases]
     variants += [(1, c, dict(ibm_local=1, ibm_force_exchange=0)) for c in cases[1:] + [two]]
     variants += [(1, cases[1], dict(ibm_local=0, ibm_force_exchange=1))]
+    # loop control through ncclAllReduce (one kernel per phase) instead of the peer-memory mailbox inside the cooperative kernel
+    variants += [(1, c, dict(ibm_local=1, ibm_force_exchange=x, ibm_single_launch=0)) for c in (cases[1], two) for x in (1, 0)]
+    variants = [(m, c, dict(dict(ibm_single_launch=1), **o)) for (m, c, o) in variants]
     F._lib.check(F.lib().fsilbm_set_option(b"halo_timeout_s", 30))
     ok = True
     iters_seen = set()
@@ -121,7 +124,7 @@ def main():
             print(f"[multi x{world}] halo={gb.halo_transport!r} ibm={opts} {case['name']}: rel err den {e_den:.2e} u {e_u:.2e} f {e_f:.2e} force {eF:.2e} bit-exact {exact} -> {'OK' if good else 'FAIL'}", flush=True)
         gb.close()
         dist.barrier()
-    for k, v in dict(ibm_local=1, ibm_force_exchange=1).items():
+    for k, v in dict(ibm_local=1, ibm_force_exchange=1, ibm_single_launch=1).items():
         F._lib.check(F.lib().fsilbm_set_option(k.encode(), v))
     if rank == 0:
         n_two = sorted(i for (nm, i) in iters_seen if nm == "two_plates_dtol")
