@@ -630,7 +630,7 @@ int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, d
     CK(cudaMalloc(&b->ibm_barrier, sizeof(unsigned int)));
     CK(cudaMemset(b->ibm_barrier, 0, sizeof(unsigned int)));
     CK(cudaMalloc(&b->stat, sizeof(double) * 6));
-    if (g_nccl.nranks > 1 && g_nccl.comm && g_halo_mode == 1)
+    if (g_nccl.nranks > 1 && g_nccl.comm && g_halo_mode == 1 && xLocal != xDim)   // collective over the ranks that share the block
         if (int rc = halo_setup(*b)) return rc;
     int slot = -1;
     for (size_t i = 0; i < g_blocks.size(); i++) if (!g_blocks[i]) { slot = (int)i; break; }
@@ -861,7 +861,7 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
     p.boxes = b.boxes;
     if (!b.ibm_active) p.boxes.n = 0;
     p.tau_all = b.tau_all; p.uuu = b.uuu;
-    const bool multi = g_nccl.nranks > 1 && g_nccl.comm;
+    const bool multi = g_nccl.nranks > 1 && g_nccl.comm && g.X != g.XG;   // a block cut into x-slabs (sons stay whole on one rank)
     const bool ghost = multi || g_force_ghost;
     p.wrap_x = ghost ? 0 : 1;
     const int variant = ((g_variant == 2 && (ghost || b.ibm_active)) || b.model >= 11) ? 0 : g_variant;
@@ -925,7 +925,7 @@ int fsilbm_block_halo_transport(fsilbm_handle h, int *mode)
 {
     Block *b = get(h);
     if (!b || !mode) return fail(FSILBM_ERR_ARG, "bad handle/argument");
-    *mode = (g_nccl.nranks > 1 && g_nccl.comm) ? (b->halo.enabled ? 2 : 1) : 0;
+    *mode = (g_nccl.nranks > 1 && g_nccl.comm && b->g.X != b->g.XG) ? (b->halo.enabled ? 2 : 1) : 0;
     return 0;
 }
 
@@ -1645,8 +1645,10 @@ int fsilbm_pair_create(fsilbm_handle father, fsilbm_handle son, int interpolateS
 {
     Block *F = get(father), *S = get(son);
     if (!F || !S || !pair || father == son) return fail(FSILBM_ERR_ARG, "bad handle/argument");
-    if (g_nccl.nranks > 1 || F->g.X != F->g.XG || S->g.X != S->g.XG)
-        return fail(FSILBM_ERR_ARG, "refinement pairs need both blocks whole on one GPU (slab-split blocks with sons: not provided)");
+    // Slab runs: a son lives whole on the rank whose father slab contains its footprint (checked below); the transfers are
+    // then local to that rank, which creates the son and the pair alone.  A son itself cut into slabs is not provided.
+    if (S->g.X != S->g.XG)
+        return fail(FSILBM_ERR_ARG, "the son block of a refinement pair must be whole on one GPU (only root blocks are cut into x-slabs)");
     const int m_gridDelta = 2;
     const Geom &gf = F->g, &gs = S->g;
     // check_blocks_params, LBMBlockComm.f90:508-544
@@ -1681,9 +1683,12 @@ int fsilbm_pair_create(fsilbm_handle father, fsilbm_handle son, int interpolateS
         p->dimS[k] = sdim[k];
         p->dimF[k] = p->f[2 * k + 1] - p->f[2 * k] + 1;
     }
-    const int fdim[3] = {gf.X, gf.Y, gf.Z};
+    const int fdim[3] = {gf.XG, gf.Y, gf.Z};
     for (int k = 0; k < 3; k++)
         if (p->f[2 * k] < 1 || p->f[2 * k + 1] > fdim[k]) return fail(FSILBM_ERR_ARG, "son block is not inside its father along axis %d", k);
+    if (p->f[0] - 1 < gf.xOffset || p->f[1] - 1 >= gf.xOffset + gf.X)
+        return fail(FSILBM_ERR_ARG, "son block spans father planes %d..%d but this rank's father slab is %d..%d: a son must lie inside one x-slab of its father",
+                    p->f[0], p->f[1], gf.xOffset + 1, gf.xOffset + gf.X);
     for (int j = 0; j < 6; j++) { p->si[j] = p->s[j] + p->sds[j] * ratio; p->fi[j] = p->f[j] + p->sds[j]; }
     // allocate_fIn_tau, :213-264
     const bool need_tau = F->tau_all || S->tau_all;

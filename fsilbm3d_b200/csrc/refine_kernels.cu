@@ -100,6 +100,7 @@ __global__ void pair_extract_kernel(const __grid_constant__ PairFaceParams p, in
     int x, y, z;
     face_xyz(p.axis, p.fplane, p.fb0 + b, p.fa0 + a, x, y, z);
     const Geom &g = p.gF;
+    x -= g.xOffset;   // father indices are global; the footprint lies inside this rank's slab (fsilbm_pair_create)
     const size_t cell = (size_t)(x + 1) * g.plane + (size_t)y * g.Z + z;
     const size_t n = (size_t)a * p.bF + b, nn = (size_t)p.aF * p.bF;
 #pragma unroll
@@ -149,6 +150,7 @@ __global__ void pair_s2f_kernel(const __grid_constant__ PairFaceParams p)
     face_xyz(p.axis, p.siplane, p.sib0 + 2 * b, p.sia0 + 2 * a, xs, ys, zs);
     face_xyz(p.axis, p.fiplane, p.fib0 + b, p.fia0 + a, xf, yf, zf);
     const Geom &gs = p.gS, &gf = p.gF;
+    xf -= gf.xOffset;
     const size_t cs = (size_t)(xs + 1) * gs.plane + (size_t)ys * gs.Z + zs;
     const size_t cf = (size_t)(xf + 1) * gf.plane + (size_t)yf * gf.Z + zf;
     double f[Q];

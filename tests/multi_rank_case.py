@@ -130,10 +130,96 @@ def main():
         n_two = sorted(i for (nm, i) in iters_seen if nm == "two_plates_dtol")
         print(f"[multi x{world}] iteration counts seen in two_plates_dtol: {n_two}", flush=True)
     ok &= flexible_plate_case(F, dist, rank, world, local)
+    ok &= refinement_case(F, dist, rank, world, local)
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+def refinement_case(F, dist, rank, world, local):
+    """Grid refinement on slabs: the root block is cut into x-slabs, a 2:1 refined son sits inside the first and inside the
+    last slab (each created, with its CommPair, by the rank that holds it only); one son carries a rigid plate.  Rank 0
+    compares the father slabs and both sons with the oracle's father + two sons tree."""
+    from tests.common import perturbed_state, rel_err
+    kw = dict(nu=0.02, uvwIn=(0.03, 0.005, 0.0), Uref=0.03, volumeForceIn=(1e-6, 0.0, 0.0), ntolLBM=3, dtolLBM=1e-30)
+    fbc, sbc = (102, 104, 301, 301, 203, 203), (0,) * 6
+    X, Y, Z = 20 * world, 16, 14
+    sdims = (17, 13, 11)
+    son_mins = [(5.0, 4.0, 3.0), (20.0 * (world - 1) + 6.0, 3.0, 2.0)]
+    son_rank = [0, world - 1]
+    scheme = 2
+    off, cnt = F.slab_range(X, rank, world)
+    gf = F.FlowCondType(**kw)
+    gF = F.LBMBlock(X, Y, Z, dh=1.0, BndConds=fbc, flow=gf, xOffset=off, xLocal=cnt, device=local)
+    gF.initialise(0.0)
+    f0F = perturbed_state((X, Y, Z), gf, seed=1)
+    f0S = [perturbed_state(sdims, gf, seed=2 + k) for k in range(2)]
+    gF.upload_fIn(np.ascontiguousarray(f0F[:, off:off + cnt]))
+    kwp = dict(origin=(8.3, 7.2, 4.1), nEL=6, len1=0.5, Nspan=4, spanlen=2.0, Lspan=0.0, chord_dir=(1.0, 0.3, 0.0), denIn=1.0)
+    groot = F.blockTreeNode(gF)
+    sons = {}
+    for k in range(2):
+        if son_rank[k] != rank:
+            continue
+        gS = F.LBMBlock(*sdims, dh=0.5, xmin=son_mins[k][0], ymin=son_mins[k][1], zmin=son_mins[k][2], BndConds=sbc, flow=gf, device=local)
+        gS.initialise(0.0)
+        gS.upload_fIn(f0S[k])
+        plates = [F.RigidPlate(**kwp)] if k == 0 else []
+        groot.add_son(F.blockTreeNode(gS, plates), scheme)
+        sons[k] = (gS, plates)
+    for nd in groot.walk():
+        nd.block.update_volume_force(); nd.block.set_boundary_conditions()
+    if rank == 0:
+        from oracle import oracle as O
+        of = O.Flow(**kw)
+        oF = O.LBMBlock(X, Y, Z, dh=1.0, BndConds=fbc, flow=of)
+        oF.initialise(0.0); oF.fIn[...] = f0F
+        oroot = O.TreeNode(oF)
+        oS, ov = [], None
+        for k in range(2):
+            b = O.LBMBlock(*sdims, dh=0.5, xmin=son_mins[k][0], ymin=son_mins[k][1], zmin=son_mins[k][2], BndConds=sbc, flow=of)
+            b.initialise(0.0); b.fIn[...] = f0S[k]
+            bodies = []
+            if k == 0:
+                pl = F.RigidPlate(**kwp)
+                ov = O.VirtualBody(pl.body.v_nelmts)
+                ov.v_Exyz[...] = pl.body.v_Exyz; ov.v_Evel[...] = pl.body.v_Evel; ov.v_Ea[...] = pl.body.v_Ea
+                bodies = [ov]
+            oroot.add_son(O.TreeNode(b, bodies), scheme)
+            oS.append(b)
+        for b in [oF] + oS:
+            b.update_volume_force(); b.set_boundary_conditions(); b.calculate_macro_quantities()
+    steps = 8
+    for n in range(1, steps + 1):
+        F.set_blktime_all(groot, float(n))
+        F.tree_collision_streaming_IBM_FEM(groot, solver=False)
+        if rank == 0:
+            O.set_blktime_all(oroot, float(n))
+            O.tree_collision_streaming_IBM_FEM(oroot)
+    payload = (gF.download_fIn(), {k: (v[0].download_fIn(), v[1][0].body.v_Eforce.copy() if v[1] else None) for k, v in sons.items()})
+    parts = [None] * world
+    dist.gather_object(payload, parts if rank == 0 else None, dst=0)
+    good = True
+    if rank == 0:
+        FF = np.concatenate([p[0] for p in parts], axis=1)
+        exact_f = bool(np.array_equal(FF, oF.fIn))
+        exact_s, e_force = True, 0.0
+        for p in parts:
+            for k, (fS, force) in p[1].items():
+                exact_s &= bool(np.array_equal(fS, oS[k].fIn))
+                if force is not None:
+                    e_force = max(e_force, rel_err(force, ov.v_Eforce))
+        good = exact_f and exact_s and e_force <= 1e-10
+        print(f"[multi x{world}] refinement on slabs (sons on ranks {son_rank}, cubic transfers, plate in son 0): father bit-exact {exact_f} "
+              f"sons bit-exact {exact_s} force {e_force:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+    for pair in groot.comm:
+        pair.close()
+    for v in sons.values():
+        v[0].close()
+    gF.close()
+    dist.barrier()
+    return good
 
 
 def flexible_plate_case(F, dist, rank, world, local):
