@@ -449,6 +449,7 @@ def main():
     ap.add_argument("--ibm-single-launch", type=int, default=1, choices=[0, 1], help="IBM penalty iteration: 1 one cooperative kernel, 0 one kernel per phase")
     ap.add_argument("--ibm-ordered", type=int, default=1, choices=[0, 1],
                     help="IBM spreading: 1 ordered per-cell gather (bit-identical to the serial reference), 0 fp64 atomics")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=int (fsilbm_set_option), repeatable")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -465,6 +466,9 @@ def main():
     F._lib.check(F.lib().fsilbm_set_option(b"halo", args.halo))
     F._lib.check(F.lib().fsilbm_set_option(b"ibm_ordered", args.ibm_ordered))
     F._lib.check(F.lib().fsilbm_set_option(b"ibm_single_launch", args.ibm_single_launch))
+    for kv in args.opt:
+        k, v = kv.split("=")
+        F._lib.check(F.lib().fsilbm_set_option(k.encode(), int(v)))
     run_gpu(args)
 
 

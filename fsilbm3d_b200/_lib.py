@@ -86,6 +86,8 @@ def lib():
     L.fsilbm_last_error.argtypes = []
     L.fsilbm_launch_count.restype = C.c_longlong
     L.fsilbm_launch_count.argtypes = []
+    L.fsilbm_ibm_early_count.restype = C.c_longlong
+    L.fsilbm_ibm_early_count.argtypes = []
     _lib = L
     return L
 

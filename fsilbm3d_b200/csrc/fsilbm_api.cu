@@ -196,6 +196,13 @@ struct Block {
     int bodies_dev_cap = 0;
     cudaStream_t ibm_stream = nullptr;                  // marker upload, stencils and cell lists run beside the compute stream
     cudaEvent_t ev_ibm = nullptr;
+    // Early IBM: collide_stream updates the x-planes around the bodies first (ev_early), so the next interaction-force call
+    // can run on its own stream beside the rest of that update instead of behind it.  early_x0/x1: GLOBAL x-planes [x0, x1)
+    // whose streamed populations are final once ev_early has passed.
+    cudaStream_t ibm_main_stream = nullptr;
+    cudaEvent_t ev_early = nullptr;
+    bool early_ok = false, in_pair = false;
+    int early_n = 0, early_x0[MAX_BOXES]{}, early_x1[MAX_BOXES]{};
     IbmCtl *ctl = nullptr;
     unsigned int *ibm_barrier = nullptr;
     bool ibm_active = false;
@@ -243,6 +250,8 @@ int g_ibm_local = 1;           // multi-rank, ordered mode: 1 a body is iterated
                                // 0 the replicated / partial-sum forms below
 int g_ibm_force_exchange = 1;  // with ibm_local: 1 every rank passes the same bodies and gets every body's forces back (one all-reduce);
                                // 0 every rank passes only the bodies near its slab (distributed lists; the call is then collective even with none)
+int g_ibm_early_blocks = 2;    // blocks per SM of the cooperative IBM kernel when it runs beside a collide-stream update
+int g_ibm_early = 1;           // 1: the planes around the bodies are updated first and the next IBM call overlaps the rest of the update
 int g_ibm_ordered = 1;         // 1: interpolation and spreading keep the reference's serial summation order (bit-reproducible); 0: shuffles + fp64 atomics
 int g_halo_mode = 1;   // 1: edge kernels store into the neighbours' memory over NVLink (default); 0: ncclSend/ncclRecv
 
@@ -530,6 +539,8 @@ extern "C" {
 
 const char *fsilbm_last_error(void) { return g_err; }
 long long fsilbm_launch_count(void) { return kernel_launch_count(); }
+static long long g_ibm_early_calls = 0;
+long long fsilbm_ibm_early_count(void) { return g_ibm_early_calls; }
 
 int fsilbm_init(int device)
 {
@@ -568,6 +579,8 @@ int fsilbm_set_option(const char *key, int value)
     if (!strcmp(key, "force_ghost")) { g_force_ghost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_single_launch")) { g_ibm_single_launch = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_replicate")) { g_ibm_replicate = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->csr_valid = false; return 0; }
+    if (!strcmp(key, "ibm_early_blocks_per_sm")) { if (value < 1 || value > 4) return fail(FSILBM_ERR_ARG, "ibm_early_blocks_per_sm must be 1..4"); g_ibm_early_blocks = value; return 0; }
+    if (!strcmp(key, "ibm_early")) { g_ibm_early = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->early_ok = false; return 0; }
     if (!strcmp(key, "ibm_local")) { g_ibm_local = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->csr_valid = false; return 0; }
     if (!strcmp(key, "ibm_force_exchange")) { g_ibm_force_exchange = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_ordered")) { g_ibm_ordered = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->csr_valid = false; return 0; }
@@ -624,7 +637,9 @@ int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, d
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CK(cudaStreamCreateWithPriority(&b->ibm_stream, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithPriority(&b->ibm_main_stream, cudaStreamNonBlocking, hi));
     }
+    CK(cudaEventCreateWithFlags(&b->ev_early, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_ibm, cudaEventDisableTiming));
     CK(cudaMalloc(&b->ctl, sizeof(IbmCtl)));
     CK(cudaMalloc(&b->ibm_barrier, sizeof(unsigned int)));
@@ -654,7 +669,8 @@ int fsilbm_block_destroy(fsilbm_handle h)
     cudaFree(b->uuu_ave); cudaFree(b->outtmp); cudaFree(b->scratch);
     cudaFree(b->boxes.u); cudaFree(b->boxes.force);
     for (auto &bd : b->bodies) bd.release();
-    cudaStreamSynchronize(b->ibm_stream);
+    cudaStreamSynchronize(b->ibm_stream); cudaStreamSynchronize(b->ibm_main_stream);
+    cudaEventDestroy(b->ev_early); cudaStreamDestroy(b->ibm_main_stream);
     cudaFree(b->bodies_dev); cudaFree(b->lead_dev); cudaFree(b->tol2); cudaFree(b->ctl); cudaFree(b->ibm_barrier);
     cudaFree(b->mk_dev); cudaFree(b->force_dev); cudaFreeHost(b->mk_pin); cudaFreeHost(b->force_pin);
     cudaEventDestroy(b->ev_ibm); cudaStreamDestroy(b->ibm_stream);
@@ -669,6 +685,7 @@ int fsilbm_block_initialise(fsilbm_handle h, double time)
 {
     Block *b = get(h);
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    b->early_ok = false;
     const double Cs2 = 1.0 / 3.0;                            // ConstParams.f90:39
     b->tau = b->flow.nu / (b->g.dh * Cs2) + 0.5;             // calculate_SRT_params, FluidDomain.f90:452
     b->Omega = 1.0 / b->tau;
@@ -726,6 +743,7 @@ int fsilbm_block_upload_fIn(fsilbm_handle h, const double *fIn)
 {
     Block *b = get(h);
     if (!b || !fIn) return fail(FSILBM_ERR_ARG, "bad handle/argument");
+    b->early_ok = false;
     const Geom &g = b->g;
     const size_t n = (size_t)g.X * g.plane;
     CK(cudaStreamSynchronize(b->stream));
@@ -812,6 +830,7 @@ int fsilbm_block_set_boundary_conditions(fsilbm_handle h)
 {
     Block *b = get(h);
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    b->early_ok = false;
     return apply_boundary_conditions(*b, b->f[b->cur]);
 }
 
@@ -865,9 +884,56 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
     const bool ghost = multi || g_force_ghost;
     p.wrap_x = ghost ? 0 : 1;
     const int variant = ((g_variant == 2 && (ghost || b.ibm_active)) || b.model >= 11) ? 0 : g_variant;
+    // Early IBM (see Block::ev_early): planes A = [box - 2, box + 2) of every stencil box first, then the rest.  After A the
+    // streamed populations of the planes [box - 1, box + 1) are final -- provided no face kernel, halo or x-wrap touches them,
+    // hence the conditions below -- and the next interaction-force call may start while the rest is still being updated.
+    int nA = 0, A0[MAX_BOXES], A1[MAX_BOXES];
+    const int lower = multi ? 1 : 0, upper = multi ? g.X - 1 : g.X;   // planes of the bulk launch (multi: the edge planes go first anyway)
+    bool early = g_ibm_early && b.ibm_active && p.boxes.n > 0 && b.model < 11 && !b.in_pair && (multi ? b.halo.enabled : !ghost);
+    if (early) {
+        const int Ns[3] = {g.XG, g.Y, g.Z};
+        for (int i = 0; i < p.boxes.n && early; i++) {
+            for (int k = 0; k < 3; k++) {
+                const int lo = p.boxes.lo[i][k], hi = lo + p.boxes.ext[i][k];
+                if (k == 0 && hi > Ns[0]) early = false;                              // wraps in x
+                if (b.periodic[k] != 1 && (lo < 3 || hi > Ns[k] - 3)) early = false;    // within reach of a face kernel
+            }
+            const int a0 = p.boxes.lo[i][0] - g.xOffset - 2, a1 = p.boxes.lo[i][0] + p.boxes.ext[i][0] - g.xOffset + 2;
+            if (a0 < lower || a1 > upper) early = false;
+            A0[nA] = a0; A1[nA] = a1; nA++;
+        }
+        if (early) {   // sort and merge
+            for (int i = 1; i < nA; i++)
+                for (int j = i; j > 0 && A0[j] < A0[j - 1]; j--) { std::swap(A0[j], A0[j - 1]); std::swap(A1[j], A1[j - 1]); }
+            int m = 0;
+            for (int i = 1; i < nA; i++) {
+                if (A0[i] <= A1[m]) A1[m] = std::max(A1[m], A1[i]);
+                else { m++; A0[m] = A0[i]; A1[m] = A1[i]; }
+            }
+            nA = m + 1;
+        }
+    }
+    b.early_ok = false;
+    auto bulk = [&](StepParams &q) -> int {   // planes [lower, upper): A first when early
+        if (!early) {
+            q.x_begin = lower; q.x_count = upper - lower;
+            return launch_collide_push(q, b.model, variant, b.stream);
+        }
+        for (int i = 0; i < nA; i++) { q.x_begin = A0[i]; q.x_count = A1[i] - A0[i]; if (launch_collide_push(q, b.model, variant, b.stream)) return 1; }
+        if (cudaEventRecord(b.ev_early, b.stream) != cudaSuccess) return 1;
+        int at = lower;
+        for (int i = 0; i <= nA; i++) {
+            const int end = i < nA ? A0[i] : upper;
+            if (end > at) { q.x_begin = at; q.x_count = end - at; if (launch_collide_push(q, b.model, variant, b.stream)) return 1; }
+            if (i < nA) at = A1[i];
+        }
+        b.early_n = nA;
+        for (int i = 0; i < nA; i++) { b.early_x0[i] = A0[i] + 1 + g.xOffset; b.early_x1[i] = A1[i] - 1 + g.xOffset; }
+        b.early_ok = true;
+        return 0;
+    };
     if (!multi) {
-        p.x_begin = 0; p.x_count = g.X;
-        if (launch_collide_push(p, b.model, variant, b.stream)) return fail(FSILBM_ERR_MODEL, "collision model %d", b.model);
+        if (bulk(p)) return fail(FSILBM_ERR_MODEL, "collision model %d", b.model);
         if (ghost) launch_wrap_x(g, fB, b.stream);
     } else if (b.halo.enabled) {
         // Edge planes first: their kernel IS the transfer (peer stores over NVLink + arrival flag); then the
@@ -882,7 +948,7 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
         e.x_begin = 0; e.x_count = 1; e.cta_counter = h.counters;
         launch_collide_push(e, b.model, variant, b.stream);
         if (g.X > 1) { e.x_begin = g.X - 1; e.cta_counter = h.counters + 1; launch_collide_push(e, b.model, variant, b.stream); }
-        if (g.X > 2) { p.x_begin = 1; p.x_count = g.X - 2; launch_collide_push(p, b.model, variant, b.stream); }
+        if (g.X > 2) bulk(p);
         HaloUnpackParams u{};
         u.g = g; u.fB = fB; u.step = h.step; u.err = h.err; u.timeout_ns = (unsigned long long)g_halo_timeout_s * 1000000000ull;
         if (h.left >= 0) { u.recv_lo = halo_slot_ptr(h.region, h.slot_bytes, 0, par); u.flag_lo = halo_flag(h.region, 0, par); }
@@ -1056,6 +1122,7 @@ int fsilbm_block_pass_macro(fsilbm_handle h)
 {
     Block *b = get(h);
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    b->early_ok = false;
     if (int rc = ensure_fields(*b, true)) return rc;
     double hF[3];
     half_force(*b, hF);
@@ -1068,6 +1135,7 @@ int fsilbm_block_pass_reset_volume_force(fsilbm_handle h)
 {
     Block *b = get(h);
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    b->early_ok = false;
     if (int rc = ensure_fields(*b, true)) return rc;
     launch_pass_fill(b->force, 3 * (size_t)b->g.X * b->g.plane, 0.0, b->stream);
     CK(cudaGetLastError());
@@ -1078,6 +1146,7 @@ int fsilbm_block_pass_add_volume_force(fsilbm_handle h)
 {
     Block *b = get(h);
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    b->early_ok = false;
     if (int rc = ensure_fields(*b, true)) return rc;
     launch_pass_add_force(field_params(*b), b->stream);
     CK(cudaGetLastError());
@@ -1088,6 +1157,7 @@ int fsilbm_block_pass_collision(fsilbm_handle h)
 {
     Block *b = get(h);
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    b->early_ok = false;
     if (!b->initialised) return fail(FSILBM_ERR_ARG, "block %d not initialised", h);
     if (int rc = ensure_fields(*b, true)) return rc;
     if (launch_pass_collision(field_params(*b), b->model, b->stream)) return fail(FSILBM_ERR_MODEL, "collision model %d", b->model);
@@ -1099,6 +1169,7 @@ int fsilbm_block_pass_halfway_bc_set(fsilbm_handle h)
 {
     Block *b = get(h);
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    b->early_ok = false;
     VelocityField vel;
     if (int rc = velocity_field(*b, b->blktime, vel)) return rc;
     for (int face = 0; face < 6; face++) {
@@ -1115,6 +1186,7 @@ int fsilbm_block_pass_streaming(fsilbm_handle h)
 {
     Block *b = get(h);
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    b->early_ok = false;
     if (b->g.X != b->g.XG) return fail(FSILBM_ERR_ARG, "the un-fused streaming pass is single-slab only");
     launch_pass_streaming(b->g, b->f[b->cur], b->f[b->cur ^ 1], b->stream);
     CK(cudaGetLastError());
@@ -1139,6 +1211,7 @@ int fsilbm_block_upload_fields(fsilbm_handle h, const double *den, const double 
 {
     Block *b = get(h);
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    b->early_ok = false;
     if (int rc = ensure_fields(*b, true)) return rc;
     CK(cudaStreamSynchronize(b->stream));
     const size_t n = (size_t)b->g.X * b->g.plane;
@@ -1436,8 +1509,28 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
             b.csr_valid = true;
         }
     }
+    // Early IBM: when every box lies inside the planes the last collide_stream finished first (and clear of the faces), the rest
+    // of this call runs on its own stream behind ev_early, beside the remainder of that update, instead of behind all of it.
+    bool use_early = b.early_ok && g_ibm_early && bx.n > 0 && (!multi || local) && ordered;
+    for (int i = 0; i < bx.n && use_early; i++) {
+        bool inside = false;
+        const int lo = bx.lo[i][0], hi = lo + bx.ext[i][0];
+        for (int k = 0; k < b.early_n; k++) inside = inside || (lo >= b.early_x0[k] && hi <= b.early_x1[k]);
+        for (int k = 1; k < 3; k++)
+            if (b.periodic[k] != 1 && (bx.lo[i][k] < 3 || bx.lo[i][k] + bx.ext[i][k] > Ns[k] - 3)) inside = false;
+        if (local && shared[kept[i]]) inside = false;
+        use_early = inside;
+    }
+    b.early_ok = false;   // one use per update
+    const cudaStream_t s_all = s;   // the stream that has seen the whole update
+    if (use_early) {
+        g_ibm_early_calls++;
+        s = b.ibm_main_stream;
+        CK(cudaStreamWaitEvent(s, b.ev_early, 0));
+    }
     CK(cudaEventRecord(b.ev_ibm, s2));
     CK(cudaStreamWaitEvent(s, b.ev_ibm, 0));
+    (void)s_all;
 
     // -- compute stream: everything that reads the populations
     if (replicate) {
@@ -1500,7 +1593,7 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         }
         lp.phase_start[nphase] = pos;
         for (int k = 0; k < nact; k++) lp.phase_of_body[k] = rank_in_group[k];
-        if (launch_ibm_loop(lp, max_markers, s)) {
+        if (launch_ibm_loop(lp, max_markers, use_early ? g_ibm_early_blocks : 0, s)) {
             cudaGetLastError();
             if (mailbox) return fail(FSILBM_ERR_CUDA, "cooperative launch of the IBM iteration failed");   // the other ranks are in the mailbox protocol
             single = false;   // no cooperative launch: take the phase-by-phase path
@@ -1671,6 +1764,8 @@ int fsilbm_pair_create(fsilbm_handle father, fsilbm_handle son, int interpolateS
                                     "an even number of grid points is needed. Otherwise an odd number is needed.");
     auto p = std::make_unique<Pair>();
     p->father = father; p->son = son; p->scheme = interpolateScheme;
+    F->in_pair = S->in_pair = true;   // the transfers rewrite planes between the steps: no early IBM on these blocks
+    F->early_ok = S->early_ok = false;
     // build_blocks_comunication, :32-96
     for (int j = 0; j < 6; j++) p->sds[j] = S->bc[j] == BCfluid ? ((j % 2 == 0) ? 1 : -1) : 0;
     int sD[3];

@@ -909,9 +909,17 @@ int ibm_loop_max_blocks()
     return max_blocks;
 }
 
-int launch_ibm_loop(const IbmLoopParams &p, int max_markers, cudaStream_t s)
+// blocks_per_sm > 0: the launch shares the SMs with a running collide-stream kernel (early IBM); one block per SM leaves that
+// kernel three of its four CTA slots (its 125 registers per thread fill the register file with four)
+int launch_ibm_loop(const IbmLoopParams &p, int max_markers, int blocks_per_sm, cudaStream_t s)
 {
-    const int max_blocks = ibm_loop_max_blocks();
+    int max_blocks = ibm_loop_max_blocks();
+    if (blocks_per_sm > 0) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms > 0 && sms * blocks_per_sm < max_blocks) max_blocks = sms * blocks_per_sm;
+    }
     int want = (max_markers + 7) / 8;           // one warp per marker of the largest phase
     long long cells = (p.boxes.ncell + 255) / 256;
     if (p.ordered) want = (max_markers + MARKERS_PER_BLOCK - 1) / MARKERS_PER_BLOCK;   // 16 lanes per marker, one thread per box cell

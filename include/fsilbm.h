@@ -62,6 +62,10 @@ int fsilbm_finalize(void);
 const char *fsilbm_last_error(void);
 /* Number of kernels this library has launched since fsilbm_init (bench.py's gpu_launches). */
 long long fsilbm_launch_count(void);
+/* Number of fsilbm_ibm_interaction_force calls that ran beside the tail of the previous collide-stream update ("early IBM":
+ * fsilbm_block_collide_stream updates the x-planes around the bodies first, so the next interaction-force call needs to wait
+ * for those planes only; option "ibm_early" = 0 turns it off).  Diagnostics/tests. */
+long long fsilbm_ibm_early_count(void);
 /* Tuning/testing switches, no reference counterpart.  key "variant": 0 push kernel (default),
  * 1 push with streaming stores, 2 pull (fully periodic blocks only; kernel sweep);
  * key "force_ghost": 1 = stream through the ghost planes even on one rank (tests the slab path);

@@ -56,6 +56,39 @@ def test_rigid_plate_bit_exact(oracle, F, moving, bc, single_launch):
         F._lib.check(F.lib().fsilbm_set_option(b"ibm_single_launch", 1))
 
 
+@pytest.mark.parametrize("bc", [(301,) * 6, (101, 104, 202, 202, 301, 301)])
+def test_early_ibm_bit_exact(oracle, F, bc):
+    """Early IBM: collide_stream updates the planes around the body first and the next interaction-force call runs beside the
+    rest of the update on its own stream.  A moving plate well inside the block (so the overlap is actually taken, checked
+    through fsilbm_ibm_early_count) must stay bit-identical to the oracle, and to the run with the overlap turned off."""
+    from tests.common import make_pair
+    flow = dict(nu=0.05, uvwIn=(0.05, 0.0, 0.0), shearRateIn=(0.0, 2e-4, 0.0), Uref=0.05, ntolLBM=4, dtolLBM=1e-30)
+    runs = {}
+    for early in (1, 0):
+        F._lib.check(F.lib().fsilbm_set_option(b"ibm_early", early))
+        try:
+            ob, gb = make_pair(oracle, F, (48, 36, 32), BndConds=bc, **flow)
+            pg, po, ovb = plates_pair(oracle, F, 1.0, moving=True, origin=(18.3, 14.2, 10.4))
+            c0 = F.lib().fsilbm_ibm_early_count()
+            for n in range(1, 26):
+                t = float(n)
+                ob.set_blktime(t)
+                po.UpdatePosVelArea(); sync_oracle_body(ovb, po)
+                it_o = ob.step([ovb])
+                po.structure(t, 1, ob.dh, ob.dh)
+                it_g = F.tree_collision_streaming_IBM_FEM(gb, [pg], time=t)
+                assert it_o == it_g == 4
+                assert np.array_equal(pg.body.v_Eforce, ovb.v_Eforce), (early, n)
+            taken = F.lib().fsilbm_ibm_early_count() - c0
+            assert taken == (24 if early else 0), taken      # every call after the first update
+            assert fluid_equal(ob, gb)
+            runs[early] = gb.download_fIn()
+            gb.close()
+        finally:
+            F._lib.check(F.lib().fsilbm_set_option(b"ibm_early", 1))
+    assert np.array_equal(runs[0], runs[1])
+
+
 def test_overlapping_bodies_and_wrap_bit_exact(oracle, F):
     """Three bodies, two of them sharing cells (Gauss-Seidel order, Solidbody.f90:898-903), early exit on the
     tolerance; then a plate that wraps periodically and folds at a wall (several nodes of one marker on one cell)."""
