@@ -32,6 +32,30 @@ def halo_plan(rank: int, nranks: int, periodic_x: bool):
     return left, right, UP_POPULATIONS, DOWN_POPULATIONS
 
 
+def ibm_box_participants(x0: int, length: int, slabs: Sequence[Tuple[int, int]], xDim: int):
+    """Which ranks iterate a body whose stencil box covers global x-planes [x0, x0+length) (modulo xDim when it wraps), and
+    what they send one another -- the host logic of fsilbm_ibm_interaction_force on slab runs (csrc/fsilbm_api.cu, "slab runs").
+    `slabs[r] = (offset, count)` of rank r.  Returns (runs, leader): runs = [(rank, dx0, dx1), ...] are the maximal stretches of
+    box planes dx in [dx0, dx1) owned by one rank, in box order; the ranks named there are the participants (one rank: no
+    communication; several: every participant sends its stretches to every other participant and then iterates the whole
+    box); leader = owner of the box's first plane, the rank that reports the body's residual to the loop control and its
+    forces to the force exchange."""
+    owner = [-1] * xDim
+    for r, (off, cnt) in enumerate(slabs):
+        for x in range(off, off + cnt):
+            owner[x] = r
+    if any(o < 0 for o in owner):
+        raise ValueError("the slabs do not cover every x-plane")
+    runs = []
+    for dx in range(length):
+        r = owner[(x0 + dx) % xDim]
+        if runs and runs[-1][0] == r:
+            runs[-1] = (r, runs[-1][1], dx + 1)
+        else:
+            runs.append((r, dx, dx + 1))
+    return runs, runs[0][0]
+
+
 def init_process_group(rank: int, nranks: int, device: int, broadcast_bytes) -> None:
     """Bind this process to `device` and join the library's NCCL communicator.
     broadcast_bytes(b: bytes|None) -> bytes must return rank 0's 128-byte id on every rank."""

@@ -101,3 +101,47 @@ def test_coupled_loop_on_oracle_cpp_vs_numpy(oracle, case, tmp_path):
     # force conservation of the spread: sum over cells of force*dh^3 = -sum of marker forces is checked in test_oracle_kat;
     # here: the nodal loads carry the whole marker force (Solidbody.f90:964-965)
     assert np.allclose(b.lodFlow[:, 0:3].sum(0), ov.v_Eforce.sum(0), rtol=1e-12, atol=1e-16)
+
+
+@pytest.mark.parametrize("threads", ["1", "3"])
+def test_advance_equals_call_by_call(tmp_path, monkeypatch, threads):
+    """SolidBodies.advance() -- nodal loads, the structural sub-steps and next step's markers of all listed bodies in ONE
+    threaded call (what the step issues behind the collide-stream launch) -- leaves every body bit-identical to the
+    reference's call-by-call sequence FluidVolumeForce_ (host half) -> Solver per sub-step -> UpdatePosVelArea_."""
+    monkeypatch.setenv("FSILBM_SOLID_THREADS", threads)
+    n = 9
+    kw = dict(dampM=0.5, dampK=1e-4, dtolFEM=1e-14, ntolFEM=20)
+    groups = [dict(KIN, fishNum=1, mesh="plate.dat", iBodyModel=2, iBodyType=1, isMotionGiven=(1,) * 6, firstXYZ=(0.3 + 0.5 * k, 0.2, 0.1), freq=0.8 + 0.1 * k)
+              for k in range(3)]
+    runs = []
+    for mode in ("calls", "advance"):
+        wd = os.path.join(str(tmp_path), mode)
+        os.makedirs(wd)
+        from fsilbm3d_b200 import solid_solver as S
+        from tests.beam_cases import BOX
+        S.write_plate_dat(os.path.join(wd, "plate.dat"), chain(n), 0.05, 0.07, (0.0, 1.0, 0.2), Nspan=3, material=MAT)
+        with open(os.path.join(wd, "inFlow.dat"), "w") as f:
+            f.write(S.inflow_text(UrefType=9, Uref=1.0, LrefType=1, Lref=1.0, isKB=2, blocks=[BOX], groups=groups, numsubstep=2, **kw))
+        sb = S.SolidBodies("inFlow.dat", (301,) * 6, cwd=wd)
+        assert len(sb.VBodies) == 3
+        rng = np.random.default_rng(C_SEED)
+        dt = 0.01
+        for k in range(1, 31):
+            for b in sb.VBodies:
+                b.UpdatePosVelArea()                    # a no-op right after advance()
+                b.v_Eforce[...] = rng.normal(size=(b.v_nelmts, 3)) * 1e-3
+            if mode == "calls":
+                for b in sb.VBodies:
+                    b.FluidLoads()
+                for s in (1, 2):
+                    sb.Solver(k * dt, s, dt, dt / 2)
+            else:
+                sb.advance([0, 1, 2], k * dt, 2, dt)
+        for b in sb.VBodies:
+            b.UpdatePosVelArea()
+        runs.append([(b.pos.copy(), b.vel.copy(), b.lodFlow.copy(), b.v_Exyz.copy(), b.v_Evel.copy(), b.FishInfo.copy()) for b in sb.VBodies])
+        sb.close()
+    for ba, bb in zip(*runs):
+        for x, y in zip(ba, bb):
+            assert np.array_equal(x, y)
+    assert np.abs(runs[0][0][0] - runs[0][1][0]).max() > 0.1   # the three bodies are different beams

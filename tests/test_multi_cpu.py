@@ -30,3 +30,18 @@ def test_halo_plan_neighbours():
     _, _, up, dn = halo_plan(3, 8, True)
     ex = [0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0]
     assert [q for q in range(19) if ex[q] == 1] == list(up) and [q for q in range(19) if ex[q] == -1] == list(dn)
+
+
+def test_ibm_box_participants():
+    """Slab runs: which ranks iterate a body and what they exchange (the rule fsilbm_ibm_interaction_force applies)."""
+    import fsilbm3d_b200 as F
+    slabs = [F.slab_range(40, r, 4) for r in range(4)]                      # 4 x 10 planes
+    assert F.ibm_box_participants(12, 6, slabs, 40) == ([(1, 0, 6)], 1)         # inside slab 1: no communication
+    assert F.ibm_box_participants(17, 8, slabs, 40) == ([(1, 0, 3), (2, 3, 8)], 1)   # across the 1|2 interface, led by rank 1
+    assert F.ibm_box_participants(36, 9, slabs, 40) == ([(3, 0, 4), (0, 4, 9)], 3)   # periodic wrap: ranks 3 and 0
+    runs, lead = F.ibm_box_participants(8, 24, slabs, 40)                       # a long body over four slabs
+    assert [r for r, _, _ in runs] == [0, 1, 2, 3] and lead == 0 and runs[-1] == (3, 22, 24)
+    two = [(0, 7), (7, 5)]                                                    # two ranks, periodic: the box re-enters rank 0
+    assert F.ibm_box_participants(5, 10, two, 12) == ([(0, 0, 2), (1, 2, 7), (0, 7, 10)], 0)
+    with pytest.raises(ValueError):
+        F.ibm_box_participants(0, 3, [(0, 5)], 8)
