@@ -88,6 +88,22 @@ module fsilbm_c
             integer(c_int), value :: h
             real(c_double), intent(out) :: den(*), uuu(*)
         end function
+        ! the same without waiting (den, uuu must be page-locked); valid after fsilbm_block_download_wait
+        integer(c_int) function fsilbm_block_download_macro_async(h, den, uuu) bind(C, name='fsilbm_block_download_macro_async')
+            import :: c_int, c_double
+            integer(c_int), value :: h
+            real(c_double), intent(out) :: den(*), uuu(*)
+        end function
+        integer(c_int) function fsilbm_block_download_wait(h) bind(C, name='fsilbm_block_download_wait')
+            import :: c_int
+            integer(c_int), value :: h
+        end function
+        ! slab runs: 0 body not iterated by this rank, 1 iterated, 2 iterated and led
+        integer(c_int) function fsilbm_ibm_body_status(h, nbody, status) bind(C, name='fsilbm_ibm_body_status')
+            import :: c_int
+            integer(c_int), value :: h, nbody
+            integer(c_int), intent(out) :: status(*)
+        end function
         integer(c_int) function fsilbm_block_field_stat(h, stat) bind(C, name='fsilbm_block_field_stat')
             import :: c_int, c_double
             integer(c_int), value :: h

@@ -199,6 +199,8 @@ struct Block {
     // Early IBM: collide_stream updates the x-planes around the bodies first (ev_early), so the next interaction-force call
     // can run on its own stream beside the rest of that update instead of behind it.  early_x0/x1: GLOBAL x-planes [x0, x1)
     // whose streamed populations are final once ev_early has passed.
+    cudaEvent_t ev_macro = nullptr, ev_io = nullptr;    // fsilbm_block_download_macro_async: den/uuu staged -> copied out on comm_stream
+    bool io_pending = false;
     cudaStream_t ibm_main_stream = nullptr;
     cudaEvent_t ev_early = nullptr;
     bool early_ok = false, in_pair = false;
@@ -397,6 +399,7 @@ int apply_boundary_conditions(Block &b, double *f)
 
 int ensure_fields(Block &b, bool need_force)
 {
+    if (b.io_pending) { CK(cudaEventSynchronize(b.ev_io)); b.io_pending = false; }   // an asynchronous read-back still copies out of den/uuu
     const size_t n = (size_t)b.g.X * b.g.plane;
     if (!b.den) CK(cudaMalloc(&b.den, sizeof(double) * n));
     if (!b.uuu) CK(cudaMalloc(&b.uuu, sizeof(double) * 3 * n));
@@ -532,6 +535,13 @@ void halo_teardown(Block &b)
     h = Block::Halo();
 }
 
+// an asynchronous read-back still copies out of the den/uuu staging fields: wait before they are overwritten
+int io_wait(Block &b)
+{
+    if (b.io_pending) { CK(cudaEventSynchronize(b.ev_io)); b.io_pending = false; }
+    return 0;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -640,6 +650,8 @@ int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, d
         CK(cudaStreamCreateWithPriority(&b->ibm_main_stream, cudaStreamNonBlocking, hi));
     }
     CK(cudaEventCreateWithFlags(&b->ev_early, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b->ev_macro, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b->ev_io, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_ibm, cudaEventDisableTiming));
     CK(cudaMalloc(&b->ctl, sizeof(IbmCtl)));
     CK(cudaMalloc(&b->ibm_barrier, sizeof(unsigned int)));
@@ -671,6 +683,7 @@ int fsilbm_block_destroy(fsilbm_handle h)
     for (auto &bd : b->bodies) bd.release();
     cudaStreamSynchronize(b->ibm_stream); cudaStreamSynchronize(b->ibm_main_stream);
     cudaEventDestroy(b->ev_early); cudaStreamDestroy(b->ibm_main_stream);
+    cudaEventDestroy(b->ev_macro); cudaEventDestroy(b->ev_io);
     cudaFree(b->bodies_dev); cudaFree(b->lead_dev); cudaFree(b->tol2); cudaFree(b->ctl); cudaFree(b->ibm_barrier);
     cudaFree(b->mk_dev); cudaFree(b->force_dev); cudaFreeHost(b->mk_pin); cudaFreeHost(b->force_pin);
     cudaEventDestroy(b->ev_ibm); cudaStreamDestroy(b->ibm_stream);
@@ -785,10 +798,38 @@ int fsilbm_block_update_volume_force(fsilbm_handle h, double out[3])
     return 0;
 }
 
+int fsilbm_block_download_macro_async(fsilbm_handle h, double *den, double *uuu)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    if (int rc = io_wait(*b)) return rc;
+    if (int rc = ensure_fields(*b, false)) return rc;
+    double hF[3];
+    half_force(*b, hF);
+    launch_macro_full(b->g, b->f[b->cur], hF, b->den, b->uuu, b->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(b->ev_macro, b->stream));
+    CK(cudaStreamWaitEvent(b->comm_stream, b->ev_macro, 0));
+    const size_t n = (size_t)b->g.X * b->g.plane;
+    if (den) CK(cudaMemcpyAsync(den, b->den, sizeof(double) * n, cudaMemcpyDeviceToHost, b->comm_stream));
+    if (uuu) CK(cudaMemcpyAsync(uuu, b->uuu, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, b->comm_stream));
+    CK(cudaEventRecord(b->ev_io, b->comm_stream));
+    b->io_pending = true;
+    return 0;
+}
+
+int fsilbm_block_download_wait(fsilbm_handle h)
+{
+    Block *b = get(h);
+    if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    return io_wait(*b);
+}
+
 int fsilbm_block_download_macro(fsilbm_handle h, double *den, double *uuu)
 {
     Block *b = get(h);
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    if (int rc = io_wait(*b)) return rc;
     if (int rc = ensure_fields(*b, false)) return rc;
     double hF[3];
     half_force(*b, hF);
@@ -851,6 +892,7 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
         // 1445-1484): materialise uuu (with the IBM correction where a body is near) before the fused kernel.
         double hF0[3];
         half_force(b, hF0);
+        if (int rc = io_wait(b)) return rc;
         launch_macro_full(g, fA, hF0, nullptr, b.uuu, b.stream, b.ibm_active ? &b.boxes : nullptr);
     }
     // per-face side buffers taken from the pre-collision state (see kernels.h FaceParams)
@@ -979,6 +1021,7 @@ int fsilbm_block_sync(fsilbm_handle h)
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
     CK(cudaStreamSynchronize(b->stream));
     CK(cudaStreamSynchronize(b->comm_stream));
+    b->io_pending = false;
     if (b->halo.enabled) {
         int e = 0;
         CK(cudaMemcpy(&e, b->halo.err, sizeof(int), cudaMemcpyDeviceToHost));

@@ -112,6 +112,14 @@ class LBMBlock:
         check(lib().fsilbm_block_download_macro(self._h, den.ctypes.data, uuu.ctypes.data))
         return den, uuu
 
+    def download_macro_async(self, den: np.ndarray, uuu: np.ndarray):
+        """den, uuu into the given (pinned) host arrays without waiting; valid after download_wait() or sync()."""
+        assert den.shape == self.shape and uuu.shape == (3,) + self.shape and den.flags.c_contiguous and uuu.flags.c_contiguous
+        check(lib().fsilbm_block_download_macro_async(self._h, den.ctypes.data, uuu.ctypes.data))
+
+    def download_wait(self):
+        check(lib().fsilbm_block_download_wait(self._h))
+
     def download_tau_all(self) -> np.ndarray:
         """tau_all (FluidDomain.f90:51), written by the LES collision models."""
         t = np.empty(self.shape)

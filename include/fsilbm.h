@@ -108,6 +108,12 @@ int fsilbm_block_update_volume_force(fsilbm_handle h, double volumeForce_out[3])
  * computes den, uuu of the local slab from the current fIn and copies them to the host.
  * Either pointer may be NULL.  (Inside a step the library derives den/uuu in registers.) */
 int fsilbm_block_download_macro(fsilbm_handle h, double *den, double *uuu);
+/* The same without waiting: den/uuu are computed into device staging fields behind the work already queued and copied to the
+ * host (PINNED memory, or the copy is not asynchronous) on the library's copy stream while later steps run -- what the
+ * reference gets from fork()ing its writer (FluidDomain.f90:1702).  The host arrays are valid after
+ * fsilbm_block_download_wait (or fsilbm_block_sync); a second read-back waits for the first. */
+int fsilbm_block_download_macro_async(fsilbm_handle h, double *den, double *uuu);
+int fsilbm_block_download_wait(fsilbm_handle h);
 /* tau_all(z,y,x) (FluidDomain.f90:51): the local relaxation time the LES models 11/14/15 write during collision
  * (:1279,1422,1505); the block's tau everywhere for the other models.  C [X][Y][Z] of the local slab. */
 int fsilbm_block_download_tau_all(fsilbm_handle h, double *tau_all);

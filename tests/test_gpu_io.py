@@ -170,3 +170,33 @@ def test_flux_probes_fieldstat(oracle, F, tmp_path):
     st = ob.ComputeFieldStat()
     assert txt.splitlines()[0] == f" FIELDSTAT L2 u {st[0]:18.12f}" and len(txt.splitlines()) == 6
     gb.close()
+
+
+def test_async_macro_readback(oracle, F):
+    """fsilbm_block_download_macro_async: den/uuu of the state at the call, copied out while later steps run."""
+    import torch
+    from tests.common import make_pair
+    ob, gb = make_pair(oracle, F, (24, 20, 28), BndConds=(101, 104, 203, 203, 301, 301), nu=0.05, uvwIn=(0.04, 0.0, 0.0), Uref=0.04,
+                       volumeForceIn=(1e-6, 0.0, 0.0))
+    for n in range(1, 6):
+        ob.set_blktime(float(n)); ob.step([])
+        F.tree_collision_streaming_IBM_FEM(gb, [], time=float(n))
+    ob.calculate_macro_quantities()
+    den = torch.empty(gb.shape, dtype=torch.float64, pin_memory=True)
+    uuu = torch.empty((3,) + gb.shape, dtype=torch.float64, pin_memory=True)
+    den.fill_(-1.0); uuu.fill_(-1.0)
+    gb.download_macro_async(den.numpy(), uuu.numpy())
+    for n in range(6, 10):                       # the update goes on while the copy is in flight
+        F.tree_collision_streaming_IBM_FEM(gb, [], time=float(n))
+    gb.download_wait()
+    assert np.array_equal(den.numpy(), ob.den) and np.array_equal(uuu.numpy(), ob.uuu)
+    # a second read-back waits for the first; the synchronous call still works in between
+    gb.download_macro_async(den.numpy(), uuu.numpy())
+    d2, u2 = gb.download_macro()
+    gb.download_wait()
+    assert np.array_equal(den.numpy(), d2) and np.array_equal(uuu.numpy(), u2)
+    for n in range(6, 10):
+        ob.set_blktime(float(n)); ob.step([])
+    ob.calculate_macro_quantities()
+    assert np.array_equal(d2, ob.den) and np.array_equal(u2, ob.uuu)
+    gb.close()
