@@ -44,6 +44,13 @@ WORKLOADS = {
     "school2048": dict(dims=(256, 512, 512), bc=(101, 104, 301, 301, 301, 301), model=1, plate="flex", layout="one_per_slab",
                        group=dict(iBodyModel=2, denR=1.0, psR=0.3, KB=0.05, KS=800.0, AoAo=(0.0, 0.0, 8.0)), numsubstep=2,
                        desc="configs[4]: one flexible plate (8192 markers each) per GPU slab, two staggered rows, 256x512x512 per GPU, single root block"),
+    # configs[4] with "multiple LBMBlockComm blocks": the same school, every plate inside its own 2:1 refined son block (321x129x385 cells
+    # of dh/2, two sub-cycles per root step, plate meshed at the son's resolution: 128 elements x 256 span markers).  A son lives whole
+    # on the rank whose root slab holds it; its IBM, structural solve and father<->son transfers are local to that rank.
+    "school2048r": dict(dims=(256, 512, 512), bc=(101, 104, 301, 301, 301, 301), model=1, plate="flex", layout="one_per_slab", refine=True,
+                        group=dict(iBodyModel=2, denR=1.0, psR=0.3, KB=0.05, KS=800.0, AoAo=(0.0, 0.0, 8.0)), numsubstep=2,
+                        desc="configs[4], multi-block: one flexible plate (32768 markers) per GPU slab, each in its own 2:1 refined son block "
+                             "(321x129x385, two sub-cycles), root 256x512x512 per GPU"),
     # diagnostic: the eight plates of school2048 inside ONE 256x512x512 block (the IBM work every rank of the replicated
     # form carries at 8 GPUs, without the collectives)
     "school8x1": dict(dims=(256, 512, 512), bc=(101, 104, 301, 301, 301, 301), model=1, plate="flex", layout="lattice", lattice=(2, 4),
@@ -109,8 +116,9 @@ def build_flex(wl, world, rank=0):
     dh = 1.0 / 64.0
     Xl, Y, Z = wl["dims"]
     wd = tempfile.mkdtemp(prefix=f"fsilbm_bench_r{rank}_")
-    xyz = np.zeros((65, 3)); xyz[:, 0] = np.linspace(0.0, 1.0, 65)   # chord 1 = 64 cells, 64 elements
-    S.write_plate_dat(os.path.join(wd, "plate.dat"), xyz, 1.0, 1.0, (0.0, 0.0, 1.0), Nspan=128)   # span 2 = 128 markers per element
+    nel = 128 if wl.get("refine") else 64                            # marker spacing = the carrier block's dh (son blocks: dh/2)
+    xyz = np.zeros((nel + 1, 3)); xyz[:, 0] = np.linspace(0.0, 1.0, nel + 1)   # chord 1 = 64 root cells
+    S.write_plate_dat(os.path.join(wd, "plate.dat"), xyz, 1.0, 1.0, (0.0, 0.0, 1.0), Nspan=2 * nel)   # span 2: one marker per cell
     groups = []
     if wl["layout"] == "one_centre":
         first = (0.5 * Xl * world * dh - 0.5 + 0.003, 0.5 * Y * dh - 0.013, 0.5 * Z * dh + 0.003)
@@ -281,7 +289,7 @@ def run_gpu(args):
         sb = build_flex(wl, world, rank)
         plates = sb.plates
         bodies_total = len(plates)
-        if world > 1:
+        if world > 1 and not wl.get("refine"):
             # Per-rank body lists: a rank holds (feeds to the library and advances structurally) only the plates that can
             # reach its slab -- chord box widened by 16 cells; the plates are anchored at their leading edge.  The IBM call is
             # then collective (loop control all-reduced), a plate across a slab interface is held by both neighbours.
@@ -297,9 +305,31 @@ def run_gpu(args):
     lib = F.lib()
 
     flex = sb is not None
+    root, son_cells, sons = None, 0, []
+    if wl.get("refine"):
+        # One son block per plate of this rank's slab: 160 x 64 x 192 root cells around the plate at half the spacing, all six faces
+        # fed by the father (BndConds 0); the plate is carried by the son (FluidDomain.f90:1974-2017).  Built by this rank alone.
+        root = F.blockTreeNode(blk)
+        mine = [p for p in plates if rank * Xl * dh <= p.body.v_Exyz[:, 0].min() < (rank + 1) * Xl * dh]
+        for p in mine:
+            le = p.body.v_Exyz.min(axis=0)                      # leading edge, lower span end
+            smin = (np.floor((le[0] - 0.75) / dh) * dh, np.floor((p.body.v_Exyz[:, 1].mean() - 0.5) / dh) * dh, np.floor((le[2] - 0.5) / dh) * dh)
+            sdims = (2 * 160 + 1, 2 * 64 + 1, 2 * 192 + 1)
+            son = F.LBMBlock(*sdims, dh=0.5 * dh, xmin=float(smin[0]), ymin=float(smin[1]), zmin=float(smin[2]), BndConds=(0,) * 6,
+                             iCollidModel=wl["model"], flow=flow, device=local)
+            son.initialise(0.0)
+            son.update_volume_force(); son.set_boundary_conditions()
+            root.add_son(F.blockTreeNode(son, [p]), 1)
+            sons.append(son)
+            son_cells += sdims[0] * sdims[1] * sdims[2]
+        plates = mine
 
     def step(n):
-        F.tree_collision_streaming_IBM_FEM(blk, plates, time=n * dh, solver=flex)
+        if root is not None:
+            F.set_blktime_all(root, n * dh)                     # main.f90:97
+            F.tree_collision_streaming_IBM_FEM(root, solver=True)
+        else:
+            F.tree_collision_streaming_IBM_FEM(blk, plates, time=n * dh, solver=flex)
 
     # ---- device-resident throughput ("value") ---------------------------------------------------------
     for n in range(args.warmup):
@@ -313,6 +343,8 @@ def run_gpu(args):
     e0.record(stream)
     for n in range(args.steps):
         step(args.warmup + n + 1)
+    if sb is not None:
+        sb.flush()      # the structural work of the last step belongs to the timed region
     e1.record(stream)
     blk.sync(); torch.cuda.synchronize()
     launches = lib.fsilbm_launch_count() - l0
@@ -332,6 +364,11 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     cells_total = float(XG) * Y * Z
+    if root is not None:   # lattice updates of ALL blocks: a son makes two updates of its cells per root step
+        extra = torch.tensor([2.0 * son_cells], dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(extra, op=dist.ReduceOp.SUM)
+        cells_total += float(extra.item())
     value = cells_total * args.steps / (ms * 1e-3) / 1e6
 
     # ---- dominant kernel alone (roofline): fused collide-stream launches back to back --------------------
@@ -386,6 +423,8 @@ def run_gpu(args):
             # one is waited for before the host arrays are reused
             blk.download_macro_async(den_host.numpy(), uuu_host.numpy())
             n_out += 1
+    if sb is not None:
+        sb.flush()
     blk.download_wait()
     blk.sync(); torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -430,10 +469,18 @@ def run_gpu(args):
                        "l2": "working set 5.1 GB per GPU (two population buffers) >> 126 MB L2; no explicit flush needed",
                        "kernel_variant": args.variant, "halo_transport": transport,
                        "structural_solver": structural,
+                       "blocks": None if root is None else {"root_cells_per_gpu": Xl * Y * Z, "son_cells_on_rank0": son_cells, "son_updates_per_root_step": 2,
+                                                            "note": "value counts the lattice updates of all blocks (root + 2 x son); roofline and e2e "
+                                                                    "transfers are the root block's"},
                        "ibm": ("ordered per-cell gather (bit-identical to the serial reference)" if args.ibm_ordered else "fp64 atomics") if wl["plate"] else None},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         emit(line)
+    if root is not None:
+        for pair in root.comm:
+            pair.close()
+        for son in sons:
+            son.close()
     blk.close()
     if world > 1:
         dist.destroy_process_group()

@@ -262,7 +262,9 @@ def tree_collision_streaming_IBM_FEM(node, plates: Sequence = (), time: Optional
     # are issued after the launch so that they overlap the device's collide-stream of the same step.
     owner = getattr(plates[0], "owner", None) if len(plates) else None
     if len(plates) and solver and owner is not None and all(getattr(p, "owner", None) is owner for p in plates):
-        owner.advance([p.body.index for p in plates], block.blktime, block.flow.numsubstep, block.dh)
+        # ... and postponed until the markers are next needed (the top of these bodies' next step), so that device work queued in
+        # between -- a son's transfers, the father's next collide-stream -- also runs while the beams are solved
+        owner.advance_later([p.body.index for p in plates], block.blktime, block.flow.numsubstep, block.dh)
     elif len(plates):
         for p in plates:
             if hasattr(p, "FluidVolumeForce"):

@@ -171,6 +171,7 @@ class Body:
         self.markers_fresh = False   # True after SolidBodies.advance(): UpdatePosVelArea_ of the coming step is done
 
     def UpdatePosVelArea(self):
+        self._o.flush()
         if self.markers_fresh:
             self.markers_fresh = False
             return
@@ -178,6 +179,7 @@ class Body:
 
     def FluidLoads(self):
         """lodFlow = 0 (Solidbody.f90:911) then the nodal-load half of FluidVolumeForce_ (:945-967) from self.v_Eforce."""
+        self._o.flush()
         self._o._ck(lib().fsolid_fluid_loads(self._o.h, self.index))
         self.count_Interp = 1
 
@@ -187,9 +189,11 @@ class Body:
         self._o._ck(lib().fsolid_set_lodflow(self._o.h, self.index, _dp(lod)))
 
     def structure(self, time: float, isubstep: int, deltat: float, subdeltat: float):
+        self._o.flush()
         self._o._ck(lib().fsolid_structure(self._o.h, self.index, float(time), int(isubstep), float(deltat), float(subdeltat)))
 
     def _get(self, what: int, shape):
+        self._o.flush()
         out = np.zeros(shape)
         self._o._ck(lib().fsolid_get(self._o.h, self.index, what, _dp(out)))
         return out
@@ -256,6 +260,7 @@ class SolidBodies:
         self.VBodies = [Body(self, i) for i in range(lib().fsolid_nfish(self.h))]
         self.plates = [Plate(b, self) for b in self.VBodies]
         self.host_seconds = 0.0
+        self._pending = []
 
     def _ck(self, rc: int):
         if rc != 0:
@@ -263,9 +268,20 @@ class SolidBodies:
 
     def Solver(self, time: float, isubstep: int, deltat: float, subdeltat: float):
         """Solver, Solidbody.f90:386-398: every body, in parallel over the bodies as the reference's OpenMP loop."""
+        self.flush()
         t0 = _time.perf_counter()
         self._ck(lib().fsolid_solver(self.h, float(time), int(isubstep), float(deltat), float(subdeltat)))
         self.host_seconds += _time.perf_counter() - t0
+
+    def advance_later(self, bodies: Sequence[int], time: float, numsubstep: int, deltat: float):
+        """advance(), postponed until something needs its result (the next UpdatePosVelArea / structure / state query of any
+        body, write, close) -- so that whatever device work the caller queues in the meantime (a son's father<->son transfers,
+        the father's next collide-stream) runs while the beams are solved.  v_Eforce must stay untouched until then."""
+        self._pending.append((list(bodies), float(time), int(numsubstep), float(deltat)))
+
+    def flush(self):
+        while self._pending:
+            self.advance(*self._pending.pop(0))
 
     def advance(self, bodies: Sequence[int], time: float, numsubstep: int, deltat: float):
         """The host work of one step for `bodies` (indices), one thread per body: nodal loads from v_Eforce, the structural
@@ -279,6 +295,7 @@ class SolidBodies:
         self.host_seconds += _time.perf_counter() - t0
 
     def write(self, what: int, time: float, cwd: str):
+        self.flush()
         old = os.getcwd()
         try:
             os.chdir(cwd)
@@ -287,6 +304,7 @@ class SolidBodies:
             os.chdir(old)
 
     def close(self):
+        self._pending = []
         if self.h:
             lib().fsolid_close(self.h)
             self.h = 0
