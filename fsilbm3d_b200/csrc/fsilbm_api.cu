@@ -1265,6 +1265,163 @@ int fsilbm_block_upload_fields(fsilbm_handle h, const double *den, const double 
 }
 
 // ---- IBM ------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+// Device storage of the bodies of a block: per-body scratch + one packed marker buffer and one packed force buffer (a single
+// H2D / D2H each, staged through pinned host memory so that the copies are truly asynchronous).
+int ibm_body_storage(Block &b, int nbody, const int *nelmts)
+{
+    cudaStream_t s = b.stream, s2 = b.ibm_stream;
+    bool relayout = (int)b.bodies.size() != nbody;
+    if (relayout) {
+        for (auto &bd : b.bodies) bd.release();
+        b.bodies.assign(nbody, BodyDev());
+        b.csr_valid = false;
+    }
+    for (int ib = 0; ib < nbody; ib++) {
+        BodyDev &bd = b.bodies[ib];
+        const int n = nelmts[ib];
+        if (n < 1) return fail(FSILBM_ERR_ARG, "body %d has no markers", ib);
+        if (bd.n != n) {
+            bd.release();
+            b.csr_valid = false;
+            relayout = true;
+            bd.n = n;
+            CK(cudaMalloc(&bd.ExyzStencil, sizeof(double) * 3 * n));
+            CK(cudaMalloc(&bd.felt, sizeof(double) * 3 * n));
+            CK(cudaMalloc(&bd.tol, sizeof(double) * n)); CK(cudaMalloc(&bd.partialU, sizeof(double) * 3 * n));
+            CK(cudaMalloc(&bd.Ei, sizeof(short) * 12 * n)); CK(cudaMalloc(&bd.Ew, sizeof(float) * 12 * n));
+            CK(cudaMalloc(&bd.cell, sizeof(int) * 12 * n)); CK(cudaMalloc(&bd.boff, sizeof(long long) * n));
+            CK(cudaMalloc(&bd.owned, 4 * n));
+        }
+    }
+    if (!relayout) return 0;
+    size_t ntot = 0;
+    b.mk_off.assign(nbody, 0); b.f_off.assign(nbody, 0);
+    for (int ib = 0; ib < nbody; ib++) { b.mk_off[ib] = 7 * ntot; b.f_off[ib] = 3 * ntot; ntot += (size_t)nelmts[ib]; }
+    b.marker_total = ntot;
+    if (ntot > b.marker_cap) {
+        CK(cudaStreamSynchronize(s)); CK(cudaStreamSynchronize(s2));
+        cudaFree(b.mk_dev); cudaFree(b.force_dev); cudaFreeHost(b.mk_pin); cudaFreeHost(b.force_pin);
+        b.mk_dev = b.force_dev = b.mk_pin = b.force_pin = nullptr;
+        CK(cudaMalloc(&b.mk_dev, sizeof(double) * 7 * ntot)); CK(cudaMalloc(&b.force_dev, sizeof(double) * 3 * ntot));
+        CK(cudaMallocHost(&b.mk_pin, sizeof(double) * 7 * ntot)); CK(cudaMallocHost(&b.force_pin, sizeof(double) * 3 * ntot));
+        b.marker_cap = ntot;
+    }
+    for (int ib = 0; ib < nbody; ib++) {
+        BodyDev &bd = b.bodies[ib];
+        const size_t n = bd.n;
+        bd.Exyz = b.mk_dev + b.mk_off[ib]; bd.Evel = bd.Exyz + 3 * n; bd.Ea = bd.Evel + 3 * n;
+        bd.Eforce = b.force_dev + b.f_off[ib];
+    }
+    return 0;
+}
+
+// Box around the stencils of one body, from the marker positions P(3,n) the stencils are (re)built from: the index arithmetic
+// of UpdateElmtInterp_ (Solidbody.f90:771-780,817-820).  floor((x - x0)*invdh) does not decrease with x, so the extreme
+// indices are those of the extreme coordinates.
+void ibm_body_box(const Geom &g, BodyDev &bd, const double *P, const int rootBC[6])
+{
+    const double invdh = 1.0 / g.dh;
+    const double mins[3] = {g.xmin, g.ymin, g.zmin};
+    const int Ns[3] = {g.XG, g.Y, g.Z};
+    double lo[3] = {P[0], P[1], P[2]}, hi[3] = {P[0], P[1], P[2]};
+    for (int e = 1; e < bd.n; e++) {
+        const double v0 = P[3 * e], v1 = P[3 * e + 1], v2 = P[3 * e + 2];
+        lo[0] = std::min(lo[0], v0); hi[0] = std::max(hi[0], v0);
+        lo[1] = std::min(lo[1], v1); hi[1] = std::max(hi[1], v1);
+        lo[2] = std::min(lo[2], v2); hi[2] = std::max(hi[2], v2);
+    }
+    for (int a = 0; a < 3; a++) {
+        int i0 = (int)floor((P[a] - mins[a]) * invdh);
+        const double x0 = mins[a] + (double)i0 * g.dh;
+        bd.cidx[a] = imod(i0, Ns[a]);
+        i0 = i0 + 1;
+        const int imin = (int)floor((lo[a] - x0) * invdh) + i0, imax = (int)floor((hi[a] - x0) * invdh) + i0;
+        bd.hbox.ax[a] = axis_interval(imin, imax, Ns[a], rootBC[2 * a] == BCPeriodic);
+    }
+    bd.have_box = true;
+}
+
+// Boxes that overlap are merged so that bodies sharing cells share storage (Gauss-Seidel coupling, Solidbody.f90:898-903).
+// Box order = order of the first member; members in body order.
+struct MBox { HostBox hb; std::vector<int> members; };
+std::vector<MBox> ibm_merge_boxes(const Block &b, int nbody)
+{
+    const int Ns[3] = {b.g.XG, b.g.Y, b.g.Z};
+    std::vector<MBox> mb(nbody);
+    for (int ib = 0; ib < nbody; ib++) { mb[ib].hb = b.bodies[ib].hbox; mb[ib].members.assign(1, ib); }
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (size_t i = 0; i < mb.size() && !changed; i++)
+            for (size_t j = i + 1; j < mb.size() && !changed; j++) {
+                bool ov = true;
+                for (int a = 0; a < 3; a++) ov = ov && overlap(mb[i].hb.ax[a], mb[j].hb.ax[a], Ns[a]);
+                if (ov) {
+                    for (int a = 0; a < 3; a++) mb[i].hb.ax[a] = merge(mb[i].hb.ax[a], mb[j].hb.ax[a], Ns[a]);
+                    mb[i].members.insert(mb[i].members.end(), mb[j].members.begin(), mb[j].members.end());
+                    mb.erase(mb.begin() + j);
+                    changed = true;
+                }
+            }
+    }
+    return mb;
+}
+
+// Slab runs: the rank that owns each global x-plane of the block (collective over the ranks, done once per block).
+int ibm_plane_owners(Block &b)
+{
+    if (!b.plane_owner.empty()) return 0;
+    const Geom &g = b.g;
+    int mine[2] = {g.xOffset, g.X}, *dsend = nullptr, *drecv = nullptr;
+    CK(cudaMalloc(&dsend, sizeof(mine))); CK(cudaMalloc(&drecv, sizeof(mine) * g_nccl.nranks));
+    CK(cudaMemcpy(dsend, mine, sizeof(mine), cudaMemcpyHostToDevice));
+    NCK(g_nccl.AllGather(dsend, drecv, sizeof(mine), kNcclChar, g_nccl.comm, b.stream));
+    CK(cudaStreamSynchronize(b.stream));
+    std::vector<int> all(2 * g_nccl.nranks);
+    CK(cudaMemcpy(all.data(), drecv, sizeof(mine) * g_nccl.nranks, cudaMemcpyDeviceToHost));
+    cudaFree(dsend); cudaFree(drecv);
+    b.plane_owner.assign(g.XG, -1);
+    for (int r = 0; r < g_nccl.nranks; r++)
+        for (int x = all[2 * r]; x < all[2 * r] + all[2 * r + 1] && x < g.XG; x++) b.plane_owner[x] = r;
+    for (int x = 0; x < g.XG; x++) if (b.plane_owner[x] < 0) { b.plane_owner.clear(); return fail(FSILBM_ERR_COMM, "x-plane %d belongs to no rank's slab", x); }
+    return 0;
+}
+
+// A stretch of box planes dx in [dx0, dx1) owned by one rank (see block_comm.ibm_box_participants for the rule in Python)
+struct Run { int rank, dx0, dx1; };
+
+// The participants of a shared box (a body across a slab interface) send one another the box planes they own: ncclSend/ncclRecv
+// between the two or three ranks concerned, one group, no collective.  Every rank walks (box, component, run) in the same
+// order, so the messages of a pair of ranks meet in posting order.
+int ibm_exchange_shared_boxes(const IbmBoxes &bx, const std::vector<int> &kept, const std::vector<char> &shared,
+                              const std::vector<std::vector<Run>> &runs, int me, cudaStream_t s)
+{
+    NCK(g_nccl.GroupStart());
+    for (int i = 0; i < bx.n; i++) {
+        const int k = kept[i];
+        if (!shared[k]) continue;
+        const size_t slab = (size_t)bx.ext[i][1] * bx.ext[i][2];
+        std::vector<int> parts;
+        for (const Run &r : runs[k]) if (std::find(parts.begin(), parts.end(), r.rank) == parts.end()) parts.push_back(r.rank);
+        for (int c = 0; c < 3; c++)
+            for (const Run &r : runs[k]) {
+                double *ptr = bx.u + (size_t)c * bx.ncell + bx.off[i] + (size_t)r.dx0 * slab;
+                const size_t cnt = (size_t)(r.dx1 - r.dx0) * slab;
+                if (r.rank == me) { for (int p : parts) if (p != me) NCK(g_nccl.Send(ptr, cnt, kNcclFloat64, p, g_nccl.comm, s)); }
+                else NCK(g_nccl.Recv(ptr, cnt, kNcclFloat64, r.rank, g_nccl.comm, s));
+            }
+    }
+    NCK(g_nccl.GroupEnd());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
 int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, const double *const *Exyz, const double *const *Evel,
                                  const double *const *Ea, double *const *Eforce, const int *restencil, double dt, int ntolLBM,
                                  double dtolLBM, const int rootBC[6], int *iterLBM_out)
@@ -1289,56 +1446,9 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
     const double tp0 = want_prof ? wall_seconds() : 0.0;
     const int me = g_nccl.rank;
 
-    // -- device marker storage: per-body scratch + one packed marker buffer and one packed force buffer (a single
-    //    H2D / D2H each, staged through pinned host memory so that the copies are truly asynchronous)
-    bool relayout = (int)b.bodies.size() != nbody;
-    if (relayout) {
-        for (auto &bd : b.bodies) bd.release();
-        b.bodies.assign(nbody, BodyDev());
-        b.csr_valid = false;
-    }
-    for (int ib = 0; ib < nbody; ib++) {
-        BodyDev &bd = b.bodies[ib];
-        const int n = nelmts[ib];
-        if (n < 1) return fail(FSILBM_ERR_ARG, "body %d has no markers", ib);
-        if (bd.n != n) {
-            bd.release();
-            b.csr_valid = false;
-            relayout = true;
-            bd.n = n;
-            CK(cudaMalloc(&bd.ExyzStencil, sizeof(double) * 3 * n));
-            CK(cudaMalloc(&bd.felt, sizeof(double) * 3 * n));
-            CK(cudaMalloc(&bd.tol, sizeof(double) * n)); CK(cudaMalloc(&bd.partialU, sizeof(double) * 3 * n));
-            CK(cudaMalloc(&bd.Ei, sizeof(short) * 12 * n)); CK(cudaMalloc(&bd.Ew, sizeof(float) * 12 * n));
-            CK(cudaMalloc(&bd.cell, sizeof(int) * 12 * n)); CK(cudaMalloc(&bd.boff, sizeof(long long) * n));
-            CK(cudaMalloc(&bd.owned, 4 * n));
-        }
-    }
-    if (relayout) {
-        size_t ntot = 0;
-        b.mk_off.assign(nbody, 0); b.f_off.assign(nbody, 0);
-        for (int ib = 0; ib < nbody; ib++) { b.mk_off[ib] = 7 * ntot; b.f_off[ib] = 3 * ntot; ntot += (size_t)nelmts[ib]; }
-        b.marker_total = ntot;
-        if (ntot > b.marker_cap) {
-            CK(cudaStreamSynchronize(s)); CK(cudaStreamSynchronize(s2));
-            cudaFree(b.mk_dev); cudaFree(b.force_dev); cudaFreeHost(b.mk_pin); cudaFreeHost(b.force_pin);
-            b.mk_dev = b.force_dev = b.mk_pin = b.force_pin = nullptr;
-            CK(cudaMalloc(&b.mk_dev, sizeof(double) * 7 * ntot)); CK(cudaMalloc(&b.force_dev, sizeof(double) * 3 * ntot));
-            CK(cudaMallocHost(&b.mk_pin, sizeof(double) * 7 * ntot)); CK(cudaMallocHost(&b.force_pin, sizeof(double) * 3 * ntot));
-            b.marker_cap = ntot;
-        }
-        for (int ib = 0; ib < nbody; ib++) {
-            BodyDev &bd = b.bodies[ib];
-            const size_t n = bd.n;
-            bd.Exyz = b.mk_dev + b.mk_off[ib]; bd.Evel = bd.Exyz + 3 * n; bd.Ea = bd.Evel + 3 * n;
-            bd.Eforce = b.force_dev + b.f_off[ib];
-        }
-    }
+    if (int rc = ibm_body_storage(b, nbody, nelmts)) return rc;
 
-    // -- host: box around the stencils of each body (same index arithmetic as UpdateElmtInterp_, :771-780,817-820).
-    //    floor((x - x0)*invdh) does not decrease with x, so the extreme indices are those of the extreme coordinates.
-    const double invdh = 1.0 / g.dh;
-    const double mins[3] = {g.xmin, g.ymin, g.zmin};
+    // -- host: the box around the stencils of each body, merged where they overlap
     const int Ns[3] = {g.XG, g.Y, g.Z};
     std::vector<char> re(nbody, 0);
     for (int ib = 0; ib < nbody; ib++) {
@@ -1346,62 +1456,14 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         re[ib] = (restencil[ib] != 0 || !bd.have_box) ? 1 : 0;
         if (!re[ib]) continue;
         b.csr_valid = false;
-        const int n = bd.n;
-        const double *P = Exyz[ib];
-        double lo[3] = {P[0], P[1], P[2]}, hi[3] = {P[0], P[1], P[2]};
-        for (int e = 1; e < n; e++) {
-            const double v0 = P[3 * e], v1 = P[3 * e + 1], v2 = P[3 * e + 2];
-            lo[0] = std::min(lo[0], v0); hi[0] = std::max(hi[0], v0);
-            lo[1] = std::min(lo[1], v1); hi[1] = std::max(hi[1], v1);
-            lo[2] = std::min(lo[2], v2); hi[2] = std::max(hi[2], v2);
-        }
-        for (int a = 0; a < 3; a++) {
-            int i0 = (int)floor((P[a] - mins[a]) * invdh);
-            const double x0 = mins[a] + (double)i0 * g.dh;
-            bd.cidx[a] = imod(i0, Ns[a]);
-            i0 = i0 + 1;
-            const int imin = (int)floor((lo[a] - x0) * invdh) + i0, imax = (int)floor((hi[a] - x0) * invdh) + i0;
-            bd.hbox.ax[a] = axis_interval(imin, imax, Ns[a], rootBC[2 * a] == BCPeriodic);
-        }
-        bd.have_box = true;
+        ibm_body_box(g, bd, Exyz[ib], rootBC);
     }
-    // merge boxes that overlap so bodies sharing cells share storage (Gauss-Seidel coupling, Solidbody.f90:898-903)
-    struct MBox { HostBox hb; std::vector<int> members; };
-    std::vector<MBox> mb(nbody);
-    for (int ib = 0; ib < nbody; ib++) { mb[ib].hb = b.bodies[ib].hbox; mb[ib].members.assign(1, ib); }
-    for (bool changed = true; changed;) {
-        changed = false;
-        for (size_t i = 0; i < mb.size() && !changed; i++)
-            for (size_t j = i + 1; j < mb.size() && !changed; j++) {
-                bool ov = true;
-                for (int a = 0; a < 3; a++) ov = ov && overlap(mb[i].hb.ax[a], mb[j].hb.ax[a], Ns[a]);
-                if (ov) {
-                    for (int a = 0; a < 3; a++) mb[i].hb.ax[a] = merge(mb[i].hb.ax[a], mb[j].hb.ax[a], Ns[a]);
-                    mb[i].members.insert(mb[i].members.end(), mb[j].members.begin(), mb[j].members.end());
-                    mb.erase(mb.begin() + j);
-                    changed = true;
-                }
-            }
-    }
+    std::vector<MBox> mb = ibm_merge_boxes(b, nbody);
     // -- slab runs: which ranks own planes of each box
-    struct Run { int rank, dx0, dx1; };
     std::vector<std::vector<Run>> runs(mb.size());
     std::vector<char> keep(mb.size(), 1), shared(mb.size(), 0);
     if (local) {
-        if (b.plane_owner.empty()) {   // collective, once: the x-slab of every rank
-            int mine[2] = {g.xOffset, g.X}, *dsend = nullptr, *drecv = nullptr;
-            CK(cudaMalloc(&dsend, sizeof(mine))); CK(cudaMalloc(&drecv, sizeof(mine) * g_nccl.nranks));
-            CK(cudaMemcpy(dsend, mine, sizeof(mine), cudaMemcpyHostToDevice));
-            NCK(g_nccl.AllGather(dsend, drecv, sizeof(mine), kNcclChar, g_nccl.comm, s));
-            CK(cudaStreamSynchronize(s));
-            std::vector<int> all(2 * g_nccl.nranks);
-            CK(cudaMemcpy(all.data(), drecv, sizeof(mine) * g_nccl.nranks, cudaMemcpyDeviceToHost));
-            cudaFree(dsend); cudaFree(drecv);
-            b.plane_owner.assign(g.XG, -1);
-            for (int r = 0; r < g_nccl.nranks; r++)
-                for (int x = all[2 * r]; x < all[2 * r] + all[2 * r + 1] && x < g.XG; x++) b.plane_owner[x] = r;
-            for (int x = 0; x < g.XG; x++) if (b.plane_owner[x] < 0) return fail(FSILBM_ERR_COMM, "x-plane %d belongs to no rank's slab", x);
-        }
+        if (int rc = ibm_plane_owners(b)) return rc;
         for (size_t k = 0; k < mb.size(); k++) {
             const Interval &ix = mb[k].hb.ax[0];
             bool mine_in = false;
@@ -1587,24 +1649,8 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         bool any_shared = false;
         for (int i = 0; i < bx.n; i++) any_shared = any_shared || shared[kept[i]];
         if (any_shared || !single) { launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s); macro_done = true; }
-        if (any_shared) {
-            NCK(g_nccl.GroupStart());
-            for (int i = 0; i < bx.n; i++) {
-                const int k = kept[i];
-                if (!shared[k]) continue;
-                const size_t slab = (size_t)bx.ext[i][1] * bx.ext[i][2];
-                std::vector<int> parts;
-                for (const Run &r : runs[k]) if (std::find(parts.begin(), parts.end(), r.rank) == parts.end()) parts.push_back(r.rank);
-                for (int c = 0; c < 3; c++)
-                    for (const Run &r : runs[k]) {
-                        double *ptr = bx.u + (size_t)c * bx.ncell + bx.off[i] + (size_t)r.dx0 * slab;
-                        const size_t cnt = (size_t)(r.dx1 - r.dx0) * slab;
-                        if (r.rank == me) { for (int p : parts) if (p != me) NCK(g_nccl.Send(ptr, cnt, kNcclFloat64, p, g_nccl.comm, s)); }
-                        else NCK(g_nccl.Recv(ptr, cnt, kNcclFloat64, r.rank, g_nccl.comm, s));
-                    }
-            }
-            NCK(g_nccl.GroupEnd());
-        }
+        if (any_shared)
+            if (int rc = ibm_exchange_shared_boxes(bx, kept, shared, runs, me, s)) return rc;
     }
     if (single) {
         // one cooperative launch for UpdateElmtInterp_, the box macro, the whole penalty iteration and the force spreading
