@@ -1627,15 +1627,17 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         use_early = inside;
     }
     b.early_ok = false;   // one use per update
-    const cudaStream_t s_all = s;   // the stream that has seen the whole update
     if (use_early) {
         g_ibm_early_calls++;
         s = b.ibm_main_stream;
         CK(cudaStreamWaitEvent(s, b.ev_early, 0));
+    } else if (local && bx.n == 0 && b.halo.enabled && g_ibm_early) {
+        // no body in this slab: what is left (loop-control exchange, force exchange) reads nothing of the fluid state, so it need
+        // not queue behind the update either -- the ranks that do iterate bodies early are then not held up by this one
+        s = b.ibm_main_stream;
     }
     CK(cudaEventRecord(b.ev_ibm, s2));
     CK(cudaStreamWaitEvent(s, b.ev_ibm, 0));
-    (void)s_all;
 
     // -- compute stream: everything that reads the populations
     if (replicate) {
