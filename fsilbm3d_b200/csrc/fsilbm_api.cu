@@ -203,7 +203,7 @@ struct Block {
     bool io_pending = false;
     cudaStream_t ibm_main_stream = nullptr;
     cudaEvent_t ev_early = nullptr;
-    bool early_ok = false, in_pair = false;
+    bool early_ok = false, is_father = false;
     int early_n = 0, early_x0[MAX_BOXES]{}, early_x1[MAX_BOXES]{};
     IbmCtl *ctl = nullptr;
     unsigned int *ibm_barrier = nullptr;
@@ -931,7 +931,7 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
     // hence the conditions below -- and the next interaction-force call may start while the rest is still being updated.
     int nA = 0, A0[MAX_BOXES], A1[MAX_BOXES];
     const int lower = multi ? 1 : 0, upper = multi ? g.X - 1 : g.X;   // planes of the bulk launch (multi: the edge planes go first anyway)
-    bool early = g_ibm_early && b.ibm_active && p.boxes.n > 0 && b.model < 11 && !b.in_pair && (multi ? b.halo.enabled : !ghost);
+    bool early = g_ibm_early && b.ibm_active && p.boxes.n > 0 && b.model < 11 && !b.is_father && (multi ? b.halo.enabled : !ghost);
     if (early) {
         const int Ns[3] = {g.XG, g.Y, g.Z};
         for (int i = 0; i < p.boxes.n && early; i++) {
@@ -1855,7 +1855,9 @@ int fsilbm_pair_create(fsilbm_handle father, fsilbm_handle son, int interpolateS
                                     "an even number of grid points is needed. Otherwise an odd number is needed.");
     auto p = std::make_unique<Pair>();
     p->father = father; p->son = son; p->scheme = interpolateScheme;
-    F->in_pair = S->in_pair = true;   // the transfers rewrite planes between the steps: no early IBM on these blocks
+    // deliver_son_to_father rewrites father nodes inside the son's footprint between the steps: no early IBM on a father.  A son
+    // only has its outermost planes rewritten (interpolation_father_to_son), and early IBM keeps 3 cells away from such faces.
+    F->is_father = true;
     F->early_ok = S->early_ok = false;
     // build_blocks_comunication, :32-96
     for (int j = 0; j < 6; j++) p->sds[j] = S->bc[j] == BCfluid ? ((j % 2 == 0) ? 1 : -1) : 0;

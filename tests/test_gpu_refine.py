@@ -110,3 +110,64 @@ def test_plate_carried_by_son_block(oracle, F):
         den, uuu = gb.download_macro()
         assert rel_err(den, ob.den) <= 1e-12 and rel_err(uuu, ob.uuu) <= 1e-12
     assert abs(pg.body.v_Eforce[:, 0].sum()) > 1e-9
+
+
+def test_plate_in_son_early_ibm(oracle, F):
+    """Early IBM on a son block: the father rewrites only the son's outermost planes (interpolation_father_to_son), so the
+    son's next interaction-force call may start behind the planes around the plate -- the first of a root step even while the
+    father is being updated.  A heaving plate well inside the son; bit-identical to the oracle tree, overlap asserted taken."""
+    from tests.common import perturbed_state
+    from tests.test_gpu_parity import sync_oracle_body
+    O = oracle
+    kw = dict(nu=0.02, uvwIn=(0.03, 0.0, 0.0), Uref=0.03, ntolLBM=3, dtolLBM=1e-30)
+    fbc, fdims, sbc, sdims, smins = (101, 104, 301, 301, 301, 301), (40, 24, 24), (0,) * 6, (41, 33, 33), (8.0, 4.0, 4.0)
+    of, gf = O.Flow(**kw), F.FlowCondType(**kw)
+    oF = O.LBMBlock(*fdims, dh=1.0, BndConds=fbc, flow=of)
+    oS = O.LBMBlock(*sdims, dh=0.5, xmin=smins[0], ymin=smins[1], zmin=smins[2], BndConds=sbc, flow=of)
+    gF = F.LBMBlock(*fdims, dh=1.0, BndConds=fbc, flow=gf)
+    gS = F.LBMBlock(*sdims, dh=0.5, xmin=smins[0], ymin=smins[1], zmin=smins[2], BndConds=sbc, flow=gf)
+    for b in (oF, oS, gF, gS):
+        b.initialise(0.0)
+    f0F, f0S = perturbed_state(fdims, of, seed=1), perturbed_state(sdims, of, seed=2)
+    oF.fIn[...] = f0F; oS.fIn[...] = f0S
+    gF.upload_fIn(f0F); gS.upload_fIn(f0S)
+    kwp = dict(origin=(15.3, 11.2, 9.6), nEL=8, len1=0.5, Nspan=10, spanlen=5.0, Lspan=0.0, chord_dir=(1.0, 0.3, 0.0), denIn=1.0,
+               XYZAmpl=(0.0, 0.6, 0.0), Freq=0.02, XYZPhi=(0.0, 0.3, 0.0))
+    pg, po = F.RigidPlate(**kwp), F.RigidPlate(**kwp)
+    ov = O.VirtualBody(pg.body.v_nelmts, v_move=1, iBodyModel=1)
+    oroot = O.TreeNode(oF)
+    oson = oroot.add_son(O.TreeNode(oS, [ov]))
+    pair = oroot.comm[0]
+    groot = F.blockTreeNode(gF); groot.add_son(F.blockTreeNode(gS, [pg]))
+    for b in (oF, oS):
+        b.update_volume_force(); b.set_boundary_conditions(); b.calculate_macro_quantities()
+    for b in (gF, gS):
+        b.update_volume_force(); b.set_boundary_conditions()
+    c0 = F.lib().fsilbm_ibm_early_count()
+    steps = 8
+    for n in range(1, steps + 1):
+        O.set_blktime_all(oroot, float(n)); F.set_blktime_all(groot, float(n))
+        ig = []
+        F.tree_collision_streaming_IBM_FEM(groot, solver=True, iters=ig)
+        # the oracle tree by hand in the order of LBMBlockComm.f90:279-318, moving the plate before each son sub-step as the
+        # reference's IBM_FEM does (extract(1) reads fIn, which the father's pre-collision work does not touch)
+        pair.extract_interpolate_layer(1)
+        O.tree_collision_streaming_IBM_FEM(O.TreeNode(oF))
+        pair.extract_interpolate_layer(2)
+        for k in range(2):
+            oS.set_blktime(oS.blktime + float(k) * oS.dh)
+            po.UpdatePosVelArea(); sync_oracle_body(ov, po)
+            io = []
+            O.tree_collision_streaming_IBM_FEM(oson, rootBC=oF.BndConds, iters=io)
+            po.structure(oS.blktime, 1, oS.dh, oS.dh)
+            pair.interpolation_father_to_son(k)
+            assert io == [3]
+        pair.deliver_son_to_father()
+        assert ig == [0, 3, 3]
+        assert np.array_equal(pg.body.v_Eforce, ov.v_Eforce), n
+    assert F.lib().fsilbm_ibm_early_count() - c0 == 2 * steps - 1     # every son call after its first update
+    assert np.array_equal(gF.download_fIn(), oF.fIn) and np.array_equal(gS.download_fIn(), oS.fIn)
+    assert np.abs(pg.body.v_Exyz - po.body.v_Exyz).max() == 0.0 and abs(pg.body.v_Eforce[:, 0].sum()) > 1e-9
+    for p in groot.comm:
+        p.close()
+    gF.close(); gS.close()
