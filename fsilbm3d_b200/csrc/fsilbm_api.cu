@@ -11,6 +11,7 @@
 #include <cstring>
 #include <chrono>
 #include <dlfcn.h>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -929,9 +930,10 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
     // Early IBM (see Block::ev_early): planes A = [box - 2, box + 2) of every stencil box first, then the rest.  After A the
     // streamed populations of the planes [box - 1, box + 1) are final -- provided no face kernel, halo or x-wrap touches them,
     // hence the conditions below -- and the next interaction-force call may start while the rest is still being updated.
-    int nA = 0, A0[MAX_BOXES], A1[MAX_BOXES];
+    int nA = 0, A0[MAX_BOXES], A1[MAX_BOXES], V0[MAX_BOXES], V1[MAX_BOXES];
     const int lower = multi ? 1 : 0, upper = multi ? g.X - 1 : g.X;   // planes of the bulk launch (multi: the edge planes go first anyway)
     bool early = g_ibm_early && b.ibm_active && p.boxes.n > 0 && b.model < 11 && !b.is_father && (multi ? b.halo.enabled : !ghost);
+    bool edge_dep = false;   // slab runs: a box reaches the slab's edge planes, whose final values also need the neighbour's halo
     if (early) {
         const int Ns[3] = {g.XG, g.Y, g.Z};
         for (int i = 0; i < p.boxes.n && early; i++) {
@@ -940,28 +942,41 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
                 if (k == 0 && hi > Ns[0]) early = false;                              // wraps in x
                 if (b.periodic[k] != 1 && (lo < 3 || hi > Ns[k] - 3)) early = false;    // within reach of a face kernel
             }
-            const int a0 = p.boxes.lo[i][0] - g.xOffset - 2, a1 = p.boxes.lo[i][0] + p.boxes.ext[i][0] - g.xOffset + 2;
-            if (a0 < lower || a1 > upper) early = false;
-            A0[nA] = a0; A1[nA] = a1; nA++;
+            int a0 = p.boxes.lo[i][0] - g.xOffset - 2, a1 = p.boxes.lo[i][0] + p.boxes.ext[i][0] - g.xOffset + 2;
+            bool cut_lo = false, cut_hi = false;
+            if (multi) {   // a box across (or next to) a slab interface: this rank's share of it, up to the edge plane
+                if (a0 < lower) { a0 = lower; cut_lo = true; }
+                if (a1 > upper) { a1 = upper; cut_hi = true; }
+                if (a1 <= a0) early = false;
+            } else if (a0 < lower || a1 > upper) early = false;
+            A0[nA] = a0; A1[nA] = a1;
+            V0[nA] = cut_lo ? 0 : a0 + 1; V1[nA] = cut_hi ? g.X : a1 - 1;
+            edge_dep = edge_dep || cut_lo || cut_hi;
+            nA++;
         }
         if (early) {   // sort and merge
             for (int i = 1; i < nA; i++)
-                for (int j = i; j > 0 && A0[j] < A0[j - 1]; j--) { std::swap(A0[j], A0[j - 1]); std::swap(A1[j], A1[j - 1]); }
+                for (int j = i; j > 0 && A0[j] < A0[j - 1]; j--) {
+                    std::swap(A0[j], A0[j - 1]); std::swap(A1[j], A1[j - 1]); std::swap(V0[j], V0[j - 1]); std::swap(V1[j], V1[j - 1]);
+                }
             int m = 0;
             for (int i = 1; i < nA; i++) {
-                if (A0[i] <= A1[m]) A1[m] = std::max(A1[m], A1[i]);
-                else { m++; A0[m] = A0[i]; A1[m] = A1[i]; }
+                if (A0[i] <= A1[m]) { A1[m] = std::max(A1[m], A1[i]); V0[m] = std::min(V0[m], V0[i]); V1[m] = std::max(V1[m], V1[i]); }
+                else { m++; A0[m] = A0[i]; A1[m] = A1[i]; V0[m] = V0[i]; V1[m] = V1[i]; }
             }
             nA = m + 1;
         }
     }
     b.early_ok = false;
-    auto bulk = [&](StepParams &q) -> int {   // planes [lower, upper): A first when early
+    // planes [lower, upper): A first when early; after_A (slab runs: the halo unpack, when a box depends on the edge planes) goes
+    // between A and the event
+    auto bulk = [&](StepParams &q, const std::function<void()> &after_A) -> int {
         if (!early) {
             q.x_begin = lower; q.x_count = upper - lower;
             return launch_collide_push(q, b.model, variant, b.stream);
         }
         for (int i = 0; i < nA; i++) { q.x_begin = A0[i]; q.x_count = A1[i] - A0[i]; if (launch_collide_push(q, b.model, variant, b.stream)) return 1; }
+        if (after_A) after_A();
         if (cudaEventRecord(b.ev_early, b.stream) != cudaSuccess) return 1;
         int at = lower;
         for (int i = 0; i <= nA; i++) {
@@ -970,12 +985,12 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
             if (i < nA) at = A1[i];
         }
         b.early_n = nA;
-        for (int i = 0; i < nA; i++) { b.early_x0[i] = A0[i] + 1 + g.xOffset; b.early_x1[i] = A1[i] - 1 + g.xOffset; }
+        for (int i = 0; i < nA; i++) { b.early_x0[i] = V0[i] + g.xOffset; b.early_x1[i] = V1[i] + g.xOffset; }
         b.early_ok = true;
         return 0;
     };
     if (!multi) {
-        if (bulk(p)) return fail(FSILBM_ERR_MODEL, "collision model %d", b.model);
+        if (bulk(p, nullptr)) return fail(FSILBM_ERR_MODEL, "collision model %d", b.model);
         if (ghost) launch_wrap_x(g, fB, b.stream);
     } else if (b.halo.enabled) {
         // Edge planes first: their kernel IS the transfer (peer stores over NVLink + arrival flag); then the
@@ -990,12 +1005,15 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
         e.x_begin = 0; e.x_count = 1; e.cta_counter = h.counters;
         launch_collide_push(e, b.model, variant, b.stream);
         if (g.X > 1) { e.x_begin = g.X - 1; e.cta_counter = h.counters + 1; launch_collide_push(e, b.model, variant, b.stream); }
-        if (g.X > 2) bulk(p);
         HaloUnpackParams u{};
         u.g = g; u.fB = fB; u.step = h.step; u.err = h.err; u.timeout_ns = (unsigned long long)g_halo_timeout_s * 1000000000ull;
         if (h.left >= 0) { u.recv_lo = halo_slot_ptr(h.region, h.slot_bytes, 0, par); u.flag_lo = halo_flag(h.region, 0, par); }
         if (h.right >= 0) { u.recv_hi = halo_slot_ptr(h.region, h.slot_bytes, 1, par); u.flag_hi = halo_flag(h.region, 1, par); }
-        launch_halo_unpack(u, b.stream);
+        // a box across the interface: its planes are final only once the neighbour's populations are folded in, so the unpack
+        // (the neighbour's edge kernel is the first launch of its update) goes right after A instead of after everything
+        bool unpacked = false;
+        if (g.X > 2) bulk(p, [&] { if (edge_dep) { launch_halo_unpack(u, b.stream); unpacked = true; } });
+        if (!unpacked) launch_halo_unpack(u, b.stream);
     } else {
         // NCCL transport: edge planes first, then the exchange on its own stream overlapped with the interior update
         p.x_begin = 0; p.x_count = 1;
@@ -1619,11 +1637,14 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
     bool use_early = b.early_ok && g_ibm_early && bx.n > 0 && (!multi || local) && ordered;
     for (int i = 0; i < bx.n && use_early; i++) {
         bool inside = false;
-        const int lo = bx.lo[i][0], hi = lo + bx.ext[i][0];
+        int lo = bx.lo[i][0], hi = lo + bx.ext[i][0];
+        const bool wraps = hi > g.XG;
+        if (multi) { lo = std::max(lo, g.xOffset); hi = std::min(hi, g.xOffset + g.X); }   // this rank's share of a box across an interface
         for (int k = 0; k < b.early_n; k++) inside = inside || (lo >= b.early_x0[k] && hi <= b.early_x1[k]);
         for (int k = 1; k < 3; k++)
             if (b.periodic[k] != 1 && (bx.lo[i][k] < 3 || bx.lo[i][k] + bx.ext[i][k] > Ns[k] - 3)) inside = false;
-        if (local && shared[kept[i]]) inside = false;
+        if (b.periodic[0] != 1 && (bx.lo[i][0] < 3 || bx.lo[i][0] + bx.ext[i][0] > Ns[0] - 3)) inside = false;
+        if (wraps) inside = false;
         use_early = inside;
     }
     b.early_ok = false;   // one use per update

@@ -131,6 +131,10 @@ def main():
         print(f"[multi x{world}] iteration counts seen in two_plates_dtol: {n_two}", flush=True)
     ok &= flexible_plate_case(F, dist, rank, world, local)
     ok &= refinement_case(F, dist, rank, world, local)
+    counts = [None] * world
+    dist.gather_object(int(F.lib().fsilbm_ibm_early_count()), counts if rank == 0 else None, dst=0)
+    if rank == 0:
+        print(f"[multi x{world}] interaction-force calls that ran beside the previous update (early IBM), per rank: {counts}", flush=True)
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()
