@@ -285,7 +285,10 @@ class SolidBodies:
 
     def advance(self, bodies: Sequence[int], time: float, numsubstep: int, deltat: float):
         """The host work of one step for `bodies` (indices), one thread per body: nodal loads from v_Eforce, the structural
-        sub-steps, UpdatePosVelArea_ for the next step (its call at the top of the next step then returns at once)."""
+        sub-steps, UpdatePosVelArea_ for the next step (its call at the top of the next step then returns at once).
+        Note for writers: v_Exyz / v_Evel then already hold the COMING step's markers, whereas the reference's
+        Write_solid_v_bodies, called after the step, still sees the markers the step used (they lag the beam by one step
+        there).  The stand-in driver (harness/), which produces the reference's files, keeps the reference's order."""
         t0 = _time.perf_counter()
         ids = (ctypes.c_int * len(bodies))(*bodies)
         self._ck(lib().fsolid_advance(self.h, len(bodies), ids, float(time), int(numsubstep), float(deltat)))
