@@ -66,14 +66,20 @@ long long fsilbm_launch_count(void);
  * fsilbm_block_collide_stream updates the x-planes around the bodies first, so the next interaction-force call needs to wait
  * for those planes only; option "ibm_early" = 0 turns it off).  Diagnostics/tests. */
 long long fsilbm_ibm_early_count(void);
-/* Tuning/testing switches, no reference counterpart.  key "variant": 0 push kernel (default),
- * 1 push with streaming stores, 2 pull (fully periodic blocks only; kernel sweep);
- * key "force_ghost": 1 = stream through the ghost planes even on one rank (tests the slab path);
- * key "ibm_single_launch": 1 (default) the whole of calculate_interaction_force is one cooperative kernel on single-rank
- * blocks, 0 one kernel per phase (the multi-rank path, which needs an all-reduce between gather and force);
- * key "halo": 1 (default) peer-memory halo over NVLink, 0 ncclSend/ncclRecv (see fsilbm_block_halo_transport);
- * key "halo_timeout_s": how long a rank waits for a neighbour's halo before fsilbm_block_sync reports
- * FSILBM_ERR_COMM (default 120). */
+/* Tuning/testing switches, no reference counterpart.
+ *   "variant"                 0 push kernel (default), 1 push with streaming stores, 2 pull (fully periodic blocks only; kernel sweep)
+ *   "force_ghost"             1 = stream through the ghost planes even on one rank (tests the slab path)
+ *   "halo"                    1 (default) peer-memory halo over NVLink, 0 ncclSend/ncclRecv (see fsilbm_block_halo_transport)
+ *   "halo_timeout_s"          how long a rank waits for a neighbour (halo flags, IBM loop-control mailbox) before it reports
+ *                             FSILBM_ERR_COMM (default 120)
+ *   "ibm_ordered"             1 (default) interpolation and spreading keep the reference's serial summation order (bit-identical to the
+ *                             serial reference, reproducible), 0 warp shuffles + fp64 atomics (round-off differences)
+ *   "ibm_single_launch"       1 (default) calculate_interaction_force is one cooperative kernel (on slab runs with the loop control
+ *                             exchanged through peer memory), 0 one kernel per phase (slab runs: ncclAllReduce of the loop control)
+ *   "ibm_early"               1 (default) fsilbm_block_collide_stream updates the x-planes around the bodies first so that the next
+ *                             fsilbm_ibm_interaction_force runs beside the rest of the update, 0 strictly one after the other
+ *   "ibm_early_blocks_per_sm" 1..4 (default 2): size of the cooperative IBM grid when it shares the SMs with that update
+ *   "ibm_local", "ibm_force_exchange", "ibm_replicate"   forms of the IBM on slab runs, see fsilbm_ibm_body_status below */
 int fsilbm_set_option(const char *key, int value);
 
 /* ---- fluid block: replaces type LBMBlock's procedures --------------------------------------- */
