@@ -1598,6 +1598,8 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         xc.cnt_local = 0.0;
         for (int ib : act) if (lead_of[ib]) xc.cnt_local = xc.cnt_local + (double)nelmts[ib];
     }
+    if (mailbox && nact > MAX_IBM_PHASE_BODIES)   // the other ranks are in the mailbox protocol: no silent switch to another path
+        return fail(FSILBM_ERR_ARG, "more than %d bodies touch this slab (ibm_single_launch = 0 lifts the limit)", MAX_IBM_PHASE_BODIES);
     bool single = (!multi || replicate || mailbox) && g_ibm_single_launch && nact <= MAX_IBM_PHASE_BODIES && nact > 0;
     Geom gsten = g;
     if (replicate || local) { gsten.xOffset = 0; gsten.X = g.XG; }   // stencil_marker: every stencil plane counts as owned
