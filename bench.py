@@ -4,11 +4,16 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W     # the reference's CPU algorithm (oracle port)
 
-Workload (BASELINE.json configs[1]): periodic body-force-driven channel, no body, 256^3 cells per
-GPU, SRT, tau = 0.8, volumeForceIn = (1e-6,0,0).  N > 1 weak-scales along x (x-slabs of 256 planes,
-global grid 256N x 256 x 256) with the one-plane halo exchange of the outgoing populations.
-One "step" = one pass of LBMBlockComm.f90:283-303 over the block (update_volume_force + the fused
-macro/force/collide/stream/boundary kernel).  Prints ONE JSON line (rank 0).
+Default workload (BASELINE.json configs[1]): periodic body-force-driven channel, no body, 256^3 cells per GPU, SRT,
+tau = 0.8, volumeForceIn = (1e-6,0,0).  N > 1 weak-scales along x (x-slabs of 256 planes, global grid 256N x 256 x 256)
+with the one-plane halo of the outgoing populations.  One "step" = one pass of LBMBlockComm.f90:283-303 over the block
+(update_volume_force + the fused macro/force/collide/stream/boundary kernel; with bodies also calculate_interaction_force
+and the host structural sub-steps).  Prints ONE JSON line (rank 0).
+
+--workload selects the other configurations of BASELINE.json (WORKLOADS below): plate512 = configs[2] (rigid plate in shear
+inflow), heave1024 = configs[3] (heaving flexible plate, 128 x-planes per GPU), school2048 = configs[4] (one flexible plate
+per GPU slab), school2048r = configs[4] with every plate in its own refined son block, school8x1 = a diagnostic with the
+eight plates in one block.
 """
 from __future__ import annotations
 
