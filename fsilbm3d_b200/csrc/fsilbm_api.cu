@@ -978,10 +978,13 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
         for (int i = 0; i < nA; i++) { q.x_begin = A0[i]; q.x_count = A1[i] - A0[i]; if (launch_collide_push(q, b.model, variant, b.stream)) return 1; }
         if (after_A) after_A();
         if (cudaEventRecord(b.ev_early, b.stream) != cudaSuccess) return 1;
+        // the rest holds no box cell (A covers every box with two planes to spare): the IBM-free instantiation of the kernel does it
+        StepParams rest = q;
+        rest.boxes.n = 0;
         int at = lower;
         for (int i = 0; i <= nA; i++) {
             const int end = i < nA ? A0[i] : upper;
-            if (end > at) { q.x_begin = at; q.x_count = end - at; if (launch_collide_push(q, b.model, variant, b.stream)) return 1; }
+            if (end > at) { rest.x_begin = at; rest.x_count = end - at; if (launch_collide_push(rest, b.model, variant, b.stream)) return 1; }
             if (i < nA) at = A1[i];
         }
         b.early_n = nA;
