@@ -4,11 +4,13 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W     # the reference's CPU algorithm (oracle port)
 
-Default workload (BASELINE.json configs[1]): periodic body-force-driven channel, no body, 256^3 cells per GPU, SRT,
-tau = 0.8, volumeForceIn = (1e-6,0,0).  N > 1 weak-scales along x (x-slabs of 256 planes, global grid 256N x 256 x 256)
-with the one-plane halo of the outgoing populations.  One "step" = one pass of LBMBlockComm.f90:283-303 over the block
-(update_volume_force + the fused macro/force/collide/stream/boundary kernel; with bodies also calculate_interaction_force
-and the host structural sub-steps).  Prints ONE JSON line (rank 0).
+Default workload: the metric is collide-stream + IBM, so the default is a configuration WITH a body.  --gpus 1 ->
+plate512 = BASELINE.json configs[2] (rigid 8192-marker plate in shear inflow, 512x256x256: the largest single-GPU
+configuration).  --gpus N > 1 -> heave1024 = configs[3] (heaving flexible plate, 128x512x512 per GPU, x-slabs; 1024x512x512 at
+8 GPUs).  Both hold 33.55 M cells per GPU, so the driver's weak-scaling ratio compares like with like.  channel256
+(configs[1], no body) is --workload channel256.  One "step" = one pass of LBMBlockComm.f90:279-338 over the block
+(update_volume_force, calculate_interaction_force, the fused macro/force/collide/stream/boundary update, and for flexible
+bodies the host structural sub-steps).  Prints ONE JSON line (rank 0).
 
 --workload selects the other configurations of BASELINE.json (WORKLOADS below): plate512 = configs[2] (rigid plate in shear
 inflow), heave1024 = configs[3] (heaving flexible plate, 128 x-planes per GPU), school2048 = configs[4] (one flexible plate
@@ -72,6 +74,36 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def host_cpu():
+    """Cores this process may use, physical cores among them and the CPU model (BASELINE.md section 3 asks for all three)."""
+    try:
+        usable = sorted(os.sched_getaffinity(0))
+    except Exception:
+        usable = list(range(os.cpu_count() or 1))
+    model, phys, cur = "unknown", set(), {}
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ":" not in ln:
+                if cur:
+                    if int(cur.get("processor", -1)) in usable:
+                        phys.add((cur.get("physical id", "0"), cur.get("core id", cur.get("processor"))))
+                    cur = {}
+                continue
+            k, v = [t.strip() for t in ln.split(":", 1)]
+            cur[k] = v
+            if k == "model name":
+                model = v
+        if cur and int(cur.get("processor", -1)) in usable:
+            phys.add((cur.get("physical id", "0"), cur.get("core id", cur.get("processor"))))
+    except Exception:
+        pass
+    return {"logical": len(usable), "physical": len(phys) or len(usable), "model": model}
+
+
+def default_workload(gpus: int) -> str:
+    return "plate512" if gpus <= 1 else "heave1024"
 
 
 class ClockSampler(threading.Thread):
@@ -156,10 +188,13 @@ def workload_flow(F_or_O_flow, wl):
 
 
 # ------------------------------------------------------------------------------------------------------
-def cpu_time_oracle(wl, dims, steps, warmup):
-    """Times the CPU restatement of the reference's OpenMP path (oracle/; kind 'port') on `dims`."""
+def cpu_time_oracle(wl, dims, steps, warmup, with_bodies=True):
+    """Times the CPU restatement of the reference's OpenMP path (oracle/; kind 'port') on `dims`.  with_bodies=False: the fluid
+    part only (calibration on a slab too thin to hold the plate)."""
     from oracle import oracle as O
     import fsilbm3d_b200 as F
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm asks for every core this process may use itself
+    O.lib().orc_omp_set_threads(host_cpu()["logical"])
     flowkw, dh = workload_flow(None, wl)
     flowkw.pop("numsubstep", None)
     fl = O.Flow(**flowkw)
@@ -168,7 +203,9 @@ def cpu_time_oracle(wl, dims, steps, warmup):
     b.initialise(0.0)
     b.update_volume_force(); b.set_boundary_conditions(); b.calculate_macro_quantities()
     bodies, plate = [], None
-    if wl["plate"] == "flex":
+    if not with_bodies:
+        pass
+    elif wl["plate"] == "flex":
         # fluid + IBM on the initial markers of the first plate, re-stencilled every step as for a moving body; the
         # structural solve is host code on both arms and is left out of the CPU sample
         flowkw.pop("numsubstep", None)
@@ -197,16 +234,29 @@ def cpu_time_oracle(wl, dims, steps, warmup):
     return X * Y * Z * steps / dt / 1e6, dt / steps, O.lib().orc_omp_max_threads()
 
 
+def bench_config(args, wl, world):
+    """The `config` object both arms print (identical for the same command line)."""
+    Xl, Y, Z = wl["dims"]
+    return {"workload": args.workload, "desc": wl["desc"], "grid_per_gpu": [Xl, Y, Z], "grid_global": [Xl * world, Y, Z],
+            "decomposition": f"x-slabs x{world}" if world > 1 else "single block",
+            "l2": "working set >= 5.1 GB per GPU (two population buffers) >> 126 MB L2; no explicit flush needed"}
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (the Fortran cannot be built here: no Fortran
-    compiler in the image; the oracle port stands in, kind 'port'), all host threads."""
+    """--impl reference: the reference's CPU algorithm on this box's host cores (the Fortran cannot be built here: no Fortran
+    compiler in the image; the C restatement of its OpenMP path stands in, kind 'port'), with every core the process may use
+    -- set here, because torchrun hands its workers OMP_NUM_THREADS=1.  MLUPS is a rate: each step is a bounded sample of the
+    workload (one GPU's share of the global grid, around the body), and the value is what this host sustains on it whatever
+    N is -- the driver's ratio at N GPUs is then N GPUs against this one host."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = max(1, args.gpus)
     wl = WORKLOADS[args.workload]
     X, Y, Z = wl["dims"]
+    cpu = host_cpu()
     # bounded sample: calibrate on a thin slab, then take the largest x extent that keeps the run in ~2 minutes
-    mlups_cal, t_cal, threads = cpu_time_oracle(wl, (16, Y, Z), 2, 1)
+    mlups_cal, t_cal, threads = cpu_time_oracle(wl, (16, Y, Z), 2, 1, with_bodies=False)
     per_plane = t_cal / 16.0
     budget = 120.0
     if wl["plate"] == "flex":
@@ -221,14 +271,16 @@ def run_reference(args):
             xs = c
             break
     mlups, t_step, threads = cpu_time_oracle(wl, (xs, Y, Z), args.steps, args.warmup)
-    sample = f"{xs}x{Y}x{Z} of the {X}x{Y}x{Z} grid, {args.steps} steps after {args.warmup} warm-up"
+    sample = (f"{xs}x{Y}x{Z} cells around the body out of the {X * world}x{Y}x{Z} grid, {args.steps} steps after {args.warmup} warm-up; "
+              f"{threads} OpenMP threads on {cpu['physical']} physical / {cpu['logical']} logical cores of {cpu['model']}")
     line = {
         "metric": METRIC, "value": mlups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "impl": "reference",
-        "config": {"workload": args.workload, "desc": wl["desc"], "grid_per_gpu": [X, Y, Z]},
-        "cpu_baseline": {"value": mlups, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "note": "C restatement of the reference OpenMP path (Fortran not buildable here)"},
+        "config": bench_config(args, wl, world),
+        "cpu_baseline": {"value": mlups, "unit": UNIT, "cores": threads, "physical_cores": cpu["physical"], "cpu_model": cpu["model"],
+                         "kind": "port", "sample": sample,
+                         "note": "C restatement of the reference OpenMP path (Fortran not buildable here); one host whatever N is"},
         "e2e": {"value": mlups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -245,6 +297,65 @@ def emit(line):
         sys.stdout.write(data.decode()); sys.stdout.flush()
     else:
         os.write(_REAL_STDOUT, data)
+
+
+# ------------------------------------------------------------------------------------------------------
+def parity_check(F, dist, rank, world, local, steps=10):
+    """A small case of the same path run in THIS process group just before the timed region, checked against the CPU oracle on
+    rank 0 (the oracle is the checker here, never the thing measured): inlet/outlet block with moving walls, a rigid plate whose
+    stencil box straddles the interface of the middle ranks, cut into `world` x-slabs, `steps` steps.  Makes multi-rank parity
+    visible in the driver's own run."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from tests.common import perturbed_state, rel_err
+    X, Y, Z = 10 * world + 1 if world > 1 else 21, 20, 24
+    bc = (102, 104, 202, 202, 301, 301)
+    kw = dict(nu=0.05, uvwIn=(0.04, 0.0, 0.0), shearRateIn=(0.0, 3e-4, 0.0), Uref=0.04, ntolLBM=3, dtolLBM=1e-30)
+    off, cnt = F.slab_range(X, rank, world)
+    flow = F.FlowCondType(**kw)
+    gb = F.LBMBlock(X, Y, Z, BndConds=bc, flow=flow, xOffset=off, xLocal=cnt, device=local)
+    gb.initialise(0.0)
+    f0 = perturbed_state((X, Y, Z), flow)
+    gb.upload_fIn(np.ascontiguousarray(f0[:, off:off + cnt]))
+    gb.update_volume_force(); gb.set_boundary_conditions()
+    plate = F.RigidPlate(origin=(X / 2.0 - 4.2, 8.3, 5.2), nEL=8, len1=1.0, Nspan=8, spanlen=8.0, Lspan=0.0, chord_dir=(1.0, 0.2, 0.0), denIn=1.0)
+    ob = ov = None
+    if rank == 0:
+        from oracle import oracle as O
+        ob = O.LBMBlock(X, Y, Z, BndConds=bc, flow=O.Flow(**kw))
+        ob.initialise(0.0)
+        ob.fIn[...] = f0
+        ob.update_volume_force(); ob.set_boundary_conditions(); ob.calculate_macro_quantities()
+        ov = O.VirtualBody(plate.body.v_nelmts, v_move=0, iBodyModel=1)
+        ov.v_Exyz[...] = plate.body.v_Exyz; ov.v_Evel[...] = plate.body.v_Evel; ov.v_Ea[...] = plate.body.v_Ea
+    iters_equal, eF = True, 0.0
+    for n in range(1, steps + 1):
+        it_g = F.tree_collision_streaming_IBM_FEM(gb, [plate], time=float(n), solver=False)
+        if rank == 0:
+            ob.set_blktime(float(n))
+            it_o = ob.step([ov])
+            iters_equal = iters_equal and it_o == it_g
+            eF = max(eF, rel_err(plate.body.v_Eforce, ov.v_Eforce))
+    den, uuu = gb.download_macro()
+    floc = gb.download_fIn()
+    parts = [(off, cnt, den, uuu, floc)]
+    if world > 1:
+        parts = [None] * world
+        dist.gather_object((off, cnt, den, uuu, floc), parts if rank == 0 else None, dst=0)
+    out = None
+    if rank == 0:
+        ob.calculate_macro_quantities()
+        DEN = np.concatenate([p[2] for p in parts], axis=0)
+        UUU = np.concatenate([p[3] for p in parts], axis=1)
+        FF = np.concatenate([p[4] for p in parts], axis=1)
+        out = {"case": f"{X}x{Y}x{Z}, BndConds {list(bc)}, rigid plate (64 markers) across the middle interface, {world} x-slab(s), {steps} steps, vs CPU oracle",
+               "fIn_bit_exact": bool(np.array_equal(FF, ob.fIn)), "den_rel_err": rel_err(DEN, ob.den), "u_rel_err": rel_err(UUU, ob.uuu),
+               "marker_force_rel_err": eF, "ibm_iterations_equal": bool(iters_equal)}
+        out["ok"] = bool(out["fIn_bit_exact"] and out["den_rel_err"] <= 1e-12 and out["u_rel_err"] <= 1e-12 and eF <= 1e-10 and iters_equal)
+    gb.close()
+    if world > 1:
+        dist.barrier()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -279,6 +390,14 @@ def run_gpu(args):
     def barrier():
         if world > 1:
             dist.barrier()
+
+    parity = None
+    if not args.no_parity_check:
+        try:
+            parity = parity_check(F, dist, rank, world, local)
+        except Exception as ex:   # reported, never hidden
+            parity = {"ok": False, "error": f"{type(ex).__name__}: {ex}"}
+    early0 = int(F.lib().fsilbm_ibm_early_count())
 
     wl = WORKLOADS[args.workload]
     Xl, Y, Z = wl["dims"]
@@ -393,17 +512,27 @@ def run_gpu(args):
         kern_ms = k0.elapsed_time(k1) / reps
     peak, peak_src = measured_peaks()
     cells_local = float(Xl) * Y * Z
-    achieved = BYTES_PER_LU * cells_local / (kern_ms * 1e-3) / 1e9
-    traffic = None
+    lu_local = cells_total / world          # lattice updates per step and GPU (son blocks count twice per root step)
+    step_ms = ms / args.steps
+    achieved = BYTES_PER_LU * lu_local / (step_ms * 1e-3) / 1e9
+    alone = BYTES_PER_LU * cells_local / (kern_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
     prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get(args.workload, {}).get("dram_bytes_per_launch")
+            rec = json.load(open(prof)).get(args.workload, {})
+            traffic, traffic_src = rec.get("dram_bytes_per_step"), rec.get("source")
         except Exception:
             traffic = None
+    # frac is the WHOLE STEP (every launch of it: collide-stream in its x-ranges, face kernels, the IBM iteration, halo unpack,
+    # and whatever host time the device had to wait for) against the 304 B per lattice update the collide-stream needs
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "collide_push_kernel", "algorithmic_bytes_per_launch": BYTES_PER_LU * cells_local, "peak_source": peak_src,
-                "kernel_ms": kern_ms}
+                "traffic_source": traffic_src,
+                "scope": "whole step: algorithmic 304 B x lattice updates per GPU / ms_per_step",
+                "algorithmic_bytes_per_step": BYTES_PER_LU * lu_local, "peak_source": peak_src,
+                "collide_alone": {"kernel": "collide_push_kernel (IBM-free instantiation, launched back to back after the run)",
+                                  "kernel_ms": kern_ms, "achieved": alone, "frac": alone / peak,
+                                  "algorithmic_bytes_per_launch": BYTES_PER_LU * cells_local}}
 
     # ---- end to end through the host API with HOST buffers ------------------------------------------------
     # What the reference driver does around this path: populations come from pinned host memory once
@@ -455,29 +584,41 @@ def run_gpu(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
+            hc = host_cpu()
             sx = Xl if (not wl["plate"] or wl["plate"] == "flex") else 320
-            steps_cpu = 6
+            steps_cpu = 12
             mlups, t_step, threads = cpu_time_oracle(wl, (sx, Y, Z), steps_cpu, 2)
-            cpu = {"value": mlups, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{sx}x{Y}x{Z}, {steps_cpu} steps after 2 warm-up ({t_step * 1e3:.0f} ms/step); "
+            cpu = {"value": mlups, "unit": UNIT, "cores": threads, "physical_cores": hc["physical"], "cpu_model": hc["model"], "kind": "port",
+                   "sample": f"{sx}x{Y}x{Z} cells around the body, {steps_cpu} steps after 2 warm-up ({t_step * 1e3:.0f} ms/step); "
                              "C restatement of the reference OpenMP path (Fortran not buildable here)"}
         except Exception as ex:   # the baseline must never take the GPU number down with it
             cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {ex}"}
+
+    if args.trace_out:
+        blk.sync(); barrier()
+        check(lib.fsilbm_set_option(b"trace", 1))
+        for n in range(5):
+            step(args.warmup + 2 * args.steps + n + 1)
+        if sb is not None:
+            sb.flush()
+        blk.sync()
+        check(lib.fsilbm_set_option(b"trace", 0))
+        check(lib.fsilbm_trace_dump(f"{args.trace_out}.rank{rank}.csv".encode()))
+        barrier()
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": args.workload, "desc": wl["desc"], "grid_per_gpu": [Xl, Y, Z], "grid_global": [XG, Y, Z],
-                       "decomposition": f"x-slabs x{world}" if world > 1 else "single block",
-                       "l2": "working set 5.1 GB per GPU (two population buffers) >> 126 MB L2; no explicit flush needed",
-                       "kernel_variant": args.variant, "halo_transport": transport,
-                       "structural_solver": structural,
-                       "blocks": None if root is None else {"root_cells_per_gpu": Xl * Y * Z, "son_cells_on_rank0": son_cells, "son_updates_per_root_step": 2,
-                                                            "note": "value counts the lattice updates of all blocks (root + 2 x son); roofline and e2e "
-                                                                    "transfers are the root block's"},
-                       "ibm": ("ordered per-cell gather (bit-identical to the serial reference)" if args.ibm_ordered else "fp64 atomics") if wl["plate"] else None},
+            "config": bench_config(args, wl, world),
+            "details": {"halo_transport": transport, "structural_solver": structural,
+                        "blocks": None if root is None else {"root_cells_per_gpu": Xl * Y * Z, "son_cells_on_rank0": son_cells, "son_updates_per_root_step": 2,
+                                                             "note": "value counts the lattice updates of all blocks (root + 2 x son); the e2e "
+                                                                     "transfers are the root block's"},
+                        "ibm": ("ordered per-cell gather (bit-identical to the serial reference)" if args.ibm_ordered else "fp64 atomics") if wl["plate"] else None,
+                        "ibm_calls_overlapped_with_update": int(lib.fsilbm_ibm_early_count()) - early0},
+            "parity_check": parity,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         emit(line)
@@ -497,8 +638,11 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
-    ap.add_argument("--workload", default="channel256", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: plate512 (configs[2]) at --gpus 1, heave1024 (configs[3]) at --gpus N > 1")
+    ap.add_argument("--trace-out", default=None, help="diagnostic: after the measurement, five more steps with the launch trace on; "
+                                                       "every rank writes <trace-out>.rank<r>.csv")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the small oracle comparison run before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flow-every", type=int, default=200, help="e2e leg: read den,uuu back to the host every this many steps")
     ap.add_argument("--halo", type=int, default=1, choices=[0, 1], help="multi-GPU halo transport: 1 peer stores over NVLink, 0 NCCL send/recv")
@@ -509,6 +653,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.workload is None:
+        args.workload = default_workload(args.gpus)
     global _REAL_STDOUT
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
@@ -517,8 +663,6 @@ def main():
         run_reference(args)
         return
     import fsilbm3d_b200 as F
-    if args.variant:
-        F._lib.check(F.lib().fsilbm_set_option(b"variant", args.variant))
     F._lib.check(F.lib().fsilbm_set_option(b"halo", args.halo))
     F._lib.check(F.lib().fsilbm_set_option(b"ibm_ordered", args.ibm_ordered))
     F._lib.check(F.lib().fsilbm_set_option(b"ibm_single_launch", args.ibm_single_launch))

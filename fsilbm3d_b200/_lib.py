@@ -56,7 +56,7 @@ def lib():
     pi, pd = C.POINTER(C.c_int), C.POINTER(C.c_double)
     ppd = C.POINTER(C.c_void_p)
     sig = {
-        "fsilbm_init": [i], "fsilbm_finalize": [], "fsilbm_set_option": [C.c_char_p, i],
+        "fsilbm_init": [i], "fsilbm_finalize": [], "fsilbm_set_option": [C.c_char_p, i], "fsilbm_trace_dump": [C.c_char_p],
         "fsilbm_block_create": [i, i, i, i, i, d, d, d, d, pi, i, pd, C.POINTER(CFlow), pi],
         "fsilbm_block_destroy": [i], "fsilbm_block_initialise": [i, d], "fsilbm_block_get": [i, i, pd],
         "fsilbm_block_upload_fIn": [i, vp], "fsilbm_block_download_fIn": [i, vp],
@@ -74,6 +74,8 @@ def lib():
         "fsilbm_block_pass_halfway_bc_set": [i], "fsilbm_block_pass_streaming": [i],
         "fsilbm_block_download_fields": [i, vp, vp, vp], "fsilbm_block_upload_fields": [i, vp, vp, vp],
         "fsilbm_ibm_interaction_force": [i, i, pi, ppd, ppd, ppd, ppd, pi, d, i, d, pi, pi],
+        "fsilbm_ibm_interaction_force_begin": [i, i, pi, ppd, ppd, ppd, pi, d, i, d, pi],
+        "fsilbm_ibm_interaction_force_wait": [i, i, ppd, pi],
         "fsilbm_ibm_download_stencil": [i, i, vp, vp],
         "fsilbm_ibm_body_status": [i, i, vp],
         "fsilbm_pair_create": [i, i, i, pi], "fsilbm_pair_destroy": [i], "fsilbm_pair_info": [i, pi],

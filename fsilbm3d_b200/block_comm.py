@@ -248,15 +248,22 @@ def tree_collision_streaming_IBM_FEM(node, plates: Sequence = (), time: Optional
     block.update_volume_force()                                             # :283
     it = 0
     collective = getattr(block, "ibm_collective", False)   # slab runs with per-rank body lists: every rank calls, even with no body
-    if len(plates) or collective:                                           # IBM_FEM, :287 -> :320-338
+    ibm = len(plates) or collective
+    split = ibm and hasattr(block, "calculate_interaction_force_begin")
+    if ibm:                                                                 # IBM_FEM, :287 -> :320-338
         for p in plates:
             p.UpdatePosVelArea()                                            # Solidbody.f90:597-600
-        it = block.calculate_interaction_force([p.body for p in plates], rootBC, collective=collective)   # :601
-    if iters is not None:
-        iters.append(it)
+        if split:   # enqueue only: the update below is issued before the host waits for the marker forces
+            block.calculate_interaction_force_begin([p.body for p in plates], rootBC, collective=collective)   # :601
+        else:
+            it = block.calculate_interaction_force([p.body for p in plates], rootBC, collective=collective)
     for pair in node.comm:
         pair.extract_interpolate_layer(1)                                   # :290
-    block.collide_stream()                                                  # :285-303 fused; asynchronous launch
+    block.collide_stream()                                                  # :285-303 fused; asynchronous launch (follows the IBM on the device)
+    if split:
+        it = block.calculate_interaction_force_wait()                       # marker forces + iterLBM back on the host
+    if iters is not None:
+        iters.append(it)
     # The host halves of FSInteraction_force -- nodal loads (Solidbody.f90:911,945-967) and Solver (:333-335) -- only read
     # the marker forces just returned and touch no fluid state.  The reference runs them before the collision; here they
     # are issued after the launch so that they overlap the device's collide-stream of the same step.

@@ -14,7 +14,7 @@ HEADERS = ["d3q19.cuh", "kernels.h", os.path.join("..", "..", "include", "fsilbm
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-std=c++17", "-lineinfo",
+    "-O3", "-std=c++17", "-lineinfo", "--threads", "0",
     # no fused multiply-add: the reference's x86-64 gfortran build has none, and the parity tests
     # compare against an oracle compiled with -ffp-contract=off (see DESIGN.md "Arithmetic")
     "-fmad=false",

@@ -60,25 +60,48 @@ __device__ __forceinline__ void cell_state(const double (&f)[Q], const double (&
 }
 
 // ---- the fused step -----------------------------------------------------------------------------
-// VARIANT 0: push (aligned loads, z-shifted stores).  VARIANT 1: same, streaming stores (st.global.cs).
-// EDGE (multi-GPU edge planes): populations that leave the slab in x are stored straight into the neighbour
-// GPU's receive planes over NVLink (peer-mapped pointers p.halo_hi / p.halo_lo) instead of the local ghost
-// plane, and the last CTA of the launch publishes the step number to the neighbours' arrival flags, so the
+// Push form: aligned loads, z-shifted stores.
+// EDGE (launches of a multi-GPU run that contain the slab's edge planes): populations that leave the slab in x are stored
+// straight into the neighbour GPU's receive planes over NVLink (peer-mapped pointers p.halo_hi / p.halo_lo) instead of the
+// local ghost plane, and the last CTA of an edge plane publishes the step number to the neighbour's arrival flag, so the
 // transfer is part of the compute kernel and needs no copy engine, no NCCL kernel and no host involvement.
 __device__ __forceinline__ int halo_slot(int q)
 {   // position of q in [1,7,9,11,13] (ex=+1) or [2,8,10,12,14] (ex=-1)
     return q <= 2 ? 0 : (q - 5) >> 1;
 }
 
-template <int MODEL, bool IBM, int VARIANT, bool EDGE>
-__global__ void __launch_bounds__(128, 4) collide_push_kernel(const __grid_constant__ StepParams p)
+// does any stencil box hold cells of global plane gx?  (uniform over a CTA: the box test per cell is skipped elsewhere)
+__device__ __forceinline__ bool plane_in_boxes(const IbmBoxes &B, int gx, int XG)
+{
+    for (int b = 0; b < B.n; b++) {
+        int dx = gx - B.lo[b][0]; if (dx < 0) dx += XG;
+        if (dx < B.ext[b][0]) return true;
+    }
+    return false;
+}
+
+// Registers: SRT and TRT fit 96 registers without spilling, i.e. FIVE CTAs of 128 threads per SM.  Memory-bound as the kernel
+// is, four would do -- the fifth slot is what the cooperative IBM kernel takes when it runs beside this one (early IBM), so
+// that it no longer pushes the update below the occupancy it needs.  MRT and the LES closures spill at 96 and keep four.
+template <int MODEL, bool IBM, bool EDGE>
+__global__ void __launch_bounds__(128, (MODEL <= 2 ? 5 : 4)) collide_push_kernel(const __grid_constant__ StepParams p)
 {
     const int Z = p.g.Z, Y = p.g.Y, X = p.g.X;
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int x = p.x_begin + blockIdx.z;
+    int x = 0;
+    {   // blockIdx.z walks the plane ranges of this launch in list order
+        int bz = blockIdx.z;
+#pragma unroll 1
+        for (int sgm = 0; sgm < p.nseg; sgm++) {
+            const int cnt = p.seg_count[sgm];
+            if (bz < cnt) { x = p.seg_begin[sgm] + bz; break; }
+            bz -= cnt;
+        }
+    }
+    const bool edge_plane = EDGE && (x == 0 || x == X - 1);
     const bool active = (z < Z && y < Y);
-    if (!EDGE && !active) return;
+    if (!edge_plane && !active) return;
     const size_t plane = p.g.plane, ps = p.g.pstride;
     if (active) {
     const size_t base = (size_t)(x + 1) * plane + (size_t)y * Z + z;
@@ -88,7 +111,8 @@ __global__ void __launch_bounds__(128, 4) collide_push_kernel(const __grid_const
     for (int q = 0; q < Q; q++) f[q] = __ldg(p.fA + q * ps + base);
 
     double den, u1, u2, u3, F1, F2, F3;
-    cell_state(f, p.hF, p.Fvol, p.boxes, IBM, p.g.xOffset + x, y, z, p.g.XG, Y, Z, den, u1, u2, u3, F1, F2, F3);
+    const bool ibm_here = IBM && plane_in_boxes(p.boxes, p.g.xOffset + x, p.g.XG);
+    cell_state(f, p.hF, p.Fvol, p.boxes, ibm_here, p.g.xOffset + x, y, z, p.g.XG, Y, Z, den, u1, u2, u3, F1, F2, F3);
     if (MODEL >= 11) {
         const LesCtx les{p.uuu, p.tau_all, X, Y, Z, x, y, z, true};
         collide<MODEL>(f, den, u1, u2, u3, F1, F2, F3, p.cc, &les);
@@ -115,63 +139,25 @@ __global__ void __launch_bounds__(128, 4) collide_push_kernel(const __grid_const
             if (EX(q) > 0 && x == X - 1 && p.halo_hi) dst = p.halo_hi + (size_t)halo_slot(q) * plane + oy[iy] + oz[iz];
             if (EX(q) < 0 && x == 0 && p.halo_lo) dst = p.halo_lo + (size_t)halo_slot(q) * plane + oy[iy] + oz[iz];
         }
-        if (VARIANT == 1) __stcs(dst, f[q]);
-        else *dst = f[q];
+        *dst = f[q];
     }
     }
-    if (EDGE) {
-        // publish: every thread's peer stores are fenced system-wide, the CTA counts in, the last CTA raises the flags
+    if (edge_plane) {
+        // publish: every thread's peer stores are fenced system-wide, the CTA counts in, the last CTA of the plane raises the flag
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0 && threadIdx.y == 0) {
-            const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
-            const unsigned int done = atomicAdd(p.cta_counter, 1u);
+            const unsigned int total = gridDim.x * gridDim.y;
+            unsigned int *counter = p.cta_counter + ((x == 0) ? 0 : 1);
+            const unsigned int done = atomicAdd(counter, 1u);
             if (done == total - 1) {
-                *p.cta_counter = 0;
+                *counter = 0;
                 __threadfence_system();
                 if (p.sig_hi && x == X - 1) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.sig_hi), "l"(p.step) : "memory"); }
                 if (p.sig_lo && x == 0) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.sig_lo), "l"(p.step) : "memory"); }
             }
         }
     }
-}
-
-// VARIANT 2: pull formulation of the same step on the same two buffers.  The streamed state is
-// not materialised: fA holds post-collision populations g and this kernel reads
-// g(x-ex,y-ey,z-ez,q) (z-shifted loads, aligned stores).  Used only for the fully periodic case by
-// the kernel sweep; the product path keeps the push form because the face rules of
-// set_boundary_conditions_ act on the streamed field.
-template <int MODEL>
-__global__ void __launch_bounds__(128, 4) collide_pull_kernel(const __grid_constant__ StepParams p)
-{
-    const int Z = p.g.Z, Y = p.g.Y, X = p.g.X;
-    const int z = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int x = p.x_begin + blockIdx.z;
-    if (z >= Z || y >= Y) return;
-    const size_t plane = p.g.plane, ps = p.g.pstride;
-    int xp = x + 1, xm = x - 1;
-    if (p.wrap_x) { if (xp == X) xp = 0; if (xm < 0) xm = X - 1; }
-    const int yp = (y + 1 == Y) ? 0 : y + 1, ym = (y == 0) ? Y - 1 : y - 1;
-    const int zp = (z + 1 == Z) ? 0 : z + 1, zm = (z == 0) ? Z - 1 : z - 1;
-    // source of population q is the cell at -e_q
-    const size_t ox[3] = {(size_t)(x + 1) * plane, (size_t)(xm + 1) * plane, (size_t)(xp + 1) * plane};
-    const size_t oy[3] = {(size_t)y * Z, (size_t)ym * Z, (size_t)yp * Z};
-    const size_t oz[3] = {(size_t)z, (size_t)zm, (size_t)zp};
-    double f[Q];
-#pragma unroll
-    for (int q = 0; q < Q; q++) {
-        const int ix = EX(q) == 0 ? 0 : (EX(q) > 0 ? 1 : 2);
-        const int iy = EY(q) == 0 ? 0 : (EY(q) > 0 ? 1 : 2);
-        const int iz = EZ(q) == 0 ? 0 : (EZ(q) > 0 ? 1 : 2);
-        f[q] = __ldg(p.fA + q * ps + ox[ix] + oy[iy] + oz[iz]);
-    }
-    double den, u1, u2, u3, F1, F2, F3;
-    cell_state(f, p.hF, p.Fvol, p.boxes, false, p.g.xOffset + x, y, z, p.g.XG, Y, Z, den, u1, u2, u3, F1, F2, F3);
-    collide<MODEL>(f, den, u1, u2, u3, F1, F2, F3, p.cc);
-    const size_t base = (size_t)(x + 1) * plane + (size_t)y * Z + z;
-#pragma unroll
-    for (int q = 0; q < Q; q++) p.fB[q * ps + base] = f[q];
 }
 
 static inline void line_block(int Z, dim3 &block, int &bz, int &by)
@@ -181,43 +167,39 @@ static inline void line_block(int Z, dim3 &block, int &bz, int &by)
     block = dim3(bz, by, 1);
 }
 
-template <int VARIANT>
-static int launch_push_variant(const StepParams &p, int model, dim3 grid, dim3 block, cudaStream_t s)
+void step_add_planes(StepParams &p, int begin, int count)
 {
+    if (count <= 0) return;
+    if (p.nseg > 0 && p.seg_begin[p.nseg - 1] + p.seg_count[p.nseg - 1] == begin) { p.seg_count[p.nseg - 1] += count; return; }
+    if (p.nseg >= MAX_SEG) return;   // cannot happen: at most 2 edge planes + MAX_BOXES ranges + MAX_BOXES + 1 gaps
+    p.seg_begin[p.nseg] = begin; p.seg_count[p.nseg] = count; p.nseg++;
+}
+
+int launch_collide_push(const StepParams &p, int model, cudaStream_t s)
+{
+    int planes = 0;
+    for (int i = 0; i < p.nseg; i++) planes += p.seg_count[i];
+    if (planes <= 0) return 0;
+    dim3 block; int bz, by;
+    line_block(p.g.Z, block, bz, by);
+    dim3 grid((p.g.Z + bz - 1) / bz, (p.g.Y + by - 1) / by, planes);
     const bool ibm = p.boxes.n > 0;
     const bool edge = p.cta_counter != nullptr;
 #define FSILBM_LAUNCH(M)                                                                                     \
     do {                                                                                                     \
-        if (edge) { if (ibm) collide_push_kernel<M, true, VARIANT, true><<<grid, block, 0, s>>>(p); else collide_push_kernel<M, false, VARIANT, true><<<grid, block, 0, s>>>(p); } \
-        else { if (ibm) collide_push_kernel<M, true, VARIANT, false><<<grid, block, 0, s>>>(p); else collide_push_kernel<M, false, VARIANT, false><<<grid, block, 0, s>>>(p); } \
+        if (edge) { if (ibm) collide_push_kernel<M, true, true><<<grid, block, 0, s>>>(p); else collide_push_kernel<M, false, true><<<grid, block, 0, s>>>(p); } \
+        else { if (ibm) collide_push_kernel<M, true, false><<<grid, block, 0, s>>>(p); else collide_push_kernel<M, false, false><<<grid, block, 0, s>>>(p); } \
     } while (0)
     if (model == 1) FSILBM_LAUNCH(1);
     else if (model == 2) FSILBM_LAUNCH(2);
     else if (model == 3) FSILBM_LAUNCH(3);
-    else if (VARIANT == 0 && model == 11) FSILBM_LAUNCH(11);
-    else if (VARIANT == 0 && model == 14) FSILBM_LAUNCH(14);
-    else if (VARIANT == 0 && model == 15) FSILBM_LAUNCH(15);
+    else if (model == 11) FSILBM_LAUNCH(11);
+    else if (model == 14) FSILBM_LAUNCH(14);
+    else if (model == 15) FSILBM_LAUNCH(15);
     else return 1;
 #undef FSILBM_LAUNCH
+    count_launch();
     return 0;
-}
-
-int launch_collide_push(const StepParams &p, int model, int variant, cudaStream_t s)
-{
-    if (p.x_count <= 0) return 0;
-    dim3 block; int bz, by;
-    line_block(p.g.Z, block, bz, by);
-    dim3 grid((p.g.Z + bz - 1) / bz, (p.g.Y + by - 1) / by, p.x_count);
-    int rc = 0;
-    if (variant == 2) {
-        if (model == 1) collide_pull_kernel<1><<<grid, block, 0, s>>>(p);
-        else if (model == 2) collide_pull_kernel<2><<<grid, block, 0, s>>>(p);
-        else if (model == 3) collide_pull_kernel<3><<<grid, block, 0, s>>>(p);
-        else rc = 1;
-    } else if (variant == 1) rc = launch_push_variant<1>(p, model, grid, block, s);
-    else rc = launch_push_variant<0>(p, model, grid, block, s);
-    if (!rc) count_launch();
-    return rc;
 }
 
 // ---- initialise_flow, FluidDomain.f90:524-544 -----------------------------------------------------
@@ -339,11 +321,8 @@ __device__ __forceinline__ void face_cell(const Geom &g, int face, int a, int b,
 __device__ __forceinline__ size_t cell_index(const Geom &g, int x, int y, int z) { return (size_t)(x + 1) * g.plane + (size_t)y * g.Z + z; }
 
 // ---- set_boundary_conditions_, FluidDomain.f90:616-1126: one face, one thread per face node ---------
-__global__ void bc_face_kernel(const __grid_constant__ FaceParams p)
+__device__ __forceinline__ void bc_face_node(const FaceParams &p, const int a, const int b)
 {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (a >= p.na) return;
     const Geom &g = p.g;
     const int face = p.face, axis = face >> 1;
     int x, y, z, x2, y2, z2, x3, y3, z3;
@@ -437,6 +416,23 @@ __global__ void bc_face_kernel(const __grid_constant__ FaceParams p)
     }
 }
 
+__global__ void bc_face_kernel(const __grid_constant__ FaceParams p)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < p.na) bc_face_node(p, a, blockIdx.y);
+}
+
+// The two faces of one axis in one launch (blockIdx.z = 0: low face, 1: high face).  Exact as long as the two rules touch
+// disjoint cells -- each reads and writes its own three outermost layers only -- which the caller guarantees (extent >= 6).
+// Faces of different axes stay separate launches in the reference's order: they share edge lines, where a later face
+// reads what an earlier one wrote (FluidDomain.f90:622-1125).
+__global__ void bc_face_pair_kernel(const __grid_constant__ FaceParams lo, const __grid_constant__ FaceParams hi)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= lo.na) return;
+    if (blockIdx.z == 0) bc_face_node(lo, a, blockIdx.y); else bc_face_node(hi, a, blockIdx.y);
+}
+
 static inline void face_grid(const FaceParams &p, dim3 &grid, dim3 &block)
 {
     block = dim3(128, 1, 1);
@@ -448,6 +444,15 @@ void launch_bc_face(const FaceParams &p, cudaStream_t s)
     dim3 grid, block;
     face_grid(p, grid, block);
     bc_face_kernel<<<grid, block, 0, s>>>(p);
+    count_launch();
+}
+
+void launch_bc_face_pair(const FaceParams &lo, const FaceParams &hi, cudaStream_t s)
+{
+    dim3 grid, block;
+    face_grid(lo, grid, block);
+    grid.z = 2;
+    bc_face_pair_kernel<<<grid, block, 0, s>>>(lo, hi);
     count_launch();
 }
 

@@ -39,6 +39,26 @@ static double wall_seconds()
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// ---- launch trace (diagnostics; option "trace") -----------------------------------------------------------
+// A timing event is recorded on the launching stream after every launch of a step, together with the host clock; the dump
+// lists, per mark, when the device finished it and when the host issued it.  This is how the step time-lines in profiles/
+// were taken (nsys is not available on the GPU boxes).
+namespace {
+struct TraceMark { cudaEvent_t ev; const char *name; int stream; double host_s; };
+std::vector<TraceMark> g_trace;
+int g_trace_on = 0;
+cudaEvent_t g_trace_origin = nullptr;
+double g_trace_origin_host = 0.0;
+void trace_mark(cudaStream_t s, int stream_id, const char *name)
+{
+    if (!g_trace_on || g_trace.size() >= 100000) return;
+    TraceMark m{nullptr, name, stream_id, wall_seconds()};
+    if (cudaEventCreate(&m.ev) != cudaSuccess || cudaEventRecord(m.ev, s) != cudaSuccess) return;
+    g_trace.push_back(m);
+}
+}  // namespace
+#define TRACE(stream, id, name) do { if (g_trace_on) trace_mark(stream, id, name); } while (0)
+
 // ---- NCCL through dlopen (only multi-rank runs need it) ------------------------------------------------
 namespace {
 typedef struct { char internal[128]; } ncclUniqueId_t;
@@ -207,6 +227,11 @@ struct Block {
     bool early_ok = false, is_father = false;
     int early_n = 0, early_x0[MAX_BOXES]{}, early_x1[MAX_BOXES]{};
     IbmCtl *ctl = nullptr;
+    IbmCtl *ctl_pin = nullptr;                          // pinned host copy of the control block, filled by the asynchronous read-back
+    // fsilbm_ibm_interaction_force_begin has enqueued a call whose results (forces, iteration count, error bits) have not been
+    // collected by fsilbm_ibm_interaction_force_wait yet; ev_ibm_done follows its last device operation on `stream`
+    struct IbmPending { bool active = false; cudaStream_t stream = nullptr; int nbody = 0, nact = 0; bool mailbox = false; double t0 = 0, t1 = 0, t2 = 0; } ibm_pending;
+    cudaEvent_t ev_ibm_done = nullptr;
     unsigned int *ibm_barrier = nullptr;
     bool ibm_active = false;
     IbmCsr csr{};                                              // cell-centric stencil lists of the ordered IBM mode
@@ -244,7 +269,7 @@ struct Pair {
     double *buf[6][2]{}, *tbuf[6][2]{};
 };
 std::vector<std::unique_ptr<Pair>> g_pairs;
-int g_variant = 0, g_force_ghost = 0;
+int g_force_ghost = 0;
 int g_halo_timeout_s = 120;   // a neighbour this late is treated as lost (the wait kernel gives up, fsilbm_block_sync reports it)
 int g_ibm_single_launch = 1;   // 1: calculate_interaction_force as one cooperative kernel on single-rank blocks; 0: one kernel per phase
 int g_ibm_replicate = 1;       // multi-rank, ordered mode: 1 every rank runs the whole penalty iteration on all-reduced box velocities (one
@@ -253,7 +278,9 @@ int g_ibm_local = 1;           // multi-rank, ordered mode: 1 a body is iterated
                                // 0 the replicated / partial-sum forms below
 int g_ibm_force_exchange = 1;  // with ibm_local: 1 every rank passes the same bodies and gets every body's forces back (one all-reduce);
                                // 0 every rank passes only the bodies near its slab (distributed lists; the call is then collective even with none)
-int g_ibm_early_blocks = 2;    // blocks per SM of the cooperative IBM kernel when it runs beside a collide-stream update
+int g_ibm_early_blocks = 1;    // blocks per SM of the cooperative IBM kernel when it runs beside a collide-stream update
+int g_ibm_early_lean = 0;      // 1: the 48-register build of the cooperative kernel when it runs beside an update
+int g_ibm_early_total = 0;     // > 0: that grid as an absolute block count
 int g_ibm_early = 1;           // 1: the planes around the bodies are updated first and the next IBM call overlaps the rest of the update
 int g_ibm_ordered = 1;         // 1: interpolation and spreading keep the reference's serial summation order (bit-reproducible); 0: shuffles + fp64 atomics
 int g_halo_mode = 1;   // 1: edge kernels store into the neighbours' memory over NVLink (default); 0: ncclSend/ncclRecv
@@ -372,27 +399,35 @@ FaceParams face_params(Block &b, int face, double *f, const double *fA, const Ve
     return p;
 }
 
-// set_boundary_conditions_ on buffer f, faces in the reference's order (FluidDomain.f90:622-1125)
+// set_boundary_conditions_ on buffer f, faces in the reference's order (FluidDomain.f90:622-1125).  The two faces of one axis
+// touch disjoint cells (their own three outermost layers) whenever the extent is >= 6, so they share one launch; the axes
+// follow one another as in the reference, because on shared edge lines a later face reads what an earlier one wrote.
 int apply_boundary_conditions(Block &b, double *f)
 {
     VelocityField vel;
     if (int rc = velocity_field(b, b.blktime, vel)) return rc;
-    for (int face = 0; face < 6; face++) {
-        const int code = b.bc[face];
-        if (code == BCPeriodic || code == BCfluid || code == BCfluid_father) continue;   // :701-702
-        if (!owns_face(b, face)) continue;
-        int na, nb;
-        face_dims(b.g, face, na, nb);
-        if (code == BCstationary_Wall_halfway || code == BCmoving_Wall_halfway) {
-            if (!b.hw_alloc[face]) {   // :660-661: the first call allocates the stash and skips the rule
-                CK(cudaMalloc(&b.stash[face], sizeof(double) * (size_t)Q * na * nb));
-                CK(cudaMemsetAsync(b.stash[face], 0, sizeof(double) * (size_t)Q * na * nb, b.stream));
-                b.hw_alloc[face] = true;
-                continue;
+    const int Ns[3] = {b.g.XG, b.g.Y, b.g.Z};
+    for (int axis = 0; axis < 3; axis++) {
+        FaceParams fp[2];
+        int nfp = 0;
+        for (int face = 2 * axis; face < 2 * axis + 2; face++) {
+            const int code = b.bc[face];
+            if (code == BCPeriodic || code == BCfluid || code == BCfluid_father) continue;   // :701-702
+            if (!owns_face(b, face)) continue;
+            int na, nb;
+            face_dims(b.g, face, na, nb);
+            if (code == BCstationary_Wall_halfway || code == BCmoving_Wall_halfway) {
+                if (!b.hw_alloc[face]) {   // :660-661: the first call allocates the stash and skips the rule
+                    CK(cudaMalloc(&b.stash[face], sizeof(double) * (size_t)Q * na * nb));
+                    CK(cudaMemsetAsync(b.stash[face], 0, sizeof(double) * (size_t)Q * na * nb, b.stream));
+                    b.hw_alloc[face] = true;
+                    continue;
+                }
             }
+            fp[nfp++] = face_params(b, face, f, nullptr, vel);
         }
-        FaceParams p = face_params(b, face, f, nullptr, vel);
-        launch_bc_face(p, b.stream);
+        if (nfp == 2 && Ns[axis] >= 6 && (axis != 0 || b.g.X == b.g.XG)) launch_bc_face_pair(fp[0], fp[1], b.stream);
+        else for (int k = 0; k < nfp; k++) launch_bc_face(fp[k], b.stream);
     }
     CK(cudaGetLastError());
     return 0;
@@ -583,14 +618,44 @@ int fsilbm_finalize(void)
     return 0;
 }
 
+int fsilbm_trace_dump(const char *path)
+{
+    if (!path) return fail(FSILBM_ERR_ARG, "null path");
+    CK(cudaDeviceSynchronize());
+    FILE *fp = fopen(path, "w");
+    if (!fp) return fail(FSILBM_ERR_ARG, "cannot write %s", path);
+    fprintf(fp, "mark,stream,device_done_us,host_issued_us\n");
+    for (const TraceMark &m : g_trace) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_trace_origin, m.ev);
+        fprintf(fp, "%s,%d,%.3f,%.3f\n", m.name, m.stream, (double)ms * 1e3, (m.host_s - g_trace_origin_host) * 1e6);
+        cudaEventDestroy(m.ev);
+    }
+    fclose(fp);
+    g_trace.clear();
+    return 0;
+}
+
 int fsilbm_set_option(const char *key, int value)
 {
     if (!key) return fail(FSILBM_ERR_ARG, "null key");
-    if (!strcmp(key, "variant")) { if (value < 0 || value > 2) return fail(FSILBM_ERR_ARG, "variant must be 0..2"); g_variant = value; return 0; }
+    if (!strcmp(key, "trace")) {
+        if (value && !g_trace_on) {
+            CK(cudaDeviceSynchronize());
+            if (!g_trace_origin) CK(cudaEventCreate(&g_trace_origin));
+            CK(cudaEventRecord(g_trace_origin, g_stream));
+            CK(cudaEventSynchronize(g_trace_origin));
+            g_trace_origin_host = wall_seconds();
+        }
+        g_trace_on = value ? 1 : 0;
+        return 0;
+    }
     if (!strcmp(key, "force_ghost")) { g_force_ghost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_single_launch")) { g_ibm_single_launch = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_replicate")) { g_ibm_replicate = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->csr_valid = false; return 0; }
     if (!strcmp(key, "ibm_early_blocks_per_sm")) { if (value < 1 || value > 4) return fail(FSILBM_ERR_ARG, "ibm_early_blocks_per_sm must be 1..4"); g_ibm_early_blocks = value; return 0; }
+    if (!strcmp(key, "ibm_early_lean")) { g_ibm_early_lean = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "ibm_early_blocks")) { if (value < 0) return fail(FSILBM_ERR_ARG, "ibm_early_blocks must be >= 0"); g_ibm_early_total = value; return 0; }
     if (!strcmp(key, "ibm_early")) { g_ibm_early = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->early_ok = false; return 0; }
     if (!strcmp(key, "ibm_local")) { g_ibm_local = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->csr_valid = false; return 0; }
     if (!strcmp(key, "ibm_force_exchange")) { g_ibm_force_exchange = value ? 1 : 0; return 0; }
@@ -655,6 +720,8 @@ int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, d
     CK(cudaEventCreateWithFlags(&b->ev_io, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_ibm, cudaEventDisableTiming));
     CK(cudaMalloc(&b->ctl, sizeof(IbmCtl)));
+    CK(cudaMallocHost(&b->ctl_pin, sizeof(IbmCtl)));
+    CK(cudaEventCreateWithFlags(&b->ev_ibm_done, cudaEventDisableTiming));
     CK(cudaMalloc(&b->ibm_barrier, sizeof(unsigned int)));
     CK(cudaMemset(b->ibm_barrier, 0, sizeof(unsigned int)));
     CK(cudaMalloc(&b->stat, sizeof(double) * 6));
@@ -686,6 +753,7 @@ int fsilbm_block_destroy(fsilbm_handle h)
     cudaEventDestroy(b->ev_early); cudaStreamDestroy(b->ibm_main_stream);
     cudaEventDestroy(b->ev_macro); cudaEventDestroy(b->ev_io);
     cudaFree(b->bodies_dev); cudaFree(b->lead_dev); cudaFree(b->tol2); cudaFree(b->ctl); cudaFree(b->ibm_barrier);
+    cudaFreeHost(b->ctl_pin); cudaEventDestroy(b->ev_ibm_done);
     cudaFree(b->mk_dev); cudaFree(b->force_dev); cudaFreeHost(b->mk_pin); cudaFreeHost(b->force_pin);
     cudaEventDestroy(b->ev_ibm); cudaStreamDestroy(b->ibm_stream);
     cudaFree(b->csr.count); cudaFree(b->csr.off); cudaFree(b->csr.entry); cudaFree(b->csr_scan_tmp); cudaFree(b->tol_partial);
@@ -882,6 +950,8 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
     if (!bp) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
     Block &b = *bp;
     if (!b.initialised) return fail(FSILBM_ERR_ARG, "block %d not initialised", h);
+    // an interaction-force call still in flight on another stream: the update reads its box fields, so it follows it ON THE DEVICE
+    if (b.ibm_pending.active && b.ibm_pending.stream != b.stream) CK(cudaStreamWaitEvent(b.stream, b.ev_ibm_done, 0));
     const Geom &g = b.g;
     const double *fA = b.f[b.cur];
     double *fB = b.f[b.cur ^ 1];
@@ -926,12 +996,11 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
     const bool multi = g_nccl.nranks > 1 && g_nccl.comm && g.X != g.XG;   // a block cut into x-slabs (sons stay whole on one rank)
     const bool ghost = multi || g_force_ghost;
     p.wrap_x = ghost ? 0 : 1;
-    const int variant = ((g_variant == 2 && (ghost || b.ibm_active)) || b.model >= 11) ? 0 : g_variant;
     // Early IBM (see Block::ev_early): planes A = [box - 2, box + 2) of every stencil box first, then the rest.  After A the
     // streamed populations of the planes [box - 1, box + 1) are final -- provided no face kernel, halo or x-wrap touches them,
     // hence the conditions below -- and the next interaction-force call may start while the rest is still being updated.
     int nA = 0, A0[MAX_BOXES], A1[MAX_BOXES], V0[MAX_BOXES], V1[MAX_BOXES];
-    const int lower = multi ? 1 : 0, upper = multi ? g.X - 1 : g.X;   // planes of the bulk launch (multi: the edge planes go first anyway)
+    const int lower = multi ? 1 : 0, upper = multi ? g.X - 1 : g.X;   // planes between the edge planes (multi: those go first anyway)
     bool early = g_ibm_early && b.ibm_active && p.boxes.n > 0 && b.model < 11 && !b.is_father && (multi ? b.halo.enabled : !ghost);
     bool edge_dep = false;   // slab runs: a box reaches the slab's edge planes, whose final values also need the neighbour's halo
     if (early) {
@@ -968,36 +1037,47 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
         }
     }
     b.early_ok = false;
-    // planes [lower, upper): A first when early; after_A (slab runs: the halo unpack, when a box depends on the edge planes) goes
-    // between A and the event
-    auto bulk = [&](StepParams &q, const std::function<void()> &after_A) -> int {
-        if (!early) {
-            q.x_begin = lower; q.x_count = upper - lower;
-            return launch_collide_push(q, b.model, variant, b.stream);
-        }
-        for (int i = 0; i < nA; i++) { q.x_begin = A0[i]; q.x_count = A1[i] - A0[i]; if (launch_collide_push(q, b.model, variant, b.stream)) return 1; }
-        if (after_A) after_A();
-        if (cudaEventRecord(b.ev_early, b.stream) != cudaSuccess) return 1;
-        // the rest holds no box cell (A covers every box with two planes to spare): the IBM-free instantiation of the kernel does it
-        StepParams rest = q;
-        rest.boxes.n = 0;
+    // The launch list (StepParams::seg_*): [edge planes of a slab] [planes A around the bodies] | [the rest].  Without early IBM
+    // the whole update is ONE launch; with it, two: everything up to A, then -- event ev_early recorded in between -- the rest,
+    // which holds no box cell (A covers every box with two planes to spare) and takes the IBM-free instantiation.
+    auto planes_first = [&](StepParams &q) {
+        if (multi) { step_add_planes(q, 0, 1); if (g.X > 1) step_add_planes(q, g.X - 1, 1); }
+        if (early) for (int i = 0; i < nA; i++) step_add_planes(q, A0[i], A1[i] - A0[i]);
+        else step_add_planes(q, lower, upper - lower);
+    };
+    auto planes_rest = [&](StepParams &q) {
         int at = lower;
         for (int i = 0; i <= nA; i++) {
             const int end = i < nA ? A0[i] : upper;
-            if (end > at) { rest.x_begin = at; rest.x_count = end - at; if (launch_collide_push(rest, b.model, variant, b.stream)) return 1; }
+            step_add_planes(q, at, end - at);
             if (i < nA) at = A1[i];
         }
+    };
+    auto note_early = [&]() {
         b.early_n = nA;
         for (int i = 0; i < nA; i++) { b.early_x0[i] = V0[i] + g.xOffset; b.early_x1[i] = V1[i] + g.xOffset; }
         b.early_ok = true;
-        return 0;
     };
+    auto refuse = [&]() { return fail(FSILBM_ERR_MODEL, "collision model %d", b.model); };
     if (!multi) {
-        if (bulk(p, nullptr)) return fail(FSILBM_ERR_MODEL, "collision model %d", b.model);
+        StepParams q = p;
+        planes_first(q);
+        TRACE(b.stream, 0, "step_begin");
+        if (launch_collide_push(q, b.model, b.stream)) return refuse();
+        TRACE(b.stream, 0, early ? "collide_A" : "collide_all");
+        if (early) {
+            CK(cudaEventRecord(b.ev_early, b.stream));
+            StepParams rest = p;
+            rest.boxes.n = 0;
+            planes_rest(rest);
+            if (launch_collide_push(rest, b.model, b.stream)) return refuse();
+            TRACE(b.stream, 0, "collide_rest");
+            note_early();
+        }
         if (ghost) launch_wrap_x(g, fB, b.stream);
     } else if (b.halo.enabled) {
-        // Edge planes first: their kernel IS the transfer (peer stores over NVLink + arrival flag); then the
-        // interior on the same stream; then wait for the neighbours' flags and fold the received planes in.
+        // The edge planes lead the launch list: their CTAs ARE the transfer (peer stores over NVLink + arrival flag raised by the
+        // last CTA of the plane).  Afterwards a small kernel waits for the neighbours' flags and folds the received planes in.
         Block::Halo &h = b.halo;
         h.step++;
         const int par = (int)(h.step & 1);
@@ -1005,32 +1085,49 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
         e.step = h.step;
         if (h.left >= 0) { e.halo_lo = halo_slot_ptr(h.peer_left, h.slot_bytes, 1, par); e.sig_lo = halo_flag(h.peer_left, 1, par); }
         if (h.right >= 0) { e.halo_hi = halo_slot_ptr(h.peer_right, h.slot_bytes, 0, par); e.sig_hi = halo_flag(h.peer_right, 0, par); }
-        e.x_begin = 0; e.x_count = 1; e.cta_counter = h.counters;
-        launch_collide_push(e, b.model, variant, b.stream);
-        if (g.X > 1) { e.x_begin = g.X - 1; e.cta_counter = h.counters + 1; launch_collide_push(e, b.model, variant, b.stream); }
+        e.cta_counter = h.counters;
+        planes_first(e);
+        TRACE(b.stream, 0, "step_begin");
+        if (launch_collide_push(e, b.model, b.stream)) return refuse();
+        TRACE(b.stream, 0, early ? "collide_edges_A" : "collide_all");
         HaloUnpackParams u{};
         u.g = g; u.fB = fB; u.step = h.step; u.err = h.err; u.timeout_ns = (unsigned long long)g_halo_timeout_s * 1000000000ull;
         if (h.left >= 0) { u.recv_lo = halo_slot_ptr(h.region, h.slot_bytes, 0, par); u.flag_lo = halo_flag(h.region, 0, par); }
         if (h.right >= 0) { u.recv_hi = halo_slot_ptr(h.region, h.slot_bytes, 1, par); u.flag_hi = halo_flag(h.region, 1, par); }
-        // a box across the interface: its planes are final only once the neighbour's populations are folded in, so the unpack
-        // (the neighbour's edge kernel is the first launch of its update) goes right after A instead of after everything
-        bool unpacked = false;
-        if (g.X > 2) bulk(p, [&] { if (edge_dep) { launch_halo_unpack(u, b.stream); unpacked = true; } });
-        if (!unpacked) launch_halo_unpack(u, b.stream);
+        if (early) {
+            // a box across the interface: its planes are final only once the neighbour's populations are folded in, so the unpack
+            // (the neighbour's edge planes lead its launch too) goes before the event instead of after everything
+            if (edge_dep) { launch_halo_unpack(u, b.stream); TRACE(b.stream, 0, "halo_unpack"); }
+            CK(cudaEventRecord(b.ev_early, b.stream));
+            StepParams rest = p;
+            rest.boxes.n = 0;
+            planes_rest(rest);
+            if (launch_collide_push(rest, b.model, b.stream)) return refuse();
+            TRACE(b.stream, 0, "collide_rest");
+            note_early();
+            if (!edge_dep) { launch_halo_unpack(u, b.stream); TRACE(b.stream, 0, "halo_unpack"); }
+        } else {
+            launch_halo_unpack(u, b.stream);
+            TRACE(b.stream, 0, "halo_unpack");
+        }
     } else {
         // NCCL transport: edge planes first, then the exchange on its own stream overlapped with the interior update
-        p.x_begin = 0; p.x_count = 1;
-        launch_collide_push(p, b.model, variant, b.stream);
-        if (g.X > 1) { p.x_begin = g.X - 1; p.x_count = 1; launch_collide_push(p, b.model, variant, b.stream); }
+        StepParams e = p;
+        step_add_planes(e, 0, 1);
+        if (g.X > 1) step_add_planes(e, g.X - 1, 1);
+        if (launch_collide_push(e, b.model, b.stream)) return refuse();
         CK(cudaEventRecord(b.ev_edge, b.stream));
         CK(cudaStreamWaitEvent(b.comm_stream, b.ev_edge, 0));
         if (int rc = halo_exchange(b, fB, b.comm_stream)) return rc;
         CK(cudaEventRecord(b.ev_comm, b.comm_stream));
-        if (g.X > 2) { p.x_begin = 1; p.x_count = g.X - 2; launch_collide_push(p, b.model, variant, b.stream); }
+        StepParams in = p;
+        step_add_planes(in, 1, g.X - 2);
+        if (launch_collide_push(in, b.model, b.stream)) return refuse();
         CK(cudaStreamWaitEvent(b.stream, b.ev_comm, 0));
     }
     CK(cudaGetLastError());
     if (int rc = apply_boundary_conditions(b, fB)) return rc;   // LBMBlockComm.f90:303
+    TRACE(b.stream, 0, "faces");
     b.cur ^= 1;
     b.ibm_active = false;
     return 0;
@@ -1443,16 +1540,17 @@ int ibm_exchange_shared_boxes(const IbmBoxes &bx, const std::vector<int> &kept, 
 
 extern "C" {
 
-int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, const double *const *Exyz, const double *const *Evel,
-                                 const double *const *Ea, double *const *Eforce, const int *restencil, double dt, int ntolLBM,
-                                 double dtolLBM, const int rootBC[6], int *iterLBM_out)
+int fsilbm_ibm_interaction_force_begin(fsilbm_handle h, int nbody, const int *nelmts, const double *const *Exyz, const double *const *Evel,
+                                       const double *const *Ea, const int *restencil, double dt, int ntolLBM,
+                                       double dtolLBM, const int rootBC[6])
 {
     Block *bp = get(h);
     if (!bp) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
     Block &b = *bp;
-    if (nbody < 0 || (nbody > 0 && (!nelmts || !Exyz || !Evel || !Ea || !Eforce || !restencil || !rootBC)))
+    if (nbody < 0 || (nbody > 0 && (!nelmts || !Exyz || !Evel || !Ea || !restencil || !rootBC)))
         return fail(FSILBM_ERR_ARG, "null argument");
-    if (iterLBM_out) *iterLBM_out = 0;
+    if (b.ibm_pending.active)
+        return fail(FSILBM_ERR_ARG, "fsilbm_ibm_interaction_force_begin: the previous call on block %d has not been collected (fsilbm_ibm_interaction_force_wait)", h);
     const Geom &g = b.g;
     cudaStream_t s = b.stream, s2 = b.ibm_stream;
     const bool multi = g_nccl.nranks > 1 && g_nccl.comm && g.X != g.XG;   // this block is split into x-slabs
@@ -1462,6 +1560,7 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
     // redundantly -- bit-identically -- by their participants; the loop control is all-reduced (two numbers per iteration).
     const bool local = multi && ordered && g_ibm_local;
     const bool lists_replicated = g_ibm_force_exchange != 0;   // every rank passes the same bodies and wants every force back
+    b.ibm_pending = Block::IbmPending();
     if (nbody == 0 && !(local && !lists_replicated)) { b.ibm_active = false; return 0; }   // Solidbody.f90:891
     static const bool want_prof = getenv("FSILBM_IBM_PROFILE") != nullptr;
     const double tp0 = want_prof ? wall_seconds() : 0.0;
@@ -1662,6 +1761,7 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         // not queue behind the update either -- the ranks that do iterate bodies early are then not held up by this one
         s = b.ibm_main_stream;
     }
+    TRACE(s2, 1, "ibm_upload_stencils");
     CK(cudaEventRecord(b.ev_ibm, s2));
     CK(cudaStreamWaitEvent(s, b.ev_ibm, 0));
 
@@ -1710,7 +1810,24 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         }
         lp.phase_start[nphase] = pos;
         for (int k = 0; k < nact; k++) lp.phase_of_body[k] = rank_in_group[k];
-        if (launch_ibm_loop(lp, max_markers, use_early ? g_ibm_early_blocks : 0, s)) {
+        // Grid of the cooperative kernel when it shares the SMs with a running update: every one of its blocks takes a CTA slot
+        // from that update for as long as the iteration lasts, and the iteration is latency-bound -- its length grows far slower
+        // than 1/blocks -- so the smallest grid that still finishes in time costs the update least.  Bodies that do not move
+        // (no re-stencil) leave the host nothing to do between two calls: the iteration may take most of the update, one block
+        // per ~110 markers (74 blocks for the 8192-marker plate: 1.683 -> 1.636 ms per step on plate512).  Moving/flexible bodies
+        // have the host's structural solve waiting for the forces: they keep ibm_early_blocks_per_sm blocks per SM.
+        int early_total = 0;
+        if (use_early) {
+            early_total = g_ibm_early_total;
+            bool any_re = false;
+            for (int ib : act) any_re = any_re || re[ib];
+            if (early_total == 0 && !any_re) {
+                static int sms = 0;
+                if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g_device);
+                early_total = std::max(sms / 4, std::min(2 * sms, (max_markers + 109) / 110));
+            }
+        }
+        if (launch_ibm_loop(lp, max_markers, use_early ? g_ibm_early_blocks : 0, early_total, use_early ? g_ibm_early_lean : 0, s)) {
             cudaGetLastError();
             if (mailbox) return fail(FSILBM_ERR_CUDA, "cooperative launch of the IBM iteration failed");   // the other ranks are in the mailbox protocol
             single = false;   // no cooperative launch: take the phase-by-phase path
@@ -1755,6 +1872,7 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         else for (int k = 0; k < nact; k++) launch_ibm_spread(views[k], bx, invh3, s);
     }
     CK(cudaGetLastError());
+    TRACE(s, use_early ? 2 : 0, "ibm_iteration");
     if (local && lists_replicated && b.marker_total) {
         // every rank wants every body's forces: the leader's values plus zeros from everybody else (exact)
         for (int k = 0; k < nact; k++)
@@ -1762,19 +1880,39 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         NCK(g_nccl.AllReduce(b.force_dev, b.force_dev, 3 * b.marker_total, kNcclFloat64, kNcclSum, g_nccl.comm, s));
     }
 
-    // -- results to the host
-    IbmCtl ctl1;
-    CK(cudaMemcpyAsync(&ctl1, b.ctl, sizeof(IbmCtl), cudaMemcpyDeviceToHost, s));
+    // -- results towards the host: control block and marker forces into pinned memory, asynchronously; the event marks the end of
+    //    everything this call put on the device.  Nothing here waits: fsilbm_block_collide_stream may be enqueued right away (it
+    //    waits for the event on the device), the host collects the results with fsilbm_ibm_interaction_force_wait.
+    CK(cudaMemcpyAsync(b.ctl_pin, b.ctl, sizeof(IbmCtl), cudaMemcpyDeviceToHost, s));
     if (b.marker_total) CK(cudaMemcpyAsync(b.force_pin, b.force_dev, sizeof(double) * 3 * b.marker_total, cudaMemcpyDeviceToHost, s));
-    const double tp2 = want_prof ? wall_seconds() : 0.0;
-    CK(cudaStreamSynchronize(s));
+    TRACE(s, use_early ? 2 : 0, "ibm_forces_d2h");
+    CK(cudaEventRecord(b.ev_ibm_done, s));
+    b.ibm_pending.active = true; b.ibm_pending.stream = s; b.ibm_pending.nbody = nbody; b.ibm_pending.nact = nact; b.ibm_pending.mailbox = mailbox;
+    b.ibm_pending.t0 = tp0; b.ibm_pending.t1 = tp1; b.ibm_pending.t2 = want_prof ? wall_seconds() : 0.0;
+    b.ibm_active = bx.n > 0;
+    return 0;
+}
+
+int fsilbm_ibm_interaction_force_wait(fsilbm_handle h, int nbody, double *const *Eforce, int *iterLBM_out)
+{
+    Block *bp = get(h);
+    if (!bp) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    Block &b = *bp;
+    if (iterLBM_out) *iterLBM_out = 0;
+    if (!b.ibm_pending.active) return 0;   // nothing was enqueued (no body: Solidbody.f90:891)
+    if (nbody != b.ibm_pending.nbody || (nbody > 0 && !Eforce)) return fail(FSILBM_ERR_ARG, "fsilbm_ibm_interaction_force_wait: %d bodies were passed to _begin", b.ibm_pending.nbody);
+    static const bool want_prof = getenv("FSILBM_IBM_PROFILE") != nullptr;
+    const int me = g_nccl.rank;
+    CK(cudaEventSynchronize(b.ev_ibm_done));
+    b.ibm_pending.active = false;
+    const IbmCtl ctl1 = *b.ctl_pin;
     for (int ib = 0; ib < nbody; ib++) memcpy(Eforce[ib], b.force_pin + b.f_off[ib], sizeof(double) * 3 * (size_t)b.bodies[ib].n);
     if (want_prof) {
         const double tp3 = wall_seconds();
-        b.ibm_host_t[0] += tp1 - tp0; b.ibm_host_t[1] += tp2 - tp1; b.ibm_host_t[2] += tp3 - tp2;
+        b.ibm_host_t[0] += b.ibm_pending.t1 - b.ibm_pending.t0; b.ibm_host_t[1] += b.ibm_pending.t2 - b.ibm_pending.t1; b.ibm_host_t[2] += tp3 - b.ibm_pending.t2;
         if ((b.ibm_prof_calls % 100) == 20) {
-            fprintf(stderr, "[ibm host, us per call] boxes %.1f  enqueue %.1f  wait %.1f  (%d of %d bodies active)\n", b.ibm_host_t[0] * 1e4, b.ibm_host_t[1] * 1e4,
-                    b.ibm_host_t[2] * 1e4, nact, nbody);
+            fprintf(stderr, "[ibm host, us per call] boxes %.1f  enqueue %.1f  begin->collected %.1f  (%d of %d bodies active)\n", b.ibm_host_t[0] * 1e4, b.ibm_host_t[1] * 1e4,
+                    b.ibm_host_t[2] * 1e4, b.ibm_pending.nact, nbody);
             b.ibm_host_t[0] = b.ibm_host_t[1] = b.ibm_host_t[2] = 0.0;
         }
         if (!b.ibm_prof) b.ibm_prof_calls++;
@@ -1784,17 +1922,27 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, 
         cudaMemcpy(hp, b.ibm_prof, sizeof(hp), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[ibm_loop phases, us]");
         for (unsigned long long k = 1; k < hp[0] && k < 63; k++) fprintf(stderr, " %.1f", (double)(hp[1 + k] - hp[k]) * 1e-3);
-        fprintf(stderr, "  (ncell %lld)\n", (long long)bx.ncell);
+        fprintf(stderr, "  (ncell %lld)\n", (long long)b.boxes.ncell);
     }
-    if (mailbox) b.halo.ctl_seq += (unsigned long long)ctl1.iter;   // the same count on every rank
+    if (b.ibm_pending.mailbox) b.halo.ctl_seq += (unsigned long long)ctl1.iter;   // the same count on every rank
     if (ctl1.err) b.csr_valid = false;
     if (ctl1.err & 8) return fail(FSILBM_ERR_COMM, "IBM loop control: a rank did not report within %d s (rank %d)", g_halo_timeout_s, me);
     if (ctl1.err & 1) return fail(FSILBM_ERR_STENCIL, "index out of xmin/xmax bound (Solidbody.f90:850,861)");
     if (ctl1.err & 4) return fail(FSILBM_ERR_STENCIL, "internal: marker stencil outside its IBM box");
     if (ctl1.err & 2) return fail(FSILBM_ERR_NAN, "Nan found in PenaltyForce (Solidbody.f90:1029)");
     if (iterLBM_out) *iterLBM_out = ctl1.iter;
-    b.ibm_active = bx.n > 0;
     return 0;
+}
+
+// calculate_interaction_force as one blocking call (Solidbody.f90:869-918): _begin + _wait
+int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts, const double *const *Exyz, const double *const *Evel,
+                                 const double *const *Ea, double *const *Eforce, const int *restencil, double dt, int ntolLBM,
+                                 double dtolLBM, const int rootBC[6], int *iterLBM_out)
+{
+    if (iterLBM_out) *iterLBM_out = 0;
+    if (nbody > 0 && !Eforce) return fail(FSILBM_ERR_ARG, "null argument");
+    if (int rc = fsilbm_ibm_interaction_force_begin(h, nbody, nelmts, Exyz, Evel, Ea, restencil, dt, ntolLBM, dtolLBM, rootBC)) return rc;
+    return fsilbm_ibm_interaction_force_wait(h, nbody, Eforce, iterLBM_out);
 }
 
 int fsilbm_ibm_body_status(fsilbm_handle h, int nbody, int *status)

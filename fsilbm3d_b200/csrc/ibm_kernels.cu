@@ -753,7 +753,10 @@ __device__ __forceinline__ void prof_stamp(const IbmLoopParams &p, int &k)
     k++;
 }
 
-__global__ void __launch_bounds__(256, 4) ibm_loop_kernel(const __grid_constant__ IbmLoopParams p)
+// MINB = 4: 64 registers per thread; MINB = 5: 48 (a few spills) -- a 256-thread block then takes exactly the register space
+// of one 96-register CTA of the collide kernel it runs beside.
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) ibm_loop_kernel(const __grid_constant__ IbmLoopParams p)
 {
     unsigned int epoch = 0;
     int pk = 0;
@@ -903,7 +906,7 @@ int ibm_loop_max_blocks()
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ibm_loop_kernel, 256, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ibm_loop_kernel<4>, 256, 0);
         max_blocks = sms * (per_sm > 0 ? per_sm : 1);
     }
     return max_blocks;
@@ -911,7 +914,7 @@ int ibm_loop_max_blocks()
 
 // blocks_per_sm > 0: the launch shares the SMs with a running collide-stream kernel (early IBM); one block per SM leaves that
 // kernel three of its four CTA slots (its 125 registers per thread fill the register file with four)
-int launch_ibm_loop(const IbmLoopParams &p, int max_markers, int blocks_per_sm, cudaStream_t s)
+int launch_ibm_loop(const IbmLoopParams &p, int max_markers, int blocks_per_sm, int blocks_total, int lean, cudaStream_t s)
 {
     int max_blocks = ibm_loop_max_blocks();
     if (blocks_per_sm > 0) {
@@ -920,6 +923,7 @@ int launch_ibm_loop(const IbmLoopParams &p, int max_markers, int blocks_per_sm, 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms > 0 && sms * blocks_per_sm < max_blocks) max_blocks = sms * blocks_per_sm;
     }
+    if (blocks_total > 0 && blocks_total < max_blocks) max_blocks = blocks_total;
     int want = (max_markers + 7) / 8;           // one warp per marker of the largest phase
     long long cells = (p.boxes.ncell + 255) / 256;
     if (p.ordered) want = (max_markers + MARKERS_PER_BLOCK - 1) / MARKERS_PER_BLOCK;   // 16 lanes per marker, one thread per box cell
@@ -927,7 +931,7 @@ int launch_ibm_loop(const IbmLoopParams &p, int max_markers, int blocks_per_sm, 
     int blocks = want < 1 ? 1 : (want > max_blocks ? max_blocks : want);
     if (cudaMemsetAsync(p.barrier, 0, sizeof(unsigned int), s) != cudaSuccess) return 1;   // the barrier counts up from zero in every launch
     void *args[] = {(void *)&p};
-    cudaError_t e = cudaLaunchCooperativeKernel((void *)ibm_loop_kernel, dim3(blocks), dim3(256), args, 0, s);
+    cudaError_t e = cudaLaunchCooperativeKernel(lean ? (void *)ibm_loop_kernel<5> : (void *)ibm_loop_kernel<4>, dim3(blocks), dim3(256), args, 0, s);
     if (e != cudaSuccess) return 1;
     count_launch();
     return 0;

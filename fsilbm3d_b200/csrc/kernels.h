@@ -33,11 +33,18 @@ struct IbmBoxes {
     double *force;           // [3][ncell]
 };
 
+// One launch of the fused step covers a list of x-plane ranges, taken in list order: blockIdx.z walks the ranges one after the
+// other.  CTAs are dispatched in blockIdx order, so the planes listed first finish first -- the slab's edge planes (whose
+// stores ARE the halo transfer) and the planes around the immersed bodies (which the next interaction-force call waits for)
+// go to the front of the list and the whole update is still one or two launches.
+constexpr int MAX_SEG = 2 * MAX_BOXES + 4;
+
 struct StepParams {
     Geom g;
     const double *fA;
     double *fB;
-    int x_begin, x_count;   // local planes processed by this launch
+    int nseg;                 // ranges of local planes processed by this launch, in this order
+    int seg_begin[MAX_SEG], seg_count[MAX_SEG];
     int wrap_x;             // 1: streaming wraps in x inside the slab (single rank, FluidDomain.f90:1603-1604,1618-1619)
     CollideConsts cc;
     double hF[3];           // 0.5d0*volumeForce(k)*dh, FluidDomain.f90:1137-1139
@@ -45,8 +52,9 @@ struct StepParams {
     IbmBoxes boxes;
     // Slab halo over NVLink peer memory (edge-plane launches of a multi-GPU run only; all null otherwise).
     // halo_hi: the right neighbour's receive planes [5][Y][Z] for the populations with ex=+1 leaving local
-    // plane X-1; halo_lo: the left neighbour's receive planes for ex=-1 leaving plane 0.  The last CTA of the
-    // launch publishes `step` to sig_hi / sig_lo (flags in the neighbours' memory) after a system fence.
+    // plane X-1; halo_lo: the left neighbour's receive planes for ex=-1 leaving plane 0.  The last CTA of an EDGE PLANE
+    // publishes `step` to sig_hi / sig_lo (flags in the neighbours' memory) after a system fence; cta_counter[0] counts the
+    // CTAs of plane 0, cta_counter[1] those of plane X-1.
     double *halo_hi, *halo_lo;
     unsigned long long *sig_hi, *sig_lo;
     unsigned int *cta_counter;
@@ -101,10 +109,12 @@ struct FieldParams {
 
 // ---- launchers (fluid_kernels.cu) ---------------------------------------------------------------
 void upload_mrt(int slot, const double *M_COLLID, const double *M_FORCE, cudaStream_t s);
-int launch_collide_push(const StepParams &p, int model, int variant, cudaStream_t s);
+int launch_collide_push(const StepParams &p, int model, cudaStream_t s);
+void step_add_planes(StepParams &p, int begin, int count);   // appends a range of local planes to the launch list
 void launch_initialise(const Geom &g, double *f, const VelocityField &vel, double denIn, cudaStream_t s);
 void launch_macro_full(const Geom &g, const double *f, const double hF[3], double *den, double *uuu, cudaStream_t s, const IbmBoxes *boxes = nullptr);
 void launch_bc_face(const FaceParams &p, cudaStream_t s);
+void launch_bc_face_pair(const FaceParams &lo, const FaceParams &hi, cudaStream_t s);   // the two faces of one axis in one launch
 void launch_stash_face(const FaceParams &p, cudaStream_t s);
 void launch_layer2_face(const FaceParams &p, cudaStream_t s);
 void launch_init_layer2(const FaceParams &p, cudaStream_t s);
@@ -196,7 +206,7 @@ struct IbmLoopParams {        // the single-launch form of calculate_interaction
 };
 // a rank that iterates no body still takes part in the loop-control exchange (one small block)
 void launch_ibm_ctl_only(const IbmCtlExchange &xc, int ntol, double dtol, double Uref, IbmCtl *ctl, cudaStream_t s);
-int launch_ibm_loop(const IbmLoopParams &p, int max_markers, int blocks_per_sm, cudaStream_t s);
+int launch_ibm_loop(const IbmLoopParams &p, int max_markers, int blocks_per_sm, int blocks_total, int lean, cudaStream_t s);
 int ibm_loop_max_blocks();
 
 // build of IbmCsr after the stencils are known: count -> scan -> fill -> per-cell sort

@@ -166,16 +166,18 @@ class LBMBlock:
         check(lib().fsilbm_block_stream(self._h, C.byref(p)))
         return p.value or 0
 
-    def calculate_interaction_force(self, bodies, rootBC=None, dt: Optional[float] = None, collective: bool = False) -> int:
-        """calculate_interaction_force, Solidbody.f90:869; returns iterLBM.  `collective`: slab run in which every rank
-        passes only the bodies near its slab (option ibm_force_exchange = 0); the call is then made even with none."""
+    def calculate_interaction_force_begin(self, bodies, rootBC=None, dt: Optional[float] = None, collective: bool = False) -> None:
+        """First half of calculate_interaction_force (Solidbody.f90:869): everything is enqueued on the device, nothing is waited
+        for.  collide_stream() may follow at once (it waits for the box fields on the device); the marker forces and iterLBM are
+        collected by calculate_interaction_force_wait().  `collective`: slab run in which every rank passes only the bodies near
+        its slab (option ibm_force_exchange = 0); the call is then made even with none."""
         n = len(bodies)
         rootBC = self.BndConds if rootBC is None else rootBC
+        self._ibm_bodies = list(bodies)
         if n == 0:
-            it = C.c_int(0)
-            check(lib().fsilbm_ibm_interaction_force(self._h, 0, None, None, None, None, None, None, self.dh if dt is None else dt,
-                                                     self.flow.ntolLBM if collective else 0, self.flow.dtolLBM, (C.c_int * 6)(*rootBC), C.byref(it)))
-            return it.value
+            check(lib().fsilbm_ibm_interaction_force_begin(self._h, 0, None, None, None, None, None, self.dh if dt is None else dt,
+                                                           self.flow.ntolLBM if collective else 0, self.flow.dtolLBM, (C.c_int * 6)(*rootBC)))
+            return
         nel = (C.c_int * n)(*[b.v_nelmts for b in bodies])
         vp = C.c_void_p
         for b in bodies:
@@ -183,14 +185,26 @@ class LBMBlock:
         ex = (vp * n)(*[b.v_Exyz.ctypes.data for b in bodies])
         ev = (vp * n)(*[b.v_Evel.ctypes.data for b in bodies])
         ea = (vp * n)(*[b.v_Ea.ctypes.data for b in bodies])
-        ef = (vp * n)(*[b.v_Eforce.ctypes.data for b in bodies])
         re = (C.c_int * n)(*[1 if (b.v_move == 1 or b.iBodyModel == 2 or b.count_Interp == 0) else 0 for b in bodies])
+        check(lib().fsilbm_ibm_interaction_force_begin(self._h, n, nel, ex, ev, ea, re, self.dh if dt is None else dt,
+                                                       self.flow.ntolLBM, self.flow.dtolLBM, (C.c_int * 6)(*rootBC)))
+
+    def calculate_interaction_force_wait(self) -> int:
+        """Second half: waits for the call enqueued by calculate_interaction_force_begin, fills v_Eforce of its bodies, returns iterLBM."""
+        bodies = getattr(self, "_ibm_bodies", [])
+        n = len(bodies)
         it = C.c_int(0)
-        check(lib().fsilbm_ibm_interaction_force(self._h, n, nel, ex, ev, ea, ef, re, self.dh if dt is None else dt,
-                                                 self.flow.ntolLBM, self.flow.dtolLBM, (C.c_int * 6)(*rootBC), C.byref(it)))
+        ef = (C.c_void_p * n)(*[b.v_Eforce.ctypes.data for b in bodies]) if n else None
+        check(lib().fsilbm_ibm_interaction_force_wait(self._h, n, ef, C.byref(it)))
         for b in bodies:
             b.count_Interp = 1
+        self._ibm_bodies = []
         return it.value
+
+    def calculate_interaction_force(self, bodies, rootBC=None, dt: Optional[float] = None, collective: bool = False) -> int:
+        """calculate_interaction_force, Solidbody.f90:869, as one blocking call; returns iterLBM."""
+        self.calculate_interaction_force_begin(bodies, rootBC, dt, collective)
+        return self.calculate_interaction_force_wait()
 
     def download_stencil(self, body_index: int, nelmts: int):
         Ei = np.empty((nelmts, 12), dtype=np.int16)

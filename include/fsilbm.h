@@ -66,8 +66,11 @@ long long fsilbm_launch_count(void);
  * fsilbm_block_collide_stream updates the x-planes around the bodies first, so the next interaction-force call needs to wait
  * for those planes only; option "ibm_early" = 0 turns it off).  Diagnostics/tests. */
 long long fsilbm_ibm_early_count(void);
+/* Diagnostics: with option "trace" = 1 a timing event is recorded after every launch of a step; this writes the marks
+ * (name, stream, device completion time, host issue time; microseconds) as CSV and clears them. */
+int fsilbm_trace_dump(const char *path);
 /* Tuning/testing switches, no reference counterpart.
- *   "variant"                 0 push kernel (default), 1 push with streaming stores, 2 pull (fully periodic blocks only; kernel sweep)
+ *   "trace"                   1 = record the launch marks that fsilbm_trace_dump writes
  *   "force_ghost"             1 = stream through the ghost planes even on one rank (tests the slab path)
  *   "halo"                    1 (default) peer-memory halo over NVLink, 0 ncclSend/ncclRecv (see fsilbm_block_halo_transport)
  *   "halo_timeout_s"          how long a rank waits for a neighbour (halo flags, IBM loop-control mailbox) before it reports
@@ -78,7 +81,8 @@ long long fsilbm_ibm_early_count(void);
  *                             exchanged through peer memory), 0 one kernel per phase (slab runs: ncclAllReduce of the loop control)
  *   "ibm_early"               1 (default) fsilbm_block_collide_stream updates the x-planes around the bodies first so that the next
  *                             fsilbm_ibm_interaction_force runs beside the rest of the update, 0 strictly one after the other
- *   "ibm_early_blocks_per_sm" 1..4 (default 2): size of the cooperative IBM grid when it shares the SMs with that update
+ *   "ibm_early_blocks_per_sm" 1..4 (default 1): size of the cooperative IBM grid when it shares the SMs with that update
+ *   "ibm_early_blocks"        > 0: that grid as an absolute number of blocks instead (0 = use the per-SM figure)
  *   "ibm_local", "ibm_force_exchange", "ibm_replicate"   forms of the IBM on slab runs, see fsilbm_ibm_body_status below */
 int fsilbm_set_option(const char *key, int value);
 
@@ -193,6 +197,18 @@ int fsilbm_ibm_interaction_force(fsilbm_handle h, int nbody, const int *nelmts,
                                  const double *const *Ea, double *const *Eforce,
                                  const int *restencil, double dt, int ntolLBM, double dtolLBM,
                                  const int rootBC[6], int *iterLBM_out);
+/* The same call in two halves, so that the host never stands between the interaction force and the update that consumes it:
+ *   _begin  enqueues everything on the device (marker upload, stencils, penalty iteration, spreading, asynchronous read-back of
+ *           v_Eforce into pinned memory) and returns at once;
+ *   fsilbm_block_collide_stream may then be called immediately -- it waits for the box fields ON THE DEVICE;
+ *   _wait   blocks until the read-back has landed, copies v_Eforce out and reports iterLBM and the reference's fatal
+ *           conditions (stencil out of the domain, NaN).  Every _begin is followed by exactly one _wait before the next _begin.
+ * fsilbm_ibm_interaction_force above is _begin followed by _wait. */
+int fsilbm_ibm_interaction_force_begin(fsilbm_handle h, int nbody, const int *nelmts,
+                                       const double *const *Exyz, const double *const *Evel,
+                                       const double *const *Ea, const int *restencil,
+                                       double dt, int ntolLBM, double dtolLBM, const int rootBC[6]);
+int fsilbm_ibm_interaction_force_wait(fsilbm_handle h, int nbody, double *const *Eforce, int *iterLBM_out);
 /* Slab runs (x-slab decomposition over several GPUs).  By default a body is iterated only by the ranks whose planes its
  * stencil box touches: a box inside one slab costs no communication at all, the two (rarely more) ranks sharing a box send
  * one another the box planes they own and then iterate it redundantly, bit-identically; the loop control of :895-906 (sum of

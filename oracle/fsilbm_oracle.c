@@ -1376,6 +1376,15 @@ void orc_pair_son_to_father(orc_pair *p)
     }
 }
 
+void orc_omp_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_omp_max_threads(void)
 {
 #ifdef _OPENMP

@@ -95,6 +95,8 @@ def lib():
     L.orc_step.restype = i
     L.orc_step.argtypes = [vp, C.POINTER(vp), i, pi, i, d, pi]
     L.orc_omp_max_threads.restype = i
+    L.orc_omp_set_threads.argtypes = [i]
+    L.orc_omp_set_threads.restype = None
     L.orc_step_pre.restype = i
     L.orc_step_pre.argtypes = [vp, C.POINTER(vp), i, pi, i, d, pi]
     L.orc_step_post.restype = i

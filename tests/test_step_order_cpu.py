@@ -34,6 +34,20 @@ class FakeBlock:
         self.log.append((self.name, "collide_stream"))
 
 
+class SplitFakeBlock(FakeBlock):
+    """A block that offers the two-halved interaction force (fsilbm_ibm_interaction_force_begin / _wait)."""
+
+    def calculate_interaction_force_begin(self, bodies, rootBC=None, collective=False):
+        self.log.append((self.name, "ibm_begin", len(bodies), collective))
+        self._bodies = bodies
+
+    def calculate_interaction_force_wait(self):
+        self.log.append((self.name, "ibm_wait"))
+        for b in self._bodies:
+            b.v_Eforce[...] = 1e-4
+        return 4
+
+
 def open_bodies(wd, n=2):
     from fsilbm3d_b200 import solid_solver as S
     import os
@@ -100,3 +114,16 @@ def test_tree_order_with_a_son():
                    ("son", "update_volume_force"), ("son", "collide_stream"), ("pair", "f2s", 0),
                    ("son", "update_volume_force"), ("son", "collide_stream"), ("pair", "f2s", 1), ("pair", "s2f")]
     assert son.blktime == 5.5 and root.blktime == 5.0
+
+
+def test_update_is_enqueued_before_the_host_waits_for_the_forces():
+    """With the two-halved call the collide-stream launch is issued between _begin and _wait: the host never stands between
+    the interaction force and the update that consumes it (the structural work still follows the forces)."""
+    sb = open_bodies(tempfile.mkdtemp(prefix="order3_"), n=1)
+    log = []
+    blk = SplitFakeBlock(log)
+    its = []
+    assert tree_collision_streaming_IBM_FEM(blk, sb.plates, time=1.0, iters=its) == 4 and its == [4]
+    assert [e[1] for e in log] == ["update_volume_force", "ibm_begin", "collide_stream", "ibm_wait"]
+    assert len(sb._pending) == 1                      # loads + sub-steps postponed behind the wait, as before
+    sb.close()
