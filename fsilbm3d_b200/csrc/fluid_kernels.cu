@@ -65,11 +65,6 @@ __device__ __forceinline__ void cell_state(const double (&f)[Q], const double (&
 // straight into the neighbour GPU's receive planes over NVLink (peer-mapped pointers p.halo_hi / p.halo_lo) instead of the
 // local ghost plane, and the last CTA of an edge plane publishes the step number to the neighbour's arrival flag, so the
 // transfer is part of the compute kernel and needs no copy engine, no NCCL kernel and no host involvement.
-__device__ __forceinline__ int halo_slot(int q)
-{   // position of q in [1,7,9,11,13] (ex=+1) or [2,8,10,12,14] (ex=-1)
-    return q <= 2 ? 0 : (q - 5) >> 1;
-}
-
 // does any stencil box hold cells of global plane gx?  (uniform over a CTA: the box test per cell is skipped elsewhere)
 __device__ __forceinline__ bool plane_in_boxes(const IbmBoxes &B, int gx, int XG)
 {
@@ -136,17 +131,19 @@ __global__ void __launch_bounds__(128, (MODEL <= 2 ? 5 : 4)) collide_push_kernel
         const int iz = EZ(q) == 0 ? 0 : (EZ(q) > 0 ? 1 : 2);
         double *dst = p.fB + q * ps + ox[ix] + oy[iy] + oz[iz];
         if (EDGE) {
-            if (EX(q) > 0 && x == X - 1 && p.halo_hi) dst = p.halo_hi + (size_t)halo_slot(q) * plane + oy[iy] + oz[iz];
-            if (EX(q) < 0 && x == 0 && p.halo_lo) dst = p.halo_lo + (size_t)halo_slot(q) * plane + oy[iy] + oz[iz];
+            if (EX(q) > 0 && x == X - 1 && p.halo_hi) dst = p.halo_hi + (size_t)q * p.halo_hi_ps + oy[iy] + oz[iz];
+            if (EX(q) < 0 && x == 0 && p.halo_lo) dst = p.halo_lo + (size_t)q * p.halo_lo_ps + oy[iy] + oz[iz];
         }
         *dst = f[q];
     }
     }
     if (edge_plane) {
-        // publish: every thread's peer stores are fenced system-wide, the CTA counts in, the last CTA of the plane raises the flag
-        __threadfence_system();
+        // publish: the CTA's stores (peer stores included) are ordered before thread 0 by the barrier, thread 0 alone fences them
+        // system-wide (fences are cumulative; one membar.sys per CTA instead of one per thread, which held the whole launch up
+        // by ~40 us), the CTA counts in, the last CTA of the plane raises the flag
         __syncthreads();
         if (threadIdx.x == 0 && threadIdx.y == 0) {
+            __threadfence_system();
             const unsigned int total = gridDim.x * gridDim.y;
             unsigned int *counter = p.cta_counter + ((x == 0) ? 0 : 1);
             const unsigned int done = atomicAdd(counter, 1u);
@@ -690,45 +687,29 @@ void launch_wrap_x(const Geom &g, double *f, cudaStream_t s)
     count_launch();
 }
 
-// Receiving side of the peer-memory halo.  Thread 0 of every CTA spins (acquire, system scope) until both
-// neighbours have published this step, then the CTA copies its share of the 10 received planes into the
-// streamed buffer: ex=+1 populations into local plane 0 (xp = 1), ex=-1 populations into plane X-1 (xp = X).
-__global__ void halo_unpack_kernel(const __grid_constant__ HaloUnpackParams p)
+// Receiving side of the peer-memory halo: the neighbours' edge planes store straight into this rank's streamed buffer, so all
+// that is left to do is to wait -- one thread, acquire loads at system scope -- until both have published this step.
+__global__ void halo_wait_kernel(const __grid_constant__ HaloWaitParams p)
 {
-    __shared__ int ok;
-    if (threadIdx.x == 0) {
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        int good = 1;
-        const unsigned long long *flags[2] = {p.flag_lo, p.flag_hi};
-        for (int sd = 0; sd < 2 && good; sd++) {
-            if (!flags[sd]) continue;
-            unsigned long long v;
-            for (;;) {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags[sd]) : "memory");
-                if (v >= p.step) break;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                if (t1 - t0 > p.timeout_ns) { good = 0; atomicExch(p.err, 1); break; }
-                __nanosleep(200);
-            }
+    if (threadIdx.x != 0) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const unsigned long long *flags[2] = {p.flag_lo, p.flag_hi};
+    for (int sd = 0; sd < 2; sd++) {
+        if (!flags[sd]) continue;
+        unsigned long long v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags[sd]) : "memory");
+            if (v >= p.step) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > p.timeout_ns) { atomicExch(p.err, 1); return; }
+            __nanosleep(200);
         }
-        ok = good;
-    }
-    __syncthreads();
-    if (!ok) return;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.g.plane) return;
-    constexpr int up[5] = {1, 7, 9, 11, 13}, dn[5] = {2, 8, 10, 12, 14};
-    const Geom &g = p.g;
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        if (p.recv_lo) p.fB[up[k] * g.pstride + (size_t)1 * g.plane + i] = __ldcg(p.recv_lo + (size_t)k * g.plane + i);
-        if (p.recv_hi) p.fB[dn[k] * g.pstride + (size_t)g.X * g.plane + i] = __ldcg(p.recv_hi + (size_t)k * g.plane + i);
     }
 }
-void launch_halo_unpack(const HaloUnpackParams &p, cudaStream_t s)
+void launch_halo_wait(const HaloWaitParams &p, cudaStream_t s)
 {
-    halo_unpack_kernel<<<(unsigned)((p.g.plane + 255) / 256), 256, 0, s>>>(p);
+    halo_wait_kernel<<<1, 32, 0, s>>>(p);
     count_launch();
 }
 

@@ -247,16 +247,20 @@ struct Block {
     struct Halo {
         bool enabled = false;
         int left = -1, right = -1;                 // neighbour ranks (-1: domain end)
-        unsigned char *region = nullptr;           // [4 x u64 flags | pad to 256 B][side 0/1][parity 0/1][5][Y][Z] doubles
+        unsigned char *region = nullptr;           // [4 x u64 arrival flags | pad to 256 B][IBM loop-control mailbox]
         unsigned char *peer_left = nullptr, *peer_right = nullptr;   // the neighbours' regions, peer-mapped through CUDA IPC
+        double *peer_f[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [left/right][buffer]: the neighbours' POPULATION buffers, peer-mapped:
+                                                   // the edge planes store what leaves the slab straight into the neighbour's streamed buffer
+        int peer_X[2] = {0, 0};                    // the neighbours' slab thickness (their buffers have X + 2 planes per population)
+        std::vector<void *> opened;                // every IPC mapping of this block, for the teardown
         std::vector<unsigned char *> peer;         // every rank's region (own pointer at the own rank): the IBM loop-control mailbox sits in its header
         bool mailbox = false;                      // all ranks mapped and nranks <= MAX_PEERS
         unsigned long long ctl_seq = 0;            // loop-control exchanges completed so far (identical on every rank)
         unsigned int *counters = nullptr;          // last-CTA counters of the two edge launches
         int *err = nullptr;
         unsigned long long step = 0;
-        size_t slot_bytes = 0;                     // 5 * Y * Z * 8
     } halo;
+    cudaEvent_t ev_pre = nullptr;                  // slab runs: the pre-collision face kernels of a step are done (the edge stream starts behind it)
 };
 
 std::vector<std::unique_ptr<Block>> g_blocks;
@@ -473,17 +477,17 @@ constexpr size_t kHaloMailboxBytes = sizeof(CtlSlot) * IBM_CTL_SLOTS * MAX_PEERS
 constexpr size_t kHaloHeaderBytes = ((kHaloFlagBytes + kHaloMailboxBytes + 4095) / 4096) * 4096;
 
 inline unsigned long long *halo_flag(unsigned char *region, int side, int parity) { return (unsigned long long *)region + (side * 2 + parity); }
-inline double *halo_slot_ptr(unsigned char *region, size_t slot_bytes, int side, int parity)
-{
-    return (double *)(region + kHaloHeaderBytes + (size_t)(side * 2 + parity) * slot_bytes);
-}
 
 // Peer-memory halo set-up (collective over the communicator; every rank creates its blocks in the same order).
-// Each rank allocates a receive region, exports it with cudaIpcGetMemHandle, the 64-byte handles are all-gathered
-// with NCCL, and each rank maps its two neighbours' regions.  From then on the edge-plane launches of
-// collide_push_kernel store outgoing populations straight into the neighbour's region over NVLink and raise a
-// flag there; no NCCL call remains on the per-step path.  Returns 0 and leaves halo.enabled = false when IPC
-// is not available (the step then uses ncclSend/ncclRecv).
+// Each rank exports its two population buffers and a small flag/mailbox region with cudaIpcGetMemHandle, the handles are
+// all-gathered with NCCL, and each rank maps its neighbours' buffers (and every rank's region: the IBM loop-control mailbox
+// lives there).  From then on the edge planes of collide_push_kernel store the populations that leave the slab straight into
+// the NEIGHBOUR'S streamed buffer over NVLink and raise a flag in its region: no staging copy, no NCCL call, no host on the
+// per-step path.  Returns 0 and leaves halo.enabled = false when IPC is not available (the step then uses ncclSend/ncclRecv).
+//
+// Why writing into the neighbour's buffer is safe: a rank starts the edge planes of step k+1 only after its step k is complete,
+// which includes having seen the neighbour's flags of step k -- and those are raised by the neighbour's edge planes of step k,
+// the only readers of the cells (plane 0 / plane X-1 of the neighbour's step-k source buffer) that step k+1's stores overwrite.
 int halo_setup(Block &b)
 {
     Block::Halo &h = b.halo;
@@ -491,22 +495,25 @@ int halo_setup(Block &b)
     const bool per = b.periodic[0] == 1;
     h.right = (r + 1 < R) ? r + 1 : (per ? 0 : -1);
     h.left = (r > 0) ? r - 1 : (per ? R - 1 : -1);
-    h.slot_bytes = sizeof(double) * 5 * b.g.plane;
-    const size_t bytes = kHaloHeaderBytes + 4 * h.slot_bytes;
+    const size_t bytes = kHaloHeaderBytes;
     CK(cudaMalloc(&h.region, bytes));
     CK(cudaMemset(h.region, 0, bytes));
     CK(cudaMalloc(&h.counters, 2 * sizeof(unsigned int)));
     CK(cudaMemset(h.counters, 0, 2 * sizeof(unsigned int)));
     CK(cudaMalloc(&h.err, sizeof(int)));
     CK(cudaMemset(h.err, 0, sizeof(int)));
-    cudaIpcMemHandle_t mine;
-    int ok = cudaIpcGetMemHandle(&mine, h.region) == cudaSuccess ? 1 : 0;
-    if (!ok) cudaGetLastError();
-    // all-gather {ok flag, handle}
-    constexpr size_t rec = 128;
+    cudaIpcMemHandle_t mine[3];
+    void *exported[3] = {h.region, b.f[0], b.f[1]};
+    int ok = 1;
+    for (int k = 0; k < 3; k++)
+        if (cudaIpcGetMemHandle(&mine[k], exported[k]) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    // all-gather {ok flag, slab thickness, three handles}
+    constexpr size_t rec = 256;
+    static_assert(8 + 3 * sizeof(cudaIpcMemHandle_t) <= rec, "record too small");
     unsigned char hostrec[rec] = {0};
     hostrec[0] = (unsigned char)ok;
-    memcpy(hostrec + 8, &mine, sizeof(mine));
+    memcpy(hostrec + 4, &b.g.X, sizeof(int));
+    memcpy(hostrec + 8, mine, sizeof(mine));
     unsigned char *dsend = nullptr, *drecv = nullptr;
     CK(cudaMalloc(&dsend, rec));
     CK(cudaMalloc(&drecv, rec * R));
@@ -520,18 +527,26 @@ int halo_setup(Block &b)
     for (int i = 0; i < R; i++) all_ok &= all[rec * i];
     int opened = 1;
     if (all_ok) {
-        auto open = [&](int peer, unsigned char **out) {
+        auto open = [&](int peer, int which) -> void * {
             cudaIpcMemHandle_t hh;
-            memcpy(&hh, all.data() + rec * peer + 8, sizeof(hh));
+            memcpy(&hh, all.data() + rec * peer + 8 + sizeof(hh) * which, sizeof(hh));
             void *ptr = nullptr;
-            if (cudaIpcOpenMemHandle(&ptr, hh, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = 0; return; }
-            *out = (unsigned char *)ptr;
+            if (cudaIpcOpenMemHandle(&ptr, hh, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = 0; return nullptr; }
+            h.opened.push_back(ptr);
+            return ptr;
         };
         // every rank's region is mapped (not only the two neighbours'): the header also carries the mailbox through which the
         // IBM penalty iteration exchanges its loop control (ibm_loop_kernel)
         h.peer.assign(R, nullptr);
         h.peer[r] = h.region;
-        for (int p = 0; p < R && opened; p++) if (p != r) open(p, &h.peer[p]);
+        for (int p = 0; p < R && opened; p++) if (p != r) h.peer[p] = (unsigned char *)open(p, 0);
+        const int nb[2] = {h.left, h.right};
+        for (int sd = 0; sd < 2 && opened; sd++) {
+            if (nb[sd] < 0) continue;
+            memcpy(&h.peer_X[sd], all.data() + rec * nb[sd] + 4, sizeof(int));
+            if (sd == 1 && nb[1] == nb[0]) { h.peer_f[1][0] = h.peer_f[0][0]; h.peer_f[1][1] = h.peer_f[0][1]; continue; }   // two ranks, periodic: one peer
+            for (int k = 0; k < 2 && opened; k++) h.peer_f[sd][k] = (double *)open(nb[sd], 1 + k);
+        }
         if (opened) {
             if (h.left >= 0) h.peer_left = h.peer[h.left];
             if (h.right >= 0) h.peer_right = h.peer[h.right];
@@ -556,9 +571,18 @@ void halo_teardown(Block &b)
 {
     Block::Halo &h = b.halo;
     if (!h.region) return;
-    for (size_t p = 0; p < h.peer.size(); p++)
-        if (h.peer[p] && h.peer[p] != h.region) cudaIpcCloseMemHandle(h.peer[p]);
+    // (the peer mappings are closed after the barrier below: a neighbour may still be storing into this rank's buffers)
     if (g_nccl.comm) {   // nobody frees a region a neighbour may still be writing into
+        int *dflag = nullptr;
+        if (cudaMalloc(&dflag, sizeof(int)) == cudaSuccess) {
+            cudaMemset(dflag, 0, sizeof(int));
+            g_nccl.AllReduce(dflag, dflag, 1, 2, kNcclSum, g_nccl.comm, b.stream);
+            cudaStreamSynchronize(b.stream);
+            cudaFree(dflag);
+        }
+    }
+    for (void *ptr : h.opened) cudaIpcCloseMemHandle(ptr);
+    if (g_nccl.comm) {   // ... and nobody frees buffers a neighbour still has mapped
         int *dflag = nullptr;
         if (cudaMalloc(&dflag, sizeof(int)) == cudaSuccess) {
             cudaMemset(dflag, 0, sizeof(int));
@@ -707,6 +731,7 @@ int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, d
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CK(cudaStreamCreateWithPriority(&b->comm_stream, cudaStreamNonBlocking, hi));
     }
+    CK(cudaEventCreateWithFlags(&b->ev_pre, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_edge, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_comm, cudaEventDisableTiming));
     {   // marker upload, stencils and cell lists slip in beside the running collide-stream kernel: their CTAs go first when SM slots free up
@@ -757,7 +782,7 @@ int fsilbm_block_destroy(fsilbm_handle h)
     cudaFree(b->mk_dev); cudaFree(b->force_dev); cudaFreeHost(b->mk_pin); cudaFreeHost(b->force_pin);
     cudaEventDestroy(b->ev_ibm); cudaStreamDestroy(b->ibm_stream);
     cudaFree(b->csr.count); cudaFree(b->csr.off); cudaFree(b->csr.entry); cudaFree(b->csr_scan_tmp); cudaFree(b->tol_partial);
-    cudaEventDestroy(b->ev_edge); cudaEventDestroy(b->ev_comm);
+    cudaEventDestroy(b->ev_edge); cudaEventDestroy(b->ev_comm); cudaEventDestroy(b->ev_pre);
     cudaStreamDestroy(b->comm_stream);
     g_blocks[h].reset();
     return 0;
@@ -1076,28 +1101,50 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
         }
         if (ghost) launch_wrap_x(g, fB, b.stream);
     } else if (b.halo.enabled) {
-        // The edge planes lead the launch list: their CTAs ARE the transfer (peer stores over NVLink + arrival flag raised by the
-        // last CTA of the plane).  Afterwards a small kernel waits for the neighbours' flags and folds the received planes in.
+        // Edge stream (high priority) beside the compute stream.  Edge stream: the two edge planes -- their CTAs ARE the
+        // transfer: what leaves the slab is stored straight into the neighbour's streamed buffer over NVLink, the last CTA of a
+        // plane raises the neighbour's arrival flag -- then a one-thread kernel that waits for the neighbours' flags of this
+        // step.  Compute stream: every other plane, in one or two launches of the plain kernel.  The two streams meet before the
+        // face kernels.  (Folding the edge planes into the main launch made every CTA of it pay for the edge instantiation:
+        // 0.84 ms per step on channel256 x2 against 0.78 on one GPU.)
         Block::Halo &h = b.halo;
         h.step++;
         const int par = (int)(h.step & 1);
+        cudaStream_t es = b.comm_stream;
+        const int nxt = b.cur ^ 1;
         StepParams e = p;
         e.step = h.step;
-        if (h.left >= 0) { e.halo_lo = halo_slot_ptr(h.peer_left, h.slot_bytes, 1, par); e.sig_lo = halo_flag(h.peer_left, 1, par); }
-        if (h.right >= 0) { e.halo_hi = halo_slot_ptr(h.peer_right, h.slot_bytes, 0, par); e.sig_hi = halo_flag(h.peer_right, 0, par); }
+        if (h.left >= 0) {    // ex = -1 populations of plane 0 -> the left neighbour's plane X_left - 1 (xp = X_left)
+            e.halo_lo = h.peer_f[0][nxt] + (size_t)h.peer_X[0] * g.plane; e.halo_lo_ps = (size_t)(h.peer_X[0] + 2) * g.plane;
+            e.sig_lo = halo_flag(h.peer_left, 1, par);
+        }
+        if (h.right >= 0) {   // ex = +1 populations of plane X-1 -> the right neighbour's plane 0 (xp = 1)
+            e.halo_hi = h.peer_f[1][nxt] + g.plane; e.halo_hi_ps = (size_t)(h.peer_X[1] + 2) * g.plane;
+            e.sig_hi = halo_flag(h.peer_right, 0, par);
+        }
         e.cta_counter = h.counters;
-        planes_first(e);
+        step_add_planes(e, 0, 1);
+        if (g.X > 1) step_add_planes(e, g.X - 1, 1);
+        CK(cudaEventRecord(b.ev_pre, b.stream));          // the previous step and this step's pre-collision face kernels
+        CK(cudaStreamWaitEvent(es, b.ev_pre, 0));
+        if (launch_collide_push(e, b.model, es)) return refuse();
+        TRACE(es, 3, "collide_edges");
+        HaloWaitParams u{};
+        u.step = h.step; u.err = h.err; u.timeout_ns = (unsigned long long)g_halo_timeout_s * 1000000000ull;
+        if (h.left >= 0) u.flag_lo = halo_flag(h.region, 0, par);
+        if (h.right >= 0) u.flag_hi = halo_flag(h.region, 1, par);
+        launch_halo_wait(u, es);
+        TRACE(es, 3, "halo_arrived");
+        CK(cudaEventRecord(b.ev_edge, es));
         TRACE(b.stream, 0, "step_begin");
-        if (launch_collide_push(e, b.model, b.stream)) return refuse();
-        TRACE(b.stream, 0, early ? "collide_edges_A" : "collide_all");
-        HaloUnpackParams u{};
-        u.g = g; u.fB = fB; u.step = h.step; u.err = h.err; u.timeout_ns = (unsigned long long)g_halo_timeout_s * 1000000000ull;
-        if (h.left >= 0) { u.recv_lo = halo_slot_ptr(h.region, h.slot_bytes, 0, par); u.flag_lo = halo_flag(h.region, 0, par); }
-        if (h.right >= 0) { u.recv_hi = halo_slot_ptr(h.region, h.slot_bytes, 1, par); u.flag_hi = halo_flag(h.region, 1, par); }
+        StepParams q = p;
+        if (early) for (int i = 0; i < nA; i++) step_add_planes(q, A0[i], A1[i] - A0[i]);
+        else step_add_planes(q, lower, upper - lower);
+        if (launch_collide_push(q, b.model, b.stream)) return refuse();
+        TRACE(b.stream, 0, early ? "collide_A" : "collide_inner");
         if (early) {
-            // a box across the interface: its planes are final only once the neighbour's populations are folded in, so the unpack
-            // (the neighbour's edge planes lead its launch too) goes before the event instead of after everything
-            if (edge_dep) { launch_halo_unpack(u, b.stream); TRACE(b.stream, 0, "halo_unpack"); }
+            // a box across the interface: its planes are final only once the neighbour's populations have arrived
+            if (edge_dep) CK(cudaStreamWaitEvent(b.stream, b.ev_edge, 0));
             CK(cudaEventRecord(b.ev_early, b.stream));
             StepParams rest = p;
             rest.boxes.n = 0;
@@ -1105,11 +1152,8 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
             if (launch_collide_push(rest, b.model, b.stream)) return refuse();
             TRACE(b.stream, 0, "collide_rest");
             note_early();
-            if (!edge_dep) { launch_halo_unpack(u, b.stream); TRACE(b.stream, 0, "halo_unpack"); }
-        } else {
-            launch_halo_unpack(u, b.stream);
-            TRACE(b.stream, 0, "halo_unpack");
         }
+        CK(cudaStreamWaitEvent(b.stream, b.ev_edge, 0));
     } else {
         // NCCL transport: edge planes first, then the exchange on its own stream overlapped with the interior update
         StepParams e = p;

@@ -50,12 +50,13 @@ struct StepParams {
     double hF[3];           // 0.5d0*volumeForce(k)*dh, FluidDomain.f90:1137-1139
     double Fvol[3];         // volumeForce(k), :1188-1190
     IbmBoxes boxes;
-    // Slab halo over NVLink peer memory (edge-plane launches of a multi-GPU run only; all null otherwise).
-    // halo_hi: the right neighbour's receive planes [5][Y][Z] for the populations with ex=+1 leaving local
-    // plane X-1; halo_lo: the left neighbour's receive planes for ex=-1 leaving plane 0.  The last CTA of an EDGE PLANE
-    // publishes `step` to sig_hi / sig_lo (flags in the neighbours' memory) after a system fence; cta_counter[0] counts the
-    // CTAs of plane 0, cta_counter[1] those of plane X-1.
+    // Slab halo over NVLink peer memory (the edge-plane launch of a multi-GPU run only; all null otherwise).
+    // halo_hi: where population q with ex=+1 leaving local plane X-1 goes = the RIGHT NEIGHBOUR'S streamed buffer at its plane 0,
+    // address halo_hi + q*halo_hi_ps + y*Z + z; halo_lo likewise for ex=-1 leaving plane 0 into the left neighbour's last plane.
+    // The last CTA of an edge plane publishes `step` to sig_hi / sig_lo (flags in the neighbours' memory) after a system
+    // fence; cta_counter[0] counts the CTAs of plane 0, cta_counter[1] those of plane X-1.
     double *halo_hi, *halo_lo;
+    size_t halo_hi_ps, halo_lo_ps;
     unsigned long long *sig_hi, *sig_lo;
     unsigned int *cta_counter;
     unsigned long long step;
@@ -64,13 +65,9 @@ struct StepParams {
     const double *uuu;        // [3][X][Y][Z] velocity field of this step (models 14, 15), written by macro_full_kernel
 };
 
-// Receiving side of the peer-memory halo: wait for both neighbours' flags, then copy the received planes
-// into the ghost-adjacent planes of the streamed buffer.
-struct HaloUnpackParams {
-    Geom g;
-    double *fB;
-    const double *recv_lo;                 // [5][Y][Z] from the left neighbour (ex=+1 populations -> local plane 0)
-    const double *recv_hi;                 // [5][Y][Z] from the right neighbour (ex=-1 populations -> local plane X-1)
+// Receiving side of the peer-memory halo: one thread waits until both neighbours have published this step (their edge planes
+// have stored into this rank's streamed buffer).
+struct HaloWaitParams {
     const unsigned long long *flag_lo, *flag_hi;
     unsigned long long step;
     int *err;                              // set to 1 if a flag did not arrive within the time limit
@@ -120,7 +117,7 @@ void launch_layer2_face(const FaceParams &p, cudaStream_t s);
 void launch_init_layer2(const FaceParams &p, cudaStream_t s);
 void launch_field_stat(const Geom &g, const double *f, const double hF[3], double invUref, double *out6, cudaStream_t s);
 void launch_wrap_x(const Geom &g, double *f, cudaStream_t s);
-void launch_halo_unpack(const HaloUnpackParams &p, cudaStream_t s);
+void launch_halo_wait(const HaloWaitParams &p, cudaStream_t s);
 // un-fused passes
 void launch_pass_fill(double *p, size_t n, double v, cudaStream_t s);
 void launch_pass_add_force(const FieldParams &p, cudaStream_t s);
