@@ -1,15 +1,9 @@
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
-timeout 600 $TR tests/multi_rank_case.py > gpurun_out/r02_multi_rank_parity_n2.txt 2>&1; echo "parity rc=$?"
-grep -c OK gpurun_out/r02_multi_rank_parity_n2.txt; grep FAIL gpurun_out/r02_multi_rank_parity_n2.txt | head -5; tail -3 gpurun_out/r02_multi_rank_parity_n2.txt
-timeout 300 $TR bench.py --gpus 2 --steps 20 --warmup 5 --workload channel256 --trace-out gpurun_out/r02g_trace_channel256_n2 > gpurun_out/r02g_bench_channel256_n2_s20.json 2> gpurun_out/err_g1.txt
-timeout 300 $TR bench.py --gpus 2 --steps 20 --warmup 5 --trace-out gpurun_out/r02g_trace_heave1024_n2 > gpurun_out/r02g_bench_heave1024_n2_s20.json 2> gpurun_out/err_g2.txt
-timeout 300 $TR bench.py --gpus 2 --steps 200 --warmup 10 > gpurun_out/r02g_bench_heave1024_n2_s200.json 2> gpurun_out/err_g3.txt
-for f in gpurun_out/r02g_bench_*.json; do python - $f <<'P'
-import json,sys
-try:
-    d=json.load(open(sys.argv[1])); r=d.get('roofline') or {}
-    print(sys.argv[1], round(d['value']), round(d['ms_per_step'],4), r.get('frac'), (r.get('collide_alone') or {}).get('kernel_ms'), d['parity_check'] and d['parity_check']['ok'])
-except Exception as e: print(sys.argv[1], 'ERR', e)
-P
-done
-tail -3 gpurun_out/err_g1.txt
+# round 2 session A: tests, default bench (plate512), launch list, ncu --set full of the IBM=true collide and the IBM loop
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02h_pytest_gpu.txt 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02h_pytest_gpu.txt
+timeout 600 python bench.py > gpurun_out/r02h_bench_default.json 2> gpurun_out/err_h1.txt; echo "bench rc=$?"; cut -c1-1500 gpurun_out/r02h_bench_default.json
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02h_bench_reference.json 2> gpurun_out/err_h2.txt; echo "ref rc=$?"; cut -c1-600 gpurun_out/r02h_bench_reference.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file gpurun_out/r02h_launches_plate512.csv python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-parity-check > gpurun_out/r02h_under_ncu.log 2>&1; echo "ncu list rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:collide_push -s 30 -c 2 -o gpurun_out/r02h_ncu_collide_ibm python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity-check > gpurun_out/r02h_under_ncu2.log 2>&1; echo "ncu collide rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ibm_loop -s 12 -c 2 -o gpurun_out/r02h_ncu_ibm_loop python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity-check > gpurun_out/r02h_under_ncu3.log 2>&1; echo "ncu ibm rc=$?"
+ls -la gpurun_out | tail -12
