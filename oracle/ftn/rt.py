@@ -541,6 +541,8 @@ def f_maxval(a, dim=None):
     d = _unwrap(a)
     if dim is not None:
         return _wrap(d.max(axis=int(dim) - 1))
+    if d.size == 0:
+        return -2147483647 - 1 if d.dtype.kind in "iu" else -np.finfo(d.dtype).max
     r = d.max()
     return int(r) if d.dtype.kind in "iu" else r
 
@@ -549,6 +551,8 @@ def f_minval(a, dim=None):
     d = _unwrap(a)
     if dim is not None:
         return _wrap(d.min(axis=int(dim) - 1))
+    if d.size == 0:
+        return 2147483647 if d.dtype.kind in "iu" else np.finfo(d.dtype).max
     r = d.min()
     return int(r) if d.dtype.kind in "iu" else r
 
