@@ -944,6 +944,9 @@ class Compiler:
                 return o.f[name]
             if type(o) is FArray and o.d.dtype == object:
                 flat = [x.f[name] for x in o.d.reshape(-1, order="F")]
+                if flat and isinstance(flat[0], Struct):
+                    a = np.empty(len(flat), dtype=object); a[:] = flat
+                    return FArray(a.reshape(o.d.shape, order="F"))
                 return rt.array_cons(flat) if o.d.ndim == 1 else FArray(np.array(flat).reshape(o.d.shape, order="F"))
             raise InterpError(f"component {name} of {type(o)}")
         return get

@@ -1,0 +1,178 @@
+"""Cases that pin the CPU oracle (and through it the CUDA path) against the REFERENCE ITSELF.
+
+Each case is one description that yields
+  (i)   the reference's own input files (inFlow.dat, plate.dat, an injected ./DatContinue/continue state) -- what
+        tests/golden/make_reference_golden.py feeds to the reference's unmodified main program, executed from its Fortran
+        sources by the interpreter in oracle/ftn/ (this image has no Fortran compiler); the populations, marker forces and
+        beam state that run leaves are committed as tests/golden/ref_<case>.npz;
+  (ii)  the same run on the C oracle (run_oracle below; tests/test_reference_golden.py, CPU);
+  (iii) the same input directory for the C++ stand-in driver over the CUDA library (tests/test_gpu_reference_golden.py).
+
+The injected state goes through the reference's own restart path (check_is_continue, FluidDomain.f90:128-237, isConCmpt=2:
+populations taken from the file, time and step start at zero, main.f90:70-75).
+"""
+import json
+import os
+import struct
+
+import numpy as np
+
+from tests.common import SEED, perturbed_state
+
+DIRS = ("DatFlow", "DatContinue", "DatInfo", "DatBody", "DatBodySpan", "DatTemp", "DatOthe")
+P0 = (0.0,) * 10
+
+
+def _fluid(dims, bc, model=1, params=P0, steps=8, uvwIn=(0.0, 0.0, 0.0), Uref=0.05, Lref=4.0, Re=20.0, wave=1e-3, **flow):
+    return dict(kind="fluid", dims=dims, bc=bc, model=model, params=params, steps=steps, uvwIn=uvwIn, Uref=Uref, Lref=Lref, Re=Re, wave=wave,
+                flow=flow)
+
+
+CASES = {
+    # collision models on a periodic box with a body force (FluidDomain.f90:1208-1263) from a perturbed state
+    "srt_periodic_force": _fluid((10, 8, 12), (301,) * 6, model=1, steps=10, volumeForceIn=(1e-6, 2e-7, -3e-7)),
+    "trt_periodic_force": _fluid((10, 8, 12), (301,) * 6, model=2, params=(3.0 / 16.0,) + (0.0,) * 9, steps=10, volumeForceIn=(1e-6, 2e-7, -3e-7)),
+    "mrt_osc_force": _fluid((8, 10, 8), (301,) * 6, model=3, steps=8, volumeForceIn=(1e-6, 0.0, 0.0), volumeForceAmp=5e-7, volumeForceFreq=0.7,
+                            volumeForcePhi=30.0),
+    # every boundary rule (set_boundary_conditions_, FluidDomain.f90:616-1190), face-order precedence on shared edges
+    "srt_all_faces_mixed": _fluid((10, 9, 8), (102, 104, 202, 204, 203, 201), steps=10, uvwIn=(0.03, 0.0, 0.0), Uref=0.03,
+                                  shearRateIn=(0.0, 5e-4, 2e-4)),
+    "trt_inlet_outlet_symmetric": _fluid((10, 8, 8), (101, 103, 302, 302, 301, 301), model=2, params=(0.25,) + (0.0,) * 9, steps=10,
+                                         uvwIn=(0.04, 0.0, 0.0), Uref=0.04),
+    "srt_oscillatory_inflow": _fluid((10, 8, 8), (101, 104, 301, 301, 301, 301), steps=10, uvwIn=(0.03, 0.0, 0.0), Uref=0.03, velocityKind=2,
+                                     shearRateIn=(0.01, 0.6, 45.0)),
+    # LES closures (FluidDomain.f90:1264-1507)
+    "les_smag_halfway_channel": _fluid((8, 9, 8), (301, 301, 203, 203, 301, 301), model=11, steps=8, volumeForceIn=(2e-6, 0.0, 0.0), wave=2e-2),
+    "les_wale_inflow": _fluid((9, 8, 8), (101, 104, 301, 301, 301, 301), model=14, steps=8, uvwIn=(0.04, 0.0, 0.0), Uref=0.04, wave=2e-2),
+    "les_vrem_periodic": _fluid((8, 8, 9), (301,) * 6, model=15, steps=8, volumeForceIn=(1e-6, 0.0, 0.0), wave=2e-2),
+}
+
+# father 12x10x10 with a 2:1 refined son (LBMBlockComm.f90:279-505), linear and cubic interpolation in time/space
+for _name, _scheme in (("refine_linear", 1), ("refine_cubic", 2)):
+    CASES[_name] = dict(kind="refine", dims=(14, 10, 10), bc=(101, 104, 301, 301, 301, 301), sdims=(11, 9, 9), smins=(4.0, 3.0, 3.0), scheme=_scheme,
+                        model=1, params=P0, steps=6, uvwIn=(0.04, 0.0, 0.0), Uref=0.04, Lref=4.0, Re=20.0, wave=1e-3,
+                        flow=dict(volumeForceIn=(1e-6, 0.0, 0.0)))
+
+# a rigid plate in prescribed heave (iBodyModel 1; Solidbody.f90:760-1049 IBM, SolidSolver.f90:1826-1857 motion)
+CASES["rigid_plate_heave"] = dict(
+    kind="body", dims=(20, 14, 14), bc=(101, 104, 202, 202, 301, 301), model=1, params=P0, steps=8, uvwIn=(0.05, 0.0, 0.0), Uref=0.05, Lref=4.0,
+    Re=40.0, wave=1e-3, flow=dict(shearRateIn=(0.0, 2e-4, 0.0)), ntolLBM=3, dtolLBM=1e-30, numsubstep=1,
+    plate=dict(nEL=4, chord=4.0, span=4.0, Nspan=4),
+    group=dict(iBodyModel=1, isMotionGiven=(1,) * 6, denR=1.0, psR=0.3, EmR=1.0, tcR=0.05, freq=0.02, XYZAmpl=(0.0, 1.0, 0.0), XYZPhi=(0.0, 20.0, 0.0),
+               AoAo=(0.0, 0.0, 10.0), firstXYZ=(6.3, 6.6, 5.2)), isKB=0)
+# a flexible plate, leading edge held, passively deforming (iBodyModel 2: the beam FEM, SolidSolver.f90:1860-2020)
+CASES["flexible_plate"] = dict(
+    kind="body", dims=(20, 14, 14), bc=(101, 104, 301, 301, 301, 301), model=1, params=P0, steps=6, uvwIn=(0.05, 0.0, 0.0), Uref=0.05, Lref=4.0,
+    Re=40.0, wave=1e-3, flow={}, ntolLBM=3, dtolLBM=1e-30, numsubstep=2,
+    plate=dict(nEL=4, chord=4.0, span=4.0, Nspan=4),
+    group=dict(iBodyModel=2, isMotionGiven=(1,) * 6, denR=1.0, psR=0.3, KB=0.02, KS=500.0, AoAo=(0.0, 0.0, 12.0), firstXYZ=(6.3, 6.6, 5.2)), isKB=1)
+
+
+def golden_path(name):
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"ref_{name}.npz")
+
+
+def initial_states(case):
+    """Seeded perturbed populations per block, [19][X][Y][Z] (the state injected through ./DatContinue/continue)."""
+    class _F:
+        pass
+    fl = _F(); fl.uvwIn = case["uvwIn"]; fl.denIn = 1.0
+    out = [perturbed_state(case["dims"], fl, wave_amp=case["wave"], seed=SEED)]
+    if case["kind"] == "refine":
+        out.append(perturbed_state(case["sdims"], fl, wave_amp=case["wave"], seed=SEED + 1))
+    return out
+
+
+def block_list(case):
+    blocks = [dict(ID=1, iCollidModel=case["model"], dims=case["dims"], dh=1.0, xyzmin=(0.0, 0.0, 0.0), BndConds=case["bc"], params=case["params"])]
+    if case["kind"] == "refine":
+        blocks.append(dict(ID=2, iCollidModel=case["model"], offsetOutput=1, dims=case["sdims"], dh=0.5, xyzmin=case["smins"], BndConds=(0,) * 6,
+                           params=case["params"]))
+    return blocks
+
+
+def write_continue(path, blocks, states):
+    """write_continue_blocks' layout (FluidDomain.f90:268-285)."""
+    with open(path, "wb") as f:
+        f.write(struct.pack("<ii", len(blocks), 0)); f.write(struct.pack("<d", 0.0))
+        for b, s in zip(blocks, states):
+            f.write(struct.pack("<4d", *b["xyzmin"], b["dh"])); f.write(struct.pack("<3i", *b["dims"]))
+            f.write(np.ascontiguousarray(s, dtype="<f8").tobytes())
+
+
+def write_inputs(case, wd):
+    """The reference's input files for this case in directory wd."""
+    from fsilbm3d_b200 import solid_solver as S
+    from tests.beam_cases import chain
+    for d in DIRS:
+        os.makedirs(os.path.join(wd, d), exist_ok=True)
+    Tref = case["Lref"] / case["Uref"]
+    total = (case["steps"] - 0.5) / Tref                    # main.f90:93: do while(time/Tref < timeSimTotal), dt = 1
+    blocks = block_list(case)
+    groups = []
+    if case["kind"] == "body":
+        p = case["plate"]
+        S.write_plate_dat(os.path.join(wd, "plate.dat"), chain(p["nEL"] + 1, p["chord"]), 0.5 * p["span"], 0.5 * p["span"], (0.0, 0.0, 1.0),
+                          Nspan=p["Nspan"])
+        groups = [dict(case["group"], fishNum=1, mesh="plate.dat")]
+    text = S.inflow_text(npsize=1, isConCmpt=2, numsubstep=case.get("numsubstep", 1), timeSimTotal=total, Re=case["Re"], uvwIn=case["uvwIn"],
+                         LrefType=1, Lref=case["Lref"], TrefType=0, UrefType=9, Uref=case["Uref"], ntolLBM=case.get("ntolLBM", 3),
+                         dtolLBM=case.get("dtolLBM", 1e-8), interpolateScheme=case.get("scheme", 1), blocks=blocks, groups=groups,
+                         isKB=case.get("isKB", 0), dtolFEM=1e-12, ntolFEM=20, **case["flow"])
+    with open(os.path.join(wd, "inFlow.dat"), "w") as f:
+        f.write(text)
+    write_continue(os.path.join(wd, "DatContinue", "continue"), blocks, initial_states(case))
+
+
+def run_oracle(O, case, sb=None):
+    """The case on the C oracle in main.f90's order.  Bodies: `sb` is the C++ structural side opened on the same input directory
+    (harness/libfsilbm_solid.so; host code on both sides of the boundary).  Returns (blocks, oracle body or None, iteration counts)."""
+    nu = case["Uref"] * case["Lref"] / case["Re"]                           # Solidbody.f90:282
+    fl = O.Flow(nu=nu, uvwIn=case["uvwIn"], Uref=case["Uref"], ntolLBM=case.get("ntolLBM", 3), dtolLBM=case.get("dtolLBM", 1e-8), **case["flow"])
+    states = initial_states(case)
+    X, Y, Z = case["dims"]
+    Fb = O.LBMBlock(X, Y, Z, dh=1.0, BndConds=case["bc"], iCollidModel=case["model"], params=case["params"], flow=fl)
+    blocks = [Fb]
+    root = O.TreeNode(Fb)
+    if case["kind"] == "refine":
+        sx, sy, sz = case["sdims"]
+        Sb = O.LBMBlock(sx, sy, sz, dh=0.5, xmin=case["smins"][0], ymin=case["smins"][1], zmin=case["smins"][2], BndConds=(0,) * 6,
+                        iCollidModel=case["model"], params=case["params"], flow=fl)
+        root.add_son(O.TreeNode(Sb), case["scheme"])
+        blocks.append(Sb)
+    for b, s in zip(blocks, states):
+        b.initialise(0.0)
+        b.fIn[...] = s
+    if case["kind"] == "refine":
+        # check_is_continue (FluidDomain.f90:166-224) gives every node the populations of the FINEST saved block containing it:
+        # the father's nodes under the son take the son's values at the coincident nodes (weights 0/1, exact)
+        (x0, y0, z0), (sx, sy, sz) = [int(v) for v in case["smins"]], case["sdims"]
+        Fb.fIn[:, x0:x0 + (sx + 1) // 2, y0:y0 + (sy + 1) // 2, z0:z0 + (sz + 1) // 2] = blocks[1].fIn[:, ::2, ::2, ::2]
+    for b in blocks:
+        b.update_volume_force(); b.set_boundary_conditions(); b.calculate_macro_quantities()
+    ov, its = None, []
+    if case["kind"] == "body":
+        body = sb.VBodies[0]
+        ov = O.VirtualBody(body.v_nelmts, v_move=body.v_move, iBodyModel=body.iBodyModel)
+        root.bodies = [ov]
+    nsub = case.get("numsubstep", 1)
+    for n in range(1, case["steps"] + 1):
+        t = float(n)
+        O.set_blktime_all(root, t)
+        if ov is not None:
+            body.UpdatePosVelArea()
+            ov.v_Exyz[...] = body.v_Exyz; ov.v_Evel[...] = body.v_Evel; ov.v_Ea[...] = body.v_Ea
+        O.tree_collision_streaming_IBM_FEM(root, iters=its)
+        if ov is not None:
+            body.v_Eforce[...] = ov.v_Eforce
+            body.FluidLoads()
+            for isub in range(1, nsub + 1):
+                body.structure(t, isub, 1.0, 1.0 / nsub)
+    for b in blocks:
+        b.calculate_macro_quantities()
+    return blocks, ov, its
+
+
+def load(name):
+    g = np.load(golden_path(name))
+    return json.loads(str(g["case"])), g
