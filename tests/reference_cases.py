@@ -100,8 +100,9 @@ def write_continue(path, blocks, states):
             f.write(np.ascontiguousarray(s, dtype="<f8").tobytes())
 
 
-def write_inputs(case, wd):
-    """The reference's input files for this case in directory wd."""
+def write_inputs(case, wd, continue_at_end=False):
+    """The reference's input files for this case in directory wd.  continue_at_end: ask for ./DatContinue/continue... at the last
+    step (main.f90:118-120), for drivers whose end state is read from that file."""
     from fsilbm3d_b200 import solid_solver as S
     from tests.beam_cases import chain
     for d in DIRS:
@@ -115,10 +116,11 @@ def write_inputs(case, wd):
         S.write_plate_dat(os.path.join(wd, "plate.dat"), chain(p["nEL"] + 1, p["chord"]), 0.5 * p["span"], 0.5 * p["span"], (0.0, 0.0, 1.0),
                           Nspan=p["Nspan"])
         groups = [dict(case["group"], fishNum=1, mesh="plate.dat")]
+    extra = dict(timeContiDelta=case["steps"] / Tref) if continue_at_end else {}
     text = S.inflow_text(npsize=1, isConCmpt=2, numsubstep=case.get("numsubstep", 1), timeSimTotal=total, Re=case["Re"], uvwIn=case["uvwIn"],
                          LrefType=1, Lref=case["Lref"], TrefType=0, UrefType=9, Uref=case["Uref"], ntolLBM=case.get("ntolLBM", 3),
                          dtolLBM=case.get("dtolLBM", 1e-8), interpolateScheme=case.get("scheme", 1), blocks=blocks, groups=groups,
-                         isKB=case.get("isKB", 0), dtolFEM=1e-12, ntolFEM=20, **case["flow"])
+                         isKB=case.get("isKB", 0), dtolFEM=1e-12, ntolFEM=20, **extra, **case["flow"])
     with open(os.path.join(wd, "inFlow.dat"), "w") as f:
         f.write(text)
     write_continue(os.path.join(wd, "DatContinue", "continue"), blocks, initial_states(case))

@@ -1,6 +1,5 @@
-# round 2 session B: full-size parity tests; ncu --set full of the IBM=true collide instantiation
+# round 2 session C: CUDA path against the reference goldens; ncu --set full of the IBM=true collide instantiation
 mkdir -p gpurun_out
-nproc; free -g | head -2
-timeout 1500 python -m pytest tests/test_gpu_fullsize.py -m gpu -x -q --durations=5 > gpurun_out/r02i_pytest_fullsize.txt 2>&1; echo "fullsize rc=$?"; tail -12 gpurun_out/r02i_pytest_fullsize.txt
-timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:collide_push_kernel<1, 1' -s 10 -c 2 -o gpurun_out/r02i_ncu_collide_ibm_true python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity-check > gpurun_out/r02i_under_ncu.log 2>&1; echo "ncu rc=$?"
+timeout 900 python -m pytest tests/test_gpu_reference_golden.py -m gpu -q > gpurun_out/r02j_pytest_reference_golden.txt 2>&1; echo "refgolden rc=$?"; tail -40 gpurun_out/r02j_pytest_reference_golden.txt
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:collide_push_kernel<1, true' -s 10 -c 2 -o gpurun_out/r02j_ncu_collide_ibm_true python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity-check > gpurun_out/r02j_under_ncu.log 2>&1; echo "ncu rc=$?"
 ls -la gpurun_out | tail -5
