@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE -- an independent numpy restatement of the reference's structural solver
 (/root/reference/src/SolidSolver.f90) and of the host half of its marker bookkeeping (Solidbody.f90:604-646,
 :945-967), written from the Fortran separately from harness/beam_solver.cpp so the two can be cross-checked.
-Parity unpinned by the reference: it ships no fixtures and no Fortran compiler exists here;
+The reference ships no fixtures and no Fortran compiler exists here; its beam solver is run by oracle/ftn/ in the flexible-plate pin
+case (tests/reference_cases.py);
 the pins are the analytic known-answer tests in tests/test_beam_kat.py.
 
 Only tests/ may import this module.  Style differs from the C++ on purpose: all elements are handled at once as

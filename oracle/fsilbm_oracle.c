@@ -7,11 +7,14 @@
  * (fIn(z,y,x,q), z fastest) and left-to-right evaluation order.  Every function
  * cites the reference file:line it follows (paths relative to /root/reference/src).
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or example inputs,
- * and it is Fortran -- no Fortran compiler exists in this environment, so the
- * reference itself cannot be run here.  This oracle is therefore pinned only by
- * (a) line-by-line review against the cited Fortran and (b) the analytic
- * known-answer tests in tests/test_oracle_kat.py.  See DESIGN.md section "Oracle".
+ * PINNED AGAINST THE REFERENCE: the reference ships no tests or golden vectors and is
+ * Fortran; no Fortran compiler exists in this environment.  Its unmodified sources are
+ * therefore executed by the interpreter in oracle/ftn/ (main.f90 from start to end on 13
+ * cases, tests/reference_cases.py); what the reference leaves is committed as
+ * tests/golden/ref_*.npz and this oracle reproduces it bit for bit
+ * (tests/test_reference_golden.py).  Also held by the analytic known-answer tests in
+ * tests/test_oracle_kat.py.  oracle/pin_with_reference.py repeats the comparison on a
+ * gfortran build where one exists.  See DESIGN.md section 5.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library.  The product (fsilbm3d_b200/, libfsilbm_b200.so) never
