@@ -163,6 +163,8 @@ struct BodyDev {
     HostBox hbox{};             // box of the stencils last built (host index arithmetic of UpdateElmtInterp_)
     int cidx[3] = {0, 0, 0};    // cell of the first marker at that time
     bool have_box = false;
+    bool stencil_valid = false;   // ExyzStencil / v_Ei / v_Ew on THIS rank match the body's current markers (slab runs: a body is
+                                  // only stencilled by the ranks that iterate it)
     int status = 0;             // last call: 0 not iterated by this rank (no plane of its box here), 1 iterated, 2 iterated and led
     void release()
     {
@@ -187,7 +189,7 @@ struct Block {
     fsilbm_flow flow{};
     double tau = 0, Omega = 0, Omega2 = 0;
     double Mc[Q * Q]{}, Mf[Q * Q]{};
-    int mrt_slot = 0;
+    int mrt_slot = -1;        // entry of the MRT matrix table (c_MRT) this block collides with; -1 = none held
     bool initialised = false;
     double *f[2] = {nullptr, nullptr};
     int cur = 0;
@@ -339,6 +341,36 @@ CollideConsts collide_consts(const Block &b)
 void half_force(const Block &b, double hF[3])
 {
     for (int k = 0; k < 3; k++) hF[k] = 0.5 * b.volumeForce[k] * b.g.dh;   // FluidDomain.f90:1137
+}
+
+// The MRT matrix table in constant memory has MRT_SLOTS entries.  An entry is keyed by its contents: blocks with the same
+// relaxation time (same dh and nu) share one, an entry is freed when its last block is destroyed or re-initialised, and a block
+// whose matrices find no free entry is refused (FSILBM_ERR_MODEL) instead of overwriting another block's.
+struct MrtEntry { int refs = 0; std::vector<double> key; };
+static MrtEntry g_mrt[MRT_SLOTS];
+static void mrt_release(int &slot)
+{
+    if (slot >= 0 && slot < MRT_SLOTS && g_mrt[slot].refs > 0) g_mrt[slot].refs--;
+    slot = -1;
+}
+static int mrt_acquire(const double *Mc, const double *Mf, cudaStream_t s, bool *fresh)
+{
+    std::vector<double> key(Mc, Mc + Q * Q);
+    key.insert(key.end(), Mf, Mf + Q * Q);
+    *fresh = false;
+    for (int i = 0; i < MRT_SLOTS; i++)
+        if (g_mrt[i].refs > 0 && g_mrt[i].key.size() == key.size() && std::memcmp(g_mrt[i].key.data(), key.data(), sizeof(double) * key.size()) == 0) {
+            g_mrt[i].refs++;
+            return i;
+        }
+    for (int i = 0; i < MRT_SLOTS; i++)
+        if (g_mrt[i].refs == 0) {
+            g_mrt[i].refs = 1;
+            g_mrt[i].key.swap(key);
+            *fresh = true;
+            return i;
+        }
+    return -1;
 }
 
 // calculate_MRT_params, FluidDomain.f90:466-522; matmul sums run over the inner index ascending from zero
@@ -755,7 +787,6 @@ int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, d
     int slot = -1;
     for (size_t i = 0; i < g_blocks.size(); i++) if (!g_blocks[i]) { slot = (int)i; break; }
     if (slot < 0) { g_blocks.emplace_back(); slot = (int)g_blocks.size() - 1; }
-    b->mrt_slot = slot % MRT_SLOTS;
     g_blocks[slot] = std::move(b);
     *out = slot;
     return 0;
@@ -768,6 +799,7 @@ int fsilbm_block_destroy(fsilbm_handle h)
     cudaStreamSynchronize(b->stream);
     cudaStreamSynchronize(b->comm_stream);
     halo_teardown(*b);
+    mrt_release(b->mrt_slot);
     for (int i = 0; i < 2; i++) cudaFree(b->f[i]);
     for (int i = 0; i < 6; i++) { cudaFree(b->stash[i]); cudaFree(b->l2den[i]); cudaFree(b->l2u[i]); }
     cudaFree(b->den); cudaFree(b->uuu); cudaFree(b->force); cudaFree(b->stat); cudaFree(b->tau_all);
@@ -802,8 +834,16 @@ int fsilbm_block_initialise(fsilbm_handle h, double time)
         b->Omega2 = 2.0 * (2.0 - b->Omega) / tmp;
     } else if (b->model == 3) {
         mrt_matrices(b->Omega, b->Mc, b->Mf);
-        upload_mrt(b->mrt_slot, b->Mc, b->Mf, b->stream);
-        CK(cudaStreamSynchronize(b->stream));   // Mc/Mf are pageable host memory
+        mrt_release(b->mrt_slot);
+        bool fresh = false;
+        b->mrt_slot = mrt_acquire(b->Mc, b->Mf, b->stream, &fresh);
+        if (b->mrt_slot < 0)
+            return fail(FSILBM_ERR_MODEL, "MRT: %d blocks with distinct relaxation matrices are alive in this process; the matrix table holds %d "
+                                          "(blocks of equal dh and nu share an entry)", MRT_SLOTS + 1, MRT_SLOTS);
+        if (fresh) {
+            upload_mrt(b->mrt_slot, b->Mc, b->Mf, b->stream);
+            CK(cudaStreamSynchronize(b->stream));   // Mc/Mf are pageable host memory
+        }
     }
     if (b->model >= 11) {                                    // tau_all = tau, FluidDomain.f90:454-455
         const size_t n = (size_t)b->g.X * b->g.plane;
@@ -1643,18 +1683,64 @@ int fsilbm_ibm_interaction_force_begin(fsilbm_handle h, int nbody, const int *ne
     std::vector<int> kept;
     for (size_t k = 0; k < mb.size(); k++) if (keep[k]) kept.push_back((int)k);
     if (local && (int)kept.size() > MAX_BOXES) return fail(FSILBM_ERR_ARG, "more than %d separate stencil boxes touch this slab", MAX_BOXES);
-    while (!local && (int)kept.size() > MAX_BOXES) {   // too many separate bodies: fold the tail into one covering box
-        MBox &a0 = mb[kept[kept.size() - 2]], &b0 = mb[kept.back()];
+    // More separate stencil boxes than the box table holds: the two whose covering box adds the fewest cells are joined (their
+    // bodies then share one box; results do not change, a box is only storage) until the table fits.  Said once on stderr.
+    auto cover = [&](const HostBox &x0, const HostBox &y0, HostBox &out) {
+        long long vol = 1;
         for (int a = 0; a < 3; a++) {
-            // covering interval of two disjoint intervals on the circle
-            Interval x = a0.hb.ax[a], y = b0.hb.ax[a], r;
+            const Interval &x = x0.ax[a], &y = y0.ax[a];
+            Interval r;
             const int d1 = imod(y.s - x.s, Ns[a]) + y.l, d2 = imod(x.s - y.s, Ns[a]) + x.l;
             if (std::max(d1, x.l) <= std::max(d2, y.l)) { r.s = x.s; r.l = std::max(d1, x.l); } else { r.s = y.s; r.l = std::max(d2, y.l); }
             if (r.l >= Ns[a]) { r.s = 0; r.l = Ns[a]; }
-            a0.hb.ax[a] = r;
+            out.ax[a] = r;
+            vol *= r.l;
         }
+        return vol;
+    };
+    auto volume = [&](const HostBox &x) { return (long long)x.ax[0].l * x.ax[1].l * x.ax[2].l; };
+    if (!local && (int)kept.size() > MAX_BOXES) {
+        static bool said = false;
+        if (!said) {
+            said = true;
+            fprintf(stderr, "fsilbm: %d separate stencil boxes in one block, the box table holds %d: nearest boxes are joined\n", (int)kept.size(), MAX_BOXES);
+        }
+    }
+    while (!local && (int)kept.size() > MAX_BOXES) {
+        size_t bi = 0, bj = 1;
+        long long best = -1;
+        HostBox tmp;
+        for (size_t i = 0; i < kept.size(); i++)
+            for (size_t j = i + 1; j < kept.size(); j++) {
+                const long long extra = cover(mb[kept[i]].hb, mb[kept[j]].hb, tmp) - volume(mb[kept[i]].hb) - volume(mb[kept[j]].hb);
+                if (best < 0 || extra < best) { best = extra; bi = i; bj = j; }
+            }
+        MBox &a0 = mb[kept[bi]], &b0 = mb[kept[bj]];
+        cover(a0.hb, b0.hb, tmp);
+        a0.hb = tmp;
         a0.members.insert(a0.members.end(), b0.members.begin(), b0.members.end());
-        kept.pop_back();
+        std::sort(a0.members.begin(), a0.members.end());
+        kept.erase(kept.begin() + bj);
+        // the covering box may now reach a third box: no cell may lie in two boxes (the kernels look a cell up in the first box
+        // that holds it), so whatever it overlaps joins it as well
+        for (bool changed = true; changed;) {
+            changed = false;
+            for (size_t j = 0; j < kept.size() && !changed; j++) {
+                if (j == bi) continue;
+                bool ov = true;
+                for (int a = 0; a < 3; a++) ov = ov && overlap(mb[kept[bi]].hb.ax[a], mb[kept[j]].hb.ax[a], Ns[a]);
+                if (!ov) continue;
+                const size_t into = std::min(bi, j), from = std::max(bi, j);   // the earlier box keeps its place (box order = first member)
+                MBox &x = mb[kept[into]], &y = mb[kept[from]];
+                cover(x.hb, y.hb, tmp);
+                x.hb = tmp;
+                x.members.insert(x.members.end(), y.members.begin(), y.members.end());
+                std::sort(x.members.begin(), x.members.end());
+                kept.erase(kept.begin() + from);
+                bi = into;
+                changed = true;
+            }
+        }
     }
     // active bodies (caller order = device order, so the cell lists keep the reference's body order), their box group and
     // whether this rank leads them (owns the first plane of their box: it reports their residual and their forces)
@@ -1670,6 +1756,12 @@ int fsilbm_ibm_interaction_force_begin(fsilbm_handle h, int nbody, const int *ne
         b.bodies[ib].status = group_of[ib] < 0 ? 0 : (lead_of[ib] ? 2 : 1);
     }
     const int nact = (int)act.size();
+    // a body that was never stencilled on this rank (its box did not touch this slab until a merge with a moving neighbour brought
+    // it here) must be, whatever the caller's restencil flag says: the flag describes the body, not this rank's copy of it
+    for (int ib : act)
+        if (!re[ib] && !b.bodies[ib].stencil_valid) { re[ib] = 1; b.csr_valid = false; }
+    for (int ib = 0; ib < nbody; ib++)
+        if (group_of[ib] < 0 && re[ib]) b.bodies[ib].stencil_valid = false;   // moved while inactive here: this rank's copy is stale
     {   // the set of active bodies decides the device body table and the cell lists
         if (b.active_prev != act) { b.csr_valid = false; b.active_prev = act; }
     }
@@ -1705,7 +1797,10 @@ int fsilbm_ibm_interaction_force_begin(fsilbm_handle h, int nbody, const int *ne
         memcpy(pin + 3 * n, Evel[ib], sizeof(double) * 3 * n);
         memcpy(pin + 6 * n, Ea[ib], sizeof(double) * n);
         CK(cudaMemcpyAsync(bd.Exyz, pin, sizeof(double) * 7 * n, cudaMemcpyHostToDevice, s2));
-        if (re[ib]) CK(cudaMemcpyAsync(bd.ExyzStencil, bd.Exyz, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, s2));
+        if (re[ib]) {
+            CK(cudaMemcpyAsync(bd.ExyzStencil, bd.Exyz, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, s2));
+            bd.stencil_valid = true;
+        }
     }
     IbmCtl ctl0;
     ctl0.iter = 0; ctl0.done = (ntolLBM <= 0) ? 1 : 0; ctl0.err = 0; ctl0.dmax = 1e10; ctl0.tol_acc = 0.0;   // :893-894
@@ -2075,8 +2170,7 @@ int fsilbm_pair_create(fsilbm_handle father, fsilbm_handle son, int interpolateS
     p->father = father; p->son = son; p->scheme = interpolateScheme;
     // deliver_son_to_father rewrites father nodes inside the son's footprint between the steps: no early IBM on a father.  A son
     // only has its outermost planes rewritten (interpolation_father_to_son), and early IBM keeps 3 cells away from such faces.
-    F->is_father = true;
-    F->early_ok = S->early_ok = false;
+    // (set once the pair is known to be valid, at the end)
     // build_blocks_comunication, :32-96
     for (int j = 0; j < 6; j++) p->sds[j] = S->bc[j] == BCfluid ? ((j % 2 == 0) ? 1 : -1) : 0;
     int sD[3];
@@ -2113,6 +2207,8 @@ int fsilbm_pair_create(fsilbm_handle father, fsilbm_handle son, int interpolateS
     for (size_t i = 0; i < g_pairs.size(); i++) if (!g_pairs[i]) { slot = (int)i; break; }
     if (slot < 0) { g_pairs.emplace_back(); slot = (int)g_pairs.size() - 1; }
     g_pairs[slot] = std::move(p);
+    F->is_father = true;
+    F->early_ok = S->early_ok = false;
     *pair = slot;
     return 0;
 }

@@ -29,18 +29,35 @@ def _name10(value: float) -> str:
     return f"{n:10d}".replace(" ", "0")
 
 
+def _whole(block, what: str) -> None:
+    """The restart helpers hold a block's full x extent: an x-slab of a multi-GPU run has to be gathered by the caller first."""
+    if block.xLocal != block.xDim or getattr(block, "xOffset", 0) != 0:
+        raise ValueError(f"{what}: block is an x-slab (planes {block.xOffset}..{block.xOffset + block.xLocal - 1} of {block.xDim}); "
+                         "gather the slabs (download_fIn per rank, concatenated along x) or write one file per rank with write_flow")
+
+
+def flow_window(block, offsetOutput: int):
+    """The part of the output window [offsetOutput, dim - offsetOutput) that lies in this block's slab: (first global plane, nx, ny,
+    nz) -- the same intersection fsilbm_block_write_flow_window takes, so the staging buffer always has the size the library fills."""
+    x0 = getattr(block, "xOffset", 0)
+    gx0, gx1 = max(offsetOutput, x0), min(block.xDim - offsetOutput, x0 + block.xLocal)
+    return gx0, max(gx1 - gx0, 0), block.yDim - 2 * offsetOutput, block.zDim - 2 * offsetOutput
+
+
 def write_flow(block, time: float, Tref: float, ID: int = 1, offsetOutput: int = 0, outputtype: int = 1, root: str = ".") -> Optional[str]:
-    """write_flow_ for one block (single slab).  Returns the path of the Flow file (None if outputtype < 1)."""
+    """write_flow_ for one block.  An x-slab writes ITS planes of the window (header: its own nx and xmin), so ranks of a slab run
+    need distinct `root` directories or IDs.  Returns the path of the Flow file (None if outputtype < 1 or the window misses the slab)."""
     if outputtype < 1:
         return None
-    X, Y, Z = block.xLocal, block.yDim, block.zDim
-    nx, ny, nz = X - 2 * offsetOutput, Y - 2 * offsetOutput, Z - 2 * offsetOutput
+    gx0, nx, ny, nz = flow_window(block, offsetOutput)
+    if nx <= 0 or ny <= 0 or nz <= 0:
+        return None
     nf = 13 if outputtype >= 2 else 4
     out = np.empty((nf, nx, ny, nz), dtype=np.float32)
     check(lib().fsilbm_block_write_flow_window(block._h, offsetOutput, outputtype, out.ctypes.data))
     os.makedirs(os.path.join(root, "DatFlow"), exist_ok=True)
     head = np.array([nx, ny, nz, ID], dtype=np.int32).tobytes() + \
-        np.array([block.xmin + offsetOutput * block.dh, block.ymin + offsetOutput * block.dh, block.zmin + offsetOutput * block.dh, block.dh],
+        np.array([block.xmin + gx0 * block.dh, block.ymin + offsetOutput * block.dh, block.zmin + offsetOutput * block.dh, block.dh],
                  dtype=np.float64).tobytes()
     path = None
     if outputtype != 2:
@@ -70,6 +87,8 @@ def read_flow(path: str):
 
 def write_continue_blocks(blocks: Sequence, step: int, time_over_Tref: float, root: str = ".") -> str:
     """write_continue_blocks (FluidDomain.f90:268-285).  `time_over_Tref` is what main.f90:118 passes (time / Tref)."""
+    for b in blocks:
+        _whole(b, "write_continue_blocks")
     os.makedirs(os.path.join(root, "DatContinue"), exist_ok=True)
     path = os.path.join(root, "DatContinue", "continue" + _name10(time_over_Tref))
     with open(path, "wb") as fh:
@@ -102,6 +121,7 @@ def regrid_from_continue(block, saved) -> Optional[np.ndarray]:
     """The trilinear re-gridding of check_is_continue (FluidDomain.f90:166-224) for one current block: every node takes
     its populations from the finest saved block that contains it; nodes no saved block covers keep their value.
     Returns the new fIn (19,X,Y,Z) or None when nothing is covered."""
+    _whole(block, "regrid_from_continue")
     order = list(range(len(saved)))                                            # sortdh, :153-165: as written there the swap
     for i in range(len(saved) - 1):                                            # test compares the UNSORTED dh of slots i and j
         for j in range(i + 1, len(saved)):

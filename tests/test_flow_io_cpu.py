@@ -27,3 +27,27 @@ def test_continue_file_reader_round_trip(tmp_path):
         fh.write(np.array([0.5, 1.5, 2.5, 0.25]).tobytes()); fh.write(np.array([3, 4, 5], np.int32).tobytes()); fh.write(f.tobytes())
     n, step, t, blocks = flow_io.read_continue_file(str(p))
     assert (n, step, t) == (1, 42, 0.75) and np.array_equal(blocks[0]["fIn"], f) and blocks[0]["dh"] == 0.25
+
+
+class _Slab:
+    def __init__(self, xDim, xOffset, xLocal):
+        self.xDim, self.xOffset, self.xLocal, self.yDim, self.zDim = xDim, xOffset, xLocal, 10, 12
+        self.xmin = self.ymin = self.zmin = 0.0
+        self.dh = 1.0
+
+
+def test_flow_window_is_the_slab_part_of_the_output_window():
+    """the staging buffer of write_flow must have the size fsilbm_block_write_flow_window fills on an x-slab."""
+    assert flow_io.flow_window(_Slab(32, 0, 32), 2) == (2, 28, 6, 8)          # whole block
+    assert flow_io.flow_window(_Slab(32, 0, 8), 2) == (2, 6, 6, 8)            # first slab loses the offset planes
+    assert flow_io.flow_window(_Slab(32, 8, 8), 2) == (8, 8, 6, 8)            # interior slab: all its planes
+    assert flow_io.flow_window(_Slab(32, 24, 8), 2) == (24, 6, 6, 8)          # last slab
+    assert flow_io.flow_window(_Slab(32, 0, 2), 2)[1] == 0                    # window misses the slab
+
+
+def test_restart_helpers_refuse_slabs():
+    import pytest
+    with pytest.raises(ValueError, match="x-slab"):
+        flow_io.write_continue_blocks([_Slab(32, 8, 8)], 1, 0.5, root="/nonexistent")
+    with pytest.raises(ValueError, match="x-slab"):
+        flow_io.regrid_from_continue(_Slab(32, 8, 8), [])

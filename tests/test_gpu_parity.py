@@ -329,3 +329,60 @@ def test_les_with_plate(oracle, F):
         assert rel_err(pg.body.v_Eforce, ovb.v_Eforce) <= TOL_FORCE
     compare_fluid(ob, gb, exact=False)
     assert rel_err(gb.download_tau_all(), ob.tau_all) <= TOL_FLUID
+
+
+def test_nine_mrt_blocks_share_or_refuse_matrix_entries(oracle, F):
+    """The MRT matrix table (constant memory) holds 8 entries keyed by content: blocks of equal relaxation time share one, a
+    ninth DISTINCT set of matrices is refused instead of overwriting block 0's (mrt_slot = slot % 8)."""
+    from tests.common import make_pair
+    pairs = []
+    for k in range(9):        # nine live MRT blocks, two distinct viscosities -> two entries
+        ob, gb = make_pair(oracle, F, (10, 8, 6), model=3, nu=0.05 if k % 2 == 0 else 0.08, volumeForceIn=(1e-6, 0.0, 0.0))
+        pairs.append((ob, gb))
+    for n in range(1, 6):
+        for ob, gb in pairs:
+            ob.set_blktime(float(n)); gb.set_blktime(float(n))
+            ob.step(); gb.step()
+    for ob, gb in pairs:
+        assert np.array_equal(gb.download_fIn(), ob.fIn)
+    # seven more distinct viscosities fill the table (2 + 6 = 8); the next one must be refused loudly
+    extra = []
+    with pytest.raises(F.FsilbmError, match="MRT"):
+        for k in range(7):
+            gb = F.LBMBlock(6, 6, 6, iCollidModel=3, flow=F.FlowCondType(nu=0.1 + 0.01 * k))
+            extra.append(gb)
+            gb.initialise(0.0)
+    assert len(extra) == 7
+    for gb in extra:
+        gb.close()
+    gb = F.LBMBlock(6, 6, 6, iCollidModel=3, flow=F.FlowCondType(nu=0.2))   # entries freed by close() are reusable
+    gb.initialise(0.0)
+    gb.close()
+    for ob, gb in pairs:
+        gb.close()
+
+
+def test_more_separate_bodies_than_box_table_entries(oracle, F):
+    """20 small plates far apart in one block: more stencil boxes than the 16-entry box table.  The nearest boxes are joined (a box
+    is only storage), and the result stays bit-identical to the oracle."""
+    from tests.common import make_pair
+    flow = dict(nu=0.05, uvwIn=(0.04, 0.0, 0.0), Uref=0.04, ntolLBM=3, dtolLBM=1e-30)
+    ob, gb = make_pair(oracle, F, (72, 60, 20), BndConds=(101, 104, 301, 301, 301, 301), **flow)
+    pgs, ovs = [], []
+    for i in range(5):
+        for j in range(4):
+            kw = dict(origin=(8.3 + 13.0 * i, 7.2 + 14.0 * j, 8.4), nEL=2, len1=1.0, Nspan=3, spanlen=3.0, Lspan=0.0, chord_dir=(1.0, 0.2, 0.0),
+                      span_dir=(0.0, 0.0, 1.0), IBPenaltyAlpha=1.0, denIn=1.0)
+            pg = F.RigidPlate(**kw)
+            ov = oracle.VirtualBody(pg.body.v_nelmts, v_move=0, iBodyModel=1)
+            ov.v_Exyz[...] = pg.body.v_Exyz; ov.v_Evel[...] = pg.body.v_Evel; ov.v_Ea[...] = pg.body.v_Ea
+            pgs.append(pg); ovs.append(ov)
+    for n in range(1, 9):
+        ob.set_blktime(float(n))
+        it_o = ob.step(ovs)
+        it_g = F.tree_collision_streaming_IBM_FEM(gb, pgs, time=float(n))
+        assert it_o == it_g == 3
+    for pg, ov in zip(pgs, ovs):
+        assert np.array_equal(pg.body.v_Eforce, ov.v_Eforce)
+    compare_fluid(ob, gb)
+    gb.close()
