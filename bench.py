@@ -549,6 +549,7 @@ def run_gpu(args):
     check = F._lib.check
     t0 = time.perf_counter()
     blk.upload_fIn(f_host.numpy())
+    upload_s = time.perf_counter() - t0
     n_out = 0
     for n in range(args.steps):
         step(args.warmup + args.steps + n + 1)
@@ -576,6 +577,7 @@ def run_gpu(args):
     h2d = f_host.numel() * 8 * world + 7 * 8 * markers * args.steps
     d2h = (den_host.numel() + uuu_host.numel()) * 8 * world * n_out + 3 * 8 * markers * args.steps
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+           "seconds": e2e_s, "upload_seconds": upload_s, "upload_gbs": f_host.numel() * 8 / upload_s / 1e9,
            "segment": f"fIn uploaded from pinned host once, {args.steps} steps through the LBMBlock API with host arguments, den+uuu read back "
                       f"to pinned host every {flow_every} steps ({n_out} read-backs, asynchronous: each overlaps the following steps and is waited for "
                       f"before the next one and at the end); wall clock, bytes averaged per step"}

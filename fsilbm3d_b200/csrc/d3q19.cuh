@@ -114,10 +114,14 @@ struct CollideConsts {
 
 // What the LES closures contained in collision_ need beyond the cell itself (models 11, 14, 15).
 struct LesCtx {
-    const double *uuu;        // [3][X][Y][Z] velocity field of this step (WALE, Vreman: neighbour differences); null for model 11
+    const double *uuu;        // velocity field of this step (WALE, Vreman: neighbour differences), pointing at local plane 0 of component
+                              // 0; null for model 11.  One GPU: [3][X][Y][Z].  x-slab: [3][X+2][Y][Z] with the neighbours' edge planes
+                              // in the ghost planes -1 and X (exchanged before the update)
     double *tau_all;          // [X][Y][Z] (FluidDomain.f90:1279,1422,1505)
-    int X, Y, Z;              // extents of the fields
-    int x, y, z;              // this cell
+    size_t ncomp;             // distance between the components of uuu
+    int X, Y, Z;              // local extents
+    int gx, XG;               // global x of this cell and global x extent: where the reference switches to one-sided differences
+    int x, y, z;              // this cell (local)
     bool write_tau;           // false when a boundary layer is collided a second time for the half-way stash
 };
 
@@ -129,10 +133,9 @@ __device__ __forceinline__ double CvremConst() { return 2.5 * 0.17 * 0.17; }
 // center_diff / onesid_diff (FluidDomain.f90:1425-1434) of uuu(.,.,.,k) along `axis`, branching as the reference does
 __device__ __forceinline__ double les_grad(const LesCtx &c, int k, int axis, double invdh)
 {
-    const size_t n = (size_t)c.X * c.Y * c.Z;
     const size_t stride = axis == 0 ? (size_t)c.Y * c.Z : (axis == 1 ? (size_t)c.Z : 1);
-    const int pos = axis == 0 ? c.x : (axis == 1 ? c.y : c.z), dim = axis == 0 ? c.X : (axis == 1 ? c.Y : c.Z);
-    const double *u = c.uuu + (size_t)k * n + ((size_t)c.x * c.Y + c.y) * c.Z + c.z;
+    const int pos = axis == 0 ? c.gx : (axis == 1 ? c.y : c.z), dim = axis == 0 ? c.XG : (axis == 1 ? c.Y : c.Z);
+    const double *u = c.uuu + (size_t)k * c.ncomp + ((size_t)c.x * c.Y + c.y) * c.Z + c.z;
     if (pos > 0 && pos < dim - 1) return (u[stride] - *(u - stride)) * invdh;
     if (pos == 0) return (-3.0 * u[0] + 4.0 * u[stride] - u[2 * stride]) * invdh;
     return (-3.0 * u[0] + 4.0 * *(u - stride) - *(u - 2 * stride)) * invdh;

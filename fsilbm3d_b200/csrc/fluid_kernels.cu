@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128, (MODEL <= 2 ? 5 : 4)) collide_push_kernel
     const bool ibm_here = IBM && plane_in_boxes(p.boxes, p.g.xOffset + x, p.g.XG);
     cell_state(f, p.hF, p.Fvol, p.boxes, ibm_here, p.g.xOffset + x, y, z, p.g.XG, Y, Z, den, u1, u2, u3, F1, F2, F3);
     if (MODEL >= 11) {
-        const LesCtx les{p.uuu, p.tau_all, X, Y, Z, x, y, z, true};
+        const LesCtx les{p.uuu, p.tau_all, p.uuu_ncomp, X, Y, Z, p.g.xOffset + x, p.g.XG, x, y, z, true};
         collide<MODEL>(f, den, u1, u2, u3, F1, F2, F3, p.cc, &les);
     } else {
         collide<MODEL>(f, den, u1, u2, u3, F1, F2, F3, p.cc);
@@ -227,7 +227,7 @@ void launch_initialise(const Geom &g, double *f, const VelocityField &vel, doubl
 }
 
 // ---- calculate_macro_quantities_ over the slab (writers, probes, un-fused pass) --------------------
-__global__ void macro_full_kernel(Geom g, const double *f, double hF1, double hF2, double hF3, double *den, double *uuu,
+__global__ void macro_full_kernel(Geom g, const double *f, double hF1, double hF2, double hF3, double *den, double *uuu, size_t ncomp,
                                   const __grid_constant__ IbmBoxes boxes)
 {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
@@ -244,19 +244,19 @@ __global__ void macro_full_kernel(Geom g, const double *f, double hF1, double hF
         const long long bc = box_lookup(boxes, g.xOffset + x, y, z, g.XG, g.Y, g.Z);
         if (bc >= 0) { u1 = boxes.u[bc]; u2 = boxes.u[boxes.ncell + bc]; u3 = boxes.u[2 * boxes.ncell + bc]; }
     }
-    const size_t n = (size_t)g.X * g.plane;
     const size_t c = (size_t)x * g.plane + (size_t)y * g.Z + z;
     if (den) den[c] = d;
-    if (uuu) { uuu[c] = u1; uuu[n + c] = u2; uuu[2 * n + c] = u3; }
+    if (uuu) { uuu[c] = u1; uuu[ncomp + c] = u2; uuu[2 * ncomp + c] = u3; }
 }
 
-void launch_macro_full(const Geom &g, const double *f, const double hF[3], double *den, double *uuu, cudaStream_t s, const IbmBoxes *boxes)
+void launch_macro_full(const Geom &g, const double *f, const double hF[3], double *den, double *uuu, cudaStream_t s, const IbmBoxes *boxes, size_t ncomp)
 {
+    if (!ncomp) ncomp = (size_t)g.X * g.plane;
     dim3 block; int bz, by;
     line_block(g.Z, block, bz, by);
     dim3 grid((g.Z + bz - 1) / bz, (g.Y + by - 1) / by, g.X);
     IbmBoxes none{};
-    macro_full_kernel<<<grid, block, 0, s>>>(g, f, hF[0], hF[1], hF[2], den, uuu, boxes ? *boxes : none);
+    macro_full_kernel<<<grid, block, 0, s>>>(g, f, hF[0], hF[1], hF[2], den, uuu, ncomp, boxes ? *boxes : none);
     count_launch();
 }
 
@@ -472,7 +472,7 @@ __global__ void stash_face_kernel(const __grid_constant__ FaceParams p)
     double den, u1, u2, u3, F1, F2, F3;
     cell_state(f, p.hF, p.Fvol, p.boxes, p.boxes.n > 0, g.xOffset + x, y, z, g.XG, g.Y, g.Z, den, u1, u2, u3, F1, F2, F3);
     if (MODEL >= 11) {
-        const LesCtx les{p.uuu, p.tau_all, g.X, g.Y, g.Z, x, y, z, false};   // the main kernel writes tau_all, not this re-collision
+        const LesCtx les{p.uuu, p.tau_all, p.uuu_ncomp, g.X, g.Y, g.Z, g.xOffset + x, g.XG, x, y, z, false};   // the main kernel writes tau_all, not this re-collision
         collide<MODEL>(f, den, u1, u2, u3, F1, F2, F3, p.cc, &les);
     } else {
         collide<MODEL>(f, den, u1, u2, u3, F1, F2, F3, p.cc);
@@ -590,7 +590,7 @@ __global__ void collision_fields_kernel(const __grid_constant__ FieldParams p)
 #pragma unroll
     for (int q = 0; q < Q; q++) f[q] = p.f[q * g.pstride + base];
     if (MODEL >= 11) {
-        const LesCtx les{p.uuu, p.tau_all, g.X, g.Y, g.Z, x, y, z, true};
+        const LesCtx les{p.uuu, p.tau_all, n, g.X, g.Y, g.Z, g.xOffset + x, g.XG, x, y, z, true};
         collide<MODEL>(f, p.den[c], p.uuu[c], p.uuu[n + c], p.uuu[2 * n + c], p.force[c], p.force[n + c], p.force[2 * n + c], p.cc, &les);
     } else {
         collide<MODEL>(f, p.den[c], p.uuu[c], p.uuu[n + c], p.uuu[2 * n + c], p.force[c], p.force[n + c], p.force[2 * n + c], p.cc);

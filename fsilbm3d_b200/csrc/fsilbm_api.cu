@@ -199,6 +199,7 @@ struct Block {
     bool hw_alloc[6]{};
     double *den = nullptr, *uuu = nullptr, *force = nullptr;   // un-fused fields / download staging
     double *tau_all = nullptr;                                 // [X][Y][Z], LES models only (FluidDomain.f90:1279,1422,1505)
+    double *uuu_les = nullptr;                                 // x-slab of a WALE / Vreman block: [3][X+2][Y][Z], neighbours' edge planes in the ghosts
     double *uuu_ave = nullptr;                                 // [9][X][Y][Z], running means of calculate_turbulent_statistic_ (:1147)
     float *outtmp = nullptr; size_t outtmp_cap = 0;            // OUTtmp staging of write_flow_ (:30,399-403)
     double *scratch = nullptr; size_t scratch_cap = 0;         // probes / flux
@@ -343,6 +344,13 @@ void half_force(const Block &b, double hF[3])
     for (int k = 0; k < 3; k++) hF[k] = 0.5 * b.volumeForce[k] * b.g.dh;   // FluidDomain.f90:1137
 }
 
+// The velocity field the WALE / Vreman closures difference: the ghost-free staging field on one GPU, the ghosted slab field otherwise.
+static inline void les_field(const Block &b, const double *&uuu, size_t &ncomp)
+{
+    if (b.uuu_les) { uuu = b.uuu_les + b.g.plane; ncomp = (size_t)(b.g.X + 2) * b.g.plane; }
+    else { uuu = b.uuu; ncomp = (size_t)b.g.X * b.g.plane; }
+}
+
 // The MRT matrix table in constant memory has MRT_SLOTS entries.  An entry is keyed by its contents: blocks with the same
 // relaxation time (same dh and nu) share one, an entry is freed when its last block is destroyed or re-initialised, and a block
 // whose matrices find no free entry is refused (FSILBM_ERR_MODEL) instead of overwriting another block's.
@@ -431,7 +439,8 @@ FaceParams face_params(Block &b, int face, double *f, const double *fA, const Ve
     p.boxes = b.boxes;
     if (!b.ibm_active) p.boxes.n = 0;
     p.model = b.model;
-    p.tau_all = b.tau_all; p.uuu = b.uuu;
+    p.tau_all = b.tau_all;
+    les_field(b, p.uuu, p.uuu_ncomp);
     return p;
 }
 
@@ -734,8 +743,8 @@ int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, d
     if (!(iCollidModel == 1 || iCollidModel == 2 || iCollidModel == 3 || iCollidModel == 11 || iCollidModel == 14 || iCollidModel == 15))
         return fail(FSILBM_ERR_MODEL, "iCollidModel %d not provided (1 SRT, 2 TRT, 3 MRT, 11 Smagorinsky, 14 WALE, 15 Vreman; 12 and 13 read "
                                       "uninitialised variables upstream, FluidDomain.f90:1245-1246,1292,1297-1304)", iCollidModel);
-    if ((iCollidModel == 14 || iCollidModel == 15) && xLocal != xDim)
-        return fail(FSILBM_ERR_MODEL, "iCollidModel %d differences velocity across x-planes; slab-split LES blocks are not provided", iCollidModel);
+    if ((iCollidModel == 14 || iCollidModel == 15) && xLocal != xDim && xLocal < 3)
+        return fail(FSILBM_ERR_MODEL, "iCollidModel %d differences velocity over three x-planes at the domain faces: a slab needs at least 3 planes", iCollidModel);
     auto b = std::make_unique<Block>();
     for (int i = 0; i < 3; i++) {   // check_periodic_boundary_, FluidDomain.f90:110-125
         b->periodic[i] = 0;
@@ -803,7 +812,7 @@ int fsilbm_block_destroy(fsilbm_handle h)
     for (int i = 0; i < 2; i++) cudaFree(b->f[i]);
     for (int i = 0; i < 6; i++) { cudaFree(b->stash[i]); cudaFree(b->l2den[i]); cudaFree(b->l2u[i]); }
     cudaFree(b->den); cudaFree(b->uuu); cudaFree(b->force); cudaFree(b->stat); cudaFree(b->tau_all);
-    cudaFree(b->uuu_ave); cudaFree(b->outtmp); cudaFree(b->scratch);
+    cudaFree(b->uuu_ave); cudaFree(b->uuu_les); cudaFree(b->outtmp); cudaFree(b->scratch);
     cudaFree(b->boxes.u); cudaFree(b->boxes.force);
     for (auto &bd : b->bodies) bd.release();
     cudaStreamSynchronize(b->ibm_stream); cudaStreamSynchronize(b->ibm_main_stream);
@@ -893,9 +902,16 @@ int fsilbm_block_upload_fIn(fsilbm_handle h, const double *fIn)
     b->early_ok = false;
     const Geom &g = b->g;
     const size_t n = (size_t)g.X * g.plane;
-    CK(cudaStreamSynchronize(b->stream));
-    for (int q = 0; q < Q; q++)
-        CK(cudaMemcpy(b->f[b->cur] + q * g.pstride + g.plane, fIn + q * n, sizeof(double) * n, cudaMemcpyHostToDevice));
+    // one strided copy (19 rows of X planes into rows of X + 2 planes), ordered after the work already queued on the block's
+    // stream; from page-locked memory it runs at the link's rate without a host round trip per population
+    if (sizeof(double) * g.pstride < ((size_t)1 << 31)) {   // cudaMemcpy2D pitches are limited to 2 GiB
+        CK(cudaMemcpy2DAsync(b->f[b->cur] + g.plane, sizeof(double) * g.pstride, fIn, sizeof(double) * n, sizeof(double) * n, Q,
+                             cudaMemcpyHostToDevice, b->stream));
+    } else {
+        for (int q = 0; q < Q; q++)
+            CK(cudaMemcpyAsync(b->f[b->cur] + q * g.pstride + g.plane, fIn + q * n, sizeof(double) * n, cudaMemcpyHostToDevice, b->stream));
+    }
+    CK(cudaStreamSynchronize(b->stream));   // the caller may reuse fIn on return
     return 0;
 }
 
@@ -905,9 +921,14 @@ int fsilbm_block_download_fIn(fsilbm_handle h, double *fIn)
     if (!b || !fIn) return fail(FSILBM_ERR_ARG, "bad handle/argument");
     const Geom &g = b->g;
     const size_t n = (size_t)g.X * g.plane;
+    if (sizeof(double) * g.pstride < ((size_t)1 << 31)) {
+        CK(cudaMemcpy2DAsync(fIn, sizeof(double) * n, b->f[b->cur] + g.plane, sizeof(double) * g.pstride, sizeof(double) * n, Q,
+                             cudaMemcpyDeviceToHost, b->stream));
+    } else {
+        for (int q = 0; q < Q; q++)
+            CK(cudaMemcpyAsync(fIn + q * n, b->f[b->cur] + q * g.pstride + g.plane, sizeof(double) * n, cudaMemcpyDeviceToHost, b->stream));
+    }
     CK(cudaStreamSynchronize(b->stream));
-    for (int q = 0; q < Q; q++)
-        CK(cudaMemcpy(fIn + q * n, b->f[b->cur] + q * g.pstride + g.plane, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -1029,7 +1050,27 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
         double hF0[3];
         half_force(b, hF0);
         if (int rc = io_wait(b)) return rc;
-        launch_macro_full(g, fA, hF0, nullptr, b.uuu, b.stream, b.ibm_active ? &b.boxes : nullptr);
+        if (g.X != g.XG) {
+            // x-slab: the differences across a slab interface need the neighbour's edge plane of THIS step's velocity (the
+            // reference switches to one-sided differences only at the domain faces, FluidDomain.f90:1343-1385): one plane each way
+            if (!(g_nccl.nranks > 1 && g_nccl.comm)) return fail(FSILBM_ERR_COMM, "a slab of a WALE/Vreman block needs the communicator (fsilbm_comm_init)");
+            const size_t nc = (size_t)(g.X + 2) * g.plane;
+            if (!b.uuu_les) { CK(cudaMalloc(&b.uuu_les, sizeof(double) * 3 * nc)); CK(cudaMemsetAsync(b.uuu_les, 0, sizeof(double) * 3 * nc, b.stream)); }
+            launch_macro_full(g, fA, hF0, nullptr, b.uuu_les + g.plane, b.stream, b.ibm_active ? &b.boxes : nullptr, nc);
+            const int R = g_nccl.nranks, r = g_nccl.rank;
+            const int right = r + 1 < R ? r + 1 : -1, left = r > 0 ? r - 1 : -1;   // no wrap: the reference never differences across a periodic x face
+            NCK(g_nccl.GroupStart());
+            for (int k = 0; k < 3; k++) {
+                double *u = b.uuu_les + (size_t)k * nc;
+                if (right >= 0) NCK(g_nccl.Send(u + (size_t)g.X * g.plane, g.plane, kNcclFloat64, right, g_nccl.comm, b.stream));        // my plane X-1
+                if (left >= 0) NCK(g_nccl.Send(u + g.plane, g.plane, kNcclFloat64, left, g_nccl.comm, b.stream));                        // my plane 0
+                if (left >= 0) NCK(g_nccl.Recv(u, g.plane, kNcclFloat64, left, g_nccl.comm, b.stream));                                  // ghost -1
+                if (right >= 0) NCK(g_nccl.Recv(u + (size_t)(g.X + 1) * g.plane, g.plane, kNcclFloat64, right, g_nccl.comm, b.stream));  // ghost X
+            }
+            NCK(g_nccl.GroupEnd());
+        } else {
+            launch_macro_full(g, fA, hF0, nullptr, b.uuu, b.stream, b.ibm_active ? &b.boxes : nullptr);
+        }
     }
     // per-face side buffers taken from the pre-collision state (see kernels.h FaceParams)
     for (int face = 0; face < 6; face++) {
@@ -1057,7 +1098,8 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
     for (int k = 0; k < 3; k++) p.Fvol[k] = b.volumeForce[k];
     p.boxes = b.boxes;
     if (!b.ibm_active) p.boxes.n = 0;
-    p.tau_all = b.tau_all; p.uuu = b.uuu;
+    p.tau_all = b.tau_all;
+    les_field(b, p.uuu, p.uuu_ncomp);
     const bool multi = g_nccl.nranks > 1 && g_nccl.comm && g.X != g.XG;   // a block cut into x-slabs (sons stay whole on one rank)
     const bool ghost = multi || g_force_ghost;
     p.wrap_x = ghost ? 0 : 1;

@@ -62,7 +62,8 @@ struct StepParams {
     unsigned long long step;
     // LES models (11 Smagorinsky, 14 WALE, 15 Vreman)
     double *tau_all;          // [X][Y][Z]
-    const double *uuu;        // [3][X][Y][Z] velocity field of this step (models 14, 15), written by macro_full_kernel
+    const double *uuu;        // velocity field of this step (models 14, 15), written by macro_full_kernel: local plane 0 of component 0
+    size_t uuu_ncomp;         // distance between its components: X*Y*Z on one GPU, (X+2)*Y*Z on an x-slab (ghost planes, see LesCtx)
 };
 
 // Receiving side of the peer-memory halo: one thread waits until both neighbours have published this step (their edge planes
@@ -93,6 +94,7 @@ struct FaceParams {
     int model;
     double *tau_all;          // LES blocks
     const double *uuu;
+    size_t uuu_ncomp;
 };
 
 struct FieldParams {
@@ -109,7 +111,9 @@ void upload_mrt(int slot, const double *M_COLLID, const double *M_FORCE, cudaStr
 int launch_collide_push(const StepParams &p, int model, cudaStream_t s);
 void step_add_planes(StepParams &p, int begin, int count);   // appends a range of local planes to the launch list
 void launch_initialise(const Geom &g, double *f, const VelocityField &vel, double denIn, cudaStream_t s);
-void launch_macro_full(const Geom &g, const double *f, const double hF[3], double *den, double *uuu, cudaStream_t s, const IbmBoxes *boxes = nullptr);
+// ncomp: distance between the components of uuu (0 = X*Y*Z, the ghost-free layout)
+void launch_macro_full(const Geom &g, const double *f, const double hF[3], double *den, double *uuu, cudaStream_t s, const IbmBoxes *boxes = nullptr,
+                       size_t ncomp = 0);
 void launch_bc_face(const FaceParams &p, cudaStream_t s);
 void launch_bc_face_pair(const FaceParams &lo, const FaceParams &hi, cudaStream_t s);   // the two faces of one axis in one launch
 void launch_stash_face(const FaceParams &p, cudaStream_t s);

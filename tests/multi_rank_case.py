@@ -46,6 +46,15 @@ def main():
     variants += [(1, cases[1], dict(ibm_local=0, ibm_force_exchange=1))]
     # loop control through ncclAllReduce (one kernel per phase) instead of the peer-memory mailbox inside the cooperative kernel
     variants += [(1, c, dict(ibm_local=1, ibm_force_exchange=x, ibm_single_launch=0)) for c in (cases[1], two) for x in (1, 0)]
+    # WALE / Vreman blocks cut into slabs: the velocity differences across an interface take the neighbour's edge plane
+    # (FluidDomain.f90:1343-1385, 1445-1484; one-sided only at the domain faces)
+    les = [dict(name="les_wale_slabs", dims=(8 * world + 3, 12, 14), bc=(101, 104, 203, 203, 301, 301), plate_origin=None, model=14, wave=2e-2,
+                flow=dict(nu=0.02, uvwIn=(0.04, 0.0, 0.0), Uref=0.04)),
+           dict(name="les_vrem_periodic_slabs", dims=(8 * world + 2, 12, 14), bc=(301,) * 6, plate_origin=None, model=15, wave=2e-2,
+                flow=dict(nu=0.02, volumeForceIn=(1e-6, 0.0, 0.0))),
+           dict(name="les_vrem_plate_slabs", dims=(10 * world + 1, 20, 24), bc=(102, 104, 202, 202, 301, 301), plate_origin="mid", model=15, wave=2e-2,
+                flow=dict(nu=0.02, uvwIn=(0.04, 0.0, 0.0), shearRateIn=(0.0, 3e-4, 0.0), Uref=0.04, ntolLBM=3, dtolLBM=1e-30))]
+    variants += [(1, c, dict(ibm_local=1, ibm_force_exchange=1)) for c in les] + [(0, les[0], dict(ibm_local=1, ibm_force_exchange=1))]
     variants = [(m, c, dict(dict(ibm_single_launch=1), **o)) for (m, c, o) in variants]
     F._lib.check(F.lib().fsilbm_set_option(b"halo_timeout_s", 30))
     ok = True
@@ -57,9 +66,9 @@ def main():
         X, Y, Z = case["dims"]
         off, cnt = F.slab_range(X, rank, world)
         flow = F.FlowCondType(**case["flow"])
-        gb = F.LBMBlock(X, Y, Z, BndConds=case["bc"], flow=flow, xOffset=off, xLocal=cnt, device=local)
+        gb = F.LBMBlock(X, Y, Z, BndConds=case["bc"], iCollidModel=case.get("model", 1), flow=flow, xOffset=off, xLocal=cnt, device=local)
         gb.initialise(0.0)
-        f0 = perturbed_state((X, Y, Z), flow)
+        f0 = perturbed_state((X, Y, Z), flow, wave_amp=case.get("wave", 1e-3))
         gb.upload_fIn(np.ascontiguousarray(f0[:, off:off + cnt]))
         gb.update_volume_force(); gb.set_boundary_conditions()
         plates = []
@@ -85,7 +94,7 @@ def main():
         if rank == 0:
             from oracle import oracle as O
             of = O.Flow(**case["flow"])
-            ob = O.LBMBlock(X, Y, Z, BndConds=case["bc"], flow=of)
+            ob = O.LBMBlock(X, Y, Z, BndConds=case["bc"], iCollidModel=case.get("model", 1), flow=of)
             ob.initialise(0.0)
             ob.fIn[...] = f0
             ob.update_volume_force(); ob.set_boundary_conditions(); ob.calculate_macro_quantities()
@@ -119,7 +128,8 @@ def main():
             e_den, e_u, e_f = rel_err(DEN, ob.den), rel_err(UUU, ob.uuu), rel_err(FF, ob.fIn)
             exact = bool(np.array_equal(FF, ob.fIn))
             # north_star's tolerances; with the ordered, replicated IBM mode (default) the slabs are in fact bit-identical
-            good = e_den <= 1e-12 and e_u <= 1e-12 and e_f <= 1e-12 and eF <= 1e-10 and exact
+            # (WALE raises to the powers 1.5, 2.5, 1.25: CUDA's pow and libm's differ in the last bit, so no bit-exactness there)
+            good = e_den <= 1e-12 and e_u <= 1e-12 and e_f <= 1e-12 and eF <= 1e-10 and (exact or case.get("model") == 14)
             ok &= good
             print(f"[multi x{world}] halo={gb.halo_transport!r} ibm={opts} {case['name']}: rel err den {e_den:.2e} u {e_u:.2e} f {e_f:.2e} force {eF:.2e} bit-exact {exact} -> {'OK' if good else 'FAIL'}", flush=True)
         gb.close()
