@@ -551,7 +551,10 @@ def run_gpu(args):
     blk.upload_fIn(f_host.numpy())
     upload_s = time.perf_counter() - t0
     n_out = 0
+    laps, lap_every = [], max(1, args.steps // 4)
     for n in range(args.steps):
+        if n % lap_every == 0:
+            laps.append(time.perf_counter() - t0)      # host clock when each quarter of the steps was ISSUED (diagnostic)
         step(args.warmup + args.steps + n + 1)
         if (n + 1) % flow_every == 0 or n + 1 == args.steps:
             # asynchronous read-back (the reference forks its writer): the copy overlaps the following steps; the previous
@@ -577,7 +580,7 @@ def run_gpu(args):
     h2d = f_host.numel() * 8 * world + 7 * 8 * markers * args.steps
     d2h = (den_host.numel() + uuu_host.numel()) * 8 * world * n_out + 3 * 8 * markers * args.steps
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-           "seconds": e2e_s, "upload_seconds": upload_s, "upload_gbs": f_host.numel() * 8 / upload_s / 1e9,
+           "seconds": e2e_s, "upload_seconds": upload_s, "quarter_issue_seconds": laps, "upload_gbs": f_host.numel() * 8 / upload_s / 1e9,
            "segment": f"fIn uploaded from pinned host once, {args.steps} steps through the LBMBlock API with host arguments, den+uuu read back "
                       f"to pinned host every {flow_every} steps ({n_out} read-backs, asynchronous: each overlaps the following steps and is waited for "
                       f"before the next one and at the end); wall clock, bytes averaged per step"}

@@ -38,6 +38,8 @@ def make(name):
     for k, b in enumerate(body_states(I)):
         for key, v in b.items():
             out[f"body{k}_{key}"] = v
+    # how often the reference entered PenaltyForce_ (Solidbody.f90:981): sum over the steps of iterLBM x number of bodies
+    out["penalty_calls"] = np.array(I.modules["solidbody"].procs["penaltyforce_"].ncalls)
     fl = I.modules["flowcondition"].vars["flow"].f
     out["derived"] = json.dumps(dict(nu=float(fl["nu"]), Uref=float(fl["uref"]), Lref=float(fl["lref"]), Tref=float(fl["tref"])))
     np.savez_compressed(RC.golden_path(name), **out)

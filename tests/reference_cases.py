@@ -68,6 +68,40 @@ CASES["flexible_plate"] = dict(
     group=dict(iBodyModel=2, isMotionGiven=(1,) * 6, denR=1.0, psR=0.3, KB=0.02, KS=500.0, AoAo=(0.0, 0.0, 12.0), firstXYZ=(6.3, 6.6, 5.2)), isKB=1)
 
 
+# two rigid plates whose stencil boxes overlap (Gauss-Seidel order over the bodies, Solidbody.f90:898-903) and a finite tolerance, so
+# that the loop control (:895-906) ends the penalty iteration early on some steps
+CASES["two_plates_gauss_seidel"] = dict(
+    kind="body", dims=(22, 16, 14), bc=(101, 104, 202, 202, 301, 301), model=1, params=P0, steps=8, uvwIn=(0.05, 0.0, 0.0), Uref=0.05, Lref=4.0,
+    Re=40.0, wave=1e-3, flow=dict(shearRateIn=(0.0, 2e-4, 0.0)), ntolLBM=6, dtolLBM=0.5, numsubstep=1,
+    plate=dict(nEL=4, chord=4.0, span=4.0, Nspan=4),
+    groups=[dict(iBodyModel=1, isMotionGiven=(1,) * 6, EmR=1.0, tcR=0.05, AoAo=(0.0, 0.0, 8.0), firstXYZ=(6.3, 6.6, 5.2)),
+            dict(iBodyModel=1, isMotionGiven=(1,) * 6, EmR=1.0, tcR=0.05, freq=0.03, XYZAmpl=(0.0, 0.8, 0.0), AoAo=(0.0, 0.0, -6.0),
+                 firstXYZ=(8.7, 8.1, 5.4))], isKB=0)
+# TRT with a heaving AND pitching rigid plate between symmetric side faces
+CASES["trt_plate_pitching"] = dict(
+    kind="body", dims=(20, 14, 14), bc=(101, 104, 302, 302, 301, 301), model=2, params=(3.0 / 16.0,) + (0.0,) * 9, steps=8, uvwIn=(0.05, 0.0, 0.0),
+    Uref=0.05, Lref=4.0, Re=40.0, wave=1e-3, flow={}, ntolLBM=3, dtolLBM=1e-30, numsubstep=1, plate=dict(nEL=4, chord=4.0, span=4.0, Nspan=4),
+    group=dict(iBodyModel=1, isMotionGiven=(1,) * 6, EmR=1.0, tcR=0.05, freq=0.02, XYZAmpl=(0.0, 0.6, 0.0), AoAAmpl=(0.0, 0.0, 10.0),
+               AoAPhi=(0.0, 0.0, 90.0), firstXYZ=(6.3, 6.6, 5.2)), isKB=0)
+# a flexible plate driven in heave and pitch at its leading edge (BASELINE configs[3] in miniature), four structural sub-steps
+CASES["flexible_plate_heaving"] = dict(
+    kind="body", dims=(20, 14, 14), bc=(101, 104, 301, 301, 301, 301), model=1, params=P0, steps=6, uvwIn=(0.04, 0.0, 0.0), Uref=0.04, Lref=4.0,
+    Re=40.0, wave=1e-3, flow={}, ntolLBM=3, dtolLBM=1e-30, numsubstep=4, plate=dict(nEL=4, chord=4.0, span=4.0, Nspan=4),
+    group=dict(iBodyModel=2, isMotionGiven=(1,) * 6, denR=2.0, psR=0.3, KB=0.05, KS=800.0, freq=0.02, XYZAmpl=(0.0, 0.8, 0.0),
+               AoAAmpl=(0.0, 0.0, 10.0), AoAPhi=(0.0, 0.0, 90.0), firstXYZ=(6.3, 6.6, 5.2)), isKB=1)
+# MRT with every kind of face and a Smagorinsky block with a plate: collision models other than SRT next to boundaries / bodies
+CASES["mrt_all_faces_mixed"] = _fluid((9, 10, 8), (101, 103, 204, 202, 201, 203), model=3, steps=8, uvwIn=(0.03, 0.0, 0.0), Uref=0.03,
+                                      shearRateIn=(0.0, 4e-4, 1e-4))
+CASES["les_smag_plate"] = dict(
+    kind="body", dims=(20, 14, 14), bc=(101, 104, 301, 301, 301, 301), model=11, params=P0, steps=6, uvwIn=(0.05, 0.0, 0.0), Uref=0.05, Lref=4.0,
+    Re=400.0, wave=2e-2, flow={}, ntolLBM=3, dtolLBM=1e-30, numsubstep=1, plate=dict(nEL=4, chord=4.0, span=4.0, Nspan=4),
+    group=dict(iBodyModel=1, isMotionGiven=(1,) * 6, EmR=1.0, tcR=0.05, AoAo=(0.0, 0.0, 15.0), firstXYZ=(6.3, 6.6, 5.2)), isKB=0)
+
+
+def case_groups(case):
+    return case["groups"] if "groups" in case else [case["group"]]
+
+
 def golden_path(name):
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"ref_{name}.npz")
 
@@ -115,7 +149,7 @@ def write_inputs(case, wd, continue_at_end=False):
         p = case["plate"]
         S.write_plate_dat(os.path.join(wd, "plate.dat"), chain(p["nEL"] + 1, p["chord"]), 0.5 * p["span"], 0.5 * p["span"], (0.0, 0.0, 1.0),
                           Nspan=p["Nspan"])
-        groups = [dict(case["group"], fishNum=1, mesh="plate.dat")]
+        groups = [dict(g, fishNum=1, mesh="plate.dat") for g in case_groups(case)]
     extra = dict(timeContiDelta=case["steps"] / Tref) if continue_at_end else {}
     text = S.inflow_text(npsize=1, isConCmpt=2, numsubstep=case.get("numsubstep", 1), timeSimTotal=total, Re=case["Re"], uvwIn=case["uvwIn"],
                          LrefType=1, Lref=case["Lref"], TrefType=0, UrefType=9, Uref=case["Uref"], ntolLBM=case.get("ntolLBM", 3),
@@ -152,27 +186,28 @@ def run_oracle(O, case, sb=None):
         Fb.fIn[:, x0:x0 + (sx + 1) // 2, y0:y0 + (sy + 1) // 2, z0:z0 + (sz + 1) // 2] = blocks[1].fIn[:, ::2, ::2, ::2]
     for b in blocks:
         b.update_volume_force(); b.set_boundary_conditions(); b.calculate_macro_quantities()
-    ov, its = None, []
+    ovs, its = [], []
     if case["kind"] == "body":
-        body = sb.VBodies[0]
-        ov = O.VirtualBody(body.v_nelmts, v_move=body.v_move, iBodyModel=body.iBodyModel)
-        root.bodies = [ov]
+        for body in sb.VBodies:
+            ovs.append(O.VirtualBody(body.v_nelmts, v_move=body.v_move, iBodyModel=body.iBodyModel))
+        root.bodies = ovs
     nsub = case.get("numsubstep", 1)
     for n in range(1, case["steps"] + 1):
         t = float(n)
         O.set_blktime_all(root, t)
-        if ov is not None:
+        for body, ov in zip(sb.VBodies if ovs else (), ovs):
             body.UpdatePosVelArea()
             ov.v_Exyz[...] = body.v_Exyz; ov.v_Evel[...] = body.v_Evel; ov.v_Ea[...] = body.v_Ea
         O.tree_collision_streaming_IBM_FEM(root, iters=its)
-        if ov is not None:
+        for body, ov in zip(sb.VBodies if ovs else (), ovs):
             body.v_Eforce[...] = ov.v_Eforce
             body.FluidLoads()
-            for isub in range(1, nsub + 1):
+        for isub in range(1, nsub + 1):          # Solver advances every carried body per sub-step (Solidbody.f90:386-397)
+            for body in (sb.VBodies if ovs else ()):
                 body.structure(t, isub, 1.0, 1.0 / nsub)
     for b in blocks:
         b.calculate_macro_quantities()
-    return blocks, ov, its
+    return blocks, (ovs[0] if len(ovs) == 1 else (ovs or None)), its
 
 
 def load(name):

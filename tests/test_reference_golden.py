@@ -36,22 +36,34 @@ def test_oracle_reproduces_the_reference_fluid(oracle, name):
 @pytest.mark.parametrize("name", [n for n in NAMES if RC.CASES[n]["kind"] == "body"])
 def test_oracle_and_cpp_structure_reproduce_the_reference_body_case(oracle, name, tmp_path):
     from fsilbm3d_b200 import solid_solver as S
-    case, g = RC.load(name)
+    case, g = RC.CASES[name], RC.load(name)[1]
     wd = str(tmp_path)
-    RC.write_inputs(RC.CASES[name], wd)
-    sb = S.SolidBodies("inFlow.dat", RC.CASES[name]["bc"], cwd=wd)
-    blocks, ov, its = RC.run_oracle(oracle, RC.CASES[name], sb)
-    body = sb.VBodies[0]
-    assert its == [RC.CASES[name].get("ntolLBM", 3)] * RC.CASES[name]["steps"]
+    RC.write_inputs(case, wd)
+    sb = S.SolidBodies("inFlow.dat", case["bc"], cwd=wd)
+    blocks, ov, its = RC.run_oracle(oracle, case, sb)
+    ovs = ov if isinstance(ov, list) else [ov]
+    flexible = any(gr["iBodyModel"] == 2 for gr in RC.case_groups(case))
+    # the reference entered PenaltyForce_ sum(iterLBM) x bodies times: same iteration counts, step by step in total
+    assert sum(its) * len(ovs) == int(g["penalty_calls"])
+    if case["dtolLBM"] > 1e-20:
+        assert min(its) < case["ntolLBM"], "the tolerance never ended the iteration early: the case does not test the loop control"
     e_f = rel_err(blocks[0].fIn, g["fIn0"])
-    e_F = rel_err(np.array(ov.v_Eforce), g["body0_v_Eforce"])
-    e_x = rel_err(np.array(ov.v_Exyz), g["body0_v_Exyz"])
-    e_p = rel_err(body.pos, g["body0_pos"])
-    e_v = rel_err(body.vel, g["body0_vel"])
-    print(f"{name}: rel err fIn {e_f:.2e} marker force {e_F:.2e} markers {e_x:.2e} beam pos {e_p:.2e} vel {e_v:.2e}; "
-          f"fIn bit-exact: {np.array_equal(blocks[0].fIn, g['fIn0'])}")
-    assert e_f <= 1e-12 and e_x <= 1e-12 and e_p <= 1e-12
-    # the Newton / CG beam solve stops at dtolFEM = 1e-12: the two structural implementations (reference Fortran, C++ stand-in) differ in
-    # accumulation order inside MATMUL / DOT_PRODUCT, which the iteration carries to ~1e-10 of the (small) nodal velocities
-    assert e_F <= 1e-10 and e_v <= 1e-8
+    exact = np.array_equal(blocks[0].fIn, g["fIn0"])
+    worst = dict(F=0.0, x=0.0, p=0.0, v=0.0)
+    for k, (body, o) in enumerate(zip(sb.VBodies, ovs)):
+        worst["F"] = max(worst["F"], rel_err(np.array(o.v_Eforce), g[f"body{k}_v_Eforce"]))
+        worst["x"] = max(worst["x"], rel_err(np.array(o.v_Exyz), g[f"body{k}_v_Exyz"]))
+        worst["p"] = max(worst["p"], rel_err(body.pos, g[f"body{k}_pos"]))
+        worst["v"] = max(worst["v"], rel_err(body.vel, g[f"body{k}_vel"]))
+        if not flexible:
+            assert np.array_equal(np.array(o.v_Eforce), g[f"body{k}_v_Eforce"]) and np.array_equal(np.array(o.v_Exyz), g[f"body{k}_v_Exyz"])
+    print(f"{name}: rel err fIn {e_f:.2e} marker force {worst['F']:.2e} markers {worst['x']:.2e} beam pos {worst['p']:.2e} vel {worst['v']:.2e}; "
+          f"fIn bit-exact: {exact}; iterations {its}")
+    if not flexible:
+        assert exact and np.array_equal(blocks[0].den, g["den0"]) and np.array_equal(blocks[0].uuu, g["uuu0"])
+    assert e_f <= 1e-12 and worst["x"] <= 1e-12 and worst["p"] <= 1e-12
+    # flexible bodies: the Newton / CG beam solve stops at dtolFEM = 1e-12; the two structural implementations (reference Fortran,
+    # C++ stand-in) differ by a few ulp per solve in the rotational degrees of freedom (accumulation order), which the stiff beam
+    # carries to ~1e-10 of the (small) nodal velocities
+    assert worst["F"] <= 1e-10 and worst["v"] <= 1e-8
     sb.close()

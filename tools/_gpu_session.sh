@@ -1,6 +1,13 @@
-# round 2 session D: whole GPU suite after the hygiene changes; ncu --set full of the IBM=true collide instantiation; default bench
+# round 2 session G (2 GPUs): e2e laps of heave1024 x2
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r02k_pytest_gpu.txt 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/r02k_pytest_gpu.txt
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:collide_push_kernel<\(int\)1, \(bool\)1' -s 10 -c 2 -o gpurun_out/r02k_ncu_collide_ibm_true python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity-check > gpurun_out/r02k_under_ncu.log 2>&1; echo "ncu rc=$?"
-timeout 600 python bench.py --steps 400 --warmup 20 --no-cpu-baseline > gpurun_out/r02k_bench_plate512_s400.json 2> gpurun_out/err_k1.txt; echo "bench rc=$?"; cut -c1-400 gpurun_out/r02k_bench_plate512_s400.json
-ls -la gpurun_out | tail -5
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
+timeout 400 $TR bench.py --gpus 2 --steps 200 --warmup 10 > gpurun_out/r02n_bench_heave1024_n2_s200.json 2> gpurun_out/err_n1.txt; echo "bench n2 rc=$?"
+python - <<'P'
+import json
+d=json.load(open('gpurun_out/r02n_bench_heave1024_n2_s200.json')); print(d['ms_per_step'], d['e2e'])
+P
+timeout 400 $TR bench.py --gpus 2 --steps 100 --warmup 10 > gpurun_out/r02n_bench_heave1024_n2_s100.json 2> gpurun_out/err_n2.txt; echo "bench n2 rc=$?"
+python - <<'P'
+import json
+d=json.load(open('gpurun_out/r02n_bench_heave1024_n2_s100.json')); print(d['ms_per_step'], d['e2e'])
+P
