@@ -276,6 +276,12 @@ module fsilbm_c
             integer(c_int), value :: interpolateScheme
             integer(c_int), intent(out) :: pair
         end function
+        integer(c_int) function fsilbm_pair_create_remote(father, owner_rank, pair) bind(C, name='fsilbm_pair_create_remote')
+            import :: c_int
+            integer(c_int), value :: father
+            integer(c_int), value :: owner_rank
+            integer(c_int), intent(out) :: pair
+        end function
         integer(c_int) function fsilbm_pair_destroy(pair) bind(C, name='fsilbm_pair_destroy')
             import :: c_int
             integer(c_int), value :: pair
@@ -330,7 +336,7 @@ module fsilbm_gpu
               gpu_refresh_host_wait, gpu_refresh_host_tau_all, gpu_update_volume_force, gpu_set_boundary_conditions, &
               gpu_collide_stream, gpu_sync, gpu_interaction_force, gpu_interaction_force_begin, gpu_interaction_force_wait, &
               gpu_body_status, gpu_download_stencil, gpu_field_stat, gpu_write_flow_window, gpu_turbulent_statistic, &
-              gpu_fluid_flux, gpu_probe_velocity, gpu_pair_create, gpu_pair_free, gpu_pair_info, gpu_extract_interpolate_layer, &
+              gpu_fluid_flux, gpu_probe_velocity, gpu_pair_create, gpu_pair_create_remote, gpu_pair_free, gpu_pair_info, gpu_extract_interpolate_layer, &
               gpu_interpolation_father_to_son, gpu_deliver_son_to_father, gpu_comm_unique_id, gpu_comm_init, gpu_comm_finalize, &
               gpu_halo_transport, gpu_pass_macro, gpu_pass_reset_volume_force, gpu_pass_add_volume_force, gpu_pass_collision, &
               gpu_pass_halfway_bc_set, gpu_pass_streaming, gpu_download_fields, gpu_upload_fields, gpu_launch_count, &
@@ -606,6 +612,12 @@ contains
     subroutine gpu_pair_create(ipair, ifather, ison, interpolateScheme)
         integer, intent(in) :: ipair, ifather, ison, interpolateScheme
         call fsilbm_check(fsilbm_pair_create(gpu_handle(ifather), gpu_handle(ison), interpolateScheme, gpu_pair(ipair)))
+    end subroutine
+    ! slab runs, a son across a slab interface: the rank next to the son's owner registers the pair (same ipair numbering); its
+    ! father block then follows the owner's transfers through device-side flags.  The transfer wrappers below are no-ops there.
+    subroutine gpu_pair_create_remote(ipair, ifather, owner_rank)
+        integer, intent(in) :: ipair, ifather, owner_rank
+        call fsilbm_check(fsilbm_pair_create_remote(gpu_handle(ifather), owner_rank, gpu_pair(ipair)))
     end subroutine
     subroutine gpu_pair_free(ipair)
         integer, intent(in) :: ipair

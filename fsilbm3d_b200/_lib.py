@@ -78,7 +78,7 @@ def lib():
         "fsilbm_ibm_interaction_force_wait": [i, i, ppd, pi],
         "fsilbm_ibm_download_stencil": [i, i, vp, vp],
         "fsilbm_ibm_body_status": [i, i, vp],
-        "fsilbm_pair_create": [i, i, i, pi], "fsilbm_pair_destroy": [i], "fsilbm_pair_info": [i, pi],
+        "fsilbm_pair_create": [i, i, i, pi], "fsilbm_pair_create_remote": [i, i, pi], "fsilbm_pair_destroy": [i], "fsilbm_pair_info": [i, pi],
         "fsilbm_pair_extract_layer": [i, i], "fsilbm_pair_father_to_son": [i, i], "fsilbm_pair_son_to_father": [i],
         "fsilbm_comm_unique_id": [C.c_char_p], "fsilbm_comm_init": [i, i, C.c_char_p], "fsilbm_comm_finalize": [],
     }

@@ -99,6 +99,22 @@ class CommPair:
         check(lib().fsilbm_pair_son_to_father(self._h))
 
 
+class RemoteSon:
+    """The neighbour's half of a son across a slab interface (fsilbm_pair_create_remote): rank `owner_rank`, directly left or
+    right of this one, holds a son of `father` whose footprint reaches into this rank's slab."""
+
+    def __init__(self, father, owner_rank: int):
+        h = C.c_int(-1)
+        check(lib().fsilbm_pair_create_remote(father._h, owner_rank, C.byref(h)))
+        self._h = h.value
+        self.father, self.owner_rank = father, owner_rank
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            lib().fsilbm_pair_destroy(self._h)
+            self._h = None
+
+
 class blockTreeNode:
     """blockTreeNode (LBMBlockComm.f90:19-25): a block, the plates it carries (carriedBodies), its sons and CommPairs."""
 

@@ -262,6 +262,12 @@ struct Block {
         unsigned int *counters = nullptr;          // last-CTA counters of the two edge launches
         int *err = nullptr;
         unsigned long long step = 0;
+        // sons across this block's slab interfaces (see Pair): pairs registered by the neighbour on either side, and the
+        // deliveries this rank has completed towards either side
+        int remote_pairs[2] = {0, 0};
+        unsigned long long remote_base[2] = {0, 0};     // halo.step when the first registration of that side was made
+        int cross_pairs[2] = {0, 0};
+        unsigned long long delivered[2] = {0, 0};
     } halo;
     cudaEvent_t ev_pre = nullptr;                  // slab runs: the pre-collision face kernels of a step are done (the edge stream starts behind it)
 };
@@ -274,6 +280,13 @@ struct Pair {
     int father = -1, son = -1, scheme = 1;
     int sds[6]{}, s[6]{}, f[6]{}, si[6]{}, fi[6]{}, dimS[3]{}, dimF[3]{};
     double *buf[6][2]{}, *tbuf[6][2]{};
+    // A son across a slab interface of its father.  On the rank that owns the son: cross[side] = the footprint reaches into the
+    // left / right neighbour's slab (its planes are read and written through the peer-mapped buffers).  On that neighbour the
+    // pair exists as a registration only (remote = true, son = -1): its father block signals every finished step to the owner
+    // and waits for the owner's delivery before it starts the next one.
+    bool cross[2] = {false, false};
+    bool remote = false;
+    int owner_side = -1;       // remote registration: where the owner is (0 left, 1 right)
 };
 std::vector<std::unique_ptr<Pair>> g_pairs;
 int g_force_ghost = 0;
@@ -518,6 +531,9 @@ constexpr size_t kHaloMailboxBytes = sizeof(CtlSlot) * IBM_CTL_SLOTS * MAX_PEERS
 constexpr size_t kHaloHeaderBytes = ((kHaloFlagBytes + kHaloMailboxBytes + 4095) / 4096) * 4096;
 
 inline unsigned long long *halo_flag(unsigned char *region, int side, int parity) { return (unsigned long long *)region + (side * 2 + parity); }
+// flags of the sons across an interface, in the same region: kind 0 = "the neighbour on `side` has finished father step n",
+// kind 1 = "the neighbour on `side` (owner of sons reaching into this slab) has delivered n son->father transfers"
+inline unsigned long long *refine_flag(unsigned char *region, int kind, int side) { return (unsigned long long *)region + (8 + kind * 2 + side); }
 
 // Peer-memory halo set-up (collective over the communicator; every rank creates its blocks in the same order).
 // Each rank exports its two population buffers and a small flag/mailbox region with cudaIpcGetMemHandle, the handles are
@@ -895,6 +911,8 @@ int fsilbm_block_get(fsilbm_handle h, int what, double *value)
     return 0;
 }
 
+static int await_deliveries(Block &b);   // sons across a slab interface: see fsilbm_block_collide_stream
+
 int fsilbm_block_upload_fIn(fsilbm_handle h, const double *fIn)
 {
     Block *b = get(h);
@@ -919,6 +937,7 @@ int fsilbm_block_download_fIn(fsilbm_handle h, double *fIn)
 {
     Block *b = get(h);
     if (!b || !fIn) return fail(FSILBM_ERR_ARG, "bad handle/argument");
+    if (int rc = await_deliveries(*b)) return rc;
     const Geom &g = b->g;
     const size_t n = (size_t)g.X * g.plane;
     if (sizeof(double) * g.pstride < ((size_t)1 << 31)) {
@@ -959,6 +978,7 @@ int fsilbm_block_download_macro_async(fsilbm_handle h, double *den, double *uuu)
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
     if (int rc = io_wait(*b)) return rc;
     if (int rc = ensure_fields(*b, false)) return rc;
+    if (int rc = await_deliveries(*b)) return rc;
     double hF[3];
     half_force(*b, hF);
     launch_macro_full(b->g, b->f[b->cur], hF, b->den, b->uuu, b->stream);
@@ -986,6 +1006,7 @@ int fsilbm_block_download_macro(fsilbm_handle h, double *den, double *uuu)
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
     if (int rc = io_wait(*b)) return rc;
     if (int rc = ensure_fields(*b, false)) return rc;
+    if (int rc = await_deliveries(*b)) return rc;
     double hF[3];
     half_force(*b, hF);
     launch_macro_full(b->g, b->f[b->cur], hF, b->den, b->uuu, b->stream);
@@ -1030,12 +1051,54 @@ int fsilbm_block_set_boundary_conditions(fsilbm_handle h)
     return apply_boundary_conditions(*b, b->f[b->cur]);
 }
 
+// Sons across a slab interface (see Pair).  A rank into whose slab a neighbour's son reaches must not touch the planes the son
+// rewrites before the neighbour's son->father delivery of the last finished step has landed: one-thread wait on the block's stream.
+static int await_deliveries(Block &b)
+{
+    Block::Halo &h = b.halo;
+    if (!h.enabled) return 0;
+    for (int sd = 0; sd < 2; sd++) {
+        if (h.remote_pairs[sd] <= 0 || h.step <= h.remote_base[sd]) continue;
+        HaloWaitParams u{};
+        u.flag_lo = refine_flag(h.region, 1, sd);
+        u.step = (h.step - h.remote_base[sd]) * (unsigned long long)h.remote_pairs[sd];
+        u.err = h.err; u.timeout_ns = (unsigned long long)g_halo_timeout_s * 1000000000ull;
+        launch_halo_wait(u, b.stream);
+    }
+    return 0;
+}
+// ... and tells the owner of such a son when its father step is complete (collide-stream, halo, face kernels)
+static void announce_father_step(Block &b)
+{
+    Block::Halo &h = b.halo;
+    if (!h.enabled) return;
+    for (int sd = 0; sd < 2; sd++) {
+        if (h.remote_pairs[sd] <= 0) continue;
+        unsigned char *owner_region = sd == 0 ? h.peer_left : h.peer_right;
+        launch_flag_signal(refine_flag(owner_region, 0, sd ^ 1), h.step, b.stream);   // the owner sees this rank on its other side
+    }
+}
+// The owner's side: wait until the neighbours whose planes a cross pair touches have finished the father step this rank is at
+static void await_father_step(Block &F, const Pair &p)
+{
+    Block::Halo &h = F.halo;
+    for (int sd = 0; sd < 2; sd++) {
+        if (!p.cross[sd] || h.step == 0) continue;
+        HaloWaitParams u{};
+        u.flag_lo = refine_flag(h.region, 0, sd);
+        u.step = h.step;
+        u.err = h.err; u.timeout_ns = (unsigned long long)g_halo_timeout_s * 1000000000ull;
+        launch_halo_wait(u, g_stream);
+    }
+}
+
 int fsilbm_block_collide_stream(fsilbm_handle h)
 {
     Block *bp = get(h);
     if (!bp) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
     Block &b = *bp;
     if (!b.initialised) return fail(FSILBM_ERR_ARG, "block %d not initialised", h);
+    if (int rc = await_deliveries(b)) return rc;
     // an interaction-force call still in flight on another stream: the update reads its box fields, so it follows it ON THE DEVICE
     if (b.ibm_pending.active && b.ibm_pending.stream != b.stream) CK(cudaStreamWaitEvent(b.stream, b.ev_ibm_done, 0));
     const Geom &g = b.g;
@@ -1254,6 +1317,7 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
     CK(cudaGetLastError());
     if (int rc = apply_boundary_conditions(b, fB)) return rc;   // LBMBlockComm.f90:303
     TRACE(b.stream, 0, "faces");
+    announce_father_step(b);
     b.cur ^= 1;
     b.ibm_active = false;
     return 0;
@@ -1263,6 +1327,7 @@ int fsilbm_block_sync(fsilbm_handle h)
 {
     Block *b = get(h);
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
+    if (int rc = await_deliveries(*b)) return rc;   // a neighbour's son may still be rewriting father nodes of this slab
     CK(cudaStreamSynchronize(b->stream));
     CK(cudaStreamSynchronize(b->comm_stream));
     b->io_pending = false;
@@ -2164,7 +2229,18 @@ PairFaceParams pair_face(const Pair &p, Block &F, Block &S, int j, int force_of)
     int axis, bAx, aAx;
     pair_axes(j, axis, bAx, aAx);
     q.gF = F.g; q.gS = S.g;
-    q.fF = F.f[F.cur]; q.fF_rw = F.f[F.cur]; q.fS = S.f[S.cur];
+    q.fS = S.f[S.cur];
+    q.fv.nseg = 1;
+    q.fv.f[0] = F.f[F.cur]; q.fv.x0[0] = F.g.xOffset; q.fv.X[0] = F.g.X; q.fv.pstride[0] = F.g.pstride;
+    for (int sd = 0; sd < 2; sd++) {
+        if (!p.cross[sd]) continue;
+        // the neighbours flip their buffers in step with this rank (one flip per collide-stream of the block on every rank)
+        const int k = q.fv.nseg++;
+        q.fv.f[k] = F.halo.peer_f[sd][F.cur];
+        q.fv.X[k] = F.halo.peer_X[sd];
+        q.fv.x0[k] = sd == 0 ? F.g.xOffset - F.halo.peer_X[0] : F.g.xOffset + F.g.X;
+        q.fv.pstride[k] = (size_t)(F.halo.peer_X[sd] + 2) * F.g.plane;
+    }
     q.axis = axis; q.scheme = p.scheme;
     q.bF = p.dimF[bAx]; q.aF = p.dimF[aAx]; q.bS = p.dimS[bAx]; q.aS = p.dimS[aAx];
     q.fplane = p.f[j] - 1; q.fb0 = p.f[2 * bAx] - 1; q.fa0 = p.f[2 * aAx] - 1;
@@ -2228,9 +2304,21 @@ int fsilbm_pair_create(fsilbm_handle father, fsilbm_handle son, int interpolateS
     const int fdim[3] = {gf.XG, gf.Y, gf.Z};
     for (int k = 0; k < 3; k++)
         if (p->f[2 * k] < 1 || p->f[2 * k + 1] > fdim[k]) return fail(FSILBM_ERR_ARG, "son block is not inside its father along axis %d", k);
-    if (p->f[0] - 1 < gf.xOffset || p->f[1] - 1 >= gf.xOffset + gf.X)
-        return fail(FSILBM_ERR_ARG, "son block spans father planes %d..%d but this rank's father slab is %d..%d: a son must lie inside one x-slab of its father",
-                    p->f[0], p->f[1], gf.xOffset + 1, gf.xOffset + gf.X);
+    if (p->f[0] - 1 < gf.xOffset || p->f[1] - 1 >= gf.xOffset + gf.X) {
+        // the footprint reaches into a neighbouring slab: possible when those planes can be addressed through the peer-mapped
+        // population buffers of the halo (one neighbour deep), and the neighbour registers the pair (fsilbm_pair_create_remote)
+        Block::Halo &h = F->halo;
+        const int lo = p->f[0] - 1, hi = p->f[1] - 1;   // 0-based global father planes touched by the transfers
+        const bool want_l = lo < gf.xOffset, want_r = hi >= gf.xOffset + gf.X;
+        const bool ok_l = !want_l || (h.enabled && h.left >= 0 && h.left == g_nccl.rank - 1 && h.peer_f[0][0] && lo >= gf.xOffset - h.peer_X[0]);
+        const bool ok_r = !want_r || (h.enabled && h.right >= 0 && h.right == g_nccl.rank + 1 && h.peer_f[1][0] && hi < gf.xOffset + gf.X + h.peer_X[1]);
+        if (!ok_l || !ok_r)
+            return fail(FSILBM_ERR_ARG, "son block spans father planes %d..%d but this rank's father slab is %d..%d: a son may reach into the directly "
+                                        "neighbouring slabs only, and only with the peer-memory halo (option \"halo\" = 1, CUDA IPC available)",
+                        p->f[0], p->f[1], gf.xOffset + 1, gf.xOffset + gf.X);
+        if (F->tau_all) return fail(FSILBM_ERR_MODEL, "a son across a slab interface of an LES father (tau_all field) is not provided");
+        p->cross[0] = want_l; p->cross[1] = want_r;
+    }
     for (int j = 0; j < 6; j++) { p->si[j] = p->s[j] + p->sds[j] * ratio; p->fi[j] = p->f[j] + p->sds[j]; }
     // allocate_fIn_tau, :213-264
     const bool need_tau = F->tau_all || S->tau_all;
@@ -2248,9 +2336,38 @@ int fsilbm_pair_create(fsilbm_handle father, fsilbm_handle son, int interpolateS
     int slot = -1;
     for (size_t i = 0; i < g_pairs.size(); i++) if (!g_pairs[i]) { slot = (int)i; break; }
     if (slot < 0) { g_pairs.emplace_back(); slot = (int)g_pairs.size() - 1; }
+    for (int sd = 0; sd < 2; sd++) if (p->cross[sd]) F->halo.cross_pairs[sd]++;
     g_pairs[slot] = std::move(p);
     F->is_father = true;
     F->early_ok = S->early_ok = false;
+    *pair = slot;
+    return 0;
+}
+
+// The neighbour's half of a son across a slab interface: rank `owner_rank` (the rank directly left or right of this one) holds a
+// son block whose footprint reaches into THIS rank's slab of `father`.  From now on this rank's father block tells the owner
+// when each of its steps is complete and does not start the next step before the owner's son->father delivery has landed.
+int fsilbm_pair_create_remote(fsilbm_handle father, int owner_rank, int *pair)
+{
+    Block *F = get(father);
+    if (!F || !pair) return fail(FSILBM_ERR_ARG, "bad handle/argument");
+    Block::Halo &h = F->halo;
+    if (!h.enabled) return fail(FSILBM_ERR_ARG, "a son across a slab interface needs the peer-memory halo (option \"halo\" = 1, CUDA IPC available)");
+    int side = -1;
+    if (owner_rank == g_nccl.rank - 1 && h.left == owner_rank) side = 0;
+    if (owner_rank == g_nccl.rank + 1 && h.right == owner_rank) side = 1;
+    if (side < 0) return fail(FSILBM_ERR_ARG, "rank %d is not a direct neighbour of rank %d in the slab decomposition", owner_rank, g_nccl.rank);
+    auto p = std::make_unique<Pair>();
+    p->father = father; p->remote = true; p->owner_side = side;
+    if (h.remote_pairs[side] == 0) h.remote_base[side] = h.step;
+    else if (h.remote_base[side] != h.step) return fail(FSILBM_ERR_ARG, "register every son across an interface before the first step after the previous registration");
+    h.remote_pairs[side]++;
+    int slot = -1;
+    for (size_t i = 0; i < g_pairs.size(); i++) if (!g_pairs[i]) { slot = (int)i; break; }
+    if (slot < 0) { g_pairs.emplace_back(); slot = (int)g_pairs.size() - 1; }
+    g_pairs[slot] = std::move(p);
+    F->is_father = true;
+    F->early_ok = false;
     *pair = slot;
     return 0;
 }
@@ -2261,6 +2378,10 @@ int fsilbm_pair_destroy(int pair)
     if (!p) return fail(FSILBM_ERR_ARG, "bad pair %d", pair);
     cudaStreamSynchronize(g_stream);
     for (int j = 0; j < 6; j++) for (int t = 0; t < 2; t++) { cudaFree(p->buf[j][t]); cudaFree(p->tbuf[j][t]); }
+    if (Block *F = get(p->father)) {
+        if (p->remote && F->halo.remote_pairs[p->owner_side] > 0) F->halo.remote_pairs[p->owner_side]--;
+        for (int sd = 0; sd < 2; sd++) if (p->cross[sd] && F->halo.cross_pairs[sd] > 0) F->halo.cross_pairs[sd]--;
+    }
     g_pairs[pair].reset();
     return 0;
 }
@@ -2278,8 +2399,10 @@ int fsilbm_pair_extract_layer(int pair, int time)
 {
     Pair *p = get_pair(pair);
     if (!p || (time != 1 && time != 2)) return fail(FSILBM_ERR_ARG, "bad pair/argument");
+    if (p->remote) return 0;   // the neighbour's registration of a son across the interface: the owner does the transfers
     Block *F = get(p->father), *S = get(p->son);
     if (!F || !S) return fail(FSILBM_ERR_ARG, "pair %d refers to a destroyed block", pair);
+    await_father_step(*F, *p);
     for (int j = 0; j < 6; j++) {
         if (S->bc[j] != BCfluid) continue;   // :354
         launch_pair_extract(pair_face(*p, *F, *S, j, 0), time, g_stream);
@@ -2292,6 +2415,7 @@ int fsilbm_pair_father_to_son(int pair, int n_timeStep)
 {
     Pair *p = get_pair(pair);
     if (!p) return fail(FSILBM_ERR_ARG, "bad pair %d", pair);
+    if (p->remote) return 0;
     Block *F = get(p->father), *S = get(p->son);
     if (!F || !S) return fail(FSILBM_ERR_ARG, "pair %d refers to a destroyed block", pair);
     for (int j = 0; j < 6; j++) {
@@ -2306,11 +2430,19 @@ int fsilbm_pair_son_to_father(int pair)
 {
     Pair *p = get_pair(pair);
     if (!p) return fail(FSILBM_ERR_ARG, "bad pair %d", pair);
+    if (p->remote) return 0;
     Block *F = get(p->father), *S = get(p->son);
     if (!F || !S) return fail(FSILBM_ERR_ARG, "pair %d refers to a destroyed block", pair);
+    await_father_step(*F, *p);
     for (int j = 0; j < 6; j++) {
         if (p->sds[j] == 0) continue;
         launch_pair_s2f(pair_face(*p, *F, *S, j, 1), g_stream);   // son's volumeForce, dh: :552-553
+    }
+    for (int sd = 0; sd < 2; sd++) {
+        if (!p->cross[sd]) continue;   // tell the neighbour that the father nodes of its slab are rewritten: it may start its next step
+        Block::Halo &h = F->halo;
+        h.delivered[sd]++;
+        launch_flag_signal(refine_flag(sd == 0 ? h.peer_left : h.peer_right, 1, sd ^ 1), h.delivered[sd], g_stream);
     }
     CK(cudaGetLastError());
     return 0;

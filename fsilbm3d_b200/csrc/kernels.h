@@ -230,10 +230,18 @@ void launch_ibm_tol_sum(const IbmBody *bodies_dev, const int *lead_dev, int nbod
 void launch_ibm_decide(const double *in2, double Uref, int ntol, double dtol, IbmCtl *ctl, cudaStream_t s);
 
 // ---- grid refinement (refine_kernels.cu): one son face coupled to its father, LBMBlockComm.f90:340-979 ----------
+// The father's populations as the rank that owns the son sees them: its own slab and, for a son across a slab interface, the
+// neighbouring slabs through their peer-mapped buffers (NVLink loads / stores from inside the face kernels).
+struct FatherView {
+    int nseg;                  // 1 (own slab only) .. 3
+    double *f[3];              // current population buffer of each segment ([19][X+2][Y][Z])
+    int x0[3], X[3];           // first global plane and thickness of each segment
+    size_t pstride[3];         // (X+2)*Y*Z of each segment
+};
+
 struct PairFaceParams {
     Geom gF, gS;
-    const double *fF;          // father populations (current buffer), read by extract
-    double *fF_rw;             // the same buffer, written by son->father
+    FatherView fv;             // father populations (current buffers): read by extract, written by son->father
     double *fS;                // son populations (current buffer)
     int axis;                  // face normal: 0 x, 1 y, 2 z; in-plane axes b (faster) and a: x faces (z,y), y faces (z,x), z faces (y,x)
     int scheme;                // flow%interpolateScheme: 2 = cubic, otherwise linear
@@ -252,6 +260,8 @@ struct PairFaceParams {
 void launch_pair_extract(const PairFaceParams &p, int time, cudaStream_t s);
 void launch_pair_f2s(const PairFaceParams &p, int t, cudaStream_t s);
 void launch_pair_s2f(const PairFaceParams &p, cudaStream_t s);
+// one-thread kernel: release-store `value` to a (possibly peer-mapped) 64-bit flag at system scope
+void launch_flag_signal(unsigned long long *flag, unsigned long long value, cudaStream_t s);
 
 // ---- output / diagnostics on device state (io_kernels.cu) ---------------------------------------------------------
 struct FlowWindowParams {

@@ -91,6 +91,14 @@ __device__ __forceinline__ void face_xyz(int axis, int pl, int b, int a, int &x,
     else { z = pl; x = a; y = b; }
 }
 
+// segment of the father view that holds global plane x (segment 0 = the own slab)
+__device__ __forceinline__ int father_segment(const FatherView &v, int x)
+{
+    int sg = 0;
+    for (int i = 1; i < v.nseg; i++) if (x >= v.x0[i] && x < v.x0[i] + v.X[i]) sg = i;
+    return sg;
+}
+
 // extract_interpolate_layer, LBMBlockComm.f90:340-505, one son face.  time 1: t1 <- father plane;
 // time 2: t2 <- father plane, t1 <- 0.5*(t1+t2).
 __global__ void pair_extract_kernel(const __grid_constant__ PairFaceParams p, int time)
@@ -100,12 +108,16 @@ __global__ void pair_extract_kernel(const __grid_constant__ PairFaceParams p, in
     int x, y, z;
     face_xyz(p.axis, p.fplane, p.fb0 + b, p.fa0 + a, x, y, z);
     const Geom &g = p.gF;
-    x -= g.xOffset;   // father indices are global; the footprint lies inside this rank's slab (fsilbm_pair_create)
+    // father indices are global; the plane lies in this rank's slab or, for a son across an interface, in a neighbour's
+    const int sg = father_segment(p.fv, x);
+    const double *fF = p.fv.f[sg];
+    const size_t ps = p.fv.pstride[sg];
+    x -= p.fv.x0[sg];
     const size_t cell = (size_t)(x + 1) * g.plane + (size_t)y * g.Z + z;
     const size_t n = (size_t)a * p.bF + b, nn = (size_t)p.aF * p.bF;
 #pragma unroll
     for (int q = 0; q < Q; q++) {
-        const double v = p.fF[q * g.pstride + cell];
+        const double v = fF[q * ps + cell];
         if (time == 1) p.buf[0][q * nn + n] = v;
         else { p.buf[1][q * nn + n] = v; p.buf[0][q * nn + n] = 0.5 * (p.buf[0][q * nn + n] + v); }
     }
@@ -150,7 +162,10 @@ __global__ void pair_s2f_kernel(const __grid_constant__ PairFaceParams p)
     face_xyz(p.axis, p.siplane, p.sib0 + 2 * b, p.sia0 + 2 * a, xs, ys, zs);
     face_xyz(p.axis, p.fiplane, p.fib0 + b, p.fia0 + a, xf, yf, zf);
     const Geom &gs = p.gS, &gf = p.gF;
-    xf -= gf.xOffset;
+    const int sg = father_segment(p.fv, xf);
+    double *fF = p.fv.f[sg];
+    const size_t psF = p.fv.pstride[sg];
+    xf -= p.fv.x0[sg];
     const size_t cs = (size_t)(xs + 1) * gs.plane + (size_t)ys * gs.Z + zs;
     const size_t cf = (size_t)(xf + 1) * gf.plane + (size_t)yf * gf.Z + zf;
     double f[Q];
@@ -161,13 +176,25 @@ __global__ void pair_s2f_kernel(const __grid_constant__ PairFaceParams p)
     const double coeff = (tauF / tauS) * 2.0;                    // :563
     grid_transform(f, coeff, p.hF[0], p.hF[1], p.hF[2]);          // son's volumeForce and dh, :552-553
 #pragma unroll
-    for (int q = 0; q < Q; q++) p.fF_rw[q * gf.pstride + cf] = f[q];
+    for (int q = 0; q < Q; q++) fF[q * psF + cf] = f[q];
+}
+
+__global__ void flag_signal_kernel(unsigned long long *flag, unsigned long long value)
+{
+    if (threadIdx.x != 0) return;
+    __threadfence_system();   // everything this stream wrote before (also into peer memory) is visible before the flag is
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");
 }
 
 void launch_pair_extract(const PairFaceParams &p, int time, cudaStream_t s)
 {
     dim3 block(128), grid((p.bF + 127) / 128, p.aF);
     pair_extract_kernel<<<grid, block, 0, s>>>(p, time);
+    count_launch();
+}
+void launch_flag_signal(unsigned long long *flag, unsigned long long value, cudaStream_t s)
+{
+    flag_signal_kernel<<<1, 32, 0, s>>>(flag, value);
     count_launch();
 }
 void launch_pair_f2s(const PairFaceParams &p, int t, cudaStream_t s)

@@ -233,6 +233,14 @@ int fsilbm_ibm_download_stencil(fsilbm_handle h, int body, short *Ei, float *Ew)
  * interpolateScheme is flow%interpolateScheme (2 = cubic, otherwise linear; FlowCondition.f90:71).
  * The tree itself (build_block_tree :195, CompareBlocks) stays with the host. */
 int fsilbm_pair_create(fsilbm_handle father, fsilbm_handle son, int interpolateScheme, int *pair);
+/* Slab runs.  A son lives whole on ONE rank.  If its footprint lies inside that rank's father slab nothing else is needed.  If it
+ * reaches into the slab of the rank directly to the left or right (a son across a slab interface), the owner's kernels read and
+ * write the neighbour's father planes through the peer-mapped population buffers of the halo (NVLink), and the NEIGHBOUR
+ * registers the pair with fsilbm_pair_create_remote(father, owner_rank, &pair): its father block then announces every finished
+ * step to the owner and waits for the owner's son->father delivery before it starts the next one (device-side flags, no host
+ * in the loop).  Both calls are made at the same point of the run (before the first step); the other pair functions are no-ops
+ * on a remote registration.  Needs option "halo" = 1 with CUDA IPC available; the father must not be an LES block. */
+int fsilbm_pair_create_remote(fsilbm_handle father, int owner_rank, int *pair);
 int fsilbm_pair_destroy(int pair);
 /* out[0:6] sds, [6:12] s, [12:18] f, [18:24] si, [24:30] fi (1-based plane indices as in CommPair, :11-18),
  * [30:33] xDimS,yDimS,zDimS, [33:36] xDimF,yDimF,zDimF */

@@ -162,18 +162,28 @@ def refinement_case(F, dist, rank, world, local):
     sdims = (17, 13, 11)
     son_mins = [(5.0, 4.0, 3.0), (20.0 * (world - 1) + 6.0, 3.0, 2.0)]
     son_rank = [0, world - 1]
+    # sons ACROSS a slab interface (father planes 15..23 resp. 16..24 around the interface at x = 20 of ranks 0|1): the owner reads and
+    # writes the neighbour's father planes over NVLink, the neighbour registers the pair (fsilbm_pair_create_remote)
+    F._lib.check(F.lib().fsilbm_set_option(b"halo", 1))
+    son_mins += [(15.0, 1.0, 1.0), (16.0, 8.0, 7.0)]
+    son_rank += [0, 1]
+    son_reach = {2: 1, 3: 0}          # son index -> the neighbouring rank its footprint reaches into
+    nsons = len(son_mins)
     scheme = 2
     off, cnt = F.slab_range(X, rank, world)
     gf = F.FlowCondType(**kw)
     gF = F.LBMBlock(X, Y, Z, dh=1.0, BndConds=fbc, flow=gf, xOffset=off, xLocal=cnt, device=local)
     gF.initialise(0.0)
     f0F = perturbed_state((X, Y, Z), gf, seed=1)
-    f0S = [perturbed_state(sdims, gf, seed=2 + k) for k in range(2)]
+    f0S = [perturbed_state(sdims, gf, seed=2 + k) for k in range(nsons)]
     gF.upload_fIn(np.ascontiguousarray(f0F[:, off:off + cnt]))
     kwp = dict(origin=(8.3, 7.2, 4.1), nEL=6, len1=0.5, Nspan=4, spanlen=2.0, Lspan=0.0, chord_dir=(1.0, 0.3, 0.0), denIn=1.0)
     groot = F.blockTreeNode(gF)
     sons = {}
-    for k in range(2):
+    remote = []
+    for k in range(nsons):
+        if son_reach.get(k) == rank:
+            remote.append(F.RemoteSon(gF, son_rank[k]))
         if son_rank[k] != rank:
             continue
         gS = F.LBMBlock(*sdims, dh=0.5, xmin=son_mins[k][0], ymin=son_mins[k][1], zmin=son_mins[k][2], BndConds=sbc, flow=gf, device=local)
@@ -184,6 +194,7 @@ def refinement_case(F, dist, rank, world, local):
         sons[k] = (gS, plates)
     for nd in groot.walk():
         nd.block.update_volume_force(); nd.block.set_boundary_conditions()
+    gF.sync(); dist.barrier()      # start-up complete on every rank before an owner reads a neighbour's father planes
     if rank == 0:
         from oracle import oracle as O
         of = O.Flow(**kw)
@@ -191,7 +202,7 @@ def refinement_case(F, dist, rank, world, local):
         oF.initialise(0.0); oF.fIn[...] = f0F
         oroot = O.TreeNode(oF)
         oS, ov = [], None
-        for k in range(2):
+        for k in range(nsons):
             b = O.LBMBlock(*sdims, dh=0.5, xmin=son_mins[k][0], ymin=son_mins[k][1], zmin=son_mins[k][2], BndConds=sbc, flow=of)
             b.initialise(0.0); b.fIn[...] = f0S[k]
             bodies = []
@@ -225,9 +236,10 @@ def refinement_case(F, dist, rank, world, local):
                 if force is not None:
                     e_force = max(e_force, rel_err(force, ov.v_Eforce))
         good = exact_f and exact_s and e_force <= 1e-10
-        print(f"[multi x{world}] refinement on slabs (sons on ranks {son_rank}, cubic transfers, plate in son 0): father bit-exact {exact_f} "
+        print(f"[multi x{world}] refinement on slabs (sons on ranks {son_rank}, sons 2 and 3 across the interface of ranks 0|1, cubic transfers, "
+              f"plate in son 0): father bit-exact {exact_f} "
               f"sons bit-exact {exact_s} force {e_force:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
-    for pair in groot.comm:
+    for pair in groot.comm + remote:
         pair.close()
     for v in sons.values():
         v[0].close()
