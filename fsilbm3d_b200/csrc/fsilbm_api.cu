@@ -292,11 +292,7 @@ std::vector<std::unique_ptr<Pair>> g_pairs;
 int g_force_ghost = 0;
 int g_halo_timeout_s = 120;   // a neighbour this late is treated as lost (the wait kernel gives up, fsilbm_block_sync reports it)
 int g_ibm_single_launch = 1;   // 1: calculate_interaction_force as one cooperative kernel on single-rank blocks; 0: one kernel per phase
-int g_ibm_replicate = 1;       // multi-rank, ordered mode: 1 every rank runs the whole penalty iteration on all-reduced box velocities (one
-                               // collective per step, bit-identical to one GPU); 0 partial interpolation sums all-reduced per body and iteration
-int g_ibm_local = 1;           // multi-rank, ordered mode: 1 a body is iterated only by the ranks whose planes its stencil box touches (default);
-                               // 0 the replicated / partial-sum forms below
-int g_ibm_force_exchange = 1;  // with ibm_local: 1 every rank passes the same bodies and gets every body's forces back (one all-reduce);
+int g_ibm_force_exchange = 1;  // slab runs: 1 every rank passes the same bodies and gets every body's forces back (one all-reduce);
                                // 0 every rank passes only the bodies near its slab (distributed lists; the call is then collective even with none)
 int g_ibm_early_blocks = 1;    // blocks per SM of the cooperative IBM kernel when it runs beside a collide-stream update
 int g_ibm_early_lean = 0;      // 1: the 48-register build of the cooperative kernel when it runs beside an update
@@ -733,12 +729,10 @@ int fsilbm_set_option(const char *key, int value)
     }
     if (!strcmp(key, "force_ghost")) { g_force_ghost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_single_launch")) { g_ibm_single_launch = value ? 1 : 0; return 0; }
-    if (!strcmp(key, "ibm_replicate")) { g_ibm_replicate = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->csr_valid = false; return 0; }
     if (!strcmp(key, "ibm_early_blocks_per_sm")) { if (value < 1 || value > 4) return fail(FSILBM_ERR_ARG, "ibm_early_blocks_per_sm must be 1..4"); g_ibm_early_blocks = value; return 0; }
     if (!strcmp(key, "ibm_early_lean")) { g_ibm_early_lean = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_early_blocks")) { if (value < 0) return fail(FSILBM_ERR_ARG, "ibm_early_blocks must be >= 0"); g_ibm_early_total = value; return 0; }
     if (!strcmp(key, "ibm_early")) { g_ibm_early = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->early_ok = false; return 0; }
-    if (!strcmp(key, "ibm_local")) { g_ibm_local = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->csr_valid = false; return 0; }
     if (!strcmp(key, "ibm_force_exchange")) { g_ibm_force_exchange = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_ordered")) { g_ibm_ordered = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->csr_valid = false; return 0; }
     if (!strcmp(key, "halo_timeout_s")) { if (value < 1) return fail(FSILBM_ERR_ARG, "halo_timeout_s must be >= 1"); g_halo_timeout_s = value; return 0; }
@@ -1749,7 +1743,10 @@ int fsilbm_ibm_interaction_force_begin(fsilbm_handle h, int nbody, const int *ne
     // Slab runs, default form ("local"): a body is iterated only by the ranks whose planes its stencil box touches.
     // Shared boxes (a body across a slab interface) exchange their owned box planes pairwise and are then iterated
     // redundantly -- bit-identically -- by their participants; the loop control is all-reduced (two numbers per iteration).
-    const bool local = multi && ordered && g_ibm_local;
+    if (multi && !ordered)
+        return fail(FSILBM_ERR_ARG, "slab runs iterate a body redundantly on the ranks that share it, which needs the ordered (bit-reproducible) IBM form: "
+                                    "option ibm_ordered = 0 is a single-GPU comparison arm");
+    const bool local = multi;
     const bool lists_replicated = g_ibm_force_exchange != 0;   // every rank passes the same bodies and wants every force back
     b.ibm_pending = Block::IbmPending();
     if (nbody == 0 && !(local && !lists_replicated)) { b.ibm_active = false; return 0; }   // Solidbody.f90:891
@@ -1931,9 +1928,6 @@ int fsilbm_ibm_interaction_force_begin(fsilbm_handle h, int nbody, const int *ne
     half_force(b, hF);
     const double invh3_pen = 0.5 * dt * ((1.0 / g.dh) * (1.0 / g.dh) * (1.0 / g.dh)) / b.flow.denIn;   // :996
     const double invh3 = (1.0 / g.dh) * (1.0 / g.dh) * (1.0 / g.dh);                                     // :936
-    // Multi-rank, replicated form (ibm_local = 0): the box velocities (owner's value, zero elsewhere: the sum is exact) are
-    // all-reduced once, then every rank runs the whole of calculate_interaction_force on the full boxes of ALL bodies.
-    const bool replicate = multi && ordered && !local && g_ibm_replicate;
     // slab runs: with every rank's mailbox mapped (peer memory) the loop control is exchanged from inside the single cooperative
     // kernel; otherwise one kernel per phase with an ncclAllReduce of the two numbers per iteration
     const bool mailbox = local && b.halo.mailbox && g_ibm_single_launch;
@@ -1948,9 +1942,9 @@ int fsilbm_ibm_interaction_force_begin(fsilbm_handle h, int nbody, const int *ne
     }
     if (mailbox && nact > MAX_IBM_PHASE_BODIES)   // the other ranks are in the mailbox protocol: no silent switch to another path
         return fail(FSILBM_ERR_ARG, "more than %d bodies touch this slab (ibm_single_launch = 0 lifts the limit)", MAX_IBM_PHASE_BODIES);
-    bool single = (!multi || replicate || mailbox) && g_ibm_single_launch && nact <= MAX_IBM_PHASE_BODIES && nact > 0;
+    bool single = (!multi || mailbox) && g_ibm_single_launch && nact <= MAX_IBM_PHASE_BODIES && nact > 0;
     Geom gsten = g;
-    if (replicate || local) { gsten.xOffset = 0; gsten.X = g.XG; }   // stencil_marker: every stencil plane counts as owned
+    if (local) { gsten.xOffset = 0; gsten.X = g.XG; }   // stencil_marker: every stencil plane counts as owned
     if (ordered && nact) {
         // stencils first (the cell lists are built from them), then the lists; both survive while no body restencils
         long long entries = 0;
@@ -1984,7 +1978,7 @@ int fsilbm_ibm_interaction_force_begin(fsilbm_handle h, int nbody, const int *ne
     }
     // Early IBM: when every box lies inside the planes the last collide_stream finished first (and clear of the faces), the rest
     // of this call runs on its own stream behind ev_early, beside the remainder of that update, instead of behind all of it.
-    bool use_early = b.early_ok && g_ibm_early && bx.n > 0 && (!multi || local) && ordered;
+    bool use_early = b.early_ok && g_ibm_early && bx.n > 0 && ordered;
     for (int i = 0; i < bx.n && use_early; i++) {
         bool inside = false;
         int lo = bx.lo[i][0], hi = lo + bx.ext[i][0];
@@ -2012,11 +2006,7 @@ int fsilbm_ibm_interaction_force_begin(fsilbm_handle h, int nbody, const int *ne
     CK(cudaStreamWaitEvent(s, b.ev_ibm, 0));
 
     // -- compute stream: everything that reads the populations
-    if (replicate) {
-        launch_ibm_macro_box(g, b.f[b.cur], hF, bx, s);
-        NCK(g_nccl.AllReduce(bx.u, bx.u, 3 * (size_t)bx.ncell, kNcclFloat64, kNcclSum, g_nccl.comm, s));
-    }
-    bool macro_done = replicate;
+    bool macro_done = false;
     if (local) {
         // every kept box: this rank's planes from its populations, zero elsewhere; then the participants of a shared box send
         // one another the planes they own (ncclSend/ncclRecv between the two or three ranks concerned, no collective)
@@ -2095,13 +2085,7 @@ int fsilbm_ibm_interaction_force_begin(fsilbm_handle h, int nbody, const int *ne
             for (int k = 0; k < nact; k++) {
                 auto gather = ordered ? launch_ibm_gather_ordered : launch_ibm_gather;
                 BodyDev &bd = b.bodies[act[k]];
-                if (!multi || replicate || local) {
-                    gather(views[k], bx, bd.partialU, b.ctl, 1, invh3_pen, s);
-                } else {
-                    gather(views[k], bx, bd.partialU, b.ctl, 0, invh3_pen, s);
-                    NCK(g_nccl.AllReduce(bd.partialU, bd.partialU, 3 * (size_t)views[k].n, kNcclFloat64, kNcclSum, g_nccl.comm, s));
-                    launch_ibm_force(views[k], bd.partialU, invh3_pen, b.ctl, s);
-                }
+                gather(views[k], bx, bd.partialU, b.ctl, 1, invh3_pen, s);
                 if (ordered) launch_ibm_scatter_ordered(b.bodies_dev, k, bx, b.csr, b.ctl, s);
                 else launch_ibm_scatter(views[k], bx, b.ctl, s);
             }

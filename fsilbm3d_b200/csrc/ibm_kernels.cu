@@ -202,8 +202,7 @@ __device__ __forceinline__ void marker_force(const IbmBody &b, int iEL, double U
 }
 
 // PenaltyForce_ interpolation, Solidbody.f90:1000-1015: one warp per marker.
-// fused != 0 (single rank): lane 0 also finishes the marker (:1016-1025); otherwise the partial
-// velocity over the locally owned stencil planes goes to partialU for the all-reduce.
+// Lane 0 also finishes the marker (:1016-1025).
 // the 64-node gather of one marker by one warp; the sums are valid in lane 0
 __device__ __forceinline__ void gather_marker(const IbmBody &b, const IbmBoxes &boxes, int iEL, int lane, double &s1, double &s2, double &s3)
 {
@@ -237,30 +236,13 @@ __global__ void ibm_gather_kernel(IbmBody b, const __grid_constant__ IbmBoxes bo
     const int iEL = warp;
     double s1, s2, s3;
     gather_marker(b, boxes, iEL, lane, s1, s2, s3);
-    if (lane == 0) {
-        if (fused) marker_force(b, iEL, s1, s2, s3, invh3);
-        else { partialU[3 * iEL + 0] = s1; partialU[3 * iEL + 1] = s2; partialU[3 * iEL + 2] = s3; }
-    }
+    if (lane == 0) marker_force(b, iEL, s1, s2, s3, invh3);
 }
 
 void launch_ibm_gather(const IbmBody &b, const IbmBoxes &boxes, double *partialU, const IbmCtl *ctl, int fused, double invh3, cudaStream_t s)
 {
     const int threads = 128, warps_per_block = threads / 32;
     ibm_gather_kernel<<<(b.n + warps_per_block - 1) / warps_per_block, threads, 0, s>>>(b, boxes, partialU, ctl, fused, invh3);
-    count_launch();
-}
-
-__global__ void ibm_force_kernel(IbmBody b, const double *sumU, double invh3, const IbmCtl *ctl)
-{
-    if (ctl->done) return;
-    const int iEL = blockIdx.x * blockDim.x + threadIdx.x;
-    if (iEL >= b.n) return;
-    marker_force(b, iEL, sumU[3 * iEL + 0], sumU[3 * iEL + 1], sumU[3 * iEL + 2], invh3);
-}
-
-void launch_ibm_force(const IbmBody &b, const double *sumU, double invh3, IbmCtl *ctl, cudaStream_t s)
-{
-    ibm_force_kernel<<<(b.n + 127) / 128, 128, 0, s>>>(b, sumU, invh3, ctl);
     count_launch();
 }
 

@@ -221,7 +221,6 @@ void launch_ibm_spread_ordered(const IbmBody *bodies_dev, const IbmBoxes &boxes,
 void launch_ibm_stencil(const Geom &g, const IbmBody &b, const IbmBoxes &boxes, const int rootBC[6], IbmCtl *ctl, cudaStream_t s);
 void launch_ibm_macro_box(const Geom &g, const double *fA, const double hF[3], const IbmBoxes &boxes, cudaStream_t s);
 void launch_ibm_gather(const IbmBody &b, const IbmBoxes &boxes, double *partialU, const IbmCtl *ctl, int fused, double invh3, cudaStream_t s);
-void launch_ibm_force(const IbmBody &b, const double *sumU, double invh3, IbmCtl *ctl, cudaStream_t s);
 void launch_ibm_scatter(const IbmBody &b, const IbmBoxes &boxes, const IbmCtl *ctl, cudaStream_t s);
 void launch_ibm_check(const IbmBody *bodies_dev, int nbody, double Uref, int ntol, double dtol, IbmCtl *ctl, cudaStream_t s);
 void launch_ibm_spread(const IbmBody &b, const IbmBoxes &boxes, double invh3, cudaStream_t s);

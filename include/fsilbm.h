@@ -76,14 +76,16 @@ int fsilbm_trace_dump(const char *path);
  *   "halo_timeout_s"          how long a rank waits for a neighbour (halo flags, IBM loop-control mailbox) before it reports
  *                             FSILBM_ERR_COMM (default 120)
  *   "ibm_ordered"             1 (default) interpolation and spreading keep the reference's serial summation order (bit-identical to the
- *                             serial reference, reproducible), 0 warp shuffles + fp64 atomics (round-off differences)
+ *                             serial reference, reproducible), 0 warp shuffles + fp64 atomics (round-off differences;
+ *                             single-GPU comparison arm, refused on slab runs)
  *   "ibm_single_launch"       1 (default) calculate_interaction_force is one cooperative kernel (on slab runs with the loop control
  *                             exchanged through peer memory), 0 one kernel per phase (slab runs: ncclAllReduce of the loop control)
  *   "ibm_early"               1 (default) fsilbm_block_collide_stream updates the x-planes around the bodies first so that the next
  *                             fsilbm_ibm_interaction_force runs beside the rest of the update, 0 strictly one after the other
  *   "ibm_early_blocks_per_sm" 1..4 (default 1): size of the cooperative IBM grid when it shares the SMs with that update
  *   "ibm_early_blocks"        > 0: that grid as an absolute number of blocks instead (0 = use the per-SM figure)
- *   "ibm_local", "ibm_force_exchange", "ibm_replicate"   forms of the IBM on slab runs, see fsilbm_ibm_body_status below */
+ *   "ibm_force_exchange"      slab runs: 1 (default) every rank passes the same body list and gets every force back, 0 per-rank lists
+ *                             (see fsilbm_ibm_body_status below) */
 int fsilbm_set_option(const char *key, int value);
 
 /* ---- fluid block: replaces type LBMBlock's procedures --------------------------------------- */
@@ -218,7 +220,6 @@ int fsilbm_ibm_interaction_force_wait(fsilbm_handle h, int nbody, double *const 
  *   option "ibm_force_exchange" = 0: every rank passes only the bodies it holds -- at least every body whose stencil box
  *     (and every body sharing cells with it) touches its slab, in the same relative order on every rank; bodies whose box
  *     is elsewhere are ignored and get zero force.  Every rank calls every step, also with nbody = 0.
- *   option "ibm_local" = 0 selects the earlier replicated form (box velocities all-reduced, every rank iterates all bodies).
  * fsilbm_ibm_body_status: per body of the last call, 0 not iterated by this rank, 1 iterated, 2 iterated and led (this rank
  * owns the first plane of its box and reported its residual and forces). */
 int fsilbm_ibm_body_status(fsilbm_handle h, int nbody, int *status);

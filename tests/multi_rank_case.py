@@ -36,16 +36,15 @@ def main():
              flow=dict(nu=0.05, uvwIn=(0.03, 0.0, 0.0), Uref=0.03, ntolLBM=4, dtolLBM=1e-30)),
     ]
     # IBM forms of a slab run (include/fsilbm.h "Slab runs"): local + same list on every rank (default), local + per-rank
-    # lists, the earlier replicated form; two plates (one inside the first slab, one across an interface) with a tolerance
+    # lists; two plates (one inside the first slab, one across an interface) with a tolerance
     # that ends the penalty iteration early on some steps, so the all-reduced loop control is what decides
     two = dict(name="two_plates_dtol", dims=(12 * world + 2, 20, 24), bc=(102, 104, 202, 202, 301, 301), plate_origin="two",
                flow=dict(nu=0.05, uvwIn=(0.04, 0.0, 0.0), shearRateIn=(0.0, 3e-4, 0.0), Uref=0.04, ntolLBM=6, dtolLBM=5e-2))
-    variants = [(1, c, dict(ibm_local=1, ibm_force_exchange=1)) for c in cases + [two]]
-    variants += [(0, c, dict(ibm_local=1, ibm_force_exchange=1)) for c in cases]
-    variants += [(1, c, dict(ibm_local=1, ibm_force_exchange=0)) for c in cases[1:] + [two]]
-    variants += [(1, cases[1], dict(ibm_local=0, ibm_force_exchange=1))]
+    variants = [(1, c, dict(ibm_force_exchange=1)) for c in cases + [two]]
+    variants += [(0, c, dict(ibm_force_exchange=1)) for c in cases]
+    variants += [(1, c, dict(ibm_force_exchange=0)) for c in cases[1:] + [two]]
     # loop control through ncclAllReduce (one kernel per phase) instead of the peer-memory mailbox inside the cooperative kernel
-    variants += [(1, c, dict(ibm_local=1, ibm_force_exchange=x, ibm_single_launch=0)) for c in (cases[1], two) for x in (1, 0)]
+    variants += [(1, c, dict(ibm_force_exchange=x, ibm_single_launch=0)) for c in (cases[1], two) for x in (1, 0)]
     # WALE / Vreman blocks cut into slabs: the velocity differences across an interface take the neighbour's edge plane
     # (FluidDomain.f90:1343-1385, 1445-1484; one-sided only at the domain faces)
     les = [dict(name="les_wale_slabs", dims=(8 * world + 3, 12, 14), bc=(101, 104, 203, 203, 301, 301), plate_origin=None, model=14, wave=2e-2,
@@ -54,7 +53,7 @@ def main():
                 flow=dict(nu=0.02, volumeForceIn=(1e-6, 0.0, 0.0))),
            dict(name="les_vrem_plate_slabs", dims=(10 * world + 1, 20, 24), bc=(102, 104, 202, 202, 301, 301), plate_origin="mid", model=15, wave=2e-2,
                 flow=dict(nu=0.02, uvwIn=(0.04, 0.0, 0.0), shearRateIn=(0.0, 3e-4, 0.0), Uref=0.04, ntolLBM=3, dtolLBM=1e-30))]
-    variants += [(1, c, dict(ibm_local=1, ibm_force_exchange=1)) for c in les] + [(0, les[0], dict(ibm_local=1, ibm_force_exchange=1))]
+    variants += [(1, c, dict(ibm_force_exchange=1)) for c in les] + [(0, les[0], dict(ibm_force_exchange=1))]
     variants = [(m, c, dict(dict(ibm_single_launch=1), **o)) for (m, c, o) in variants]
     F._lib.check(F.lib().fsilbm_set_option(b"halo_timeout_s", 30))
     ok = True
@@ -134,7 +133,7 @@ def main():
             print(f"[multi x{world}] halo={gb.halo_transport!r} ibm={opts} {case['name']}: rel err den {e_den:.2e} u {e_u:.2e} f {e_f:.2e} force {eF:.2e} bit-exact {exact} -> {'OK' if good else 'FAIL'}", flush=True)
         gb.close()
         dist.barrier()
-    for k, v in dict(ibm_local=1, ibm_force_exchange=1, ibm_single_launch=1).items():
+    for k, v in dict(ibm_force_exchange=1, ibm_single_launch=1).items():
         F._lib.check(F.lib().fsilbm_set_option(k.encode(), v))
     if rank == 0:
         n_two = sorted(i for (nm, i) in iters_seen if nm == "two_plates_dtol")
