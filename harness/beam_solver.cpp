@@ -154,6 +154,8 @@ void Segment::UpdateMatrix(const double coeffs[8], double gamma, double dampM, d
     if (dampK > 0.0)
         for (int i = 0; i < 12; i++)
             for (int j = 0; j < 12; j++) m_coefMat[i][j] = m_coefMat[i][j] + coeffs[1] * dampK * m_stfMat[i][j];
+    for (int i = 0; i < 12; i++)
+        for (int j = 0; j < 12; j++) m_coefT[j][i] = m_coefMat[i][j];
 }
 
 void Segment::UpdateLoad(const double coeffs[8], double dampM, double dampK, const std::vector<double> &dspO, const std::vector<double> &dsp,
@@ -210,10 +212,13 @@ void Segment::Multiply(const std::vector<double> &x, std::vector<double> &b) con
 {
     double lx[12], lb[12];
     for (int i = 0; i < 12; i++) lx[i] = x[m_localToGlobal[i]];
-    for (int i = 0; i < 12; i++) {
-        double s = 0.0;
-        for (int j = 0; j < 12; j++) s += m_coefMat[i][j] * lx[j];
-        lb[i] = s;
+    // row i: ((0 + K(i,1) x(1)) + K(i,2) x(2)) + ... as MATMUL accumulates it; the loops are turned inside out (column by column,
+    // all rows at once) so that the twelve independent sums advance together in vector registers -- same additions, same order per row
+    for (int i = 0; i < 12; i++) lb[i] = 0.0;
+    for (int j = 0; j < 12; j++) {
+        const double xj = lx[j];
+        const double *col = m_coefT[j].data();
+        for (int i = 0; i < 12; i++) lb[i] += col[i] * xj;
     }
     LocToGlobal(lb, b);
 }

@@ -43,6 +43,7 @@ struct Segment {   // type Segment, SolidSolver.f90:13-56
     Mat3 triad_ee{}, triad_n1{}, triad_n2{}, m_rotMat{};
     double m_property[8]{};
     Mat12 m_coefMat{}, m_tanMat{}, m_stfMat{}, m_masMat{}, m_geoMat{};
+    Mat12 m_coefT{};     // transpose of m_coefMat (kept by UpdateMatrix): Multiply walks it column by column
 
     void Build(int p0Id, int p1Id, int itype_, int Nspan_, const std::vector<std::array<double, 8>> &xyz, const std::array<double, 8> &material,
                const std::vector<std::array<int, 6>> &boundary);                                                  // :60

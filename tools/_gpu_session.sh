@@ -1,5 +1,4 @@
-# round 2 session I (2 GPUs): multi-rank parity with sons across the interface
+# round 2 session J: whole GPU suite after the IBM arm removal and the cross-slab son work
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
-timeout 600 $TR tests/multi_rank_case.py > gpurun_out/r02p_multi_rank_parity_n2.txt 2>&1; echo "parity rc=$?"
-grep -c " OK" gpurun_out/r02p_multi_rank_parity_n2.txt; grep "FAIL\|Error\|error\|refinement" gpurun_out/r02p_multi_rank_parity_n2.txt | head -8 | cut -c1-400; tail -4 gpurun_out/r02p_multi_rank_parity_n2.txt | cut -c1-300
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r02q_pytest_gpu.txt 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/r02q_pytest_gpu.txt
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
