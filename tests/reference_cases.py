@@ -98,6 +98,23 @@ CASES["les_smag_plate"] = dict(
     group=dict(iBodyModel=1, isMotionGiven=(1,) * 6, EmR=1.0, tcR=0.05, AoAo=(0.0, 0.0, 15.0), firstXYZ=(6.3, 6.6, 5.2)), isKB=0)
 
 
+# a rigid plate inside a 2:1 refined son block: the plate is carried by the son (FindCarrierFluidBlock, FluidDomain.f90:1974-2017), the IBM
+# runs at the son's spacing twice per root step, the stencil folding still uses the ROOT block's boundary codes (Solidbody.f90:337)
+CASES["plate_in_son"] = dict(
+    kind="refine_body", dims=(16, 12, 12), bc=(101, 104, 301, 301, 301, 301), sdims=(17, 13, 13), smins=(4.0, 3.0, 3.0), scheme=1, carrier_son=True,
+    model=1, params=P0, steps=5, uvwIn=(0.05, 0.0, 0.0), Uref=0.05, Lref=4.0, Re=40.0, wave=1e-3, flow={}, ntolLBM=3, dtolLBM=1e-30, numsubstep=1,
+    plate=dict(nEL=6, chord=3.0, span=3.0, Nspan=6),
+    group=dict(iBodyModel=1, isMotionGiven=(1,) * 6, EmR=1.0, tcR=0.05, AoAo=(0.0, 0.0, 10.0), firstXYZ=(6.3, 5.6, 4.7)), isKB=0)
+
+
+def has_son(case):
+    return "sdims" in case
+
+
+def has_body(case):
+    return "plate" in case
+
+
 def case_groups(case):
     return case["groups"] if "groups" in case else [case["group"]]
 
@@ -112,14 +129,14 @@ def initial_states(case):
         pass
     fl = _F(); fl.uvwIn = case["uvwIn"]; fl.denIn = 1.0
     out = [perturbed_state(case["dims"], fl, wave_amp=case["wave"], seed=SEED)]
-    if case["kind"] == "refine":
+    if has_son(case):
         out.append(perturbed_state(case["sdims"], fl, wave_amp=case["wave"], seed=SEED + 1))
     return out
 
 
 def block_list(case):
     blocks = [dict(ID=1, iCollidModel=case["model"], dims=case["dims"], dh=1.0, xyzmin=(0.0, 0.0, 0.0), BndConds=case["bc"], params=case["params"])]
-    if case["kind"] == "refine":
+    if has_son(case):
         blocks.append(dict(ID=2, iCollidModel=case["model"], offsetOutput=1, dims=case["sdims"], dh=0.5, xyzmin=case["smins"], BndConds=(0,) * 6,
                            params=case["params"]))
     return blocks
@@ -145,7 +162,7 @@ def write_inputs(case, wd, continue_at_end=False):
     total = (case["steps"] - 0.5) / Tref                    # main.f90:93: do while(time/Tref < timeSimTotal), dt = 1
     blocks = block_list(case)
     groups = []
-    if case["kind"] == "body":
+    if has_body(case):
         p = case["plate"]
         S.write_plate_dat(os.path.join(wd, "plate.dat"), chain(p["nEL"] + 1, p["chord"]), 0.5 * p["span"], 0.5 * p["span"], (0.0, 0.0, 1.0),
                           Nspan=p["Nspan"])
@@ -170,7 +187,7 @@ def run_oracle(O, case, sb=None):
     Fb = O.LBMBlock(X, Y, Z, dh=1.0, BndConds=case["bc"], iCollidModel=case["model"], params=case["params"], flow=fl)
     blocks = [Fb]
     root = O.TreeNode(Fb)
-    if case["kind"] == "refine":
+    if has_son(case):
         sx, sy, sz = case["sdims"]
         Sb = O.LBMBlock(sx, sy, sz, dh=0.5, xmin=case["smins"][0], ymin=case["smins"][1], zmin=case["smins"][2], BndConds=(0,) * 6,
                         iCollidModel=case["model"], params=case["params"], flow=fl)
@@ -179,7 +196,7 @@ def run_oracle(O, case, sb=None):
     for b, s in zip(blocks, states):
         b.initialise(0.0)
         b.fIn[...] = s
-    if case["kind"] == "refine":
+    if has_son(case):
         # check_is_continue (FluidDomain.f90:166-224) gives every node the populations of the FINEST saved block containing it:
         # the father's nodes under the son take the son's values at the coincident nodes (weights 0/1, exact)
         (x0, y0, z0), (sx, sy, sz) = [int(v) for v in case["smins"]], case["sdims"]
@@ -187,10 +204,17 @@ def run_oracle(O, case, sb=None):
     for b in blocks:
         b.update_volume_force(); b.set_boundary_conditions(); b.calculate_macro_quantities()
     ovs, its = [], []
-    if case["kind"] == "body":
+    if has_body(case):
         for body in sb.VBodies:
             ovs.append(O.VirtualBody(body.v_nelmts, v_move=body.v_move, iBodyModel=body.iBodyModel))
-        root.bodies = ovs
+        if case.get("carrier_son"):
+            # carried by the son: IBM_FEM runs inside the son's two sub-cycles (LBMBlockComm.f90:307-317); the structural sub-steps
+            # there leave a rigid body without prescribed motion where it is, so the markers are set once
+            assert all(b.v_move == 0 and b.iBodyModel == 1 for b in sb.VBodies)
+            root.sons[0].bodies = ovs
+            root.sons[0].rootBC = case["bc"]
+        else:
+            root.bodies = ovs
     nsub = case.get("numsubstep", 1)
     for n in range(1, case["steps"] + 1):
         t = float(n)
