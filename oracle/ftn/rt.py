@@ -1009,14 +1009,15 @@ class Fmt:
             return sv.rjust(w) if len(sv) <= w else "*" * w
         if code in ("E", "D", "G"):
             dd = d or 0
-            if fv == 0:
-                mant, ex = 0.0, 0
+            if fv == 0 or dd == 0:
+                digits, ex = "0" * dd, 0
             else:
-                ex = int(math.floor(math.log10(abs(fv)))) + 1
-                mant = fv / 10.0 ** ex
-                if abs(round(mant, dd)) >= 1.0:
-                    mant /= 10.0; ex += 1
-            sv = f"{mant:.{dd}f}{'D' if code == 'D' else 'E'}{'+' if ex >= 0 else '-'}{abs(ex):02d}"
+                # dd significant digits, correctly rounded from the exact binary value (as the Fortran run-time library does)
+                m = f"{abs(fv):.{dd - 1}e}"
+                mant, e10 = m.split("e")
+                digits, ex = mant.replace(".", ""), int(e10) + 1
+            sign = "-" if (fv < 0 or (fv == 0 and math.copysign(1.0, fv) < 0)) else ""
+            sv = f"{sign}0.{digits}{'D' if code == 'D' else 'E'}{'+' if ex >= 0 else '-'}{abs(ex):02d}"
             if w and len(sv) > w and sv.startswith("0."):
                 sv = sv[1:]
             elif w and len(sv) > w and sv.startswith("-0."):

@@ -40,6 +40,9 @@ def make(name):
             out[f"body{k}_{key}"] = v
     # how often the reference entered PenaltyForce_ (Solidbody.f90:981): sum over the steps of iterLBM x number of bodies
     out["penalty_calls"] = np.array(I.modules["solidbody"].procs["penaltyforce_"].ncalls)
+    if case.get("outputs"):      # the files the reference wrote, byte for byte
+        for rel, data in RC.output_files(wd).items():
+            out["file:" + rel] = np.frombuffer(data, dtype=np.uint8)
     fl = I.modules["flowcondition"].vars["flow"].f
     out["derived"] = json.dumps(dict(nu=float(fl["nu"]), Uref=float(fl["uref"]), Lref=float(fl["lref"]), Tref=float(fl["tref"])))
     np.savez_compressed(RC.golden_path(name), **out)

@@ -107,6 +107,13 @@ CASES["plate_in_son"] = dict(
     group=dict(iBodyModel=1, isMotionGiven=(1,) * 6, EmR=1.0, tcR=0.05, AoAo=(0.0, 0.0, 10.0), firstXYZ=(6.3, 5.6, 4.7)), isKB=0)
 
 
+# the reference's output files (main.f90:124-143): flow fields at the first and last step, flux and probe lines at the last step
+CASES["outputs_inlet_outlet"] = dict(_fluid((12, 9, 10), (101, 104, 202, 202, 301, 301), steps=6, uvwIn=(0.04, 0.0, 0.0), Uref=0.04,
+                                            shearRateIn=(0.0, 3e-4, 0.0), volumeForceIn=(5e-7, 0.0, 0.0)),
+                                     outputs=True, probes=[(3.5, 4.25, 6.0), (8.0, 2.0, 1.5)])
+CASES["outputs_two_blocks"] = dict(CASES["refine_linear"], steps=4, outputs=True, probes=[(6.25, 4.5, 5.0)])
+
+
 def has_son(case):
     return "sdims" in case
 
@@ -168,6 +175,8 @@ def write_inputs(case, wd, continue_at_end=False):
                           Nspan=p["Nspan"])
         groups = [dict(g, fishNum=1, mesh="plate.dat") for g in case_groups(case)]
     extra = dict(timeContiDelta=case["steps"] / Tref) if continue_at_end else {}
+    if case.get("outputs"):
+        extra.update(timeFlowDelta=case["steps"] / Tref, timeInfoDelta=case["steps"] / Tref, fluidProbes=case["probes"], inWhichBlock=1)
     text = S.inflow_text(npsize=1, isConCmpt=2, numsubstep=case.get("numsubstep", 1), timeSimTotal=total, Re=case["Re"], uvwIn=case["uvwIn"],
                          LrefType=1, Lref=case["Lref"], TrefType=0, UrefType=9, Uref=case["Uref"], ntolLBM=case.get("ntolLBM", 3),
                          dtolLBM=case.get("dtolLBM", 1e-8), interpolateScheme=case.get("scheme", 1), blocks=blocks, groups=groups,
@@ -232,6 +241,18 @@ def run_oracle(O, case, sb=None):
     for b in blocks:
         b.calculate_macro_quantities()
     return blocks, (ovs[0] if len(ovs) == 1 else (ovs or None)), its
+
+
+def output_files(wd):
+    """{relative path: bytes} of the flow / flux / probe files a run left in its work directory."""
+    out = {}
+    for sub, pat in (("DatFlow", "Flow"), ("DatInfo", "FluidFlux"), ("DatInfo", "FluidProbes")):
+        d = os.path.join(wd, sub)
+        for fn in sorted(os.listdir(d)) if os.path.isdir(d) else ():
+            if fn.startswith(pat):
+                with open(os.path.join(d, fn), "rb") as f:
+                    out[f"{sub}/{fn}"] = f.read()
+    return out
 
 
 def load(name):

@@ -68,3 +68,43 @@ def test_oracle_and_cpp_structure_reproduce_the_reference_body_case(oracle, name
     # carries to ~1e-10 of the (small) nodal velocities
     assert worst["F"] <= 1e-10 and worst["v"] <= 1e-8
     sb.close()
+
+
+@pytest.mark.parametrize("name", [n for n in NAMES if RC.CASES[n].get("outputs")])
+def test_output_files_of_the_reference(oracle, name):
+    """The files the reference wrote (main.f90:124-143), byte for byte, against what the oracle's end state and the product's
+    host-side formatters (fsilbm3d_b200.flow_io) give: flow fields as real(4) (FluidDomain.f90:1640-1723), flux and probe lines in
+    E20.10 (FluidDomain.f90:2051-2054, FlowCondition.f90:218-219)."""
+    from fsilbm3d_b200 import flow_io
+    case, g = RC.CASES[name], RC.load(name)[1]
+    files = {k[5:]: bytes(g[k]) for k in g.files if k.startswith("file:")}
+    blocks, _, _ = RC.run_oracle(oracle, case)
+    Uref, Tref = case["Uref"], case["Lref"] / case["Uref"]
+    tname = flow_io._name10(case["steps"] / Tref)
+    for k, b in enumerate(blocks):
+        o = 0 if k == 0 else 1                                    # offsetOutput of the son block in these cases
+        sl = (slice(o, b.xDim - o), slice(o, b.yDim - o), slice(o, b.zDim - o))
+        want = np.array([b.xDim - 2 * o, b.yDim - 2 * o, b.zDim - 2 * o, k + 1], np.int32).tobytes()
+        want += np.array([b.xmin + o * b.dh, b.ymin + o * b.dh, b.zmin + o * b.dh, b.dh]).tobytes()
+        want += ((1.0 / 3.0) * (b.den[sl] - 1.0)).astype(np.float32).tobytes()
+        for c in range(3):
+            want += (b.uuu[(c,) + sl] * (1.0 / Uref)).astype(np.float32).tobytes()
+        assert files[f"DatFlow/Flow{tname}_b{k + 1:03d}"] == want, f"flow file of block {k + 1}"
+    # flux through the inlet, middle and outlet planes of the root block, trapezoid weights on y and z
+    b = blocks[0]
+    wy = np.ones(b.yDim); wy[0] = wy[-1] = 0.5
+    wz = np.ones(b.zDim); wz[0] = wz[-1] = 0.5
+    per = lambda lo, hi: 1.0 if (lo == 301 and hi == 301) else 0.0
+    Yref = (b.yDim - 1) * b.dh + per(case["bc"][2], case["bc"][3]) * b.dh
+    Zref = (b.zDim - 1) * b.dh + per(case["bc"][4], case["bc"][5]) * b.dh
+    vals = []
+    for ix in (0, (b.xDim + 1) // 2 - 1, b.xDim - 1):
+        acc = 0.0
+        for kz in range(b.zDim):                                   # the reference's loop order: k outer, j inner
+            for jy in range(b.yDim):
+                acc = acc + b.uuu[0, ix, jy, kz] * b.den[ix, jy, kz] * b.dh * b.dh * wy[jy] * wz[kz]
+        vals.append(acc / (1.0 * Uref * Zref * Yref))
+    line = "".join(flow_io._e20_10(v) for v in (case["steps"] / Tref, *vals))
+    got = files["DatInfo/FluidFlux.dat"].decode().splitlines()
+    assert got[0] == ' VARIABLES = "t"  "inlet"  "middle"  "outlet"' and got[1] == line
+    assert len([k for k in files if "FluidProbes" in k]) == len(case["probes"])
