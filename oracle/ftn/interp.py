@@ -64,11 +64,11 @@ class Struct:
 
 
 class VarInfo:
-    __slots__ = ("name", "code", "clen", "tname", "dims", "alloc", "param", "optional", "intent", "save", "init", "dummy", "line")
+    __slots__ = ("name", "code", "clen", "tname", "dims", "alloc", "param", "optional", "intent", "save", "init", "dummy", "line", "value")
 
     def __init__(self, name, code, clen=None, tname=None, dims=None):
         self.name, self.code, self.clen, self.tname, self.dims = name, code, clen, tname, dims
-        self.alloc = self.param = self.optional = self.save = self.dummy = False
+        self.alloc = self.param = self.optional = self.save = self.dummy = self.value = False
         self.intent = None
         self.init = None
         self.line = 0
@@ -101,6 +101,7 @@ class ProcRT:
         self.scope = None
         self.entry = self.body = None
         self.ncalls = 0
+        self.cname = getattr(node, "cname", None)      # bind(C) interface: the procedure lives in the bound C library
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -245,6 +246,7 @@ class Interp:
         self.io = rt.IO(cwd, echo)
         self.forked = False
         self.stats = {}
+        self.clib = None           # ctypes library that bind(C) interfaces resolve into (bind_c_library)
         self.builtin_subs = {
             "omp_set_num_threads": lambda *a, **k: None,
             "mywait": lambda *a, **k: None,
@@ -252,15 +254,42 @@ class Interp:
         }
 
     # -- loading
+    ISO_C_BINDING = """
+module iso_c_binding
+    implicit none
+    integer, parameter :: c_int = 4, c_short = 2, c_long = 8, c_long_long = 8, c_size_t = 8, c_double = 8, c_float = 4, c_char = 1, c_bool = 1
+    character(len=1), parameter :: c_null_char = achar(0)
+    type c_ptr
+        integer(8) :: addr = 0
+    end type
+    type(c_ptr) :: c_null_ptr
+end module iso_c_binding
+"""
+
+    def bind_c_library(self, lib):
+        """bind(C) interfaces call into this library (a path or a ctypes.CDLL); iso_c_binding becomes available."""
+        import ctypes
+        self.clib = ctypes.CDLL(lib) if isinstance(lib, str) else lib
+        if "iso_c_binding" not in self.modules:
+            self.load_text(self.ISO_C_BINDING, "<iso_c_binding>")
+        return self
+
     def load(self, paths):
         for p in paths:
             with open(p) as f:
-                units = parse_source(f.read(), p)
+                self.load_text(f.read(), p)
+        return self
+
+    def load_text(self, text, fname):
+        if True:
+            units = parse_source(text, fname)
             for u in units:
                 if u.t == "module":
                     m = ModuleRT(u)
                     self.modules[m.name] = m
                     for pn in u.procs:
+                        m.procs[pn.name] = self._mkproc(pn, m, None)
+                    for pn in getattr(u, "interfaces", []):
                         m.procs[pn.name] = self._mkproc(pn, m, None)
                 elif u.kind == "program":
                     self.programs[u.name] = self._mkproc(u, None, None)
@@ -358,6 +387,9 @@ class Interp:
                 if k not in fr:
                     raise InterpError(f"{p.name}: no dummy argument {k}")
                 fr[k] = v
+        if p.cname is not None:
+            from . import cbind
+            return cbind.call(self, p, fr)
         p.entry(fr)
         p.body(fr)
         return fr
@@ -397,9 +429,10 @@ class Compiler:
                 clen = Node("num", k="i", v="1")
         dims = ent.dims if ent.dims is not None else d.attrs.get("dimension")
         info = VarInfo(ent.name, code, clen, spec.tname, dims)
-        info.alloc = bool(d.attrs.get("allocatable"))
+        info.alloc = bool(d.attrs.get("allocatable")) or bool(d.attrs.get("pointer"))
         info.param = bool(d.attrs.get("parameter"))
         info.optional = bool(d.attrs.get("optional"))
+        info.value = bool(d.attrs.get("value"))
         info.intent = d.attrs.get("intent")
         info.save = bool(d.attrs.get("save")) or (ent.init is not None)
         info.init = ent.init
@@ -1136,6 +1169,13 @@ class Compiler:
 
     def funcref(self, p):
         name = p.name
+        if name in ("c_loc", "c_associated") and p.args is not None and self.I.clib is not None:
+            from . import cbind
+            a0 = self.expr(p.args[0])
+            cptr_t = self.sc.lookup_type("c_ptr")
+            if name == "c_loc":
+                return lambda fr: cbind.c_loc(self, cptr_t, a0(fr))
+            return lambda fr: a0(fr).f["addr"] != 0
         proc = self.sc.lookup_proc(name)
         if proc is not None and p.args is not None:
             args = self.actual_args(p.args)
@@ -1392,6 +1432,12 @@ class Compiler:
                     return RETURN
                 raise FortranStop("exit(%s)" % args[0][1](fr))
             return myexit
+        if name == "c_f_pointer":
+            from . import cbind
+            src = args[0][1]
+            acc = self.var_access(argnodes[1].parts[0].name)
+            shp = args[2][1] if len(args) > 2 else None
+            return lambda fr: acc[1](fr, cbind.c_f_pointer(acc[2], src(fr), None if shp is None else shp(fr)))
         if name in I.builtin_subs:
             fn = I.builtin_subs[name]
             return lambda fr: fn(*[g(fr) for kw, g, s in args])

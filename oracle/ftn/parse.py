@@ -401,7 +401,7 @@ class Parser:
         no, s, toks = self.cur()
         name = toks[1].val
         self.i += 1
-        mod = Node("module", name=name, uses=[], decls=[], types=[], procs=[], line=no)
+        mod = Node("module", name=name, uses=[], decls=[], types=[], procs=[], interfaces=[], line=no)
         self.parse_spec(mod)
         no, s, toks = self.cur()
         if self.kw(toks, "contains"):
@@ -425,8 +425,14 @@ class Parser:
         while self.cur():
             no, s, toks = self.cur()
             if self.kw(toks, "use"):
-                unit.uses.append(toks[1].val)
+                # use name | use name, only: ... | use, intrinsic :: name
+                dc = next((j for j, tk in enumerate(toks) if tk.kind == "op" and tk.val == "::"), None)
+                unit.uses.append(toks[dc + 1].val if dc is not None else toks[1].val)
                 self.i += 1
+            elif self.kw(toks, "import"):
+                self.i += 1
+            elif self.kw(toks, "interface") and len(toks) == 1:
+                unit.interfaces.extend(self.parse_interface())
             elif self.kw(toks, "implicit"):
                 self.i += 1
             elif (self.kw(toks, "private") or self.kw(toks, "public")) and not is_assignment(toks):
@@ -592,8 +598,16 @@ class Parser:
         if k < len(toks) and toks[k].kind == "id" and toks[k].val == "result":
             result = toks[k + 2].val
         self.i += 1
+        cname = None
+        bi = next((j for j in range(k, len(toks)) if toks[j].kind == "id" and toks[j].val == "bind"), None)
+        if bi is not None:      # bind(C [, name='...'])
+            e = match_paren(toks, bi + 1)
+            cname = name
+            for j in range(bi + 2, e):
+                if toks[j].kind == "str":
+                    cname = toks[j].val
         proc = Node("proc", kind=kind, name=name, args=args, result=result, rtype=rtype, uses=[], decls=[], types=[], body=[], procs=[], line=no,
-                    file=self.fname)
+                    file=self.fname, interfaces=[], cname=cname)
         self.parse_spec(proc)
         proc.body = self.parse_block(("contains", "end"))
         no, s, toks = self.cur()
@@ -610,6 +624,20 @@ class Parser:
             self.err(f"expected end of {kind} {name}")
         self.i += 1
         return proc
+
+    def parse_interface(self):
+        """interface ... end interface: explicit interfaces of external (here: bind(C)) procedures."""
+        self.i += 1
+        out = []
+        while True:
+            no, s, toks = self.cur()
+            if self.kw(toks, "end", "interface") or self.kw(toks, "endinterface"):
+                self.i += 1
+                return out
+            h = self.proc_header(toks)
+            if not h:
+                self.err("expected a procedure interface")
+            out.append(self.parse_proc(h))
 
     def block_end(self, toks, enders):
         """Does this statement close the current block?  enders: tuple of words; 'end' matches 'end xxx' / 'endxxx'."""
