@@ -105,6 +105,7 @@ def test_driver_over_the_shim_matches_the_oracle(oracle, tmp_path, with_plate):
         its += ob.step(ovs)
     f1 = np.fromfile(os.path.join(wd, "f1.bin")).reshape(ob.fIn.shape)
     assert np.array_equal(f1, ob.fIn), f"max |df| {np.abs(f1 - ob.fIn).max():.3e}"
+    ob.calculate_macro_quantities()                       # main.f90:107 before computeFieldStat_blocks (:150)
     st = ob.ComputeFieldStat()
     assert lines[-1] == f" FIELDSTAT L2 u {st[0]:18.12f}"
     assert lines[-2] == f" tau {3.0 * flowkw['nu'] + 0.5:10.6f} IBM iterations {its:6d}"

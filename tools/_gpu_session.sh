@@ -1,3 +1,3 @@
-# round 2 session L: CUDA path against all reference goldens (incl. plate in son, output files)
+# round 2 session M: the Fortran driver over the shim, executed by the interpreter against the CUDA library
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_reference_golden.py -m gpu -q > gpurun_out/r02s_pytest_reference_golden.txt 2>&1; echo "rc=$?"; tail -30 gpurun_out/r02s_pytest_reference_golden.txt | cut -c1-300
+timeout 600 python -m pytest tests/test_fortran_shim.py -q -rs > gpurun_out/r02t_pytest_fortran_shim.txt 2>&1; echo "rc=$?"; tail -30 gpurun_out/r02t_pytest_fortran_shim.txt | cut -c1-400
