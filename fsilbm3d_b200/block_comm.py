@@ -132,7 +132,8 @@ class blockTreeNode:
             yield from s.walk()
 
 
-HOIST_SON_IBM = True    # see tree_collision_streaming_IBM_FEM
+import os as _os
+HOIST_SON_IBM = _os.environ.get("FSILBM_NO_HOIST") is None    # see tree_collision_streaming_IBM_FEM (the variable is a measurement switch)
 
 MachineTolerace = 1.0e-12   # ConstParams.f90:36 (name as spelt there)
 

@@ -1,10 +1,11 @@
-# round 2 session N (4 GPUs): the driver's own commands at N=4, both arms
+# round 2 session O: hoisted son IBM -- refinement tests, plate-in-son golden, school2048r on one GPU with and without
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511"
-timeout 400 $TR bench.py --impl reference --gpus 4 --steps 20 --warmup 5 > gpurun_out/r02u_bench_reference_n4.json 2> gpurun_out/err_u0.txt; echo "ref rc=$?"; cut -c1-200 gpurun_out/r02u_bench_reference_n4.json
-timeout 400 $TR bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/r02u_bench_default_n4_s20.json 2> gpurun_out/err_u1.txt; echo "bench rc=$?"
+timeout 600 python -m pytest tests/test_gpu_refine.py tests/test_gpu_reference_golden.py -m gpu -q -k "refine or son or plate" > gpurun_out/r02v_pytest.txt 2>&1; echo "rc=$?"; tail -5 gpurun_out/r02v_pytest.txt | cut -c1-300
+timeout 400 python bench.py --workload school2048r --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/r02v_bench_school2048r_n1_hoist.json 2> gpurun_out/err_v1.txt; echo "rc=$?"
+FSILBM_NO_HOIST=1 timeout 400 python bench.py --workload school2048r --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/r02v_bench_school2048r_n1_nohoist.json 2> gpurun_out/err_v2.txt; echo "rc=$?"
 python - <<'P'
 import json
-d=json.load(open('gpurun_out/r02u_bench_default_n4_s20.json')); r=d['roofline']
-print(d['config']['workload'], round(d['value']), round(d['ms_per_step'],4), round(r['frac'],4), round(d['e2e']['value']), d['parity_check']['ok'], d['clocks'])
+for t in ('hoist','nohoist'):
+    d=json.load(open(f'gpurun_out/r02v_bench_school2048r_n1_{t}.json')); r=d['roofline']
+    print(t, round(d['value']), round(d['ms_per_step'],4), round(r['frac'],4), d['details']['structural_solver']['host_ms_per_step_all_bodies'], d['clocks']['sm_mhz'])
 P
