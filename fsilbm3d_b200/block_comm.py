@@ -132,9 +132,6 @@ class blockTreeNode:
             yield from s.walk()
 
 
-import os as _os
-HOIST_SON_IBM = _os.environ.get("FSILBM_NO_HOIST") is None    # see tree_collision_streaming_IBM_FEM (the variable is a measurement switch)
-
 MachineTolerace = 1.0e-12   # ConstParams.f90:36 (name as spelt there)
 
 
@@ -264,36 +261,20 @@ def tree_collision_streaming_IBM_FEM(node, plates: Sequence = (), time: Optional
     if time is not None:
         block.set_blktime(time)
     rootBC = block.BndConds if rootBC is None else rootBC
+    block.update_volume_force()                                             # :283
     it = 0
     collective = getattr(block, "ibm_collective", False)   # slab runs with per-rank body lists: every rank calls, even with no body
     ibm = len(plates) or collective
     split = ibm and hasattr(block, "calculate_interaction_force_begin")
-    begun = getattr(node, "_ibm_begun", False)             # the father already issued this step's first half (see below)
-    node._ibm_begun = False
-    if not begun:
-        block.update_volume_force()                                         # :283
-        if ibm:                                                             # IBM_FEM, :287 -> :320-338
-            for p in plates:
-                p.UpdatePosVelArea()                                        # Solidbody.f90:597-600
-            if split:   # enqueue only: the update below is issued before the host waits for the marker forces
-                block.calculate_interaction_force_begin([p.body for p in plates], rootBC, collective=collective)   # :601
-            else:
-                it = block.calculate_interaction_force([p.body for p in plates], rootBC, collective=collective)
+    if ibm:                                                                 # IBM_FEM, :287 -> :320-338
+        for p in plates:
+            p.UpdatePosVelArea()                                            # Solidbody.f90:597-600
+        if split:   # enqueue only: the update below is issued before the host waits for the marker forces
+            block.calculate_interaction_force_begin([p.body for p in plates], rootBC, collective=collective)   # :601
+        else:
+            it = block.calculate_interaction_force([p.body for p in plates], rootBC, collective=collective)
     for pair in node.comm:
         pair.extract_interpolate_layer(1)                                   # :290
-    # A son's first sub-cycle starts with its own interaction force, which reads the SON's state only (the father reaches the son
-    # through interpolation_father_to_son AFTER the son's update, LBMBlockComm.f90:312-313).  Issuing that call before this block's
-    # update changes no value, but the son's marker forces reach the host while this (much larger) update runs, so the structural
-    # sub-steps that must finish before the son's second sub-cycle are hidden behind it instead of behind the son's own small update.
-    if HOIST_SON_IBM:
-        for son in node.sons:
-            sb, sp = son.block, son.plates
-            if len(sp) and hasattr(sb, "calculate_interaction_force_begin") and not getattr(sb, "ibm_collective", False):
-                sb.update_volume_force()                                    # blktime of sub-cycle 0 = the father's (:311 adds 0)
-                for p in sp:
-                    p.UpdatePosVelArea()
-                sb.calculate_interaction_force_begin([p.body for p in sp], rootBC)
-                son._ibm_begun = True
     block.collide_stream()                                                  # :285-303 fused; asynchronous launch (follows the IBM on the device)
     if split:
         it = block.calculate_interaction_force_wait()                       # marker forces + iterLBM back on the host

@@ -127,42 +127,3 @@ def test_update_is_enqueued_before_the_host_waits_for_the_forces():
     assert [e[1] for e in log] == ["update_volume_force", "ibm_begin", "collide_stream", "ibm_wait"]
     assert len(sb._pending) == 1                      # loads + sub-steps postponed behind the wait, as before
     sb.close()
-
-
-def test_first_interaction_force_of_a_son_is_issued_before_the_fathers_update():
-    """A plate carried by a son: the son's first interaction-force call (which reads the son's state only) is enqueued BEFORE the
-    father's update, so that its marker forces are on the host -- and the structural sub-steps under way -- while the father's
-    large update runs; the second sub-cycle keeps the reference's order.  Every value is unchanged: only independent work moved."""
-    sb = open_bodies(tempfile.mkdtemp(prefix="order4_"), n=1)
-    log = []
-
-    class FakePair:
-        def extract_interpolate_layer(self, t): log.append(("pair", "extract", t))
-        def interpolation_father_to_son(self, n): log.append(("pair", "f2s", n))
-        def deliver_son_to_father(self): log.append(("pair", "s2f"))
-
-    root, son = SplitFakeBlock(log, "root", dh=1.0), SplitFakeBlock(log, "son", dh=0.5)
-    node = blockTreeNode(root)
-    node.sons.append(blockTreeNode(son, sb.plates)); node.comm.append(FakePair())
-    F.set_blktime_all(node, 3.0)
-    its = []
-    tree_collision_streaming_IBM_FEM(node, iters=its)
-    names = [(e[0], e[1]) for e in log]
-    assert names == [("root", "update_volume_force"), ("pair", "extract"),
-                     ("son", "update_volume_force"), ("son", "ibm_begin"),            # hoisted: sub-cycle 0 of the son
-                     ("root", "collide_stream"), ("pair", "extract"),
-                     ("son", "collide_stream"), ("son", "ibm_wait"), ("pair", "f2s"),
-                     ("son", "update_volume_force"), ("son", "ibm_begin"), ("son", "collide_stream"), ("son", "ibm_wait"), ("pair", "f2s"),
-                     ("pair", "s2f")]
-    assert its == [0, 4, 4] and son.blktime == 3.5
-    import fsilbm3d_b200.block_comm as BC
-    BC.HOIST_SON_IBM = False
-    try:
-        log.clear()
-        F.set_blktime_all(node, 4.0)
-        tree_collision_streaming_IBM_FEM(node)
-        names = [(e[0], e[1]) for e in log]
-        assert names[:4] == [("root", "update_volume_force"), ("pair", "extract"), ("root", "collide_stream"), ("pair", "extract")]
-    finally:
-        BC.HOIST_SON_IBM = True
-    sb.close()
