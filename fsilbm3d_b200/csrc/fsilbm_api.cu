@@ -294,7 +294,7 @@ int g_halo_timeout_s = 120;   // a neighbour this late is treated as lost (the w
 int g_ibm_single_launch = 1;   // 1: calculate_interaction_force as one cooperative kernel on single-rank blocks; 0: one kernel per phase
 int g_ibm_force_exchange = 1;  // slab runs: 1 every rank passes the same bodies and gets every body's forces back (one all-reduce);
                                // 0 every rank passes only the bodies near its slab (distributed lists; the call is then collective even with none)
-int g_ibm_early_blocks = 1;    // blocks per SM of the cooperative IBM kernel when it runs beside a collide-stream update
+int g_ibm_early_blocks = 0;    // blocks per SM of the cooperative IBM kernel when it runs beside a collide-stream update; 0 = chosen per call
 int g_ibm_early_lean = 0;      // 1: the 48-register build of the cooperative kernel when it runs beside an update
 int g_ibm_early_total = 0;     // > 0: that grid as an absolute block count
 int g_ibm_early = 1;           // 1: the planes around the bodies are updated first and the next IBM call overlaps the rest of the update
@@ -729,7 +729,7 @@ int fsilbm_set_option(const char *key, int value)
     }
     if (!strcmp(key, "force_ghost")) { g_force_ghost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_single_launch")) { g_ibm_single_launch = value ? 1 : 0; return 0; }
-    if (!strcmp(key, "ibm_early_blocks_per_sm")) { if (value < 1 || value > 4) return fail(FSILBM_ERR_ARG, "ibm_early_blocks_per_sm must be 1..4"); g_ibm_early_blocks = value; return 0; }
+    if (!strcmp(key, "ibm_early_blocks_per_sm")) { if (value < 0 || value > 4) return fail(FSILBM_ERR_ARG, "ibm_early_blocks_per_sm must be 0 (automatic) or 1..4"); g_ibm_early_blocks = value; return 0; }
     if (!strcmp(key, "ibm_early_lean")) { g_ibm_early_lean = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_early_blocks")) { if (value < 0) return fail(FSILBM_ERR_ARG, "ibm_early_blocks must be >= 0"); g_ibm_early_total = value; return 0; }
     if (!strcmp(key, "ibm_early")) { g_ibm_early = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->early_ok = false; return 0; }
@@ -2052,7 +2052,24 @@ int fsilbm_ibm_interaction_force_begin(fsilbm_handle h, int nbody, const int *ne
         // (no re-stencil) leave the host nothing to do between two calls: the iteration may take most of the update, one block
         // per ~110 markers (74 blocks for the 8192-marker plate: 1.683 -> 1.636 ms per step on plate512).  Moving/flexible bodies
         // have the host's structural solve waiting for the forces: they keep ibm_early_blocks_per_sm blocks per SM.
-        int early_total = 0;
+        int early_total = 0, early_bps = g_ibm_early_blocks;
+        if (use_early && early_bps == 0) {
+            // One block per SM costs the update beside it least, but the iteration must not outlast that update: what is left of it
+            // (the planes outside the ranges it finished first) against the iteration's length at one block per SM (measured:
+            // ntol x markers x 7.5 ns -- 0.3 ms for 8 192 markers x 5, 1.25 ms for 32 768 x 5).  A large body in a small block (a plate
+            // meshed at a refined son's spacing) gets up to four blocks per SM; a root-block body keeps one.
+            long long total_markers = 0;
+            for (int k = 0; k < nact; k++) total_markers += views[k].n;
+            double planes_rest = (double)g.X;
+            for (int k = 0; k < b.early_n; k++) {
+                const int lo = std::max(b.early_x0[k], g.xOffset), hi = std::min(b.early_x1[k], g.xOffset + g.X);
+                if (hi > lo) planes_rest -= (double)(hi - lo);
+            }
+            const double t_rest_us = std::max(planes_rest, 1.0) * (double)g.plane * 304.0 / 6.2e6;
+            const double t_ibm_us = (double)std::max(ntolLBM, 1) * (double)total_markers * 0.0075;
+            early_bps = (int)std::ceil(t_ibm_us / t_rest_us);
+            early_bps = std::max(1, std::min(4, early_bps));
+        }
         if (use_early) {
             early_total = g_ibm_early_total;
             bool any_re = false;
@@ -2063,7 +2080,7 @@ int fsilbm_ibm_interaction_force_begin(fsilbm_handle h, int nbody, const int *ne
                 early_total = std::max(sms / 4, std::min(2 * sms, (max_markers + 109) / 110));
             }
         }
-        if (launch_ibm_loop(lp, max_markers, use_early ? g_ibm_early_blocks : 0, early_total, use_early ? g_ibm_early_lean : 0, s)) {
+        if (launch_ibm_loop(lp, max_markers, use_early ? early_bps : 0, early_total, use_early ? g_ibm_early_lean : 0, s)) {
             cudaGetLastError();
             if (mailbox) return fail(FSILBM_ERR_CUDA, "cooperative launch of the IBM iteration failed");   // the other ranks are in the mailbox protocol
             single = false;   // no cooperative launch: take the phase-by-phase path

@@ -82,7 +82,9 @@ int fsilbm_trace_dump(const char *path);
  *                             exchanged through peer memory), 0 one kernel per phase (slab runs: ncclAllReduce of the loop control)
  *   "ibm_early"               1 (default) fsilbm_block_collide_stream updates the x-planes around the bodies first so that the next
  *                             fsilbm_ibm_interaction_force runs beside the rest of the update, 0 strictly one after the other
- *   "ibm_early_blocks_per_sm" 1..4 (default 1): size of the cooperative IBM grid when it shares the SMs with that update
+ *   "ibm_early_blocks_per_sm" 0 (default): the cooperative IBM grid that shares the SMs with that update is sized per call -- one block per
+ *                             SM unless the iteration would outlast the rest of the update (a large body in a small block), then up to 4;
+ *                             1..4 fixes it
  *   "ibm_early_blocks"        > 0: that grid as an absolute number of blocks instead (0 = use the per-SM figure)
  *   "ibm_force_exchange"      slab runs: 1 (default) every rank passes the same body list and gets every force back, 0 per-rank lists
  *                             (see fsilbm_ibm_body_status below) */
