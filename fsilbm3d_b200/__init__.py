@@ -12,11 +12,11 @@ from .fluid_domain import LBMBlock
 from .solid_body import VirtualBody, RigidPlate
 from . import flow_io
 from .block_comm import (tree_collision_streaming_IBM_FEM, slab_range, init_process_group, halo_plan, CommPair, RemoteSon, blockTreeNode,
-                         build_block_tree, CompareBlocks, find_carrier_fluidblock, set_blktime_all, ibm_box_participants)
+                         build_block_tree, CompareBlocks, find_carrier_fluidblock, set_blktime_all, ibm_box_participants, son_slab_plan)
 
 __all__ = [
     "FlowCondType", "FsilbmError", "lib", "library_path", "exported_symbols", "declared_symbols",
     "LBMBlock", "VirtualBody", "RigidPlate", "flow_io", "tree_collision_streaming_IBM_FEM", "slab_range",
     "init_process_group", "halo_plan", "CommPair", "RemoteSon", "blockTreeNode", "build_block_tree", "CompareBlocks",
-    "find_carrier_fluidblock", "set_blktime_all", "ibm_box_participants",
+    "find_carrier_fluidblock", "set_blktime_all", "ibm_box_participants", "son_slab_plan",
 ]

@@ -3,6 +3,7 @@ decomposition plumbing (one process per GPU; torch.distributed only hands the NC
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Optional, Sequence, Tuple
 
 from ._lib import check, ensure_init, lib
@@ -54,6 +55,34 @@ def ibm_box_participants(x0: int, length: int, slabs: Sequence[Tuple[int, int]],
         else:
             runs.append((r, dx, dx + 1))
     return runs, runs[0][0]
+
+
+def son_slab_plan(father_xmin: float, father_dh: float, slabs: Sequence[Tuple[int, int]], son_xmin: float, son_xDim: int, son_dh: float,
+                  son_periodic_x: bool = False):
+    """Where a son block goes on a slab run (include/fsilbm.h "Slab runs", fsilbm_pair_create / fsilbm_pair_create_remote).
+    `slabs[r] = (offset, count)` of rank r's father slab.  Returns (owner, remote): `owner` creates the son block and the pair
+    (the rank holding most of the footprint, the lower rank on a tie); `remote` lists the ranks -- directly left / right of the owner
+    -- that must call fsilbm_pair_create_remote(father, owner) because the footprint reaches into their slabs.  The footprint is
+    the father planes f(1)..f(2) of build_blocks_comunication (LBMBlockComm.f90:58-66).  Raises ValueError when it does not fit
+    into the owner's slab and its two neighbours (a son that wide has to be split by the user)."""
+    sD = son_xDim - (1 if son_periodic_x else 0)
+    ratio = int(math.floor(father_dh / son_dh + 0.5))
+    f0 = int(math.floor((son_xmin - father_xmin) / father_dh + 1.5)) - 1           # 0-based first father plane
+    f1 = f0 + (sD - 1) // ratio
+    owner_of = {}
+    for r, (off, cnt) in enumerate(slabs):
+        for x in range(off, off + cnt):
+            owner_of[x] = r
+    if f0 not in owner_of or f1 not in owner_of:
+        raise ValueError(f"son block spans father planes {f0 + 1}..{f1 + 1}: not inside its father")
+    counts = {}
+    for x in range(f0, f1 + 1):
+        counts[owner_of[x]] = counts.get(owner_of[x], 0) + 1
+    owner = max(sorted(counts), key=lambda r: counts[r])
+    remote = sorted(r for r in counts if r != owner)
+    if any(abs(r - owner) != 1 for r in remote):
+        raise ValueError(f"son block spans father planes {f0 + 1}..{f1 + 1} on ranks {sorted(counts)}: more than the owner's slab and its two neighbours")
+    return owner, remote
 
 
 def init_process_group(rank: int, nranks: int, device: int, broadcast_bytes) -> None:

@@ -167,6 +167,10 @@ def refinement_case(F, dist, rank, world, local):
     son_mins += [(15.0, 1.0, 1.0), (16.0, 8.0, 7.0)]
     son_rank += [0, 1]
     son_reach = {2: 1, 3: 0}          # son index -> the neighbouring rank its footprint reaches into
+    slabs = [F.slab_range(X, r, world) for r in range(world)]
+    for k in range(4):                # the host-side plan says the same
+        owner, remote = F.son_slab_plan(0.0, 1.0, slabs, son_mins[k][0], sdims[0], 0.5)
+        assert owner == son_rank[k] and remote == ([son_reach[k]] if k in son_reach else []), (k, owner, remote)
     nsons = len(son_mins)
     scheme = 2
     off, cnt = F.slab_range(X, rank, world)
