@@ -545,6 +545,10 @@ def run_gpu(args):
     den_host = torch.empty((Xl, Y, Z), dtype=torch.float64, pin_memory=True)
     uuu_host = torch.empty((3, Xl, Y, Z), dtype=torch.float64, pin_memory=True)
     blk.download_fIn(f_host.numpy())
+    # warm-up of the read-back path: its device staging fields (den, uuu: 1 GB for 33.5 M cells) are allocated on first use, and a
+    # cudaMalloc of that size inside the timed region costs anything between 10 and 250 ms depending on the box
+    blk.download_macro_async(den_host.numpy(), uuu_host.numpy())
+    blk.download_wait()
     blk.sync(); torch.cuda.synchronize(); barrier()
     check = F._lib.check
     t0 = time.perf_counter()
