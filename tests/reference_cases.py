@@ -112,6 +112,10 @@ CASES["outputs_inlet_outlet"] = dict(_fluid((12, 9, 10), (101, 104, 202, 202, 30
                                             shearRateIn=(0.0, 3e-4, 0.0), volumeForceIn=(5e-7, 0.0, 0.0)),
                                      outputs=True, probes=[(3.5, 4.25, 6.0), (8.0, 2.0, 1.5)])
 CASES["outputs_two_blocks"] = dict(CASES["refine_linear"], steps=4, outputs=True, probes=[(6.25, 4.5, 5.0)])
+# outputtype 3: running means of u and of the Reynolds stresses (calculate_turbulent_statistic_, FluidDomain.f90:1147-1172, with its
+# real(4) 1/n) and the MeanFlow file next to the flow file
+CASES["outputs_mean_flow"] = dict(_fluid((10, 9, 8), (301, 301, 203, 203, 301, 301), steps=6, volumeForceIn=(2e-6, 0.0, 0.0), wave=2e-2),
+                                  outputs=True, outputtype=3, probes=[(4.5, 3.25, 2.0)])
 
 
 def has_son(case):
@@ -142,7 +146,8 @@ def initial_states(case):
 
 
 def block_list(case):
-    blocks = [dict(ID=1, iCollidModel=case["model"], dims=case["dims"], dh=1.0, xyzmin=(0.0, 0.0, 0.0), BndConds=case["bc"], params=case["params"])]
+    blocks = [dict(ID=1, iCollidModel=case["model"], dims=case["dims"], dh=1.0, xyzmin=(0.0, 0.0, 0.0), BndConds=case["bc"], params=case["params"],
+                   outputtype=case.get("outputtype", 1))]
     if has_son(case):
         blocks.append(dict(ID=2, iCollidModel=case["model"], offsetOutput=1, dims=case["sdims"], dh=0.5, xyzmin=case["smins"], BndConds=(0,) * 6,
                            params=case["params"]))
@@ -246,7 +251,7 @@ def run_oracle(O, case, sb=None):
 def output_files(wd):
     """{relative path: bytes} of the flow / flux / probe files a run left in its work directory."""
     out = {}
-    for sub, pat in (("DatFlow", "Flow"), ("DatInfo", "FluidFlux"), ("DatInfo", "FluidProbes")):
+    for sub, pat in (("DatFlow", "Flow"), ("DatFlow", "MeanFlow"), ("DatInfo", "FluidFlux"), ("DatInfo", "FluidProbes")):
         d = os.path.join(wd, sub)
         for fn in sorted(os.listdir(d)) if os.path.isdir(d) else ():
             if fn.startswith(pat):

@@ -108,3 +108,25 @@ def test_output_files_of_the_reference(oracle, name):
     got = files["DatInfo/FluidFlux.dat"].decode().splitlines()
     assert got[0] == ' VARIABLES = "t"  "inlet"  "middle"  "outlet"' and got[1] == line
     assert len([k for k in files if "FluidProbes" in k]) == len(case["probes"])
+    if case.get("outputtype", 1) >= 2:
+        # running means of calculate_turbulent_statistic_ (FluidDomain.f90:1147-1172; invStep = 1/real(n) in real(4)), start step 0
+        # (main.f90:76-80 with timeWriteBegin = 0), from the oracle's velocity after every step
+        ave = np.zeros((9,) + blocks[0].den.shape)
+        for step in range(1, case["steps"] + 1):
+            bk, _, _ = RC.run_oracle(oracle, dict(case, steps=step))
+            u = bk[0].uuu
+            inv = float(np.float32(1) / np.float32(step - 0 + 1))
+            for c in range(3):
+                ave[c] = ave[c] * (1.0 - inv) + inv * u[c]
+            for c in range(3):
+                ave[3 + c] = ave[3 + c] * (1.0 - inv) + inv * (u[c] - ave[c]) * (u[c] - ave[c])
+            for n, (a, c) in enumerate(((0, 1), (0, 2), (1, 2))):
+                ave[6 + n] = ave[6 + n] * (1.0 - inv) + inv * (u[a] - ave[a]) * (u[c] - ave[c])
+        b = blocks[0]
+        want = np.array([b.xDim, b.yDim, b.zDim, 1], np.int32).tobytes() + np.array([b.xmin, b.ymin, b.zmin, b.dh]).tobytes()
+        want += ((1.0 / 3.0) * (b.den - 1.0)).astype(np.float32).tobytes()
+        for c in range(3):
+            want += (ave[c] * (1.0 / Uref)).astype(np.float32).tobytes()
+        for c in range(3, 9):
+            want += (ave[c] * (1.0 / Uref / Uref)).astype(np.float32).tobytes()
+        assert files["DatFlow/MeanFlow_b001"] == want
