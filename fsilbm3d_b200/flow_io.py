@@ -203,16 +203,13 @@ def write_fluid_information(block, time: float, Tref: float, Uref: float, coords
 
 
 def _e20_10(v: float) -> str:
-    """Fortran edit descriptor E20.10: 0.dddddddddde+XX right-adjusted in 20 columns."""
+    """Fortran edit descriptor E20.10: 0.dddddddddde+XX right-adjusted in 20 columns, ten significant digits correctly rounded
+    from the binary value (as the Fortran run-time library does)."""
     if v == 0.0:
         return "    0.0000000000E+00"
-    exp = int(math.floor(math.log10(abs(v)))) + 1
-    mant = v / 10.0 ** exp
-    s = f"{mant:.10f}"
-    if abs(float(s)) >= 1.0:      # rounding carried into the leading digit
-        exp += 1
-        s = f"{v / 10.0 ** exp:.10f}"
-    return f"{s}E{exp:+03d}".rjust(20)
+    mant, e10 = f"{abs(v):.9e}".split("e")
+    s = f"{'-' if v < 0 else ''}0.{mant.replace('.', '')}E{int(e10) + 1:+03d}"
+    return s.rjust(20)
 
 
 def fieldstat_lines(block) -> str:

@@ -707,40 +707,44 @@ void BeamSolver::calculate_angle_material(double Lref, double Uref, double denIn
         umaxIn = std::max(umaxIn, std::fabs(uuuIn[k]));
     }
     uMax = std::max({uMax, umaxIn, 2.0 * m_pi * amax * Freq, 2.0 * m_pi * rmax * Freq});
+    // Fortran's x**n with an integer n is a primary of the product chain it stands in and is expanded along GCC's power tree:
+    // Uref**2 = Uref*Uref (so KS*denIn*Uref**2 is (KS*denIn)*(Uref*Uref), not ((KS*denIn)*Uref)*Uref), x**5 = (x*x)*((x*x)*x)
+    const double U2 = Uref * Uref;
+    auto pow5 = [](double x) { const double x2 = x * x; return x2 * (x2 * x); };
     nLthck = 0.0;   // left undefined by the reference when isKB is neither 0 nor 1
     if (P->isKB == 0) {
         for (Segment &e : m_elements) {
             const double len = e.spanlen;
-            e.m_property[0] = EmR * denIn * Uref * Uref;
+            e.m_property[0] = EmR * denIn * U2;
             e.m_property[1] = e.m_property[0] / (2.0 * (1.0 + psR));
             nLthck = tcR * Lref;
             e.m_property[2] = len * nLthck;
             e.m_property[3] = denR * len * Lref * denIn / e.m_property[2];
             const double ratio = nLthck / len;
-            e.m_property[5] = len * (nLthck * nLthck * nLthck) / 3.0 * (1.0 - 0.63 * ratio + 0.052 * std::pow(ratio, 5));
+            e.m_property[5] = len * (nLthck * nLthck * nLthck) / 3.0 * (1.0 - 0.63 * ratio + 0.052 * pow5(ratio));
             e.m_property[6] = len * (nLthck * nLthck * nLthck) / 12.0;
             e.m_property[7] = nLthck * (len * len * len) / 12.0;
         }
         const double len = m_elements[0].spanlen;
-        KB = m_elements[0].m_property[0] * m_elements[0].m_property[6] / (denIn * Uref * Uref * Lref * Lref * Lref * len);
-        KS = m_elements[0].m_property[0] * m_elements[0].m_property[2] / (denIn * Uref * Uref * Lref * len);
+        KB = m_elements[0].m_property[0] * m_elements[0].m_property[6] / (denIn * U2 * (Lref * Lref * Lref) * len);
+        KS = m_elements[0].m_property[0] * m_elements[0].m_property[2] / (denIn * U2 * Lref * len);
     }
     if (P->isKB == 1) {
         for (Segment &e : m_elements) {
             const double len = e.spanlen;
             nLthck = std::sqrt(KB / KS * 12.0) * Lref;
             e.m_property[2] = len * nLthck;
-            e.m_property[0] = KS * denIn * Uref * Uref * Lref * len / e.m_property[2];
+            e.m_property[0] = KS * denIn * U2 * Lref * len / e.m_property[2];
             e.m_property[1] = e.m_property[0] / (2.0 * (1.0 + psR));
             e.m_property[3] = denR * len * Lref * denIn / e.m_property[2];
             const double ratio = nLthck / len;
-            e.m_property[5] = len * (nLthck * nLthck * nLthck) / 3.0 * (1.0 - 0.63 * ratio + 0.052 * std::pow(ratio, 5));
+            e.m_property[5] = len * (nLthck * nLthck * nLthck) / 3.0 * (1.0 - 0.63 * ratio + 0.052 * pow5(ratio));
             e.m_property[6] = len * (nLthck * nLthck * nLthck) / 12.0;
             e.m_property[7] = nLthck * (len * len * len) / 12.0;
         }
         const double len = m_elements[0].spanlen;
         nLthck = m_elements[0].m_property[2] / len;
-        EmR = m_elements[0].m_property[0] / (denIn * Uref * Uref);
+        EmR = m_elements[0].m_property[0] / (denIn * U2);
         tcR = nLthck / Lref;
     }
 }

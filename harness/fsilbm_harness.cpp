@@ -372,15 +372,17 @@ bool check_is_continue(int &step, double &time, int isContinue)
     return true;
 }
 
-std::string e20_10(double v)   // Fortran E20.10
+std::string e20_10(double v)   // Fortran E20.10: 0.dddddddddd E+xx, ten significant digits correctly rounded from the binary value
 {
     if (v == 0.0) return "    0.0000000000E+00";
-    int ex = (int)std::floor(std::log10(std::fabs(v))) + 1;
     char m[64];
-    std::snprintf(m, sizeof(m), "%.10f", v / std::pow(10.0, ex));
-    if (std::fabs(std::atof(m)) >= 1.0) { ex++; std::snprintf(m, sizeof(m), "%.10f", v / std::pow(10.0, ex)); }
+    std::snprintf(m, sizeof(m), "%.9E", std::fabs(v));          // d.dddddddddE+xx, exact decimal rounding by the C library
+    std::string digits;
+    digits += m[0];
+    digits.append(m + 2, 9);
+    const int ex = std::atoi(std::strchr(m, 'E') + 1) + 1;
     char out[96];
-    std::snprintf(out, sizeof(out), "%sE%+03d", m, ex);
+    std::snprintf(out, sizeof(out), "%s0.%sE%+03d", v < 0 ? "-" : "", digits.c_str(), ex);
     std::string s(out);
     return std::string(s.size() < 20 ? 20 - s.size() : 0, ' ') + s;
 }

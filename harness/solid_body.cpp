@@ -271,9 +271,10 @@ void SolidBodies::calculate_reference_params(FlowCond &flow) const
     else if (flow.TrefType == 1) flow.Tref = 1 / maxFreq();
     else std::printf(" Use input reference time\n");
     flow.Aref = flow.Uref / flow.Tref;
-    flow.Fref = 0.5 * flow.denIn * flow.Uref * flow.Uref * flow.Asfac;
-    flow.Eref = 0.5 * flow.denIn * flow.Uref * flow.Uref * flow.Asfac * flow.Lref;
-    flow.Pref = 0.5 * flow.denIn * flow.Uref * flow.Uref * flow.Asfac * flow.Uref;
+    // Uref**2 is a primary of the product chain in the Fortran (Solidbody.f90:278-280): (0.5*denIn)*(Uref*Uref)*..., not ((0.5*denIn)*Uref)*Uref
+    flow.Fref = 0.5 * flow.denIn * (flow.Uref * flow.Uref) * flow.Asfac;
+    flow.Eref = 0.5 * flow.denIn * (flow.Uref * flow.Uref) * flow.Asfac * flow.Lref;
+    flow.Pref = 0.5 * flow.denIn * (flow.Uref * flow.Uref) * flow.Asfac * flow.Uref;
     flow.nu = flow.Uref * flow.Lref / flow.Re;
     flow.Mu = flow.nu * flow.denIn;
 }
