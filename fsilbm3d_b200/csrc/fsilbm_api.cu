@@ -1359,12 +1359,19 @@ int fsilbm_block_write_flow_window(fsilbm_handle h, int offsetOutput, int output
     // window in global x: [off, XG-off), intersected with the local slab
     const int gx0 = std::max(offsetOutput, g.xOffset), gx1 = std::min(g.XG - offsetOutput, g.xOffset + g.X);
     FlowWindowParams p{};
-    p.g = g; p.f = b->f[b->cur]; p.uuu_ave = b->uuu_ave;
+    p.g = g; p.f = b->f[b->cur];
     p.x0 = gx0 - g.xOffset; p.off = offsetOutput;
     p.nx = gx1 - gx0; p.ny = g.Y - 2 * offsetOutput; p.nz = g.Z - 2 * offsetOutput;
     if (p.nx <= 0 || p.ny <= 0 || p.nz <= 0) return 0;
     p.outputtype = outputtype;
-    if (outputtype >= 2 && !b->uuu_ave) return fail(FSILBM_ERR_ARG, "outputtype >= 2 needs fsilbm_block_turbulent_statistic to have run");
+    if (outputtype >= 2 && !b->uuu_ave) {
+        // the reference allocates uuu_ave with the block (FluidDomain.f90:390) and zeroes it in initialise_ (:539): its first write_flow_blocks call
+        // (main.f90:84, before any step) writes those zeros
+        const size_t nave = (size_t)g.X * g.plane;
+        CK(cudaMalloc(&b->uuu_ave, sizeof(double) * 9 * nave));
+        CK(cudaMemsetAsync(b->uuu_ave, 0, sizeof(double) * 9 * nave, b->stream));
+    }
+    p.uuu_ave = b->uuu_ave;
     half_force(*b, p.hF);
     p.denIn = b->flow.denIn; p.invUref = 1.0 / b->flow.Uref; p.invUrefs = 1.0 / b->flow.Uref / b->flow.Uref;   // :1650-1651
     const int nfields = outputtype >= 2 ? 13 : 4;

@@ -89,6 +89,15 @@ CASES["flexible_plate_heaving"] = dict(
     Re=40.0, wave=1e-3, flow={}, ntolLBM=3, dtolLBM=1e-30, numsubstep=4, plate=dict(nEL=4, chord=4.0, span=4.0, Nspan=4),
     group=dict(iBodyModel=2, isMotionGiven=(1,) * 6, denR=2.0, psR=0.3, KB=0.05, KS=800.0, freq=0.02, XYZAmpl=(0.0, 0.8, 0.0),
                AoAAmpl=(0.0, 0.0, 10.0), AoAPhi=(0.0, 0.0, 90.0), firstXYZ=(6.3, 6.6, 5.2)), isKB=1)
+# structural variants of the flexible plate: explicit modulus / thickness (isKB = 0) with a hinged leading edge (rotation about z free);
+# Rayleigh damping, a dissipative Newmark pair, reduced geometric stiffness and a three-dimensional incidence
+CASES["flexible_plate_hinged_iskb0"] = dict(
+    CASES["flexible_plate"], steps=4, isKB=0,
+    group=dict(iBodyModel=2, isMotionGiven=(1, 1, 1, 1, 1, 0), denR=1.0, psR=0.3, EmR=2.0e3, tcR=0.02, AoAo=(0.0, 0.0, 12.0), firstXYZ=(6.3, 6.6, 5.2)))
+CASES["flexible_plate_damped_3d"] = dict(
+    CASES["flexible_plate"], steps=4, solid=dict(dampK=0.01, dampM=0.02, NewmarkGamma=0.6, NewmarkBeta=0.3025, GeoGamma=0.5, IBPenaltyAlpha=0.8),
+    group=dict(iBodyModel=2, isMotionGiven=(1,) * 6, denR=1.0, psR=0.3, KB=0.02, KS=500.0, freq=0.03, XYZAmpl=(0.2, 0.6, 0.0), XYZPhi=(10.0, 20.0, 0.0),
+               AoAo=(5.0, -7.0, 12.0), AoAAmpl=(0.0, 0.0, 8.0), AoAPhi=(0.0, 0.0, 45.0), firstXYZ=(6.3, 6.6, 5.2)))
 # MRT with every kind of face and a Smagorinsky block with a plate: collision models other than SRT next to boundaries / bodies
 CASES["mrt_all_faces_mixed"] = _fluid((9, 10, 8), (101, 103, 204, 202, 201, 203), model=3, steps=8, uvwIn=(0.03, 0.0, 0.0), Uref=0.03,
                                       shearRateIn=(0.0, 4e-4, 1e-4))
@@ -185,7 +194,7 @@ def write_inputs(case, wd, continue_at_end=False):
     text = S.inflow_text(npsize=1, isConCmpt=2, numsubstep=case.get("numsubstep", 1), timeSimTotal=total, Re=case["Re"], uvwIn=case["uvwIn"],
                          LrefType=1, Lref=case["Lref"], TrefType=0, UrefType=9, Uref=case["Uref"], ntolLBM=case.get("ntolLBM", 3),
                          dtolLBM=case.get("dtolLBM", 1e-8), interpolateScheme=case.get("scheme", 1), blocks=blocks, groups=groups,
-                         isKB=case.get("isKB", 0), dtolFEM=1e-12, ntolFEM=20, **extra, **case["flow"])
+                         isKB=case.get("isKB", 0), dtolFEM=1e-12, ntolFEM=20, **extra, **case.get("solid", {}), **case["flow"])
     with open(os.path.join(wd, "inFlow.dat"), "w") as f:
         f.write(text)
     write_continue(os.path.join(wd, "DatContinue", "continue"), blocks, initial_states(case))
