@@ -53,6 +53,14 @@ for _name, _scheme in (("refine_linear", 1), ("refine_cubic", 2)):
                         model=1, params=P0, steps=6, uvwIn=(0.04, 0.0, 0.0), Uref=0.04, Lref=4.0, Re=20.0, wave=1e-3,
                         flow=dict(volumeForceIn=(1e-6, 0.0, 0.0)))
 
+# a son that is periodic in y (even number of nodes, closures of interpolate_fIn, LBMBlockComm.f90:857-871) under a TRT father, cubic;
+# Smagorinsky father and son (tau_all fields interpolated and rescaled, interpolate_tau :907-956)
+CASES["refine_cubic_periodic_son_trt"] = dict(
+    kind="refine", dims=(14, 10, 10), bc=(101, 104, 301, 301, 301, 301), sdims=(13, 20, 11), smins=(4.0, 0.0, 2.0), sbc=(0, 0, 301, 301, 0, 0),
+    scheme=2, model=2, params=(3.0 / 16.0,) + (0.0,) * 9, smodel=1, sparams=P0, steps=6, uvwIn=(0.04, 0.0, 0.0), Uref=0.04, Lref=4.0, Re=20.0,
+    wave=1e-3, flow=dict(volumeForceIn=(1e-6, 0.0, 0.0)))
+CASES["refine_les_smag"] = dict(CASES["refine_linear"], model=11, wave=2e-2, steps=5)
+
 # a rigid plate in prescribed heave (iBodyModel 1; Solidbody.f90:760-1049 IBM, SolidSolver.f90:1826-1857 motion)
 CASES["rigid_plate_heave"] = dict(
     kind="body", dims=(20, 14, 14), bc=(101, 104, 202, 202, 301, 301), model=1, params=P0, steps=8, uvwIn=(0.05, 0.0, 0.0), Uref=0.05, Lref=4.0,
@@ -98,6 +106,13 @@ CASES["flexible_plate_damped_3d"] = dict(
     CASES["flexible_plate"], steps=4, solid=dict(dampK=0.01, dampM=0.02, NewmarkGamma=0.6, NewmarkBeta=0.3025, GeoGamma=0.5, IBPenaltyAlpha=0.8),
     group=dict(iBodyModel=2, isMotionGiven=(1,) * 6, denR=1.0, psR=0.3, KB=0.02, KS=500.0, freq=0.03, XYZAmpl=(0.2, 0.6, 0.0), XYZPhi=(10.0, 20.0, 0.0),
                AoAo=(5.0, -7.0, 12.0), AoAAmpl=(0.0, 0.0, 8.0), AoAPhi=(0.0, 0.0, 45.0), firstXYZ=(6.3, 6.6, 5.2)))
+# stencil folding at the faces (trimedindex, Solidbody.f90:834-866): one plate two cells above a moving wall (mirror 0 -> 2) and across the
+# periodic z face (wrap), one below a half-way wall (0 -> 1)
+CASES["plates_near_walls"] = dict(
+    kind="body", dims=(20, 12, 12), bc=(101, 104, 202, 203, 301, 301), model=1, params=P0, steps=6, uvwIn=(0.05, 0.0, 0.0), Uref=0.05, Lref=4.0,
+    Re=40.0, wave=1e-3, flow=dict(shearRateIn=(0.0, 2e-4, 0.0)), ntolLBM=3, dtolLBM=1e-30, numsubstep=1, plate=dict(nEL=4, chord=4.0, span=4.0, Nspan=4),
+    groups=[dict(iBodyModel=1, isMotionGiven=(1,) * 6, EmR=1.0, tcR=0.05, firstXYZ=(6.3, 1.4, 10.1)),
+            dict(iBodyModel=1, isMotionGiven=(1,) * 6, EmR=1.0, tcR=0.05, AoAo=(0.0, 0.0, -4.0), firstXYZ=(9.2, 9.8, 5.3))], isKB=0)
 # MRT with every kind of face and a Smagorinsky block with a plate: collision models other than SRT next to boundaries / bodies
 CASES["mrt_all_faces_mixed"] = _fluid((9, 10, 8), (101, 103, 204, 202, 201, 203), model=3, steps=8, uvwIn=(0.03, 0.0, 0.0), Uref=0.03,
                                       shearRateIn=(0.0, 4e-4, 1e-4))
@@ -158,8 +173,8 @@ def block_list(case):
     blocks = [dict(ID=1, iCollidModel=case["model"], dims=case["dims"], dh=1.0, xyzmin=(0.0, 0.0, 0.0), BndConds=case["bc"], params=case["params"],
                    outputtype=case.get("outputtype", 1))]
     if has_son(case):
-        blocks.append(dict(ID=2, iCollidModel=case["model"], offsetOutput=1, dims=case["sdims"], dh=0.5, xyzmin=case["smins"], BndConds=(0,) * 6,
-                           params=case["params"]))
+        blocks.append(dict(ID=2, iCollidModel=case.get("smodel", case["model"]), offsetOutput=1, dims=case["sdims"], dh=0.5, xyzmin=case["smins"],
+                           BndConds=case.get("sbc", (0,) * 6), params=case.get("sparams", case["params"])))
     return blocks
 
 
@@ -212,8 +227,8 @@ def run_oracle(O, case, sb=None):
     root = O.TreeNode(Fb)
     if has_son(case):
         sx, sy, sz = case["sdims"]
-        Sb = O.LBMBlock(sx, sy, sz, dh=0.5, xmin=case["smins"][0], ymin=case["smins"][1], zmin=case["smins"][2], BndConds=(0,) * 6,
-                        iCollidModel=case["model"], params=case["params"], flow=fl)
+        Sb = O.LBMBlock(sx, sy, sz, dh=0.5, xmin=case["smins"][0], ymin=case["smins"][1], zmin=case["smins"][2], BndConds=case.get("sbc", (0,) * 6),
+                        iCollidModel=case.get("smodel", case["model"]), params=case.get("sparams", case["params"]), flow=fl)
         root.add_son(O.TreeNode(Sb), case["scheme"])
         blocks.append(Sb)
     for b, s in zip(blocks, states):
