@@ -2324,12 +2324,13 @@ int fsilbm_pair_create(fsilbm_handle father, fsilbm_handle son, int interpolateS
             return fail(FSILBM_ERR_ARG, "son block spans father planes %d..%d but this rank's father slab is %d..%d: a son may reach into the directly "
                                         "neighbouring slabs only, and only with the peer-memory halo (option \"halo\" = 1, CUDA IPC available)",
                         p->f[0], p->f[1], gf.xOffset + 1, gf.xOffset + gf.X);
-        if (F->tau_all) return fail(FSILBM_ERR_MODEL, "a son across a slab interface of an LES father (tau_all field) is not provided");
+        if (F->model >= 11) return fail(FSILBM_ERR_MODEL, "a son across a slab interface of an LES father (tau_all field) is not provided");
         p->cross[0] = want_l; p->cross[1] = want_r;
     }
     for (int j = 0; j < 6; j++) { p->si[j] = p->s[j] + p->sds[j] * ratio; p->fi[j] = p->f[j] + p->sds[j]; }
     // allocate_fIn_tau, :213-264
-    const bool need_tau = F->tau_all || S->tau_all;
+    // (by collision model, not by whether tau_all exists yet: the reference builds its block tree before initialise_, main.f90:34,50)
+    const bool need_tau = F->model >= 11 || S->model >= 11;
     for (int j = 0; j < 6; j++) {
         if (S->bc[j] != BCfluid) continue;
         int axis, bAx, aAx;
