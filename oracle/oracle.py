@@ -316,11 +316,15 @@ class TreeNode:
         return node
 
 
-def tree_collision_streaming_IBM_FEM(node: TreeNode, rootBC=None, iters: Optional[list] = None):
-    """LBMBlockComm.f90:279-318 (FEM Solver excluded), recursion over the block tree."""
+def tree_collision_streaming_IBM_FEM(node: TreeNode, rootBC=None, iters: Optional[list] = None, before_ibm=None, after_ibm=None):
+    """LBMBlockComm.f90:279-318 (FEM Solver excluded), recursion over the block tree.  before_ibm(node) / after_ibm(node): the
+    caller's host work around IBM_FEM of each node (:287,320-338): marker update before, nodal loads and structural sub-steps
+    (with the node's own blktime and dh) after."""
     L = lib()
     b = node.block
     rootBC = b.BndConds if rootBC is None else rootBC
+    if before_ibm is not None:
+        before_ibm(node)
     arr = (C.c_void_p * max(1, len(node.bodies)))(*[v._h for v in node.bodies])
     it = C.c_int(0)
     rc = L.orc_step_pre(b._h, arr, len(node.bodies), (C.c_int * 6)(*rootBC), b.flow.ntolLBM, b.flow.dtolLBM, C.byref(it))   # :283-288
@@ -328,6 +332,8 @@ def tree_collision_streaming_IBM_FEM(node: TreeNode, rootBC=None, iters: Optiona
         raise ValueError(f"oracle: step_pre failed rc={rc}")
     if iters is not None:
         iters.append(it.value)
+    if after_ibm is not None:
+        after_ibm(node)
     for pair in node.comm:
         pair.extract_interpolate_layer(1)                                 # :290
     rc = L.orc_step_post(b._h)                                            # :293-303
@@ -338,7 +344,7 @@ def tree_collision_streaming_IBM_FEM(node: TreeNode, rootBC=None, iters: Optiona
     for son, pair in zip(node.sons, node.comm):                           # :307-317
         for n_timeStep in range(2):
             son.block.set_blktime(son.block.blktime + float(n_timeStep) * son.block.dh)   # :311
-            tree_collision_streaming_IBM_FEM(son, rootBC, iters)
+            tree_collision_streaming_IBM_FEM(son, rootBC, iters, before_ibm, after_ibm)
             pair.interpolation_father_to_son(n_timeStep)
         pair.deliver_son_to_father()
 

@@ -142,6 +142,22 @@ CASES["outputs_mean_flow"] = dict(_fluid((10, 9, 8), (301, 301, 203, 203, 301, 3
                                   outputs=True, outputtype=3, probes=[(4.5, 3.25, 2.0)])
 
 
+# WALE and Vreman with a plate: the velocity they difference is the IBM-corrected one (calculate_interaction_force has rewritten uuu near
+# the body before collision_, LBMBlockComm.f90:287-293)
+CASES["les_vrem_plate"] = dict(CASES["les_smag_plate"], model=15)
+CASES["les_wale_plate"] = dict(CASES["les_smag_plate"], model=14)
+
+
+# a HEAVING rigid plate and a FLEXIBLE plate carried by a refined son: IBM_FEM runs inside the son's two sub-cycles with the son's time
+# and spacing (LBMBlockComm.f90:307-317,320-338: dt_solid = dh_son / numsubstep)
+CASES["heaving_plate_in_son"] = dict(CASES["plate_in_son"], steps=4,
+                                     group=dict(iBodyModel=1, isMotionGiven=(1,) * 6, EmR=1.0, tcR=0.05, freq=0.04, XYZAmpl=(0.0, 0.4, 0.0),
+                                                AoAo=(0.0, 0.0, 10.0), firstXYZ=(6.3, 5.6, 4.7)))
+CASES["flexible_plate_in_son"] = dict(CASES["plate_in_son"], steps=4, numsubstep=2, isKB=1,
+                                      group=dict(iBodyModel=2, isMotionGiven=(1,) * 6, denR=1.0, psR=0.3, KB=0.02, KS=500.0, AoAo=(0.0, 0.0, 10.0),
+                                                 firstXYZ=(6.3, 5.6, 4.7)))
+
+
 def has_son(case):
     return "sdims" in case
 
@@ -245,28 +261,29 @@ def run_oracle(O, case, sb=None):
     if has_body(case):
         for body in sb.VBodies:
             ovs.append(O.VirtualBody(body.v_nelmts, v_move=body.v_move, iBodyModel=body.iBodyModel))
-        if case.get("carrier_son"):
-            # carried by the son: IBM_FEM runs inside the son's two sub-cycles (LBMBlockComm.f90:307-317); the structural sub-steps
-            # there leave a rigid body without prescribed motion where it is, so the markers are set once
-            assert all(b.v_move == 0 and b.iBodyModel == 1 for b in sb.VBodies)
-            root.sons[0].bodies = ovs
-            root.sons[0].rootBC = case["bc"]
-        else:
-            root.bodies = ovs
+        carrier = root.sons[0] if case.get("carrier_son") else root      # FindCarrierFluidBlock: the finest block that holds the bodies
+        carrier.bodies = ovs
     nsub = case.get("numsubstep", 1)
+
+    def before_ibm(node):          # UpdatePosVelArea of FSInteraction_force (Solidbody.f90:597-600)
+        if node.bodies:
+            for body, ov in zip(sb.VBodies, ovs):
+                body.UpdatePosVelArea()
+                ov.v_Exyz[...] = body.v_Exyz; ov.v_Evel[...] = body.v_Evel; ov.v_Ea[...] = body.v_Ea
+
+    def after_ibm(node):           # nodal loads, then IBM_FEM's sub-steps with the carrier's blktime and dh (LBMBlockComm.f90:325,332-335)
+        if node.bodies:
+            dh = node.block.dh
+            for body, ov in zip(sb.VBodies, ovs):
+                body.v_Eforce[...] = ov.v_Eforce
+                body.FluidLoads()
+            for isub in range(1, nsub + 1):      # Solver advances every carried body per sub-step (Solidbody.f90:386-397)
+                for body in sb.VBodies:
+                    body.structure(node.block.blktime, isub, dh, dh / nsub)
+
     for n in range(1, case["steps"] + 1):
-        t = float(n)
-        O.set_blktime_all(root, t)
-        for body, ov in zip(sb.VBodies if ovs else (), ovs):
-            body.UpdatePosVelArea()
-            ov.v_Exyz[...] = body.v_Exyz; ov.v_Evel[...] = body.v_Evel; ov.v_Ea[...] = body.v_Ea
-        O.tree_collision_streaming_IBM_FEM(root, iters=its)
-        for body, ov in zip(sb.VBodies if ovs else (), ovs):
-            body.v_Eforce[...] = ov.v_Eforce
-            body.FluidLoads()
-        for isub in range(1, nsub + 1):          # Solver advances every carried body per sub-step (Solidbody.f90:386-397)
-            for body in (sb.VBodies if ovs else ()):
-                body.structure(t, isub, 1.0, 1.0 / nsub)
+        O.set_blktime_all(root, float(n))
+        O.tree_collision_streaming_IBM_FEM(root, iters=its, before_ibm=before_ibm, after_ibm=after_ibm)
     for b in blocks:
         b.calculate_macro_quantities()
     return blocks, (ovs[0] if len(ovs) == 1 else (ovs or None)), its
