@@ -9,7 +9,7 @@
  *
  * PINNED AGAINST THE REFERENCE: the reference ships no tests or golden vectors and is
  * Fortran; no Fortran compiler exists in this environment.  Its unmodified sources are
- * therefore executed by the interpreter in oracle/ftn/ (main.f90 from start to end on 31
+ * therefore executed by the interpreter in oracle/ftn/ (main.f90 from start to end on 32
  * cases, tests/reference_cases.py); what the reference leaves is committed as
  * tests/golden/ref_*.npz and this oracle reproduces it bit for bit
  * (tests/test_reference_golden.py).  Also held by the analytic known-answer tests in

@@ -158,8 +158,27 @@ CASES["flexible_plate_in_son"] = dict(CASES["plate_in_son"], steps=4, numsubstep
                                                  firstXYZ=(6.3, 5.6, 4.7)))
 
 
+# three levels and two sons: root (dh 1) with a son (dh 0.5) that carries a grandson (dh 0.25, four sub-cycles per root step), and a second
+# son elsewhere in the root -- build_block_tree / array_to_tree (LBMBlockComm.f90:98-211) and the nested sub-cycling (:307-317)
+CASES["three_levels_two_sons"] = dict(
+    kind="refine", dims=(18, 12, 12), bc=(101, 104, 301, 301, 301, 301), scheme=2, model=1, params=P0, steps=3, uvwIn=(0.04, 0.0, 0.0), Uref=0.04,
+    Lref=4.0, Re=20.0, wave=1e-3, flow=dict(volumeForceIn=(1e-6, 0.0, 0.0)),
+    sons=[dict(dims=(13, 11, 11), mins=(3.0, 3.0, 3.0), dh=0.5), dict(dims=(9, 9, 9), mins=(4.0, 4.0, 4.0), dh=0.25),
+          dict(dims=(9, 9, 9), mins=(11.0, 5.0, 4.0), dh=0.5)])
+
+
+def son_list(case):
+    """Every block below the root: dicts with dims, mins, dh (and optionally bc, model, params)."""
+    if "sons" in case:
+        return case["sons"]
+    if "sdims" in case:
+        return [dict(dims=case["sdims"], mins=case["smins"], dh=0.5, bc=case.get("sbc", (0,) * 6), model=case.get("smodel", case["model"]),
+                     params=case.get("sparams", case["params"]))]
+    return []
+
+
 def has_son(case):
-    return "sdims" in case
+    return bool(son_list(case))
 
 
 def has_body(case):
@@ -180,17 +199,45 @@ def initial_states(case):
         pass
     fl = _F(); fl.uvwIn = case["uvwIn"]; fl.denIn = 1.0
     out = [perturbed_state(case["dims"], fl, wave_amp=case["wave"], seed=SEED)]
-    if has_son(case):
-        out.append(perturbed_state(case["sdims"], fl, wave_amp=case["wave"], seed=SEED + 1))
+    for k, sn in enumerate(son_list(case)):
+        out.append(perturbed_state(sn["dims"], fl, wave_amp=case["wave"], seed=SEED + 1 + k))
+    return out
+
+
+def restart_states(case):
+    """initial_states as check_is_continue (FluidDomain.f90:128-237) hands them to the blocks: every node takes the populations of the
+    FIRST saved block, in the reference's dh-"sorted" order, that contains it, by trilinear interpolation (weights 0/1 at coincident
+    nodes).  That order is what the reference's exchange loop produces (:153-165 compares the UNSORTED dh of slots i and j): with more
+    than two levels it is not finest-first -- e.g. a grandson is re-gridded from its father's saved state.  The re-gridding is the
+    product's host-side restatement (fsilbm3d_b200.flow_io.regrid_from_continue), which the goldens therefore pin as well."""
+    from fsilbm3d_b200 import flow_io
+    st = initial_states(case)
+    geo = [dict(dims=case["dims"], mins=(0.0, 0.0, 0.0), dh=1.0)] + list(son_list(case))
+    saved = [dict(xmin=g["mins"][0], ymin=g["mins"][1], zmin=g["mins"][2], dh=g["dh"], xDim=g["dims"][0], yDim=g["dims"][1], zDim=g["dims"][2], fIn=f)
+             for g, f in zip(geo, st)]
+
+    class _Blk:
+        def __init__(self, g, f):
+            self.xDim, self.yDim, self.zDim = g["dims"]
+            self.xLocal, self.xOffset = self.xDim, 0
+            self.xmin, self.ymin, self.zmin = g["mins"]
+            self.dh, self._f = g["dh"], f
+
+        def download_fIn(self):
+            return self._f
+    out = []
+    for g, f in zip(geo, st):
+        r = flow_io.regrid_from_continue(_Blk(g, f), saved)
+        out.append(np.ascontiguousarray(f if r is None else r))
     return out
 
 
 def block_list(case):
     blocks = [dict(ID=1, iCollidModel=case["model"], dims=case["dims"], dh=1.0, xyzmin=(0.0, 0.0, 0.0), BndConds=case["bc"], params=case["params"],
                    outputtype=case.get("outputtype", 1))]
-    if has_son(case):
-        blocks.append(dict(ID=2, iCollidModel=case.get("smodel", case["model"]), offsetOutput=1, dims=case["sdims"], dh=0.5, xyzmin=case["smins"],
-                           BndConds=case.get("sbc", (0,) * 6), params=case.get("sparams", case["params"])))
+    for k, sn in enumerate(son_list(case)):
+        blocks.append(dict(ID=2 + k, iCollidModel=sn.get("model", case["model"]), offsetOutput=1, dims=sn["dims"], dh=sn["dh"], xyzmin=sn["mins"],
+                           BndConds=sn.get("bc", (0,) * 6), params=sn.get("params", case["params"])))
     return blocks
 
 
@@ -236,25 +283,34 @@ def run_oracle(O, case, sb=None):
     (harness/libfsilbm_solid.so; host code on both sides of the boundary).  Returns (blocks, oracle body or None, iteration counts)."""
     nu = case["Uref"] * case["Lref"] / case["Re"]                           # Solidbody.f90:282
     fl = O.Flow(nu=nu, uvwIn=case["uvwIn"], Uref=case["Uref"], ntolLBM=case.get("ntolLBM", 3), dtolLBM=case.get("dtolLBM", 1e-8), **case["flow"])
-    states = initial_states(case)
+    states = restart_states(case)
     X, Y, Z = case["dims"]
     Fb = O.LBMBlock(X, Y, Z, dh=1.0, BndConds=case["bc"], iCollidModel=case["model"], params=case["params"], flow=fl)
     blocks = [Fb]
-    root = O.TreeNode(Fb)
-    if has_son(case):
-        sx, sy, sz = case["sdims"]
-        Sb = O.LBMBlock(sx, sy, sz, dh=0.5, xmin=case["smins"][0], ymin=case["smins"][1], zmin=case["smins"][2], BndConds=case.get("sbc", (0,) * 6),
-                        iCollidModel=case.get("smodel", case["model"]), params=case.get("sparams", case["params"]), flow=fl)
-        root.add_son(O.TreeNode(Sb), case["scheme"])
+    nodes = [O.TreeNode(Fb)]
+    root = nodes[0]
+    geo = [dict(dims=case["dims"], mins=(0.0, 0.0, 0.0), dh=1.0)] + list(son_list(case))
+    for sn in son_list(case):
+        sx, sy, sz = sn["dims"]
+        Sb = O.LBMBlock(sx, sy, sz, dh=sn["dh"], xmin=sn["mins"][0], ymin=sn["mins"][1], zmin=sn["mins"][2], BndConds=sn.get("bc", (0,) * 6),
+                        iCollidModel=sn.get("model", case["model"]), params=sn.get("params", case["params"]), flow=fl)
         blocks.append(Sb)
-    for b, s in zip(blocks, states):
+        nodes.append(O.TreeNode(Sb))
+
+    def upper(g, k):       # xmax of read_fuild_blocks (FluidDomain.f90:94-105): one spacing further on a periodic axis
+        bc = g.get("bc", (0,) * 6)
+        return g["mins"][k] + (g["dims"][k] - 1) * g["dh"] + (g["dh"] if bc[2 * k] == 301 and bc[2 * k + 1] == 301 else 0.0)
+
+    def inside(a, b):      # block a lies in block b (CompareBlocks, LBMBlockComm.f90)
+        return all(geo[b]["mins"][k] <= geo[a]["mins"][k] and upper(geo[a], k) <= upper(geo[b], k) for k in range(3))
+    geo[0] = dict(geo[0], bc=case["bc"])
+    for i in range(1, len(geo)):   # father = the finest coarser block that contains it (array_to_tree, LBMBlockComm.f90:135-193)
+        cands = [j for j in range(len(geo)) if j != i and geo[j]["dh"] > geo[i]["dh"] and inside(i, j)]
+        fa = min(cands, key=lambda j: geo[j]["dh"])
+        nodes[fa].add_son(nodes[i], case["scheme"])
+    for b, st in zip(blocks, states):
         b.initialise(0.0)
-        b.fIn[...] = s
-    if has_son(case):
-        # check_is_continue (FluidDomain.f90:166-224) gives every node the populations of the FINEST saved block containing it:
-        # the father's nodes under the son take the son's values at the coincident nodes (weights 0/1, exact)
-        (x0, y0, z0), (sx, sy, sz) = [int(v) for v in case["smins"]], case["sdims"]
-        Fb.fIn[:, x0:x0 + (sx + 1) // 2, y0:y0 + (sy + 1) // 2, z0:z0 + (sz + 1) // 2] = blocks[1].fIn[:, ::2, ::2, ::2]
+        b.fIn[...] = st
     for b in blocks:
         b.update_volume_force(); b.set_boundary_conditions(); b.calculate_macro_quantities()
     ovs, its = [], []
