@@ -707,10 +707,11 @@ void BeamSolver::calculate_angle_material(double Lref, double Uref, double denIn
         umaxIn = std::max(umaxIn, std::fabs(uuuIn[k]));
     }
     uMax = std::max({uMax, umaxIn, 2.0 * m_pi * amax * Freq, 2.0 * m_pi * rmax * Freq});
-    // Fortran's x**n with an integer n is a primary of the product chain it stands in and is expanded along GCC's power tree:
-    // Uref**2 = Uref*Uref (so KS*denIn*Uref**2 is (KS*denIn)*(Uref*Uref), not ((KS*denIn)*Uref)*Uref), x**5 = (x*x)*((x*x)*x)
+    // Fortran's x**n with an integer n is a primary of the product chain it stands in: Uref**2 = Uref*Uref, so KS*denIn*Uref**2 is
+    // (KS*denIn)*(Uref*Uref), not ((KS*denIn)*Uref)*Uref.  Beyond x**2 gfortran (without fast-math) calls libgcc's __powidf2, which
+    // squares and multiplies from the low bit: x**5 = x*((x*x)*(x*x)), x**3 = x*(x*x)
     const double U2 = Uref * Uref;
-    auto pow5 = [](double x) { const double x2 = x * x; return x2 * (x2 * x); };
+    auto pow5 = [](double x) { const double x2 = x * x; return x * (x2 * x2); };
     nLthck = 0.0;   // left undefined by the reference when isKB is neither 0 nor 1
     if (P->isKB == 0) {
         for (Segment &e : m_elements) {

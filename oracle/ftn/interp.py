@@ -9,7 +9,8 @@ Evaluation rules that matter for the pins:
   * operators are applied exactly as written, left to right within a precedence level, parentheses kept; no re-association,
     no fused multiply-add, no extended precision: every operation rounds to the type Fortran gives it (real(4) literals stay
     single until promoted by the other operand);
-  * SUM / DOT_PRODUCT / MATMUL accumulate sequentially in array element order; x**n with integer n is repeated multiplication;
+  * SUM / DOT_PRODUCT / MATMUL accumulate sequentially in array element order; x**n with integer n multiplies as libgcc's __powidf2
+    does (what gfortran emits for real**integer beyond x**2 without fast-math);
   * !$OMP lines are comments, i.e. the program runs as its serial build (the order the C oracle restates);
   * scalar arguments are passed by copy-in / copy-out, arrays and derived types by reference (equivalent for a conforming
     program).

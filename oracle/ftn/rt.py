@@ -222,24 +222,19 @@ def fdiv(a, b):
     return _wrap(ua / ub)
 
 
-_POWI_TABLE = [0, 1, 1, 2, 2, 3, 3, 4, 4, 6, 5, 6, 6, 10, 7, 9, 8, 16, 9, 16, 10, 12, 11, 13, 12, 17, 13, 18, 14, 24, 15, 26, 16]
-
-
-def _powi(x, n, cache):
-    """x**n by multiplications along GCC's power tree (tree-ssa-math-opts.c powi_as_mults), each power computed once."""
-    if n in cache:
-        return cache[n]
-    if n < len(_POWI_TABLE):
-        i = _POWI_TABLE[n]
-        r = _powi(x, n - i, cache) * _powi(x, i, cache)
-    elif n & 1:
-        d = n & 0xFF if False else 1
-        r = _powi(x, n - 1, cache) * _powi(x, 1, cache)
-    else:
-        h = _powi(x, n // 2, cache)
-        r = h * h
-    cache[n] = r
-    return r
+def _powi(x, n, cache=None):
+    """x**n for a real x and an integer n > 0 as libgcc's __powidf2 computes it (square and multiply from the low bit): gfortran
+    expands real**integer inline only for exponents -1..2 unless -funsafe-math-optimizations is given (trans-expr.c,
+    gfc_conv_cst_int_power) and otherwise emits __builtin_powi, which the middle end leaves as the library call without fast-math.
+    For n <= 4 this coincides with the multiplication chains of GCC's power tree; x**5 is x*((x*x)*(x*x))."""
+    y = x if (n & 1) else None
+    n >>= 1
+    while n:
+        x = x * x
+        if n & 1:
+            y = x if y is None else y * x
+        n >>= 1
+    return y
 
 
 def fpow(a, b):
@@ -252,7 +247,7 @@ def fpow(a, b):
             return _wrap(np.where(np.abs(ua) == 1, ua ** (-n), 0)) if isinstance(ua, np.ndarray) else (ua ** (-n) if abs(ua) == 1 else 0)
         if n == 0:
             return _wrap(ua * 0 + 1)
-        r = _powi(ua, abs(n), {1: ua})
+        r = _powi(ua, abs(n))
         return _wrap(r if n > 0 else 1.0 / r)
     return _wrap(np.power(ua, ub))
 

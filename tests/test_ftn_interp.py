@@ -62,7 +62,7 @@ end program
     assert (v["i1"], v["i2"], v["i3"], v["i4"], v["i5"]) == (3, -3, -1, 3, -2)
     x = np.float64(1.1)
     assert v["p3"] == x * x * x
-    assert v["p5"] == (x * x) * ((x * x) * x)          # GCC's power tree for n = 5: x^2 * x^3
+    assert v["p5"] == x * ((x * x) * (x * x))          # libgcc's __powidf2 for n = 5: x * (x^2)^2
     assert v["pm2"] == 1.0 / 9.0
     assert v["s1"] == 2.0
     assert v["s2"] == (1e16 + (1.0 - 1e16)) + 1.0
