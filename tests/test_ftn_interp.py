@@ -397,3 +397,21 @@ def test_reference_sources_parse_and_load():
     ee = m.vars["ee"]
     assert ee.lb == (0, 1) and ee.d.shape == (19, 3) and ee.d[7].tolist() == [1, 1, 0]
     assert m.vars["wt"].d[0] == 1.0 / 3.0 and m.vars["oppo"].d.tolist()[7] == 10
+
+
+def test_integer_powers_match_libgcc_powidf2():
+    """real**integer beyond x**2 is a call of libgcc's __powidf2 in a gfortran build without fast-math: the interpreter's chain of
+    multiplications must give the same bits as the libgcc of this machine."""
+    import ctypes
+    from oracle.ftn import rt
+    try:
+        fn = ctypes.CDLL("libgcc_s.so.1").__powidf2
+    except (OSError, AttributeError):
+        pytest.skip("libgcc_s.so.1 / __powidf2 not available")
+    fn.restype, fn.argtypes = ctypes.c_double, [ctypes.c_double, ctypes.c_int]
+    rng = np.random.default_rng(7)
+    for x in np.concatenate([rng.uniform(0.01, 3.0, 200), -rng.uniform(0.01, 3.0, 50)]):
+        for n in range(1, 13):
+            assert float(rt.fpow(np.float64(x), n)) == fn(float(x), n), (x, n)
+        for n in (-1, -2, -3, -5):
+            assert float(rt.fpow(np.float64(x), n)) == fn(float(x), n), (x, n)
