@@ -538,16 +538,16 @@ def run_gpu(args):
     # What the reference driver does around this path: populations come from pinned host memory once
     # (check_is_continue / initialise), then every step goes through the public API with host arguments (the
     # time scalar; with a body 7n marker doubles down and 3n force doubles up inside
-    # fsilbm_ibm_interaction_force), and every `flow_every` steps den+uuu are read back to pinned host memory
-    # (what write_flow_ needs; main.f90:130 timeFlowDelta cadence).  All copies are inside the timed region.
+    # fsilbm_ibm_interaction_force), and every `flow_every` steps the output staging array of write_flow_ (OUTtmp:
+    # p,u,v,w as real(4), FluidDomain.f90:1640-1699; main.f90:130 timeFlowDelta cadence) is read back to pinned host
+    # memory.  All copies are inside the timed region.
     flow_every = args.flow_every
     f_host = torch.empty((19, Xl, Y, Z), dtype=torch.float64, pin_memory=True)
-    den_host = torch.empty((Xl, Y, Z), dtype=torch.float64, pin_memory=True)
-    uuu_host = torch.empty((3, Xl, Y, Z), dtype=torch.float64, pin_memory=True)
+    out_host = torch.empty((4, Xl, Y, Z), dtype=torch.float32, pin_memory=True)
     blk.download_fIn(f_host.numpy())
-    # warm-up of the read-back path: its device staging fields (den, uuu: 1 GB for 33.5 M cells) are allocated on first use, and a
+    # warm-up of the read-back path: its device staging buffer (0.5 GB for 33.5 M cells) is allocated on first use, and a
     # cudaMalloc of that size inside the timed region costs anything between 10 and 250 ms depending on the box
-    blk.download_macro_async(den_host.numpy(), uuu_host.numpy())
+    blk.write_flow_window_async(out_host.numpy(), 0, 1)
     blk.download_wait()
     blk.sync(); torch.cuda.synchronize(); barrier()
     check = F._lib.check
@@ -562,8 +562,8 @@ def run_gpu(args):
         step(args.warmup + args.steps + n + 1)
         if (n + 1) % flow_every == 0 or n + 1 == args.steps:
             # asynchronous read-back (the reference forks its writer): the copy overlaps the following steps; the previous
-            # one is waited for before the host arrays are reused
-            blk.download_macro_async(den_host.numpy(), uuu_host.numpy())
+            # one is waited for before the host array is reused
+            blk.write_flow_window_async(out_host.numpy(), 0, 1)
             n_out += 1
     if sb is not None:
         sb.flush()
@@ -582,12 +582,12 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         markers = float(t.item())
     h2d = f_host.numel() * 8 * world + 7 * 8 * markers * args.steps
-    d2h = (den_host.numel() + uuu_host.numel()) * 8 * world * n_out + 3 * 8 * markers * args.steps
+    d2h = out_host.numel() * 4 * world * n_out + 3 * 8 * markers * args.steps
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
            "seconds": e2e_s, "upload_seconds": upload_s, "quarter_issue_seconds": laps, "upload_gbs": f_host.numel() * 8 / upload_s / 1e9,
-           "segment": f"fIn uploaded from pinned host once, {args.steps} steps through the LBMBlock API with host arguments, den+uuu read back "
-                      f"to pinned host every {flow_every} steps ({n_out} read-backs, asynchronous: each overlaps the following steps and is waited for "
-                      f"before the next one and at the end); wall clock, bytes averaged per step"}
+           "segment": f"fIn uploaded from pinned host once, {args.steps} steps through the LBMBlock API with host arguments, write_flow_'s staging array "
+                      f"(p,u,v,w as real(4)) read back to pinned host every {flow_every} steps ({n_out} read-backs, asynchronous: each overlaps the "
+                      f"following steps and is waited for before the next one and at the end); wall clock, bytes averaged per step"}
 
     # ---- CPU baseline on this box's cores (rank 0, N = 1 only) ----------------------------------------------
     cpu = None

@@ -143,6 +143,14 @@ module fsilbm_c
             integer(c_int), value :: outputtype
             real(c_float), intent(inout) :: out(*)
         end function
+        integer(c_int) function fsilbm_block_write_flow_window_async(h, offsetOutput, &
+                outputtype, out) bind(C, name='fsilbm_block_write_flow_window_async')
+            import :: c_float, c_int
+            integer(c_int), value :: h
+            integer(c_int), value :: offsetOutput
+            integer(c_int), value :: outputtype
+            real(c_float), intent(inout) :: out(*)
+        end function
         integer(c_int) function fsilbm_block_turbulent_statistic(h, step, step_s) bind(C, name='fsilbm_block_turbulent_statistic')
             import :: c_int
             integer(c_int), value :: h
@@ -335,7 +343,7 @@ module fsilbm_gpu
               gpu_initialise_block, gpu_upload_fIn, gpu_refresh_host_fIn, gpu_refresh_host_macro, gpu_refresh_host_macro_async, &
               gpu_refresh_host_wait, gpu_refresh_host_tau_all, gpu_update_volume_force, gpu_set_boundary_conditions, &
               gpu_collide_stream, gpu_sync, gpu_interaction_force, gpu_interaction_force_begin, gpu_interaction_force_wait, &
-              gpu_body_status, gpu_download_stencil, gpu_field_stat, gpu_write_flow_window, gpu_turbulent_statistic, &
+              gpu_body_status, gpu_download_stencil, gpu_field_stat, gpu_write_flow_window, gpu_write_flow_window_async, gpu_turbulent_statistic, &
               gpu_fluid_flux, gpu_probe_velocity, gpu_pair_create, gpu_pair_create_remote, gpu_pair_free, gpu_pair_info, gpu_extract_interpolate_layer, &
               gpu_interpolation_father_to_son, gpu_deliver_son_to_father, gpu_comm_unique_id, gpu_comm_init, gpu_comm_finalize, &
               gpu_halo_transport, gpu_pass_macro, gpu_pass_reset_volume_force, gpu_pass_add_volume_force, gpu_pass_collision, &
@@ -587,6 +595,13 @@ contains
         integer, intent(in) :: iblock, offsetOutput, outputtype
         real(c_float), intent(out) :: outtmp(*)
         call fsilbm_check(fsilbm_block_write_flow_window(gpu_handle(iblock), offsetOutput, outputtype, outtmp))
+    end subroutine
+    ! the same without waiting (outtmp page-locked): filled while the following steps run, valid after gpu_refresh_host_wait --
+    ! the overlap the reference gets from fork()ing its writer (FluidDomain.f90:1702)
+    subroutine gpu_write_flow_window_async(iblock, offsetOutput, outputtype, outtmp)
+        integer, intent(in) :: iblock, offsetOutput, outputtype
+        real(c_float), intent(out) :: outtmp(*)
+        call fsilbm_check(fsilbm_block_write_flow_window_async(gpu_handle(iblock), offsetOutput, outputtype, outtmp))
     end subroutine
     ! replaces calculate_turbulent_statistic_ (FluidDomain.f90:1147-1172), main.f90:108
     subroutine gpu_turbulent_statistic(iblock, step, step_s)

@@ -64,7 +64,8 @@ def lib():
         "fsilbm_block_download_macro": [i, vp, vp],
         "fsilbm_block_download_macro_async": [i, vp, vp],
         "fsilbm_block_download_wait": [i], "fsilbm_block_download_tau_all": [i, vp], "fsilbm_block_field_stat": [i, pd],
-        "fsilbm_block_write_flow_window": [i, i, i, vp], "fsilbm_block_turbulent_statistic": [i, i, i],
+        "fsilbm_block_write_flow_window": [i, i, i, vp], "fsilbm_block_write_flow_window_async": [i, i, i, vp],
+        "fsilbm_block_turbulent_statistic": [i, i, i],
         "fsilbm_block_fluid_flux": [i, pd], "fsilbm_block_probe_velocity": [i, i, vp, vp],
         "fsilbm_block_set_boundary_conditions": [i], "fsilbm_block_collide_stream": [i], "fsilbm_block_sync": [i],
         "fsilbm_block_stream": [i, C.POINTER(C.c_void_p)],

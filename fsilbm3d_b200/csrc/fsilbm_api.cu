@@ -226,8 +226,10 @@ struct Block {
     cudaEvent_t ev_macro = nullptr, ev_io = nullptr;    // fsilbm_block_download_macro_async: den/uuu staged -> copied out on comm_stream
     bool io_pending = false;
     cudaStream_t ibm_main_stream = nullptr;
+    cudaStream_t body_stream = nullptr;                 // single-rank early IBM: the planes around the bodies (high priority), beside the rest on `stream`
     cudaEvent_t ev_early = nullptr;
     bool early_ok = false, is_father = false;
+    double update_clock_us = 0.0;                       // g_update_clock_us right after this block's last update was issued
     int early_n = 0, early_x0[MAX_BOXES]{}, early_x1[MAX_BOXES]{};
     IbmCtl *ctl = nullptr;
     IbmCtl *ctl_pin = nullptr;                          // pinned host copy of the control block, filled by the asynchronous read-back
@@ -297,6 +299,8 @@ int g_ibm_force_exchange = 1;  // slab runs: 1 every rank passes the same bodies
 int g_ibm_early_blocks = 0;    // blocks per SM of the cooperative IBM kernel when it runs beside a collide-stream update; 0 = chosen per call
 int g_ibm_early_lean = 0;      // 1: the 48-register build of the cooperative kernel when it runs beside an update
 int g_ibm_early_total = 0;     // > 0: that grid as an absolute block count
+double g_update_clock_us = 0.0;   // estimated device time of every collide-stream update issued so far (all blocks share the compute stream)
+int g_update_split = 1;        // one GPU, early IBM: 1 the planes around the bodies on the body stream beside the rest; 0 queued before the rest
 int g_ibm_early = 1;           // 1: the planes around the bodies are updated first and the next IBM call overlaps the rest of the update
 int g_ibm_ordered = 1;         // 1: interpolation and spreading keep the reference's serial summation order (bit-reproducible); 0: shuffles + fp64 atomics
 int g_halo_mode = 1;   // 1: edge kernels store into the neighbours' memory over NVLink (default); 0: ncclSend/ncclRecv
@@ -730,6 +734,7 @@ int fsilbm_set_option(const char *key, int value)
     if (!strcmp(key, "force_ghost")) { g_force_ghost = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_single_launch")) { g_ibm_single_launch = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_early_blocks_per_sm")) { if (value < 0 || value > 4) return fail(FSILBM_ERR_ARG, "ibm_early_blocks_per_sm must be 0 (automatic) or 1..4"); g_ibm_early_blocks = value; return 0; }
+    if (!strcmp(key, "update_split")) { g_update_split = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_early_lean")) { g_ibm_early_lean = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_early_blocks")) { if (value < 0) return fail(FSILBM_ERR_ARG, "ibm_early_blocks must be >= 0"); g_ibm_early_total = value; return 0; }
     if (!strcmp(key, "ibm_early")) { g_ibm_early = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->early_ok = false; return 0; }
@@ -790,6 +795,7 @@ int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, d
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CK(cudaStreamCreateWithPriority(&b->ibm_stream, cudaStreamNonBlocking, hi));
         CK(cudaStreamCreateWithPriority(&b->ibm_main_stream, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithPriority(&b->body_stream, cudaStreamNonBlocking, hi));
     }
     CK(cudaEventCreateWithFlags(&b->ev_early, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_macro, cudaEventDisableTiming));
@@ -825,8 +831,8 @@ int fsilbm_block_destroy(fsilbm_handle h)
     cudaFree(b->uuu_ave); cudaFree(b->uuu_les); cudaFree(b->outtmp); cudaFree(b->scratch);
     cudaFree(b->boxes.u); cudaFree(b->boxes.force);
     for (auto &bd : b->bodies) bd.release();
-    cudaStreamSynchronize(b->ibm_stream); cudaStreamSynchronize(b->ibm_main_stream);
-    cudaEventDestroy(b->ev_early); cudaStreamDestroy(b->ibm_main_stream);
+    cudaStreamSynchronize(b->ibm_stream); cudaStreamSynchronize(b->ibm_main_stream); cudaStreamSynchronize(b->body_stream);
+    cudaEventDestroy(b->ev_early); cudaStreamDestroy(b->ibm_main_stream); cudaStreamDestroy(b->body_stream);
     cudaEventDestroy(b->ev_macro); cudaEventDestroy(b->ev_io);
     cudaFree(b->bodies_dev); cudaFree(b->lead_dev); cudaFree(b->tol2); cudaFree(b->ctl); cudaFree(b->ibm_barrier);
     cudaFreeHost(b->ctl_pin); cudaEventDestroy(b->ev_ibm_done);
@@ -1093,13 +1099,69 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
     Block &b = *bp;
     if (!b.initialised) return fail(FSILBM_ERR_ARG, "block %d not initialised", h);
     if (int rc = await_deliveries(b)) return rc;
-    // an interaction-force call still in flight on another stream: the update reads its box fields, so it follows it ON THE DEVICE
-    if (b.ibm_pending.active && b.ibm_pending.stream != b.stream) CK(cudaStreamWaitEvent(b.stream, b.ev_ibm_done, 0));
     const Geom &g = b.g;
     const double *fA = b.f[b.cur];
     double *fB = b.f[b.cur ^ 1];
     VelocityField vel;
     if (int rc = velocity_field(b, b.blktime, vel)) return rc;
+    const bool multi = g_nccl.nranks > 1 && g_nccl.comm && g.X != g.XG;   // a block cut into x-slabs (sons stay whole on one rank)
+    const bool ghost = multi || g_force_ghost;
+    // Early IBM (see Block::ev_early): planes A = [box - 2, box + 2) of every stencil box are updated apart from the rest.  After A
+    // the streamed populations of the planes [box - 1, box + 1) are final -- provided no face kernel, halo or x-wrap touches them,
+    // hence the conditions below -- and the next interaction-force call may start while the rest is still being updated.
+    int nA = 0, A0[MAX_BOXES], A1[MAX_BOXES], V0[MAX_BOXES], V1[MAX_BOXES];
+    const int lower = multi ? 1 : 0, upper = multi ? g.X - 1 : g.X;   // planes between the edge planes (multi: those go first anyway)
+    const IbmBoxes &bxs = b.boxes;
+    bool early = g_ibm_early && b.ibm_active && bxs.n > 0 && b.model < 11 && !b.is_father && (multi ? b.halo.enabled : !ghost);
+    bool edge_dep = false;   // slab runs: a box reaches the slab's edge planes, whose final values also need the neighbour's halo
+    if (early) {
+        const int Ns[3] = {g.XG, g.Y, g.Z};
+        for (int i = 0; i < bxs.n && early; i++) {
+            for (int k = 0; k < 3; k++) {
+                const int lo = bxs.lo[i][k], hi = lo + bxs.ext[i][k];
+                if (k == 0 && hi > Ns[0]) early = false;                              // wraps in x
+                if (b.periodic[k] != 1 && (lo < 3 || hi > Ns[k] - 3)) early = false;    // within reach of a face kernel
+            }
+            int a0 = bxs.lo[i][0] - g.xOffset - 2, a1 = bxs.lo[i][0] + bxs.ext[i][0] - g.xOffset + 2;
+            bool cut_lo = false, cut_hi = false;
+            if (multi) {   // a box across (or next to) a slab interface: this rank's share of it, up to the edge plane
+                if (a0 < lower) { a0 = lower; cut_lo = true; }
+                if (a1 > upper) { a1 = upper; cut_hi = true; }
+                if (a1 <= a0) early = false;
+            } else if (a0 < lower || a1 > upper) early = false;
+            A0[nA] = a0; A1[nA] = a1;
+            V0[nA] = cut_lo ? 0 : a0 + 1; V1[nA] = cut_hi ? g.X : a1 - 1;
+            edge_dep = edge_dep || cut_lo || cut_hi;
+            nA++;
+        }
+        if (early) {   // sort and merge
+            for (int i = 1; i < nA; i++)
+                for (int j = i; j > 0 && A0[j] < A0[j - 1]; j--) {
+                    std::swap(A0[j], A0[j - 1]); std::swap(A1[j], A1[j - 1]); std::swap(V0[j], V0[j - 1]); std::swap(V1[j], V1[j - 1]);
+                }
+            int m = 0;
+            for (int i = 1; i < nA; i++) {
+                if (A0[i] <= A1[m]) { A1[m] = std::max(A1[m], A1[i]); V0[m] = std::min(V0[m], V0[i]); V1[m] = std::max(V1[m], V1[i]); }
+                else { m++; A0[m] = A0[i]; A1[m] = A1[i]; V0[m] = V0[i]; V1[m] = V1[i]; }
+            }
+            nA = m + 1;
+        }
+    }
+    b.early_ok = false;
+    // An interaction-force call still in flight on another stream: whatever reads its box fields follows it ON THE DEVICE.  On one
+    // GPU with early IBM that is only the launch over the planes A: it goes to the block's high-priority body stream behind that
+    // call, while the rest of the update -- which holds no box cell -- starts on the compute stream at once.  If the iteration is
+    // over when the update begins, the body stream's CTAs are scheduled first and A is finished first, as if the two launches were
+    // queued one after the other; if it is not (a large body in a small block), the device updates the rest meanwhile instead of
+    // idling, and A still finishes as early as its input allows, which is what the next interaction-force call waits for.
+    const bool ibm_inflight = b.ibm_pending.active && b.ibm_pending.stream != b.stream;
+    const bool split = early && !multi && g_update_split;
+    cudaStream_t sA = split ? b.body_stream : b.stream;
+    if (split) {
+        CK(cudaEventRecord(b.ev_pre, b.stream));          // the previous step (and whatever else was queued on the compute stream)
+        CK(cudaStreamWaitEvent(sA, b.ev_pre, 0));
+    }
+    if (ibm_inflight) CK(cudaStreamWaitEvent(sA, b.ev_ibm_done, 0));
 
     if (b.model == 14 || b.model == 15) {
         // WALE / Vreman difference the velocity of this step across neighbouring cells (FluidDomain.f90:1343-1385,
@@ -1141,10 +1203,10 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
                 CK(cudaMalloc(&b.l2u[face], sizeof(double) * 3 * (size_t)na * nb));
             }
             FaceParams p = face_params(b, face, fB, fA, vel);
-            launch_layer2_face(p, b.stream);
+            launch_layer2_face(p, sA);
         } else if ((code == BCstationary_Wall_halfway || code == BCmoving_Wall_halfway) && b.hw_alloc[face]) {
             FaceParams p = face_params(b, face, fB, fA, vel);
-            launch_stash_face(p, b.stream);   // halfwayBCset_, LBMBlockComm.f90:296
+            launch_stash_face(p, sA);   // halfwayBCset_, LBMBlockComm.f90:296
         }
     }
 
@@ -1157,50 +1219,7 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
     if (!b.ibm_active) p.boxes.n = 0;
     p.tau_all = b.tau_all;
     les_field(b, p.uuu, p.uuu_ncomp);
-    const bool multi = g_nccl.nranks > 1 && g_nccl.comm && g.X != g.XG;   // a block cut into x-slabs (sons stay whole on one rank)
-    const bool ghost = multi || g_force_ghost;
     p.wrap_x = ghost ? 0 : 1;
-    // Early IBM (see Block::ev_early): planes A = [box - 2, box + 2) of every stencil box first, then the rest.  After A the
-    // streamed populations of the planes [box - 1, box + 1) are final -- provided no face kernel, halo or x-wrap touches them,
-    // hence the conditions below -- and the next interaction-force call may start while the rest is still being updated.
-    int nA = 0, A0[MAX_BOXES], A1[MAX_BOXES], V0[MAX_BOXES], V1[MAX_BOXES];
-    const int lower = multi ? 1 : 0, upper = multi ? g.X - 1 : g.X;   // planes between the edge planes (multi: those go first anyway)
-    bool early = g_ibm_early && b.ibm_active && p.boxes.n > 0 && b.model < 11 && !b.is_father && (multi ? b.halo.enabled : !ghost);
-    bool edge_dep = false;   // slab runs: a box reaches the slab's edge planes, whose final values also need the neighbour's halo
-    if (early) {
-        const int Ns[3] = {g.XG, g.Y, g.Z};
-        for (int i = 0; i < p.boxes.n && early; i++) {
-            for (int k = 0; k < 3; k++) {
-                const int lo = p.boxes.lo[i][k], hi = lo + p.boxes.ext[i][k];
-                if (k == 0 && hi > Ns[0]) early = false;                              // wraps in x
-                if (b.periodic[k] != 1 && (lo < 3 || hi > Ns[k] - 3)) early = false;    // within reach of a face kernel
-            }
-            int a0 = p.boxes.lo[i][0] - g.xOffset - 2, a1 = p.boxes.lo[i][0] + p.boxes.ext[i][0] - g.xOffset + 2;
-            bool cut_lo = false, cut_hi = false;
-            if (multi) {   // a box across (or next to) a slab interface: this rank's share of it, up to the edge plane
-                if (a0 < lower) { a0 = lower; cut_lo = true; }
-                if (a1 > upper) { a1 = upper; cut_hi = true; }
-                if (a1 <= a0) early = false;
-            } else if (a0 < lower || a1 > upper) early = false;
-            A0[nA] = a0; A1[nA] = a1;
-            V0[nA] = cut_lo ? 0 : a0 + 1; V1[nA] = cut_hi ? g.X : a1 - 1;
-            edge_dep = edge_dep || cut_lo || cut_hi;
-            nA++;
-        }
-        if (early) {   // sort and merge
-            for (int i = 1; i < nA; i++)
-                for (int j = i; j > 0 && A0[j] < A0[j - 1]; j--) {
-                    std::swap(A0[j], A0[j - 1]); std::swap(A1[j], A1[j - 1]); std::swap(V0[j], V0[j - 1]); std::swap(V1[j], V1[j - 1]);
-                }
-            int m = 0;
-            for (int i = 1; i < nA; i++) {
-                if (A0[i] <= A1[m]) { A1[m] = std::max(A1[m], A1[i]); V0[m] = std::min(V0[m], V0[i]); V1[m] = std::max(V1[m], V1[i]); }
-                else { m++; A0[m] = A0[i]; A1[m] = A1[i]; V0[m] = V0[i]; V1[m] = V1[i]; }
-            }
-            nA = m + 1;
-        }
-    }
-    b.early_ok = false;
     // The launch list (StepParams::seg_*): [edge planes of a slab] [planes A around the bodies] | [the rest].  Without early IBM
     // the whole update is ONE launch; with it, two: everything up to A, then -- event ev_early recorded in between -- the rest,
     // which holds no box cell (A covers every box with two planes to spare) and takes the IBM-free instantiation.
@@ -1227,15 +1246,16 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
         StepParams q = p;
         planes_first(q);
         TRACE(b.stream, 0, "step_begin");
-        if (launch_collide_push(q, b.model, b.stream)) return refuse();
-        TRACE(b.stream, 0, early ? "collide_A" : "collide_all");
+        if (launch_collide_push(q, b.model, sA)) return refuse();
+        TRACE(sA, split ? 4 : 0, early ? "collide_A" : "collide_all");
         if (early) {
-            CK(cudaEventRecord(b.ev_early, b.stream));
+            CK(cudaEventRecord(b.ev_early, sA));
             StepParams rest = p;
             rest.boxes.n = 0;
             planes_rest(rest);
             if (launch_collide_push(rest, b.model, b.stream)) return refuse();
             TRACE(b.stream, 0, "collide_rest");
+            if (split) CK(cudaStreamWaitEvent(b.stream, b.ev_early, 0));   // the two streams meet before the face kernels
             note_early();
         }
         if (ghost) launch_wrap_x(g, fB, b.stream);
@@ -1314,6 +1334,8 @@ int fsilbm_block_collide_stream(fsilbm_handle h)
     announce_father_step(b);
     b.cur ^= 1;
     b.ibm_active = false;
+    g_update_clock_us += (double)g.X * (double)g.plane * 304.0 / 6.2e6;
+    b.update_clock_us = g_update_clock_us;
     return 0;
 }
 
@@ -1350,11 +1372,12 @@ int fsilbm_block_stream(fsilbm_handle h, void **stream)
 }
 
 // ---- output / diagnostics computed on the device state ------------------------------------
-int fsilbm_block_write_flow_window(fsilbm_handle h, int offsetOutput, int outputtype, float *out)
+static int flow_window(fsilbm_handle h, int offsetOutput, int outputtype, float *out, bool async)
 {
     Block *b = get(h);
     if (!b || !out) return fail(FSILBM_ERR_ARG, "bad handle/argument");
     if (outputtype < 1) return 0;   // FluidDomain.f90:1639
+    if (int rc = io_wait(*b)) return rc;   // an earlier asynchronous read-back may still be copying out of the staging buffer
     const Geom &g = b->g;
     // window in global x: [off, XG-off), intersected with the local slab
     const int gx0 = std::max(offsetOutput, g.xOffset), gx1 = std::min(g.XG - offsetOutput, g.xOffset + g.X);
@@ -1386,10 +1409,21 @@ int fsilbm_block_write_flow_window(fsilbm_handle h, int offsetOutput, int output
     if (outputtype == 2) CK(cudaMemsetAsync(b->outtmp, 0, sizeof(float) * 4 * (n / nfields), b->stream));   // fields 0:3 are not refreshed (:1653)
     launch_flow_window(p, b->stream);
     CK(cudaGetLastError());
+    if (async) {   // the copy leaves on the copy stream while later steps run; fsilbm_block_download_wait collects it
+        CK(cudaEventRecord(b->ev_macro, b->stream));
+        CK(cudaStreamWaitEvent(b->comm_stream, b->ev_macro, 0));
+        CK(cudaMemcpyAsync(out, b->outtmp, sizeof(float) * n, cudaMemcpyDeviceToHost, b->comm_stream));
+        CK(cudaEventRecord(b->ev_io, b->comm_stream));
+        b->io_pending = true;
+        return 0;
+    }
     CK(cudaMemcpyAsync(out, b->outtmp, sizeof(float) * n, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
     return 0;
 }
+
+int fsilbm_block_write_flow_window(fsilbm_handle h, int offsetOutput, int outputtype, float *out) { return flow_window(h, offsetOutput, outputtype, out, false); }
+int fsilbm_block_write_flow_window_async(fsilbm_handle h, int offsetOutput, int outputtype, float *out) { return flow_window(h, offsetOutput, outputtype, out, true); }
 
 int fsilbm_block_turbulent_statistic(fsilbm_handle h, int step, int step_s)
 {
@@ -2072,7 +2106,10 @@ int fsilbm_ibm_interaction_force_begin(fsilbm_handle h, int nbody, const int *ne
                 const int lo = std::max(b.early_x0[k], g.xOffset), hi = std::min(b.early_x1[k], g.xOffset + g.X);
                 if (hi > lo) planes_rest -= (double)(hi - lo);
             }
-            const double t_rest_us = std::max(planes_rest, 1.0) * (double)g.plane * 304.0 / 6.2e6;
+            // ... plus the updates of OTHER blocks issued since (a son's first call of a root step is issued behind its father's
+            // update, which is many times longer than the son's own: the iteration then runs beside that, and one block per SM --
+            // which costs the update beside it least -- is early enough)
+            const double t_rest_us = std::max(planes_rest, 1.0) * (double)g.plane * 304.0 / 6.2e6 + (g_update_clock_us - b.update_clock_us);
             const double t_ibm_us = (double)std::max(ntolLBM, 1) * (double)total_markers * 0.0075;
             early_bps = (int)std::ceil(t_ibm_us / t_rest_us);
             early_bps = std::max(1, std::min(4, early_bps));
@@ -2412,10 +2449,13 @@ int fsilbm_pair_extract_layer(int pair, int time)
     Block *F = get(p->father), *S = get(p->son);
     if (!F || !S) return fail(FSILBM_ERR_ARG, "pair %d refers to a destroyed block", pair);
     await_father_step(*F, *p);
+    PairFaces ps{};
     for (int j = 0; j < 6; j++) {
         if (S->bc[j] != BCfluid) continue;   // :354
-        launch_pair_extract(pair_face(*p, *F, *S, j, 0), time, g_stream);
+        ps.face[ps.n++] = pair_face(*p, *F, *S, j, 0);
     }
+    launch_pair_extract(ps, time, g_stream);
+    TRACE(g_stream, 0, "pair_extract");
     CK(cudaGetLastError());
     return 0;
 }
@@ -2427,10 +2467,13 @@ int fsilbm_pair_father_to_son(int pair, int n_timeStep)
     if (p->remote) return 0;
     Block *F = get(p->father), *S = get(p->son);
     if (!F || !S) return fail(FSILBM_ERR_ARG, "pair %d refers to a destroyed block", pair);
+    PairFaces ps{};
     for (int j = 0; j < 6; j++) {
         if (p->sds[j] == 0) continue;
-        launch_pair_f2s(pair_face(*p, *F, *S, j, 0), n_timeStep == 0 ? 0 : 1, g_stream);   // father's volumeForce, dh: :663-664
+        ps.face[ps.n++] = pair_face(*p, *F, *S, j, 0);   // father's volumeForce, dh: :663-664
     }
+    launch_pair_f2s(ps, n_timeStep == 0 ? 0 : 1, g_stream);
+    TRACE(g_stream, 0, "pair_f2s");
     CK(cudaGetLastError());
     return 0;
 }
@@ -2443,16 +2486,19 @@ int fsilbm_pair_son_to_father(int pair)
     Block *F = get(p->father), *S = get(p->son);
     if (!F || !S) return fail(FSILBM_ERR_ARG, "pair %d refers to a destroyed block", pair);
     await_father_step(*F, *p);
+    PairFaces ps{};
     for (int j = 0; j < 6; j++) {
         if (p->sds[j] == 0) continue;
-        launch_pair_s2f(pair_face(*p, *F, *S, j, 1), g_stream);   // son's volumeForce, dh: :552-553
+        ps.face[ps.n++] = pair_face(*p, *F, *S, j, 1);   // son's volumeForce, dh: :552-553
     }
+    launch_pair_s2f(ps, g_stream);
     for (int sd = 0; sd < 2; sd++) {
         if (!p->cross[sd]) continue;   // tell the neighbour that the father nodes of its slab are rewritten: it may start its next step
         Block::Halo &h = F->halo;
         h.delivered[sd]++;
         launch_flag_signal(refine_flag(sd == 0 ? h.peer_left : h.peer_right, 1, sd ^ 1), h.delivered[sd], g_stream);
     }
+    TRACE(g_stream, 0, "pair_s2f");
     CK(cudaGetLastError());
     return 0;
 }

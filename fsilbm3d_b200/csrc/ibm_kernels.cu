@@ -414,36 +414,59 @@ struct GatherSmem { double p[3][64][MARKERS_PER_BLOCK]; };   // [component][node
 
 // m0: first marker of this block's batch.  Must be called by all 256 threads of the block.  Returns |dU| of the marker
 // finished by this thread (threads 0..15), else 0.
+// Every load of a batch is issued before anything waits for one: the stencil offsets, weights and ownership flags of a marker
+// come first, then all twelve velocity loads of a lane; the finishing threads fetch their marker's velocity, area and force
+// sum before the products are formed.  (With the loads inside the `owned` branches each of the four x-planes cost its own
+// three dependent round trips to L2 / HBM -- beside a running collide-stream update the box fields are mostly NOT in L2 --
+// and the interpolation of 32 768 markers took 160 us per sweep whatever the grid.)  A plane that is not owned contributes
+// nothing to the sum, exactly as the skipped iteration of the reference loop: its products are replaced by +0, and
+// s + (+0) = s for every s this chain can hold (it starts from +0).
 __device__ __forceinline__ double gather_batch_ordered(const IbmBody &b, const IbmBoxes &boxes, int m0, GatherSmem &sm, double *partialU, int fused, double invh3)
 {
     const int mi = threadIdx.x / MARKER_LANES, gl = threadIdx.x & (MARKER_LANES - 1);
     const int iEL = m0 + mi;
+    const bool fin = threadIdx.x < MARKERS_PER_BLOCK && m0 + (int)threadIdx.x < b.n;
+    const int m = m0 + threadIdx.x;
+    double ev1 = 0.0, ev2 = 0.0, ev3 = 0.0, ea = 0.0, ef1 = 0.0, ef2 = 0.0, ef3 = 0.0;
+    unsigned int own_m = 0;
+    if (fin) {
+        own_m = *(const unsigned int *)(b.owned + 4 * m);
+        if (fused) {
+            ev1 = b.Evel[3 * m + 0]; ev2 = b.Evel[3 * m + 1]; ev3 = b.Evel[3 * m + 2];
+            ea = b.Ea[m];
+            ef1 = b.Eforce[3 * m + 0]; ef2 = b.Eforce[3 * m + 1]; ef3 = b.Eforce[3 * m + 2];
+        }
+    }
     if (iEL < b.n) {
         const int bb = gl >> 2, c = gl & 3;
-        const long long base = b.boff[iEL] + b.cell[12 * iEL + 4 + bb] + b.cell[12 * iEL + 8 + c];
-        const double ry = (double)b.Ew[12 * iEL + 4 + bb], rz = (double)b.Ew[12 * iEL + 8 + c];
+        const int *cl = b.cell + 12 * iEL;
+        const float *ew = b.Ew + 12 * iEL;
+        const unsigned int own = *(const unsigned int *)(b.owned + 4 * iEL);
+        const long long base = b.boff[iEL] + cl[4 + bb] + cl[8 + c];
+        const double ry = (double)ew[4 + bb], rz = (double)ew[8 + c];
         const double *u1 = boxes.u, *u2 = boxes.u + boxes.ncell, *u3 = boxes.u + 2 * boxes.ncell;
+        long long idx[4];
+        double rx[4], v1[4], v2[4], v3[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) { idx[a] = base + cl[a]; rx[a] = (double)ew[a]; }   // offsets of a plane that is not owned are valid too (0 at worst)
+#pragma unroll
+        for (int a = 0; a < 4; a++) { v1[a] = u1[idx[a]]; v2[a] = u2[idx[a]]; v3[a] = u3[idx[a]]; }
 #pragma unroll
         for (int a = 0; a < 4; a++) {
-            double p1 = 0.0, p2 = 0.0, p3 = 0.0;
-            if (b.owned[4 * iEL + a]) {
-                const long long idx = base + b.cell[12 * iEL + a];
-                const double rx = (double)b.Ew[12 * iEL + a];
-                p1 = u1[idx] * rx * ry * rz;   // :1012
-                p2 = u2[idx] * rx * ry * rz;
-                p3 = u3[idx] * rx * ry * rz;
-            }
-            sm.p[0][16 * a + gl][mi] = p1; sm.p[1][16 * a + gl][mi] = p2; sm.p[2][16 * a + gl][mi] = p3;
+            const bool o = ((own >> (8 * a)) & 0xffu) != 0;
+            const double p1 = v1[a] * rx[a] * ry * rz;   // :1012
+            const double p2 = v2[a] * rx[a] * ry * rz;
+            const double p3 = v3[a] * rx[a] * ry * rz;
+            sm.p[0][16 * a + gl][mi] = o ? p1 : 0.0; sm.p[1][16 * a + gl][mi] = o ? p2 : 0.0; sm.p[2][16 * a + gl][mi] = o ? p3 : 0.0;
         }
     }
     __syncthreads();
     double tol = 0.0;
-    if (threadIdx.x < MARKERS_PER_BLOCK && m0 + (int)threadIdx.x < b.n) {
-        const int m = m0 + threadIdx.x;
+    if (fin) {
         double s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
         for (int a = 0; a < 4; a++) {
-            if (!b.owned[4 * m + a]) continue;
+            if (((own_m >> (8 * a)) & 0xffu) == 0) continue;
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 s1 = s1 + sm.p[0][16 * a + k][threadIdx.x];
@@ -451,8 +474,18 @@ __device__ __forceinline__ double gather_batch_ordered(const IbmBody &b, const I
                 s3 = s3 + sm.p[2][16 * a + k][threadIdx.x];
             }
         }
-        if (fused) { marker_force(b, m, s1, s2, s3, invh3); tol = b.tol[m]; }
-        else { partialU[3 * m + 0] = s1; partialU[3 * m + 1] = s2; partialU[3 * m + 2] = s3; }
+        if (fused) {   // marker_force (:1016-1025) on the values fetched above
+            const double d1 = ev1 - s1, d2 = ev2 - s2, d3 = ev3 - s3;
+            const double f1 = d1 * ea, f2 = d2 * ea, f3 = d3 * ea;
+            tol = fabs(d1) + fabs(d2) + fabs(d3);
+            b.tol[m] = tol;
+            b.Eforce[3 * m + 0] = ef1 + f1;
+            b.Eforce[3 * m + 1] = ef2 + f2;
+            b.Eforce[3 * m + 2] = ef3 + f3;
+            b.felt[3 * m + 0] = f1 * invh3;
+            b.felt[3 * m + 1] = f2 * invh3;
+            b.felt[3 * m + 2] = f3 * invh3;
+        } else { partialU[3 * m + 0] = s1; partialU[3 * m + 1] = s2; partialU[3 * m + 2] = s3; }
     }
     __syncthreads();
     return tol;
@@ -487,14 +520,18 @@ __device__ __forceinline__ void scatter_cell(const IbmBody *bodies, const IbmBox
     if (beg == end) return;
     double u1 = boxes.u[c], u2 = boxes.u[boxes.ncell + c], u3 = boxes.u[2 * boxes.ncell + c];
     bool any = false;
+    // four entries at a time: all weights and forces are fetched before the ordered subtraction, so the dependent loads of
+    // the entries overlap instead of queueing behind one another; the keys of the NEXT four are requested before those loads
+    // are waited for, so a group costs one round trip to memory, not two
+    unsigned long long key[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) key[j] = beg + j < end ? csr.entry[beg + j] : ~0ull;
     for (int e0 = beg; e0 < end; e0 += 4) {
-        // four entries at a time: all keys, then all weights and forces, are fetched before the ordered subtraction, so the
-        // dependent loads of the entries overlap instead of queueing behind one another
-        unsigned long long key[4];
+        unsigned long long nkey[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) nkey[j] = e0 + 4 + j < end ? csr.entry[e0 + 4 + j] : ~0ull;
         double q1[4], q2[4], q3[4];
         bool act[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) key[j] = e0 + j < end ? csr.entry[e0 + j] : ~0ull;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int body = (int)(key[j] >> 40);
@@ -512,6 +549,8 @@ __device__ __forceinline__ void scatter_cell(const IbmBody *bodies, const IbmBox
 #pragma unroll
         for (int j = 0; j < 4; j++)
             if (act[j]) { u1 = u1 - q1[j]; u2 = u2 - q2[j]; u3 = u3 - q3[j]; any = true; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) key[j] = nkey[j];
     }
     if (any) { boxes.u[c] = u1; boxes.u[boxes.ncell + c] = u2; boxes.u[2 * boxes.ncell + c] = u3; }
 }
@@ -522,11 +561,14 @@ __device__ __forceinline__ void spread_cell(const IbmBody *bodies, const IbmBoxe
     const int beg = csr.off[c], end = csr.off[c + 1];
     if (beg == end) return;
     double f1 = boxes.force[c], f2 = boxes.force[boxes.ncell + c], f3 = boxes.force[2 * boxes.ncell + c];
-    for (int e0 = beg; e0 < end; e0 += 4) {
-        unsigned long long key[4];
-        double q1[4], q2[4], q3[4];
+    unsigned long long key[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) key[j] = e0 + j < end ? csr.entry[e0 + j] : ~0ull;
+    for (int j = 0; j < 4; j++) key[j] = beg + j < end ? csr.entry[beg + j] : ~0ull;
+    for (int e0 = beg; e0 < end; e0 += 4) {
+        unsigned long long nkey[4];   // requested before this group's weights and forces are waited for (see scatter_cell)
+#pragma unroll
+        for (int j = 0; j < 4; j++) nkey[j] = e0 + 4 + j < end ? csr.entry[e0 + 4 + j] : ~0ull;
+        double q1[4], q2[4], q3[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             q1[j] = 0.0; q2[j] = 0.0; q3[j] = 0.0;
@@ -543,6 +585,8 @@ __device__ __forceinline__ void spread_cell(const IbmBody *bodies, const IbmBoxe
 #pragma unroll
         for (int j = 0; j < 4; j++)
             if (e0 + j < end) { f1 = f1 + q1[j]; f2 = f2 + q2[j]; f3 = f3 + q3[j]; }   // :974
+#pragma unroll
+        for (int j = 0; j < 4; j++) key[j] = nkey[j];
     }
     boxes.force[c] = f1; boxes.force[boxes.ncell + c] = f2; boxes.force[2 * boxes.ncell + c] = f3;
 }
@@ -593,25 +637,34 @@ __global__ void ibm_csr_nodes_kernel(const IbmBody *bodies, IbmCsr csr)
 
 __global__ void ibm_csr_sort_kernel(IbmCsr csr, long long ncell)
 {
-    // one warp per cell: rank sort of up to 32 keys (all distinct), longer lists by insertion
-    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= ncell) return;
+    // A warp looks at 32 consecutive cells (one coalesced read of their offsets) and then sorts, one after the other, only those
+    // that hold more than one entry -- five in six box cells hold none: rank sort of up to 32 keys (all distinct) across the
+    // lanes, longer lists by insertion.  (One warp per cell spent most of its 109 us on empty cells.)
+    const long long c0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5;
+    if (c0 >= ncell) return;
     const int lane = threadIdx.x & 31;
-    const int beg = csr.off[c], end = csr.off[c + 1], cnt = end - beg;
-    if (cnt <= 1) return;
-    if (cnt <= 32) {
-        const unsigned long long k = lane < cnt ? csr.entry[beg + lane] : ~0ull;
-        int rank = 0;
-        for (int j = 0; j < cnt; j++) rank += __shfl_sync(0xffffffffu, k, j) < k ? 1 : 0;
-        __syncwarp();
-        if (lane < cnt) csr.entry[beg + rank] = k;
-    } else if (lane == 0) {
-        for (int i = beg + 1; i < end; i++) {
-            const unsigned long long k = csr.entry[i];
-            int j = i - 1;
-            while (j >= beg && csr.entry[j] > k) { csr.entry[j + 1] = csr.entry[j]; j--; }
-            csr.entry[j + 1] = k;
+    const long long cl = c0 + lane;
+    const int mybeg = cl < ncell ? csr.off[cl] : 0, myend = cl < ncell ? csr.off[cl + 1] : 0;
+    unsigned int todo = __ballot_sync(0xffffffffu, myend - mybeg > 1);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int beg = __shfl_sync(0xffffffffu, mybeg, src), end = __shfl_sync(0xffffffffu, myend, src), cnt = end - beg;
+        if (cnt <= 32) {
+            const unsigned long long k = lane < cnt ? csr.entry[beg + lane] : ~0ull;
+            int rank = 0;
+            for (int j = 0; j < cnt; j++) rank += __shfl_sync(0xffffffffu, k, j) < k ? 1 : 0;
+            __syncwarp();
+            if (lane < cnt) csr.entry[beg + rank] = k;
+        } else if (lane == 0) {
+            for (int i = beg + 1; i < end; i++) {
+                const unsigned long long k = csr.entry[i];
+                int j = i - 1;
+                while (j >= beg && csr.entry[j] > k) { csr.entry[j + 1] = csr.entry[j]; j--; }
+                csr.entry[j + 1] = k;
+            }
         }
+        __syncwarp();
     }
 }
 
@@ -632,7 +685,7 @@ int launch_ibm_csr_build(const IbmBody *bodies_dev, int nbody, int max_n, const 
     count_launch();
     ibm_csr_nodes_kernel<true><<<grid, 256, 0, s>>>(bodies_dev, csr);
     count_launch();
-    ibm_csr_sort_kernel<<<(unsigned)((boxes.ncell * 32 + 127) / 128), 128, 0, s>>>(csr, boxes.ncell);
+    ibm_csr_sort_kernel<<<(unsigned)((boxes.ncell + 127) / 128), 128, 0, s>>>(csr, boxes.ncell);   // 32 cells per warp
     count_launch();
     return 0;
 }

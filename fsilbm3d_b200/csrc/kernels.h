@@ -256,9 +256,11 @@ struct PairFaceParams {
     const double *tauF_all, *tauS_all;   // tau_all fields [X][Y][Z] of LES blocks, else null
     double hF[3];              // 0.5*volumeForce*dh of the block whose force enters fIn_GridTransform
 };
-void launch_pair_extract(const PairFaceParams &p, int time, cudaStream_t s);
-void launch_pair_f2s(const PairFaceParams &p, int t, cudaStream_t s);
-void launch_pair_s2f(const PairFaceParams &p, cudaStream_t s);
+// the coupled faces of one pair, in the reference's face order (j = 1..6 of LBMBlockComm.f90:354, 669)
+struct PairFaces { int n; PairFaceParams face[6]; };
+void launch_pair_extract(const PairFaces &ps, int time, cudaStream_t s);
+void launch_pair_f2s(const PairFaces &ps, int t, cudaStream_t s);
+void launch_pair_s2f(const PairFaces &ps, cudaStream_t s);
 // one-thread kernel: release-store `value` to a (possibly peer-mapped) 64-bit flag at system scope
 void launch_flag_signal(unsigned long long *flag, unsigned long long value, cudaStream_t s);
 

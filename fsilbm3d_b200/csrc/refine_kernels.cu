@@ -99,27 +99,34 @@ __device__ __forceinline__ int father_segment(const FatherView &v, int x)
     return sg;
 }
 
-// extract_interpolate_layer, LBMBlockComm.f90:340-505, one son face.  time 1: t1 <- father plane;
-// time 2: t2 <- father plane, t1 <- 0.5*(t1+t2).
-__global__ void pair_extract_kernel(const __grid_constant__ PairFaceParams p, int time)
+// extract_interpolate_layer, LBMBlockComm.f90:340-505: every coupled son face in one launch (blockIdx.z = face; the faces fill
+// separate buffers).  time 1: t1 <- father plane; time 2: t2 <- father plane, t1 <- 0.5*(t1+t2).
+__global__ void pair_extract_kernel(const __grid_constant__ PairFaces ps, int time)
 {
+    const PairFaceParams &p = ps.face[blockIdx.z];
     const int b = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
-    if (b >= p.bF) return;
+    if (b >= p.bF || a >= p.aF) return;
     int x, y, z;
     face_xyz(p.axis, p.fplane, p.fb0 + b, p.fa0 + a, x, y, z);
     const Geom &g = p.gF;
     // father indices are global; the plane lies in this rank's slab or, for a son across an interface, in a neighbour's
     const int sg = father_segment(p.fv, x);
     const double *fF = p.fv.f[sg];
-    const size_t ps = p.fv.pstride[sg];
+    const size_t ps_ = p.fv.pstride[sg];
     x -= p.fv.x0[sg];
     const size_t cell = (size_t)(x + 1) * g.plane + (size_t)y * g.Z + z;
     const size_t n = (size_t)a * p.bF + b, nn = (size_t)p.aF * p.bF;
+    double v[Q], o[Q];
 #pragma unroll
-    for (int q = 0; q < Q; q++) {
-        const double v = fF[q * ps + cell];
-        if (time == 1) p.buf[0][q * nn + n] = v;
-        else { p.buf[1][q * nn + n] = v; p.buf[0][q * nn + n] = 0.5 * (p.buf[0][q * nn + n] + v); }
+    for (int q = 0; q < Q; q++) v[q] = fF[q * ps_ + cell];
+    if (time == 1) {
+#pragma unroll
+        for (int q = 0; q < Q; q++) p.buf[0][q * nn + n] = v[q];
+    } else {
+#pragma unroll
+        for (int q = 0; q < Q; q++) o[q] = p.buf[0][q * nn + n];
+#pragma unroll
+        for (int q = 0; q < Q; q++) { p.buf[1][q * nn + n] = v[q]; p.buf[0][q * nn + n] = 0.5 * (o[q] + v[q]); }
     }
     if (p.tbuf[0]) {   // tau_F?t1 / t2 only exist when a block carries a tau_all field (LES models)
         const double t = p.tauF_all ? p.tauF_all[(size_t)x * g.plane + (size_t)y * g.Z + z] : p.tauF;
@@ -128,23 +135,66 @@ __global__ void pair_extract_kernel(const __grid_constant__ PairFaceParams p, in
     }
 }
 
-// interpolation_father_to_son, LBMBlockComm.f90:655-806, one son face
-__global__ void pair_f2s_kernel(const __grid_constant__ PairFaceParams p, int t)
+// interpolation_father_to_son, LBMBlockComm.f90:655-806: every coupled son face in one launch (blockIdx.z = face), one thread per
+// son node.  The reference takes the faces one after the other, so a node on an edge or corner of the son keeps the value of the
+// LAST face that holds it: a thread whose node also lies on the boundary plane of a later face of the list leaves it to that face
+// (every face covers its whole plane, and the values come from the layer buffers only, never from the son: no other coupling
+// between the faces).
+// Linear scheme, node outside the periodic closures (all but one row / column of a periodic son face): which coarse values a node
+// combines depends on the parity of (b, a) only, not on the population -- so the two row offsets are worked out once and the 19
+// populations become 19 x (1..4) INDEPENDENT loads, all in flight together, combined exactly as interp_b / interp_a combine them
+// ((F + F) * 0.5 along b, then (row + row) * 0.5 along a).  Walking interp_node population by population (the general path, kept
+// for the cubic scheme and the closures) is one dependent round trip to memory per population: 187 us per call on the six faces of
+// a 321 x 129 x 385 son, whose whole update takes 830.
+__global__ void __launch_bounds__(128) pair_f2s_kernel(const __grid_constant__ PairFaces ps, int t)
 {
+    const PairFaceParams &p = ps.face[blockIdx.z];
     const int b = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
-    if (b >= p.bS) return;
-    const size_t nn = (size_t)p.aF * p.bF;
-    double f[Q];
-#pragma unroll 1
-    for (int q = 0; q < Q; q++) {
-        CoarseView F{p.buf[t] + q * nn, p.bF};
-        f[q] = interp_node(F, p.scheme, p.bS, p.aS, b + 1, a + 1);
-    }
+    if (b >= p.bS || a >= p.aS) return;
     int x, y, z;
     face_xyz(p.axis, p.splane, b, a, x, y, z);
+    for (int k = blockIdx.z + 1; k < ps.n; k++) {
+        const int ax = ps.face[k].axis, pl = ps.face[k].splane;
+        if ((ax == 0 ? x : (ax == 1 ? y : z)) == pl) return;
+    }
+    const size_t nn = (size_t)p.aF * p.bF;
+    const int bStmp = (p.bS & 1) ? p.bS : p.bS - 1, aStmp = (p.aS & 1) ? p.aS : p.aS - 1;
+    const int B = b + 1, A = a + 1;   // 1-based, as the reference counts
+    double f[Q];
+    if (p.scheme != 2 && B <= bStmp && A <= aStmp) {
+        const bool be = !(B & 1), ae = !(A & 1);
+        const int c = (be ? B - 1 : B) / 2 + 1;                              // interp_b: F(b/2+1, .) or F(b1, .) + F(b1+1, .)
+        const int r0 = (ae ? A - 1 : A) / 2 + 1, r1 = (A + 1) / 2 + 1;        // interp_a: the row itself, or rows a-1 and a+1
+        const size_t o0 = (size_t)(r0 - 1) * p.bF + (c - 1), o1 = (size_t)(r1 - 1) * p.bF + (c - 1);
+        const double *base = p.buf[t];
+        double v00[Q], v01[Q], v10[Q], v11[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            v00[q] = base[q * nn + o0];
+            v01[q] = be ? base[q * nn + o0 + 1] : 0.0;
+            v10[q] = ae ? base[q * nn + o1] : 0.0;
+            v11[q] = (ae && be) ? base[q * nn + o1 + 1] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const double lo = be ? (v00[q] + v01[q]) * 0.5 : v00[q];
+            const double hi = be ? (v10[q] + v11[q]) * 0.5 : v10[q];
+            f[q] = ae ? (lo + hi) * 0.5 : lo;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < Q; k++) f[k] = 0.0;
+#pragma unroll 1
+        for (int q = 0; q < Q; q++) {
+            CoarseView F{p.buf[t] + q * nn, p.bF};
+            const double v = interp_node(F, p.scheme, p.bS, p.aS, B, A);
+#pragma unroll
+            for (int k = 0; k < Q; k++) f[k] = k == q ? v : f[k];   // keeps f in registers (no dynamic indexing)
+        }
+    }
     const Geom &g = p.gS;
     double tauF = p.tauF;   // constant tau: the linear interpolation of a constant is that constant, bit for bit
-    if (p.tbuf[0]) { CoarseView T{p.tbuf[t], p.bF}; tauF = interp_node(T, 1, p.bS, p.aS, b + 1, a + 1); }
+    if (p.tbuf[0]) { CoarseView T{p.tbuf[t], p.bF}; tauF = interp_node(T, 1, p.bS, p.aS, B, A); }
     const double tauS = p.tauS_all ? p.tauS_all[(size_t)x * g.plane + (size_t)y * g.Z + z] : p.tauS;
     const double coeff = (tauS / tauF) / 2.0;                    // :688
     grid_transform(f, coeff, p.hF[0], p.hF[1], p.hF[2]);          // father's volumeForce and dh, :663-664
@@ -153,11 +203,14 @@ __global__ void pair_f2s_kernel(const __grid_constant__ PairFaceParams p, int t)
     for (int q = 0; q < Q; q++) p.fS[q * g.pstride + cell] = f[q];
 }
 
-// deliver_son_to_father, LBMBlockComm.f90:546-653, one son face: father plane fi(j) <- son plane si(j), stride 2
-__global__ void pair_s2f_kernel(const __grid_constant__ PairFaceParams p)
+// deliver_son_to_father, LBMBlockComm.f90:546-653: father plane fi(j) <- son plane si(j), stride 2; every coupled face in one launch
+// (blockIdx.z = face).  Where the rectangles of two faces meet, both take the father node from the son node that coincides with it
+// -- the same node, the same expressions -- so the faces may run side by side.
+__global__ void pair_s2f_kernel(const __grid_constant__ PairFaces ps)
 {
+    const PairFaceParams &p = ps.face[blockIdx.z];
     const int b = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
-    if (b >= p.nb) return;
+    if (b >= p.nb || a >= p.na) return;
     int xs, ys, zs, xf, yf, zf;
     face_xyz(p.axis, p.siplane, p.sib0 + 2 * b, p.sia0 + 2 * a, xs, ys, zs);
     face_xyz(p.axis, p.fiplane, p.fib0 + b, p.fia0 + a, xf, yf, zf);
@@ -186,10 +239,13 @@ __global__ void flag_signal_kernel(unsigned long long *flag, unsigned long long 
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");
 }
 
-void launch_pair_extract(const PairFaceParams &p, int time, cudaStream_t s)
+void launch_pair_extract(const PairFaces &ps, int time, cudaStream_t s)
 {
-    dim3 block(128), grid((p.bF + 127) / 128, p.aF);
-    pair_extract_kernel<<<grid, block, 0, s>>>(p, time);
+    if (ps.n <= 0) return;
+    int mb = 0, ma = 0;
+    for (int i = 0; i < ps.n; i++) { mb = ps.face[i].bF > mb ? ps.face[i].bF : mb; ma = ps.face[i].aF > ma ? ps.face[i].aF : ma; }
+    dim3 block(128), grid((mb + 127) / 128, ma, ps.n);
+    pair_extract_kernel<<<grid, block, 0, s>>>(ps, time);
     count_launch();
 }
 void launch_flag_signal(unsigned long long *flag, unsigned long long value, cudaStream_t s)
@@ -197,17 +253,22 @@ void launch_flag_signal(unsigned long long *flag, unsigned long long value, cuda
     flag_signal_kernel<<<1, 32, 0, s>>>(flag, value);
     count_launch();
 }
-void launch_pair_f2s(const PairFaceParams &p, int t, cudaStream_t s)
+void launch_pair_f2s(const PairFaces &ps, int t, cudaStream_t s)
 {
-    dim3 block(128), grid((p.bS + 127) / 128, p.aS);
-    pair_f2s_kernel<<<grid, block, 0, s>>>(p, t);
+    if (ps.n <= 0) return;
+    int mb = 0, ma = 0;
+    for (int i = 0; i < ps.n; i++) { mb = ps.face[i].bS > mb ? ps.face[i].bS : mb; ma = ps.face[i].aS > ma ? ps.face[i].aS : ma; }
+    dim3 block(128), grid((mb + 127) / 128, ma, ps.n);
+    pair_f2s_kernel<<<grid, block, 0, s>>>(ps, t);
     count_launch();
 }
-void launch_pair_s2f(const PairFaceParams &p, cudaStream_t s)
+void launch_pair_s2f(const PairFaces &ps, cudaStream_t s)
 {
-    if (p.nb <= 0 || p.na <= 0) return;
-    dim3 block(128), grid((p.nb + 127) / 128, p.na);
-    pair_s2f_kernel<<<grid, block, 0, s>>>(p);
+    int mb = 0, ma = 0;
+    for (int i = 0; i < ps.n; i++) { mb = ps.face[i].nb > mb ? ps.face[i].nb : mb; ma = ps.face[i].na > ma ? ps.face[i].na : ma; }
+    if (ps.n <= 0 || mb <= 0 || ma <= 0) return;
+    dim3 block(128), grid((mb + 127) / 128, ma, ps.n);
+    pair_s2f_kernel<<<grid, block, 0, s>>>(ps);
     count_launch();
 }
 

@@ -120,6 +120,12 @@ class LBMBlock:
     def download_wait(self):
         check(lib().fsilbm_block_download_wait(self._h))
 
+    def write_flow_window_async(self, out: np.ndarray, offsetOutput: int = 0, outputtype: int = 1):
+        """OUTtmp of write_flow_ (FluidDomain.f90:1640-1699: p,u,v,w as real(4), C [nfields][nx][ny][nz] over the output window)
+        into the given (pinned) float32 array without waiting; valid after download_wait() or sync()."""
+        assert out.dtype == np.float32 and out.flags.c_contiguous
+        check(lib().fsilbm_block_write_flow_window_async(self._h, offsetOutput, outputtype, out.ctypes.data))
+
     def download_tau_all(self) -> np.ndarray:
         """tau_all (FluidDomain.f90:51), written by the LES collision models."""
         t = np.empty(self.shape)

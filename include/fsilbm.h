@@ -82,6 +82,9 @@ int fsilbm_trace_dump(const char *path);
  *                             exchanged through peer memory), 0 one kernel per phase (slab runs: ncclAllReduce of the loop control)
  *   "ibm_early"               1 (default) fsilbm_block_collide_stream updates the x-planes around the bodies first so that the next
  *                             fsilbm_ibm_interaction_force runs beside the rest of the update, 0 strictly one after the other
+ *   "update_split"            1 (default) on one GPU the launch over those planes goes to a high-priority stream of its own behind the
+ *                             interaction-force call while the rest of the update starts at once on the compute stream (the device never
+ *                             waits for an iteration that outlasts the previous update), 0 both launches queued on the compute stream
  *   "ibm_early_blocks_per_sm" 0 (default): the cooperative IBM grid that shares the SMs with that update is sized per call -- one block per
  *                             SM unless the iteration would outlast the rest of the update (a large body in a small block), then up to 4;
  *                             1..4 fixes it
@@ -139,13 +142,16 @@ int fsilbm_block_field_stat(fsilbm_handle h, double out[6]);
  *  - write_flow_ staging (FluidDomain.f90:1640-1699): fills `out` = OUTtmp as real(4), C [nfields][nx][ny][nz] over the
  *    window [offsetOutput, dim-offsetOutput) of the local slab; fields p,u,v,w (outputtype 1) or those + <u>,<v>,<w>,
  *    <uu>,<vv>,<ww>,<uv>,<uw>,<vw> (13 fields, outputtype >= 2).  The caller writes the file header and these bytes
- *    (and forks if it wants to: the buffer is plain host memory).
+ *    (and forks if it wants to: the buffer is plain host memory).  `_async` returns once the work is queued: `out` (PINNED
+ *    memory) is filled on the copy stream while later steps run and is valid after fsilbm_block_download_wait -- the
+ *    reference's own overlap of output and computation (its fork()ed writer, :1702), at half the bytes of den/uuu in fp64.
  *  - calculate_turbulent_statistic_ (:1147-1172): running means kept on the device (real(4) 1/n quirk of :1153 kept).
  *  - write_fluid_flux (:2019-2046): out = un-normalised fluxIn, fluxMid, fluxOut of the planes this rank owns
  *    (sum over ranks, then divide by denIn*Uref*Zref*Yref as :2051-2054 does).
  *  - write_fluid_information / grid_value_interpolation (FlowCondition.f90:195-222, Util.f90:123-157): trilinear
  *    velocity at n probe points, C [n][3]; contributions of corners this rank owns (sum over ranks). */
 int fsilbm_block_write_flow_window(fsilbm_handle h, int offsetOutput, int outputtype, float *out);
+int fsilbm_block_write_flow_window_async(fsilbm_handle h, int offsetOutput, int outputtype, float *out);
 int fsilbm_block_turbulent_statistic(fsilbm_handle h, int step, int step_s);
 int fsilbm_block_fluid_flux(fsilbm_handle h, double out[3]);
 int fsilbm_block_probe_velocity(fsilbm_handle h, int n, const double *coords, double *velocity);

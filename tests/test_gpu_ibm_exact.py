@@ -64,8 +64,11 @@ def test_early_ibm_bit_exact(oracle, F, bc):
     from tests.common import make_pair
     flow = dict(nu=0.05, uvwIn=(0.05, 0.0, 0.0), shearRateIn=(0.0, 2e-4, 0.0), Uref=0.05, ntolLBM=4, dtolLBM=1e-30)
     runs = {}
-    for early in (1, 0):
+    # (early, split): split = the planes around the body on the high-priority body stream beside the rest (the default) or
+    # queued before the rest on the compute stream
+    for early, split in ((1, 1), (1, 0), (0, 1)):
         F._lib.check(F.lib().fsilbm_set_option(b"ibm_early", early))
+        F._lib.check(F.lib().fsilbm_set_option(b"update_split", split))
         try:
             ob, gb = make_pair(oracle, F, (48, 36, 32), BndConds=bc, **flow)
             pg, po, ovb = plates_pair(oracle, F, 1.0, moving=True, origin=(18.3, 14.2, 10.4))
@@ -78,15 +81,16 @@ def test_early_ibm_bit_exact(oracle, F, bc):
                 po.structure(t, 1, ob.dh, ob.dh)
                 it_g = F.tree_collision_streaming_IBM_FEM(gb, [pg], time=t)
                 assert it_o == it_g == 4
-                assert np.array_equal(pg.body.v_Eforce, ovb.v_Eforce), (early, n)
+                assert np.array_equal(pg.body.v_Eforce, ovb.v_Eforce), (early, split, n)
             taken = F.lib().fsilbm_ibm_early_count() - c0
             assert taken == (24 if early else 0), taken      # every call after the first update
             assert fluid_equal(ob, gb)
-            runs[early] = gb.download_fIn()
+            runs[(early, split)] = gb.download_fIn()
             gb.close()
         finally:
             F._lib.check(F.lib().fsilbm_set_option(b"ibm_early", 1))
-    assert np.array_equal(runs[0], runs[1])
+            F._lib.check(F.lib().fsilbm_set_option(b"update_split", 1))
+    assert np.array_equal(runs[(0, 1)], runs[(1, 1)]) and np.array_equal(runs[(1, 0)], runs[(1, 1)])
 
 
 def test_overlapping_bodies_and_wrap_bit_exact(oracle, F):

@@ -200,3 +200,37 @@ def test_async_macro_readback(oracle, F):
     ob.calculate_macro_quantities()
     assert np.array_equal(d2, ob.den) and np.array_equal(u2, ob.uuu)
     gb.close()
+
+
+def test_async_flow_window_readback(oracle, F):
+    """fsilbm_block_write_flow_window_async: OUTtmp of write_flow_ (real(4) p,u,v,w over the output window) of the state at the call,
+    copied out while later steps run; identical to the synchronous call's bytes."""
+    import torch
+    from tests.common import make_pair
+    ob, gb = make_pair(oracle, F, (24, 20, 28), BndConds=(101, 104, 203, 203, 301, 301), nu=0.05, uvwIn=(0.04, 0.0, 0.0), Uref=0.04,
+                       volumeForceIn=(1e-6, 0.0, 0.0))
+    for n in range(1, 6):
+        F.tree_collision_streaming_IBM_FEM(gb, [], time=float(n))
+    off = 2
+    _, nx, ny, nz = F.flow_io.flow_window(gb, off)
+    want = np.empty((4, nx, ny, nz), dtype=np.float32)
+    F._lib.check(F.lib().fsilbm_block_write_flow_window(gb._h, off, 1, want.ctypes.data))
+    out = torch.empty((4, nx, ny, nz), dtype=torch.float32, pin_memory=True)
+    out.fill_(-7.0)
+    gb.write_flow_window_async(out.numpy(), off, 1)
+    for n in range(6, 10):                       # the update goes on while the copy is in flight
+        F.tree_collision_streaming_IBM_FEM(gb, [], time=float(n))
+    gb.download_wait()
+    assert np.array_equal(out.numpy(), want)
+    # ... and it is what the reference stores: den/uuu of the oracle at that step, scaled and cast as FluidDomain.f90:1650-1660 does
+    for n in range(1, 6):
+        ob.set_blktime(float(n)); ob.step([])
+    ob.calculate_macro_quantities()
+    sl = (slice(off, 24 - off), slice(off, 20 - off), slice(off, 28 - off))
+    invUref = 1.0 / ob.flow.Uref
+    assert np.array_equal(out.numpy()[1], (ob.uuu[0][sl] * invUref).astype(np.float32))
+    # a second asynchronous read-back waits for the first (one staging buffer)
+    gb.write_flow_window_async(out.numpy(), off, 1)
+    gb.write_flow_window_async(out.numpy(), off, 1)
+    gb.download_wait()
+    gb.close()
