@@ -1,15 +1,14 @@
-# round 2 session AJ: cell-list sort by 32 cells per warp; son-to-father faces in one launch
+# round 2 session AK (2 GPUs): multi-rank parity after the IBM / transfer kernel changes; the driver's N=2 commands
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_ibm_exact.py tests/test_gpu_fsi.py tests/test_gpu_refine.py tests/test_gpu_reference_golden.py tests/test_gpu_harness.py -m gpu -q -x > gpurun_out/r02aj_pytest.txt 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02aj_pytest.txt | cut -c1-300
-timeout 400 python bench.py --workload school2048r --steps 100 --warmup 10 --no-cpu-baseline --no-parity-check > gpurun_out/r02aj_school2048r.json 2> gpurun_out/err_aj1.txt; echo "rc=$?"
-timeout 400 python bench.py --workload school2048r --steps 100 --warmup 10 --no-cpu-baseline --no-parity-check --trace-out gpurun_out/r02aj_trace_school2048r > gpurun_out/r02aj_school2048r_tr.json 2> gpurun_out/err_aj2.txt; echo "rc=$?"
-timeout 300 python bench.py --workload heave1024 --steps 100 --warmup 10 --no-cpu-baseline --no-parity-check > gpurun_out/r02aj_heave1024.json 2> gpurun_out/err_aj3.txt; echo "rc=$?"
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tests/multi_rank_case.py > gpurun_out/r02ak_multi_rank_parity_n2.txt 2>&1; echo "parity rc=$?"; grep -c "OK" gpurun_out/r02ak_multi_rank_parity_n2.txt; grep -v "OK$" gpurun_out/r02ak_multi_rank_parity_n2.txt | tail -8 | cut -c1-250
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 bench.py --impl reference --gpus 2 --steps 20 --warmup 5 > gpurun_out/r02ak_ref_n2.json 2> gpurun_out/err_ak0.txt; echo "ref rc=$?"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r02ak_bench_n2_s20.json 2> gpurun_out/err_ak1.txt; echo "bench rc=$?"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 2 --steps 200 --warmup 10 --no-cpu-baseline > gpurun_out/r02ak_bench_n2_s200.json 2> gpurun_out/err_ak2.txt; echo "bench rc=$?"
 python - <<'P'
 import json,glob
-for f in sorted(glob.glob('gpurun_out/r02aj_*.json')):
+for f in sorted(glob.glob('gpurun_out/r02ak_*.json')):
     try:
-        d=json.load(open(f)); r=d['roofline']
-        print(f.split('/')[-1], round(d['value']), round(d['ms_per_step'],4), round(r['frac'],4), round(r['collide_alone']['kernel_ms'],4), d['clocks']['sm_mhz'], round(d['e2e']['value']), d['e2e']['seconds'], d['details']['structural_solver']['host_ms_per_step_all_bodies'])
+        d=json.load(open(f)); r=d.get('roofline') or {}
+        print(f.split('/')[-1], round(d['value']), round(d['ms_per_step'],4), r.get('frac'), d.get('clocks',{}).get('sm_mhz'), round(d['e2e']['value']), d.get('parity_check',{}) and d['parity_check'].get('ok'))
     except Exception as e: print(f, 'ERR', e)
 P
-head -30 gpurun_out/r02aj_trace_school2048r.rank0.csv
