@@ -1,14 +1,17 @@
-# round 2 session AK (2 GPUs): multi-rank parity after the IBM / transfer kernel changes; the driver's N=2 commands
+# round 2 session AM: heave1024 on one GPU -- what the IBM grid beside the update costs (lean build, fewer blocks, no overlap)
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tests/multi_rank_case.py > gpurun_out/r02ak_multi_rank_parity_n2.txt 2>&1; echo "parity rc=$?"; grep -c "OK" gpurun_out/r02ak_multi_rank_parity_n2.txt; grep -v "OK$" gpurun_out/r02ak_multi_rank_parity_n2.txt | tail -8 | cut -c1-250
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 bench.py --impl reference --gpus 2 --steps 20 --warmup 5 > gpurun_out/r02ak_ref_n2.json 2> gpurun_out/err_ak0.txt; echo "ref rc=$?"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r02ak_bench_n2_s20.json 2> gpurun_out/err_ak1.txt; echo "bench rc=$?"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 2 --steps 200 --warmup 10 --no-cpu-baseline > gpurun_out/r02ak_bench_n2_s200.json 2> gpurun_out/err_ak2.txt; echo "bench rc=$?"
+run() { tag=$1; shift; timeout 300 python bench.py --workload heave1024 --steps 100 --warmup 10 --no-cpu-baseline --no-parity-check "$@" > gpurun_out/r02am_heave1024_$tag.json 2> gpurun_out/err_am_$tag.txt; echo "$tag rc=$?"; }
+run base
+run lean --opt ibm_early_lean=1
+run b74 --opt ibm_early_blocks=74
+run b74lean --opt ibm_early_blocks=74 --opt ibm_early_lean=1
+run b296 --opt ibm_early_blocks_per_sm=2
+run noearly --opt ibm_early=0
 python - <<'P'
 import json,glob
-for f in sorted(glob.glob('gpurun_out/r02ak_*.json')):
+for f in sorted(glob.glob('gpurun_out/r02am_*.json')):
     try:
         d=json.load(open(f)); r=d.get('roofline') or {}
-        print(f.split('/')[-1], round(d['value']), round(d['ms_per_step'],4), r.get('frac'), d.get('clocks',{}).get('sm_mhz'), round(d['e2e']['value']), d.get('parity_check',{}) and d['parity_check'].get('ok'))
+        print(f.split('/')[-1], round(d['value']), round(d['ms_per_step'],4), round(r.get('frac'),4), round(r['collide_alone']['kernel_ms'],4), d.get('clocks',{}).get('sm_mhz'), d['details']['structural_solver']['host_ms_per_step_all_bodies'])
     except Exception as e: print(f, 'ERR', e)
 P
