@@ -1,17 +1,14 @@
-# round 2 session AM: heave1024 on one GPU -- what the IBM grid beside the update costs (lean build, fewer blocks, no overlap)
+# round 2 session AO: whole GPU suite at HEAD, smoke, the driver's two N=1 commands, launch lists of the default bench and of school2048r
 mkdir -p gpurun_out
-run() { tag=$1; shift; timeout 300 python bench.py --workload heave1024 --steps 100 --warmup 10 --no-cpu-baseline --no-parity-check "$@" > gpurun_out/r02am_heave1024_$tag.json 2> gpurun_out/err_am_$tag.txt; echo "$tag rc=$?"; }
-run base
-run lean --opt ibm_early_lean=1
-run b74 --opt ibm_early_blocks=74
-run b74lean --opt ibm_early_blocks=74 --opt ibm_early_lean=1
-run b296 --opt ibm_early_blocks_per_sm=2
-run noearly --opt ibm_early=0
+timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/r02ao_pytest.txt 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02ao_pytest.txt | cut -c1-300
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02ao_ref.json 2> gpurun_out/err_ao_ref.txt; echo "ref rc=$?"
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02ao_bench.json 2> gpurun_out/err_ao_bench.txt; echo "bench rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 220 --csv --log-file gpurun_out/r02ao_launches_school2048r.csv python bench.py --workload school2048r --steps 4 --warmup 3 --no-cpu-baseline --no-parity-check > gpurun_out/r02ao_under_ncu1.log 2>&1; echo "ncu rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 120 --csv --log-file gpurun_out/r02ao_launches_plate512.csv python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-parity-check > gpurun_out/r02ao_under_ncu2.log 2>&1; echo "ncu rc=$?"
 python - <<'P'
-import json,glob
-for f in sorted(glob.glob('gpurun_out/r02am_*.json')):
-    try:
-        d=json.load(open(f)); r=d.get('roofline') or {}
-        print(f.split('/')[-1], round(d['value']), round(d['ms_per_step'],4), round(r.get('frac'),4), round(r['collide_alone']['kernel_ms'],4), d.get('clocks',{}).get('sm_mhz'), d['details']['structural_solver']['host_ms_per_step_all_bodies'])
-    except Exception as e: print(f, 'ERR', e)
+import json
+for f in ('gpurun_out/r02ao_ref.json','gpurun_out/r02ao_bench.json'):
+    d=json.load(open(f)); r=d.get('roofline') or {}
+    print(f.split('/')[-1], round(d['value'],1), round(d['ms_per_step'],4), r.get('frac'), d.get('clocks'), d['e2e']['value'], (d.get('parity_check') or {}).get('ok'), d.get('gpu_launches'))
 P
