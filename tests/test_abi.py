@@ -125,3 +125,18 @@ def test_fortran_shim_binds_every_symbol():
         ends = len(re.findall(rf"(?m)^end {kw}", text))
         if kw != "type":
             assert opens == ends, (kw, opens, ends)
+
+
+def test_every_option_is_documented():
+    """Every key fsilbm_set_option accepts is described in the header's option table (and nothing else is listed there)."""
+    import re
+    ROOT = os.path.join(os.path.dirname(F.__file__), "..")
+    src = open(os.path.join(ROOT, "fsilbm3d_b200", "csrc", "fsilbm_api.cu")).read()
+    body = src[src.index("int fsilbm_set_option("):]
+    body = body[:body.index("\n}\n")]
+    keys = set(re.findall(r'strcmp\(key, "([a-z_0-9]+)"\)', body))
+    assert len(keys) >= 10
+    header = open(os.path.join(ROOT, "include", "fsilbm.h")).read()
+    table = header[header.index("Tuning/testing switches"):header.index("int fsilbm_set_option(")]
+    listed = set(re.findall(r'^ \*   "([a-z_0-9]+)"', table, flags=re.M))
+    assert keys == listed, (keys - listed, listed - keys)
