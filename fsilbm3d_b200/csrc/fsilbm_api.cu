@@ -223,7 +223,7 @@ struct Block {
     // Early IBM: collide_stream updates the x-planes around the bodies first (ev_early), so the next interaction-force call
     // can run on its own stream beside the rest of that update instead of behind it.  early_x0/x1: GLOBAL x-planes [x0, x1)
     // whose streamed populations are final once ev_early has passed.
-    cudaEvent_t ev_macro = nullptr, ev_io = nullptr;    // fsilbm_block_download_macro_async: den/uuu staged -> copied out on comm_stream
+    cudaEvent_t ev_macro = nullptr, ev_io = nullptr;    // asynchronous read-backs: den/uuu or OUTtmp staged -> copied out on io_stream
     bool io_pending = false;
     cudaStream_t ibm_main_stream = nullptr;
     cudaStream_t body_stream = nullptr;                 // single-rank early IBM: the planes around the bodies (high priority), beside the rest on `stream`
@@ -247,6 +247,7 @@ struct Block {
     unsigned long long *ibm_prof = nullptr; int ibm_prof_calls = 0;
     double ibm_host_t[3] = {0.0, 0.0, 0.0};   // FSILBM_IBM_PROFILE: host seconds in box set-up / enqueue / wait, summed over 100 calls
     cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaStream_t io_stream = nullptr;                   // device-to-host copies of the asynchronous read-backs (not the comm stream: on a slab that one carries the edge planes)
     cudaEvent_t ev_edge = nullptr, ev_comm = nullptr;
     // peer-memory halo (multi-GPU): see halo_setup
     struct Halo {
@@ -297,7 +298,6 @@ int g_ibm_single_launch = 1;   // 1: calculate_interaction_force as one cooperat
 int g_ibm_force_exchange = 1;  // slab runs: 1 every rank passes the same bodies and gets every body's forces back (one all-reduce);
                                // 0 every rank passes only the bodies near its slab (distributed lists; the call is then collective even with none)
 int g_ibm_early_blocks = 0;    // blocks per SM of the cooperative IBM kernel when it runs beside a collide-stream update; 0 = chosen per call
-int g_ibm_early_lean = 0;      // 1: the 48-register build of the cooperative kernel when it runs beside an update
 int g_ibm_early_total = 0;     // > 0: that grid as an absolute block count
 double g_update_clock_us = 0.0;   // estimated device time of every collide-stream update issued so far (all blocks share the compute stream)
 int g_update_split = 1;        // one GPU, early IBM: 1 the planes around the bodies on the body stream beside the rest; 0 queued before the rest
@@ -735,7 +735,6 @@ int fsilbm_set_option(const char *key, int value)
     if (!strcmp(key, "ibm_single_launch")) { g_ibm_single_launch = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_early_blocks_per_sm")) { if (value < 0 || value > 4) return fail(FSILBM_ERR_ARG, "ibm_early_blocks_per_sm must be 0 (automatic) or 1..4"); g_ibm_early_blocks = value; return 0; }
     if (!strcmp(key, "update_split")) { g_update_split = value ? 1 : 0; return 0; }
-    if (!strcmp(key, "ibm_early_lean")) { g_ibm_early_lean = value ? 1 : 0; return 0; }
     if (!strcmp(key, "ibm_early_blocks")) { if (value < 0) return fail(FSILBM_ERR_ARG, "ibm_early_blocks must be >= 0"); g_ibm_early_total = value; return 0; }
     if (!strcmp(key, "ibm_early")) { g_ibm_early = value ? 1 : 0; for (auto &bp : g_blocks) if (bp) bp->early_ok = false; return 0; }
     if (!strcmp(key, "ibm_force_exchange")) { g_ibm_force_exchange = value ? 1 : 0; return 0; }
@@ -786,6 +785,7 @@ int fsilbm_block_create(int xDim, int yDim, int zDim, int xOffset, int xLocal, d
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CK(cudaStreamCreateWithPriority(&b->comm_stream, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithFlags(&b->io_stream, cudaStreamNonBlocking));
     }
     CK(cudaEventCreateWithFlags(&b->ev_pre, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_edge, cudaEventDisableTiming));
@@ -823,6 +823,7 @@ int fsilbm_block_destroy(fsilbm_handle h)
     if (!b) return fail(FSILBM_ERR_ARG, "bad handle %d", h);
     cudaStreamSynchronize(b->stream);
     cudaStreamSynchronize(b->comm_stream);
+    cudaStreamSynchronize(b->io_stream);
     halo_teardown(*b);
     mrt_release(b->mrt_slot);
     for (int i = 0; i < 2; i++) cudaFree(b->f[i]);
@@ -840,7 +841,7 @@ int fsilbm_block_destroy(fsilbm_handle h)
     cudaEventDestroy(b->ev_ibm); cudaStreamDestroy(b->ibm_stream);
     cudaFree(b->csr.count); cudaFree(b->csr.off); cudaFree(b->csr.entry); cudaFree(b->csr_scan_tmp); cudaFree(b->tol_partial);
     cudaEventDestroy(b->ev_edge); cudaEventDestroy(b->ev_comm); cudaEventDestroy(b->ev_pre);
-    cudaStreamDestroy(b->comm_stream);
+    cudaStreamDestroy(b->comm_stream); cudaStreamDestroy(b->io_stream);
     g_blocks[h].reset();
     return 0;
 }
@@ -984,11 +985,11 @@ int fsilbm_block_download_macro_async(fsilbm_handle h, double *den, double *uuu)
     launch_macro_full(b->g, b->f[b->cur], hF, b->den, b->uuu, b->stream);
     CK(cudaGetLastError());
     CK(cudaEventRecord(b->ev_macro, b->stream));
-    CK(cudaStreamWaitEvent(b->comm_stream, b->ev_macro, 0));
+    CK(cudaStreamWaitEvent(b->io_stream, b->ev_macro, 0));
     const size_t n = (size_t)b->g.X * b->g.plane;
-    if (den) CK(cudaMemcpyAsync(den, b->den, sizeof(double) * n, cudaMemcpyDeviceToHost, b->comm_stream));
-    if (uuu) CK(cudaMemcpyAsync(uuu, b->uuu, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, b->comm_stream));
-    CK(cudaEventRecord(b->ev_io, b->comm_stream));
+    if (den) CK(cudaMemcpyAsync(den, b->den, sizeof(double) * n, cudaMemcpyDeviceToHost, b->io_stream));
+    if (uuu) CK(cudaMemcpyAsync(uuu, b->uuu, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, b->io_stream));
+    CK(cudaEventRecord(b->ev_io, b->io_stream));
     b->io_pending = true;
     return 0;
 }
@@ -1348,6 +1349,7 @@ int fsilbm_block_sync(fsilbm_handle h)
     if (int rc = await_deliveries(*b)) return rc;   // a neighbour's son may still be rewriting father nodes of this slab
     CK(cudaStreamSynchronize(b->stream));
     CK(cudaStreamSynchronize(b->comm_stream));
+    CK(cudaStreamSynchronize(b->io_stream));
     b->io_pending = false;
     if (b->halo.enabled) {
         int e = 0;
@@ -1413,9 +1415,9 @@ static int flow_window(fsilbm_handle h, int offsetOutput, int outputtype, float 
     CK(cudaGetLastError());
     if (async) {   // the copy leaves on the copy stream while later steps run; fsilbm_block_download_wait collects it
         CK(cudaEventRecord(b->ev_macro, b->stream));
-        CK(cudaStreamWaitEvent(b->comm_stream, b->ev_macro, 0));
-        CK(cudaMemcpyAsync(out, b->outtmp, sizeof(float) * n, cudaMemcpyDeviceToHost, b->comm_stream));
-        CK(cudaEventRecord(b->ev_io, b->comm_stream));
+        CK(cudaStreamWaitEvent(b->io_stream, b->ev_macro, 0));
+        CK(cudaMemcpyAsync(out, b->outtmp, sizeof(float) * n, cudaMemcpyDeviceToHost, b->io_stream));
+        CK(cudaEventRecord(b->ev_io, b->io_stream));
         b->io_pending = true;
         return 0;
     }
@@ -2126,7 +2128,7 @@ int fsilbm_ibm_interaction_force_begin(fsilbm_handle h, int nbody, const int *ne
                 early_total = std::max(sms / 4, std::min(2 * sms, (max_markers + 109) / 110));
             }
         }
-        if (launch_ibm_loop(lp, max_markers, use_early ? early_bps : 0, early_total, use_early ? g_ibm_early_lean : 0, s)) {
+        if (launch_ibm_loop(lp, max_markers, use_early ? early_bps : 0, early_total, s)) {
             cudaGetLastError();
             if (mailbox) return fail(FSILBM_ERR_CUDA, "cooperative launch of the IBM iteration failed");   // the other ranks are in the mailbox protocol
             single = false;   // no cooperative launch: take the phase-by-phase path

@@ -788,8 +788,8 @@ __device__ __forceinline__ void prof_stamp(const IbmLoopParams &p, int &k)
     k++;
 }
 
-// MINB = 4: 64 registers per thread; MINB = 5: 48 (a few spills) -- a 256-thread block then takes exactly the register space
-// of one 96-register CTA of the collide kernel it runs beside.
+// MINB = 4: 64 registers per thread, no spills.  (A 48-register build, MINB = 5 -- a 256-thread block then takes exactly the register
+// space of one 96-register CTA of the collide kernel it runs beside -- was measured slower on every workload and is gone.)
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB) ibm_loop_kernel(const __grid_constant__ IbmLoopParams p)
 {
@@ -949,7 +949,7 @@ int ibm_loop_max_blocks()
 
 // blocks_per_sm > 0: the launch shares the SMs with a running collide-stream kernel (early IBM); one block per SM leaves that
 // kernel three of its four CTA slots (its 125 registers per thread fill the register file with four)
-int launch_ibm_loop(const IbmLoopParams &p, int max_markers, int blocks_per_sm, int blocks_total, int lean, cudaStream_t s)
+int launch_ibm_loop(const IbmLoopParams &p, int max_markers, int blocks_per_sm, int blocks_total, cudaStream_t s)
 {
     int max_blocks = ibm_loop_max_blocks();
     if (blocks_per_sm > 0) {
@@ -966,7 +966,7 @@ int launch_ibm_loop(const IbmLoopParams &p, int max_markers, int blocks_per_sm, 
     int blocks = want < 1 ? 1 : (want > max_blocks ? max_blocks : want);
     if (cudaMemsetAsync(p.barrier, 0, sizeof(unsigned int), s) != cudaSuccess) return 1;   // the barrier counts up from zero in every launch
     void *args[] = {(void *)&p};
-    cudaError_t e = cudaLaunchCooperativeKernel(lean ? (void *)ibm_loop_kernel<5> : (void *)ibm_loop_kernel<4>, dim3(blocks), dim3(256), args, 0, s);
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)ibm_loop_kernel<4>, dim3(blocks), dim3(256), args, 0, s);
     if (e != cudaSuccess) return 1;
     count_launch();
     return 0;

@@ -207,7 +207,7 @@ struct IbmLoopParams {        // the single-launch form of calculate_interaction
 };
 // a rank that iterates no body still takes part in the loop-control exchange (one small block)
 void launch_ibm_ctl_only(const IbmCtlExchange &xc, int ntol, double dtol, double Uref, IbmCtl *ctl, cudaStream_t s);
-int launch_ibm_loop(const IbmLoopParams &p, int max_markers, int blocks_per_sm, int blocks_total, int lean, cudaStream_t s);
+int launch_ibm_loop(const IbmLoopParams &p, int max_markers, int blocks_per_sm, int blocks_total, cudaStream_t s);
 int ibm_loop_max_blocks();
 
 // build of IbmCsr after the stencils are known: count -> scan -> fill -> per-cell sort

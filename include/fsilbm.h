@@ -89,8 +89,6 @@ int fsilbm_trace_dump(const char *path);
  *                             SM unless the iteration would outlast the rest of the update (a large body in a small block), then up to 4;
  *                             1..4 fixes it
  *   "ibm_early_blocks"        > 0: that grid as an absolute number of blocks instead (0 = use the per-SM figure)
- *   "ibm_early_lean"          1 = the 48-register build of that kernel (a block then takes exactly one CTA slot of the update beside it, at
- *                             the price of a few spills); 0 (default) the 64-register build -- measured faster on every workload
  *   "ibm_force_exchange"      slab runs: 1 (default) every rank passes the same body list and gets every force back, 0 per-rank lists
  *                             (see fsilbm_ibm_body_status below) */
 int fsilbm_set_option(const char *key, int value);
