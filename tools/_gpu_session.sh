@@ -1,6 +1,5 @@
-# round 2 session AR: after the removal of the 48-register IBM build and the separate copy stream of the asynchronous read-backs
+# round 2 session AS (2 GPUs): the driver's N=2 command at the final HEAD (asynchronous read-back on its own copy stream on slabs)
 mkdir -p gpurun_out
-timeout 100 python -m pytest tests/test_gpu_io.py tests/test_gpu_ibm_exact.py -m gpu -q -x > gpurun_out/r02ar_pytest.txt 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r02ar_pytest.txt | cut -c1-200
-timeout 90 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02ar_bench.json 2> gpurun_out/err_ar.txt; echo "bench rc=$?"
+timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29561 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r02as_bench_n2_s20.json 2> gpurun_out/err_as.txt; echo "bench rc=$?"
 python -c "
-import json; d=json.load(open('gpurun_out/r02ar_bench.json')); print(round(d['value']), d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['parity_check']['ok'])"
+import json; d=json.load(open('gpurun_out/r02as_bench_n2_s20.json')); print(round(d['value']), d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['parity_check']['ok'])"
