@@ -124,6 +124,12 @@ class LBMBlock:
         """OUTtmp of write_flow_ (FluidDomain.f90:1640-1699: p,u,v,w as real(4), C [nfields][nx][ny][nz] over the output window)
         into the given (pinned) float32 array without waiting; valid after download_wait() or sync()."""
         assert out.dtype == np.float32 and out.flags.c_contiguous
+        # the library fills nfields * (window of the local slab) floats: the array must hold exactly that (see flow_io.flow_window)
+        from .flow_io import flow_window
+        _, nx, ny, nz = flow_window(self, offsetOutput)
+        want = (13 if outputtype >= 2 else 4) * nx * ny * nz
+        if out.size != want:
+            raise ValueError(f"write_flow_window_async: the staging array holds {out.size} values, the window needs {want}")
         check(lib().fsilbm_block_write_flow_window_async(self._h, offsetOutput, outputtype, out.ctypes.data))
 
     def download_tau_all(self) -> np.ndarray:

@@ -51,3 +51,18 @@ def test_restart_helpers_refuse_slabs():
         flow_io.write_continue_blocks([_Slab(32, 8, 8)], 1, 0.5, root="/nonexistent")
     with pytest.raises(ValueError, match="x-slab"):
         flow_io.regrid_from_continue(_Slab(32, 8, 8), [])
+
+
+def test_async_flow_window_refuses_a_staging_array_of_the_wrong_size():
+    """The library fills nfields x window floats through a raw pointer: the mirror checks the array before the call."""
+    import pytest
+    from fsilbm3d_b200.fluid_domain import LBMBlock
+    slab = _Slab(32, 8, 8)
+    slab._h = -1
+    with pytest.raises(ValueError, match="staging array"):
+        LBMBlock.write_flow_window_async(slab, np.empty(4 * 8 * 6 * 8 - 1, dtype=np.float32), 2, 1)
+    with pytest.raises(ValueError, match="staging array"):
+        LBMBlock.write_flow_window_async(slab, np.empty(4 * 8 * 6 * 8, dtype=np.float32), 2, 2)     # 13 fields wanted
+    with pytest.raises(Exception) as ei:                                                             # right size: reaches the library
+        LBMBlock.write_flow_window_async(slab, np.empty(4 * 8 * 6 * 8, dtype=np.float32), 2, 1)
+    assert not isinstance(ei.value, ValueError)
