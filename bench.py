@@ -115,7 +115,38 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.device, self.rows, self._stop_evt = device, [], threading.Event()
 
+    def _run_nvml(self) -> bool:
+        """Polls NVML directly (a few hundred samples per second, so that a 20-step timed region of 30 ms still holds several);
+        False if NVML is not usable here, then nvidia-smi is polled instead."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        bits = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+        while not self._stop_evt.is_set():
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                except Exception:
+                    r = 0
+                self.rows.append([str(self.device), str(sm), str(mx), "", ""] + ["Active" if r & b else "Not Active" for b, _ in bits])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.003)
+        try:
+            pynvml.nvmlShutdown()
+        except Exception:
+            pass
+        return True
+
     def run(self):
+        if self._run_nvml():
+            return
         while not self._stop_evt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
