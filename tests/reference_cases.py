@@ -60,6 +60,12 @@ CASES["refine_cubic_periodic_son_trt"] = dict(
     scheme=2, model=2, params=(3.0 / 16.0,) + (0.0,) * 9, smodel=1, sparams=P0, steps=6, uvwIn=(0.04, 0.0, 0.0), Uref=0.04, Lref=4.0, Re=20.0,
     wave=1e-3, flow=dict(volumeForceIn=(1e-6, 0.0, 0.0)))
 CASES["refine_les_smag"] = dict(CASES["refine_linear"], model=11, wave=2e-2, steps=5)
+# a son periodic in y AND z: only its two x faces are coupled, and they carry the closures of interpolate_fIn in both face directions plus
+# the corner closure (LBMBlockComm.f90:857-871 cubic, :892-905 linear); one case per scheme
+for _name, _scheme in (("refine_linear_periodic_son_yz", 1), ("refine_cubic_periodic_son_yz", 2)):
+    CASES[_name] = dict(kind="refine", dims=(14, 10, 10), bc=(101, 104, 301, 301, 301, 301), sdims=(13, 20, 20), smins=(4.0, 0.0, 0.0),
+                        sbc=(0, 0, 301, 301, 301, 301), scheme=_scheme, model=1, params=P0, steps=5, uvwIn=(0.04, 0.0, 0.0), Uref=0.04, Lref=4.0,
+                        Re=20.0, wave=1e-3, flow=dict(volumeForceIn=(1e-6, 0.0, 0.0)))
 
 # a rigid plate in prescribed heave (iBodyModel 1; Solidbody.f90:760-1049 IBM, SolidSolver.f90:1826-1857 motion)
 CASES["rigid_plate_heave"] = dict(

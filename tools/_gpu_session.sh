@@ -1,6 +1,3 @@
-# round 2 session AU: clocks sampled through NVML during the timed region (several samples even in a 30 ms region)
+# round 2 session AV: the two new pin cases (sons periodic in y and z) through both GPU routes
 mkdir -p gpurun_out
-timeout 60 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline --no-parity-check > gpurun_out/r02au_bench.json 2> gpurun_out/err_au.txt; echo "bench rc=$?"
-python -c "
-import json; d=json.load(open('gpurun_out/r02au_bench.json')); print(round(d['value']), d['ms_per_step'], d['e2e']['value'], d['clocks'])"
-tail -3 gpurun_out/err_au.txt | cut -c1-200
+timeout 30 python -m pytest tests/test_gpu_reference_golden.py -m gpu -q -x -k "periodic_son_yz" > gpurun_out/r02av_pytest.txt 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02av_pytest.txt | cut -c1-300
