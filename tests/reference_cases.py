@@ -122,6 +122,14 @@ CASES["plates_near_walls"] = dict(
 # MRT with every kind of face and a Smagorinsky block with a plate: collision models other than SRT next to boundaries / bodies
 CASES["mrt_all_faces_mixed"] = _fluid((9, 10, 8), (101, 103, 204, 202, 201, 203), model=3, steps=8, uvwIn=(0.03, 0.0, 0.0), Uref=0.03,
                                       shearRateIn=(0.0, 4e-4, 1e-4))
+# configs[2] in small, started the way a first run starts: isConCmpt = 0, i.e. from initialise_ itself (FluidDomain.f90:433-545: f_eq of the
+# sheared inflow profile, evaluate_shear_velocity :1803-1810) instead of an injected state -- a rigid plate in shear inflow between moving
+# walls.  Oracle-against-reference only (gpu=False): the CUDA initialise_ is held against the oracle's in tests/test_gpu_parity.py.
+CASES["plate_in_shear_from_initialise"] = dict(
+    kind="body", dims=(22, 14, 12), bc=(101, 104, 202, 202, 301, 301), model=1, params=P0, steps=8, uvwIn=(0.05, 0.0, 0.0), Uref=0.05, Lref=4.0,
+    Re=40.0, wave=0.0, flow=dict(shearRateIn=(0.0, 3e-4, 0.0)), ntolLBM=5, dtolLBM=1e-30, numsubstep=1, plate=dict(nEL=4, chord=4.0, span=4.0, Nspan=4),
+    group=dict(iBodyModel=1, isMotionGiven=(1,) * 6, EmR=1.0, tcR=0.05, AoAo=(0.0, 0.0, 8.0), firstXYZ=(7.3, 6.6, 4.2)), isKB=0,
+    from_initialise=True, gpu=False)
 CASES["les_smag_plate"] = dict(
     kind="body", dims=(20, 14, 14), bc=(101, 104, 301, 301, 301, 301), model=11, params=P0, steps=6, uvwIn=(0.05, 0.0, 0.0), Uref=0.05, Lref=4.0,
     Re=400.0, wave=2e-2, flow={}, ntolLBM=3, dtolLBM=1e-30, numsubstep=1, plate=dict(nEL=4, chord=4.0, span=4.0, Nspan=4),
@@ -275,13 +283,14 @@ def write_inputs(case, wd, continue_at_end=False):
     extra = dict(timeContiDelta=case["steps"] / Tref) if continue_at_end else {}
     if case.get("outputs"):
         extra.update(timeFlowDelta=case["steps"] / Tref, timeInfoDelta=case["steps"] / Tref, fluidProbes=case["probes"], inWhichBlock=1)
-    text = S.inflow_text(npsize=1, isConCmpt=2, numsubstep=case.get("numsubstep", 1), timeSimTotal=total, Re=case["Re"], uvwIn=case["uvwIn"],
+    text = S.inflow_text(npsize=1, isConCmpt=0 if case.get("from_initialise") else 2, numsubstep=case.get("numsubstep", 1), timeSimTotal=total, Re=case["Re"], uvwIn=case["uvwIn"],
                          LrefType=1, Lref=case["Lref"], TrefType=0, UrefType=9, Uref=case["Uref"], ntolLBM=case.get("ntolLBM", 3),
                          dtolLBM=case.get("dtolLBM", 1e-8), interpolateScheme=case.get("scheme", 1), blocks=blocks, groups=groups,
                          isKB=case.get("isKB", 0), dtolFEM=1e-12, ntolFEM=20, **extra, **case.get("solid", {}), **case["flow"])
     with open(os.path.join(wd, "inFlow.dat"), "w") as f:
         f.write(text)
-    write_continue(os.path.join(wd, "DatContinue", "continue"), blocks, initial_states(case))
+    if not case.get("from_initialise"):
+        write_continue(os.path.join(wd, "DatContinue", "continue"), blocks, initial_states(case))
 
 
 def run_oracle(O, case, sb=None):
@@ -289,7 +298,7 @@ def run_oracle(O, case, sb=None):
     (harness/libfsilbm_solid.so; host code on both sides of the boundary).  Returns (blocks, oracle body or None, iteration counts)."""
     nu = case["Uref"] * case["Lref"] / case["Re"]                           # Solidbody.f90:282
     fl = O.Flow(nu=nu, uvwIn=case["uvwIn"], Uref=case["Uref"], ntolLBM=case.get("ntolLBM", 3), dtolLBM=case.get("dtolLBM", 1e-8), **case["flow"])
-    states = restart_states(case)
+    states = None if case.get("from_initialise") else restart_states(case)
     X, Y, Z = case["dims"]
     Fb = O.LBMBlock(X, Y, Z, dh=1.0, BndConds=case["bc"], iCollidModel=case["model"], params=case["params"], flow=fl)
     blocks = [Fb]
@@ -314,9 +323,10 @@ def run_oracle(O, case, sb=None):
         cands = [j for j in range(len(geo)) if j != i and geo[j]["dh"] > geo[i]["dh"] and inside(i, j)]
         fa = min(cands, key=lambda j: geo[j]["dh"])
         nodes[fa].add_son(nodes[i], case["scheme"])
-    for b, st in zip(blocks, states):
+    for k, b in enumerate(blocks):
         b.initialise(0.0)
-        b.fIn[...] = st
+        if states is not None:
+            b.fIn[...] = states[k]
     for b in blocks:
         b.update_volume_force(); b.set_boundary_conditions(); b.calculate_macro_quantities()
     ovs, its = [], []
