@@ -60,6 +60,10 @@ CASES["refine_cubic_periodic_son_trt"] = dict(
     scheme=2, model=2, params=(3.0 / 16.0,) + (0.0,) * 9, smodel=1, sparams=P0, steps=6, uvwIn=(0.04, 0.0, 0.0), Uref=0.04, Lref=4.0, Re=20.0,
     wave=1e-3, flow=dict(volumeForceIn=(1e-6, 0.0, 0.0)))
 CASES["refine_les_smag"] = dict(CASES["refine_linear"], model=11, wave=2e-2, steps=5)
+# MRT father and MRT son: the son's relaxation matrices are built from ITS tau (dh / 2), FluidDomain.f90:466-522, and fIn_GridTransform
+# rescales the non-equilibrium part between the two (LBMBlockComm.f90:958-979).  Oracle-against-reference only (gpu=False): the CUDA side of
+# several MRT blocks with different matrices is held against the oracle in tests/test_gpu_parity.py
+CASES["refine_mrt_father_and_son"] = dict(CASES["refine_linear"], model=3, steps=5, gpu=False)
 # a son periodic in y AND z: only its two x faces are coupled, and they carry the closures of interpolate_fIn in both face directions plus
 # the corner closure (LBMBlockComm.f90:857-871 cubic, :892-905 linear); one case per scheme
 for _name, _scheme in (("refine_linear_periodic_son_yz", 1), ("refine_cubic_periodic_son_yz", 2)):
