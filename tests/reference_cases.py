@@ -107,6 +107,13 @@ CASES["flexible_plate_heaving"] = dict(
     Re=40.0, wave=1e-3, flow={}, ntolLBM=3, dtolLBM=1e-30, numsubstep=4, plate=dict(nEL=4, chord=4.0, span=4.0, Nspan=4),
     group=dict(iBodyModel=2, isMotionGiven=(1,) * 6, denR=2.0, psR=0.3, KB=0.05, KS=800.0, freq=0.02, XYZAmpl=(0.0, 0.8, 0.0),
                AoAAmpl=(0.0, 0.0, 10.0), AoAPhi=(0.0, 0.0, 90.0), firstXYZ=(6.3, 6.6, 5.2)), isKB=1)
+# the same plate over 30 steps (120 structural sub-steps, a softer and longer beam of 8 elements): the closed fluid-structure loop amplifies a
+# one-ulp difference within a few steps (that is how the Young's-modulus slip was found), so a long run is the sharp test of the whole
+# chain -- IBM order, nodal loads, Newton / CG iteration path.  Oracle-against-reference only (gpu=False).
+CASES["flexible_plate_heaving_30_steps"] = dict(
+    CASES["flexible_plate_heaving"], steps=30, plate=dict(nEL=8, chord=4.0, span=4.0, Nspan=4),
+    group=dict(iBodyModel=2, isMotionGiven=(1,) * 6, denR=2.0, psR=0.3, KB=0.02, KS=600.0, freq=0.02, XYZAmpl=(0.0, 0.8, 0.0),
+               AoAAmpl=(0.0, 0.0, 10.0), AoAPhi=(0.0, 0.0, 90.0), firstXYZ=(6.3, 6.6, 5.2)), gpu=False)
 # structural variants of the flexible plate: explicit modulus / thickness (isKB = 0) with a hinged leading edge (rotation about z free);
 # Rayleigh damping, a dissipative Newmark pair, reduced geometric stiffness and a three-dimensional incidence
 CASES["flexible_plate_hinged_iskb0"] = dict(
