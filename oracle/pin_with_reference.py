@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Cross-checks the committed reference goldens against a GFORTRAN BUILD of the reference.  Test infrastructure only.
 
-tests/golden/ref_*.npz hold what the reference's own main program leaves on the 37 cases of tests/reference_cases.py; they were
+tests/golden/ref_*.npz hold what the reference's own main program leaves on the 38 cases of tests/reference_cases.py; they were
 produced in an image without a Fortran compiler by executing the reference's unmodified sources with the interpreter in
 oracle/ftn/ (DESIGN.md section 5).  Where gfortran exists this script closes the remaining gap (interpreter vs compiler):
 

@@ -114,6 +114,16 @@ CASES["flexible_plate_heaving_30_steps"] = dict(
     CASES["flexible_plate_heaving"], steps=30, plate=dict(nEL=8, chord=4.0, span=4.0, Nspan=4),
     group=dict(iBodyModel=2, isMotionGiven=(1,) * 6, denR=2.0, psR=0.3, KB=0.02, KS=600.0, freq=0.02, XYZAmpl=(0.0, 0.8, 0.0),
                AoAAmpl=(0.0, 0.0, 10.0), AoAPhi=(0.0, 0.0, 90.0), firstXYZ=(6.3, 6.6, 5.2)), gpu=False)
+# configs[4] in small: TWO flexible plates in tandem, the second in the wake of the first and close enough for their stencil boxes to meet
+# (Gauss-Seidel order of the penalty sweeps, Solidbody.f90:898-903; Solver over all bodies per sub-step, :386-397), one heaving, one passive,
+# with a tolerance that ends some iterations early.  Oracle-against-reference only (gpu=False).
+CASES["two_flexible_plates_tandem"] = dict(
+    kind="body", dims=(26, 16, 14), bc=(101, 104, 301, 301, 301, 301), model=1, params=P0, steps=12, uvwIn=(0.04, 0.0, 0.0), Uref=0.04, Lref=4.0,
+    Re=40.0, wave=1e-3, flow={}, ntolLBM=6, dtolLBM=0.3, numsubstep=2, plate=dict(nEL=4, chord=4.0, span=4.0, Nspan=4),
+    groups=[dict(iBodyModel=2, isMotionGiven=(1,) * 6, denR=2.0, psR=0.3, KB=0.05, KS=800.0, freq=0.02, XYZAmpl=(0.0, 0.8, 0.0),
+                 firstXYZ=(6.3, 7.6, 5.2)),
+            dict(iBodyModel=2, isMotionGiven=(1,) * 6, denR=1.5, psR=0.3, KB=0.03, KS=600.0, AoAo=(0.0, 0.0, 6.0), firstXYZ=(11.4, 8.2, 5.4))],
+    isKB=1, gpu=False)
 # structural variants of the flexible plate: explicit modulus / thickness (isKB = 0) with a hinged leading edge (rotation about z free);
 # Rayleigh damping, a dissipative Newmark pair, reduced geometric stiffness and a three-dimensional incidence
 CASES["flexible_plate_hinged_iskb0"] = dict(
